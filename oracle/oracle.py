@@ -1,0 +1,318 @@
+"""ctypes binding of the CPU oracle (oracle/fdm_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  The product package never does.
+
+The date -> tau mapping of dividends (``fd_american_option_pricer.py:304-315``) and the
+pricer-level compositions stay in Python here; the PDE solve itself
+(``_solve_grid``, ``fd_american_option_pricer.py:554-602``;
+``discrete_barrier_fdm_pricer_cn.py:219-302``) is the C restatement.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libfdm_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
+    src = os.path.join(_HERE, "fdm_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
+    return _LIB_PATH
+
+
+class _FdoAmerican(C.Structure):
+    _fields_ = [
+        ("spot", C.c_double), ("strike", C.c_double), ("T", C.c_double), ("sigma", C.c_double),
+        ("r", C.c_double), ("b", C.c_double), ("s_max_mult", C.c_double),
+        ("is_call", C.c_int32), ("model", C.c_int32), ("n_space", C.c_int32),
+        ("n_time", C.c_int32), ("rannacher", C.c_int32), ("n_div", C.c_int32),
+        ("div_tau", C.POINTER(C.c_double)), ("div_cash", C.POINTER(C.c_double)),
+    ]
+
+
+class _FdoAmericanInfo(C.Structure):
+    _fields_ = [
+        ("spot_idx", C.c_int32), ("strike_idx", C.c_int32), ("n_steps_total", C.c_int32),
+        ("ex_lo", C.c_int32), ("ex_hi", C.c_int32),
+        ("dx", C.c_double), ("S_min", C.c_double), ("S_max", C.c_double), ("price", C.c_double),
+        ("seg_steps", C.c_int32 * 16), ("n_seg", C.c_int32),
+    ]
+
+
+class _FdoBarrier(C.Structure):
+    _fields_ = [
+        ("S0", C.c_double), ("K", C.c_double), ("T", C.c_double), ("sigma", C.c_double),
+        ("r_disc", C.c_double), ("b_carry", C.c_double),
+        ("lower_barrier", C.c_double), ("upper_barrier", C.c_double), ("rebate", C.c_double),
+        ("is_call", C.c_int32), ("ko_kind", C.c_int32), ("apply_KO", C.c_int32),
+        ("N_space", C.c_int32), ("N_time", C.c_int32), ("n_monitor", C.c_int32),
+        ("monitor_times", C.POINTER(C.c_double)),
+    ]
+
+
+class _FdoBarrierInfo(C.Structure):
+    _fields_ = [
+        ("S_min", C.c_double), ("S_max", C.c_double), ("dx", C.c_double),
+        ("price", C.c_double), ("delta", C.c_double), ("gamma", C.c_double),
+        ("n_monitor_steps", C.c_int32), ("greek_idx", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.fdo_american_solve.restype = C.c_int
+        L.fdo_american_solve.argtypes = [C.POINTER(_FdoAmerican), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                         C.POINTER(_FdoAmericanInfo)]
+        L.fdo_barrier_configure.restype = C.c_int
+        L.fdo_barrier_configure.argtypes = [C.POINTER(_FdoBarrier), C.c_int32, C.c_int32,
+                                            C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.fdo_barrier_solve.restype = C.c_int
+        L.fdo_barrier_solve.argtypes = [C.POINTER(_FdoBarrier), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                        C.POINTER(_FdoBarrierInfo)]
+        L.fdo_american_batch.restype = C.c_int
+        L.fdo_american_batch.argtypes = [C.c_int64, C.POINTER(_FdoAmerican), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32]
+        L.fdo_barrier_batch.restype = C.c_int
+        L.fdo_barrier_batch.argtypes = [C.c_int64, C.POINTER(_FdoBarrier), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32]
+        L.fdo_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _dptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+# --------------------------------------------------------------------------------------
+# American
+# --------------------------------------------------------------------------------------
+
+@dataclass
+class AmericanResult:
+    V: np.ndarray
+    s_nodes: np.ndarray
+    price: float
+    spot_idx: int
+    strike_idx: int
+    ex_lo: int
+    ex_hi: int
+    dx: float
+    S_min: float
+    S_max: float
+    seg_steps: List[int]
+    ex_trace: Optional[np.ndarray]
+
+
+def _am_struct(spot, strike, T, sigma, r, b, is_call, model, n_space, n_time, rannacher,
+               s_max_mult, div_tau, div_cash):
+    p = _FdoAmerican()
+    p.spot, p.strike, p.T, p.sigma, p.r, p.b = spot, strike, T, sigma, r, b
+    p.s_max_mult = s_max_mult
+    p.is_call, p.model = int(bool(is_call)), int(model)
+    p.n_space, p.n_time, p.rannacher = int(n_space), int(n_time), int(rannacher)
+    p.n_div = len(div_tau)
+    p.div_tau = _dptr(div_tau) if len(div_tau) else None
+    p.div_cash = _dptr(div_cash) if len(div_cash) else None
+    return p
+
+
+def american_solve(spot: float, strike: float, T: float, sigma: float, r: float, b: float,
+                   is_call: bool, model: int = 0, n_space: int = 400, n_time: int = 400,
+                   rannacher: int = 2, s_max_mult: float = 4.5,
+                   divs_tau: Sequence[Tuple[float, float]] = (),
+                   trace: bool = False) -> AmericanResult:
+    """One ``_solve_grid`` (fd_american_option_pricer.py:554-602) + ``_interp_price``.
+
+    ``divs_tau`` = [(tau_div, cash)] ascending in tau, as ``_div_times_tau`` returns.
+    ``model``: 0 equity, 1 Black-76 (fd_american_black76.py).
+    """
+    div_tau = np.ascontiguousarray([d[0] for d in divs_tau], dtype=np.float64)
+    div_cash = np.ascontiguousarray([d[1] for d in divs_tau], dtype=np.float64)
+    p = _am_struct(spot, strike, T, sigma, r, b, is_call, model, n_space, n_time, rannacher,
+                   s_max_mult, div_tau, div_cash)
+    V = np.empty(n_space + 1, dtype=np.float64)
+    s = np.empty(n_space + 1, dtype=np.float64)
+    max_steps = n_time + 4 * (len(divs_tau) + 1) + 8
+    ex = np.full(2 * max_steps, -2, dtype=np.int32) if trace else None
+    info = _FdoAmericanInfo()
+    rc = lib().fdo_american_solve(C.byref(p), _dptr(V), _dptr(s),
+                                  ex.ctypes.data_as(C.POINTER(C.c_int32)) if trace else None,
+                                  C.byref(info))
+    if rc != 0:
+        raise ValueError(f"fdo_american_solve failed rc={rc}")
+    return AmericanResult(
+        V=V, s_nodes=s, price=info.price, spot_idx=info.spot_idx, strike_idx=info.strike_idx,
+        ex_lo=info.ex_lo, ex_hi=info.ex_hi, dx=info.dx, S_min=info.S_min, S_max=info.S_max,
+        seg_steps=[info.seg_steps[i] for i in range(min(info.n_seg, 16))],
+        ex_trace=ex[: 2 * info.n_steps_total].reshape(-1, 2) if trace else None,
+    )
+
+
+def local_cubic_delta_gamma(s: np.ndarray, V: np.ndarray, Sx: float) -> Tuple[float, float]:
+    """``_local_cubic_delta_gamma`` (fd_american_option_pricer.py:632-653)."""
+    n = len(s) - 1
+    i_near = int(np.argmin(np.abs(s - Sx)))          # first minimum, like min(range, key=)
+    i_near = min(max(i_near, 1), n - 2)
+    idx = [i_near - 1, i_near, i_near + 1, i_near + 2]
+    x = np.array([s[j] for j in idx], dtype=float)
+    y = np.array([V[j] for j in idx], dtype=float)
+    z = x - Sx
+    M = np.vstack([z ** 3, z ** 2, z, np.ones_like(z)]).T
+    a, b, c, d = np.linalg.solve(M, y)
+    return float(c), float(2.0 * b)
+
+
+def american_batch_prices(params: Sequence[dict], n_threads: int = 0):
+    """OpenMP batch of American solves (CPU baseline).  Each dict = american_solve kwargs."""
+    n = len(params)
+    arr = (_FdoAmerican * n)()
+    keep = []
+    for i, kw in enumerate(params):
+        divs = kw.get("divs_tau", ())
+        div_tau = np.ascontiguousarray([d[0] for d in divs], dtype=np.float64)
+        div_cash = np.ascontiguousarray([d[1] for d in divs], dtype=np.float64)
+        keep.append((div_tau, div_cash))
+        arr[i] = _am_struct(kw["spot"], kw["strike"], kw["T"], kw["sigma"], kw["r"], kw["b"],
+                            kw["is_call"], kw.get("model", 0), kw.get("n_space", 400),
+                            kw.get("n_time", 400), kw.get("rannacher", 2),
+                            kw.get("s_max_mult", 4.5), div_tau, div_cash)
+    price = np.empty(n, dtype=np.float64)
+    lo = np.empty(n, dtype=np.int32)
+    hi = np.empty(n, dtype=np.int32)
+    rc = lib().fdo_american_batch(n, arr, _dptr(price), lo.ctypes.data_as(C.POINTER(C.c_int32)),
+                                  hi.ctypes.data_as(C.POINTER(C.c_int32)), int(n_threads))
+    if rc != 0:
+        raise ValueError("fdo_american_batch: at least one solve failed")
+    return price, lo, hi
+
+
+# --------------------------------------------------------------------------------------
+# Barrier
+# --------------------------------------------------------------------------------------
+
+@dataclass
+class BarrierResult:
+    V: np.ndarray
+    s_nodes: np.ndarray
+    price: float
+    delta: float
+    gamma: float
+    S_min: float
+    S_max: float
+    dx: float
+    monitor_steps: List[int]
+    greek_idx: int
+    N_space: int
+    N_time: int
+
+
+_KO = {"none": 0, "down-and-out": 1, "up-and-out": 2}
+
+
+def _bar_struct(S0, K, T, sigma, r_disc, b_carry, is_call, barrier_type, lower_barrier,
+                upper_barrier, rebate, mon, N_space, N_time, apply_KO):
+    p = _FdoBarrier()
+    p.S0, p.K, p.T, p.sigma, p.r_disc, p.b_carry = S0, K, T, sigma, r_disc, b_carry
+    p.lower_barrier = float("nan") if lower_barrier is None else float(lower_barrier)
+    p.upper_barrier = float("nan") if upper_barrier is None else float(upper_barrier)
+    p.rebate = rebate
+    p.is_call = int(bool(is_call))
+    p.ko_kind = _KO.get(barrier_type, 0)
+    p.apply_KO = int(bool(apply_KO))
+    p.N_space = int(N_space or 0)
+    p.N_time = int(N_time or 0)
+    p.n_monitor = len(mon)
+    p.monitor_times = _dptr(mon) if len(mon) else None
+    return p
+
+
+def barrier_configure(S0, K, T, sigma, r_disc, b_carry, is_call, barrier_type,
+                      lower_barrier=None, upper_barrier=None, rebate=0.0, monitor_times=None,
+                      N_space=None, N_time=None):
+    """``configure_grid`` (discrete_barrier_fdm_pricer_cn.py:59-118) -> (S_min,S_max,N_space,N_time)."""
+    mon = np.ascontiguousarray(monitor_times or [], dtype=np.float64)
+    p = _bar_struct(S0, K, T, sigma, r_disc, b_carry, is_call, barrier_type, lower_barrier,
+                    upper_barrier, rebate, mon, N_space, N_time, True)
+    smin, smax = C.c_double(), C.c_double()
+    ns, nt = C.c_int32(), C.c_int32()
+    rc = lib().fdo_barrier_configure(C.byref(p), int(N_space or 0), int(N_time or 0),
+                                     C.byref(smin), C.byref(smax), C.byref(ns), C.byref(nt))
+    if rc != 0:
+        raise ValueError("T, sigma and S0 must be positive")
+    return smin.value, smax.value, ns.value, nt.value
+
+
+def barrier_solve(S0, K, T, sigma, r_disc, b_carry, is_call, barrier_type,
+                  lower_barrier=None, upper_barrier=None, rebate=0.0, monitor_times=None,
+                  N_space=None, N_time=None, apply_KO=True) -> BarrierResult:
+    """One barrier ``_solve_grid(apply_KO)`` + price/delta/gamma from the grid."""
+    _, _, ns, nt = barrier_configure(S0, K, T, sigma, r_disc, b_carry, is_call, barrier_type,
+                                     lower_barrier, upper_barrier, rebate, monitor_times,
+                                     N_space, N_time)
+    mon = np.ascontiguousarray(monitor_times or [], dtype=np.float64)
+    p = _bar_struct(S0, K, T, sigma, r_disc, b_carry, is_call, barrier_type, lower_barrier,
+                    upper_barrier, rebate, mon, ns, nt, apply_KO)
+    V = np.empty(ns + 1, dtype=np.float64)
+    s = np.empty(ns + 1, dtype=np.float64)
+    flags = np.zeros(nt + 1, dtype=np.int32)
+    info = _FdoBarrierInfo()
+    rc = lib().fdo_barrier_solve(C.byref(p), _dptr(V), _dptr(s),
+                                 flags.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(info))
+    if rc != 0:
+        raise ValueError(f"fdo_barrier_solve failed rc={rc}")
+    return BarrierResult(V=V, s_nodes=s, price=info.price, delta=info.delta, gamma=info.gamma,
+                         S_min=info.S_min, S_max=info.S_max, dx=info.dx,
+                         monitor_steps=[int(k) for k in np.nonzero(flags)[0]],
+                         greek_idx=info.greek_idx, N_space=ns, N_time=nt)
+
+
+def barrier_batch_prices(params: Sequence[dict], n_threads: int = 0):
+    """OpenMP batch of barrier solves (CPU baseline).  Each dict = barrier_solve kwargs with
+    N_space / N_time already fixed."""
+    n = len(params)
+    arr = (_FdoBarrier * n)()
+    keep = []
+    for i, kw in enumerate(params):
+        mon = np.ascontiguousarray(kw.get("monitor_times") or [], dtype=np.float64)
+        keep.append(mon)
+        arr[i] = _bar_struct(kw["S0"], kw["K"], kw["T"], kw["sigma"], kw["r_disc"], kw["b_carry"],
+                             kw["is_call"], kw["barrier_type"], kw.get("lower_barrier"),
+                             kw.get("upper_barrier"), kw.get("rebate", 0.0), mon,
+                             kw["N_space"], kw["N_time"], kw.get("apply_KO", True))
+    price = np.empty(n, dtype=np.float64)
+    delta = np.empty(n, dtype=np.float64)
+    gamma = np.empty(n, dtype=np.float64)
+    rc = lib().fdo_barrier_batch(n, arr, _dptr(price), _dptr(delta), _dptr(gamma), int(n_threads))
+    if rc != 0:
+        raise ValueError("fdo_barrier_batch: at least one solve failed")
+    return price, delta, gamma
+
+
+def max_threads() -> int:
+    return int(lib().fdo_max_threads())
+
+
+def norm_cdf(x: float) -> float:
+    """discrete_barrier_fdm_pricer_cn.py:16-18"""
+    return 0.5 * (1.0 + math.erf(x / math.sqrt(2.0)))
