@@ -1,0 +1,1128 @@
+// fdm_b200.cu -- sm_100a kernels and C ABI of the batched finite-difference PDE engine.
+//
+// One warp owns one PDE solve.  The n-1 interior unknowns are split into 32 contiguous chunks
+// of C nodes; each lane keeps its chunk of V, dt*lambda, payoff and the LU coefficients in
+// registers for the whole time march.  Nothing but the per-solve scalars is read from HBM and
+// nothing but prices / stencils / exercise intervals is written back.
+//
+// What one time step computes (reference: fd_american_option_pricer.py:467-509,
+// discrete_barrier_fdm_pricer_cn.py:278-300), restated so that the work per node is 9 FP64
+// instructions instead of the reference's 22 flops:
+//
+//   reference                                    here (p = 1/theta, q = (1-theta)/theta, L = dt*lambda)
+//   rhs = B V + dt*lam  (+ boundary terms)       B = p I - q A  =>  A^-1 (B V + L) = A^-1 (p V + L) - q V
+//   Vt  = A^-1 rhs      (Thomas, 2 divisions)    exact LU of the Toeplitz A hoisted out of the loop:
+//                                                   u_i  = R_i - m_i u_{i-1}            m_i  = A_L / den_{i-1}
+//                                                   xs_i = u_i - cc_i xs_{i+1}          cc_i = A_U / den_{i+1}
+//                                                   Vt_i = inv_i xs_i                   inv_i = 1 / den_i
+//                                                with den_i the reference's pivots (same recurrence, :443-451)
+//   vc  = Vt - dt*lam ; V = max(phi, vc)         vc = inv*xs - (q V + L) ; ex = phi > vc ; V = ex ? phi : vc
+//   lam = max(0, lam + (phi - Vt)/dt)            L  = ex ? phi - vc : 0     (identical in exact arithmetic)
+//
+// The two first-order recurrences run across the warp as (local pass, 5-level shuffle scan of
+// affine maps, local pass with the carry).  Dirichlet boundary terms enter as the carries of
+// lane 0 / lane 31, so no per-node masking is needed.
+//
+// No CPU fallback exists: every entry point fails with FDM_ERR_NO_DEVICE / FDM_ERR_CUDA if the
+// GPU path cannot run.
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "fdm_b200.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int SCAN_LEVELS = 5;
+constexpr int DIRECT_TERMS = 6;
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, const char *detail = "")
+{
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+#define FDM_CUDA(call)                                                                \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) return fail(FDM_ERR_CUDA, #call ": %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+
+// s_j = exp(x_min + j*dx), fd_american_option_pricer.py:239-240 (two roundings, no FMA).
+// noinline: every caller must get bit-identical node values.
+__device__ __noinline__ double node_s(double x_min, double dx, int j)
+{
+    return exp(__dadd_rn(x_min, __dmul_rn((double)j, dx)));
+}
+
+__device__ __forceinline__ double payoff(double s, double k, bool is_call)
+{
+    double v = is_call ? __dsub_rn(s, k) : __dsub_rn(k, s);
+    return v > 0.0 ? v : 0.0;
+}
+
+// Dirichlet values at time-to-maturity tau: fd_american_option_pricer.py:286-298,
+// fd_american_black76.py:291-314, discrete_barrier_fdm_pricer_cn.py:153-171.
+__device__ __forceinline__ void boundary_values(bool is_call, bool b76, double r, double b, double k,
+                                                double s_top, double tau, double &vmin, double &vmax)
+{
+    if (b76) {
+        double disc = exp(__dmul_rn(-r, tau));
+        if (is_call) { vmin = 0.0; vmax = __dmul_rn(disc, __dsub_rn(s_top, k)); }
+        else         { vmin = __dmul_rn(disc, k); vmax = 0.0; }
+    } else if (is_call) {
+        vmin = 0.0;
+        vmax = __dsub_rn(__dmul_rn(s_top, exp(__dmul_rn(__dsub_rn(b, r), tau))),
+                         __dmul_rn(k, exp(__dmul_rn(-r, tau))));
+    } else {
+        vmin = __dmul_rn(k, exp(__dmul_rn(-r, tau)));
+        vmax = 0.0;
+    }
+}
+
+struct PhaseScalars {
+    // Boundary term of this lane: lane 0 owns row 0 (V_min side), lane 31 the top row (V_max side).
+    // carry = cB * V_bdry(now) - cA * V_bdry(next step): rhs -= A * V_next (:482-483) plus the
+    // boundary column of the explicit operator B (:476-480); zero on every other lane.
+    double cA, cB;
+    double p, q;                 // 1/theta, (1-theta)/theta
+    int terms;                   // carries: 2/4/6-term direct weighted sum; 0 = Kogge-Stone scan
+};
+
+// Shared-memory tables of one warp (doubles):
+//   tab  [32*C+2]            pivot reciprocals during setup; value vector for read-out / dividends
+//   Af,Ab[SCAN_LEVELS][32]   Kogge-Stone multipliers, forward / backward sweep
+//   Wf,Wb[DIRECT_TERMS][32]  weights of the direct carry sum
+//   Hf,Hb[2][32]             half-chunk multipliers
+template <int C>
+struct WarpTables {
+    double *tab, *Af, *Ab, *Wf, *Wb, *Hf, *Hb;
+    __device__ explicit WarpTables(double *base)
+    {
+        tab = base;
+        Af = tab + (32 * C + 2);
+        Ab = Af + SCAN_LEVELS * 32;
+        Wf = Ab + SCAN_LEVELS * 32;
+        Wb = Wf + DIRECT_TERMS * 32;
+        Hf = Wb + DIRECT_TERMS * 32;
+        Hb = Hf + 2 * 32;
+    }
+    __device__ double *end() const { return Hb + 2 * 32; }
+};
+
+template <int C>
+constexpr int warp_smem_doubles() { return (32 * C + 2) + 2 * SCAN_LEVELS * 32 + 2 * DIRECT_TERMS * 32 + 4 * 32; }
+
+// Builds the per-lane LU coefficient registers for one (theta, dt) phase and the carry tables
+// (shared memory).  The pivots follow the reference's recurrence den_0 = A_C,
+// den_i = A_C - A_L * A_U / den_{i-1} (fd_american_option_pricer.py:443-451) with one
+// reciprocal per row; they converge bit-wise to a fixed point after a few dozen rows, after
+// which the table is constant.
+template <int C, bool AMER>
+__device__ __forceinline__ void setup_phase(double theta, double dt, double a, double c, double bcoef,
+                                            int n_int, int lane, double (&nm)[C], double (&ncc)[C],
+                                            double (&inv)[C], const WarpTables<C> &T, PhaseScalars &ph)
+{
+    constexpr int H = (C + 1) / 2;
+    const double A_L = __dmul_rn(__dmul_rn(-theta, dt), a);
+    const double A_C = __dsub_rn(1.0, __dmul_rn(__dmul_rn(theta, dt), bcoef));
+    const double A_U = __dmul_rn(__dmul_rn(-theta, dt), c);
+    const double B_L = __dmul_rn(__dmul_rn(__dsub_rn(1.0, theta), dt), a);
+    const double B_U = __dmul_rn(__dmul_rn(__dsub_rn(1.0, theta), dt), c);
+    ph.p = 1.0 / theta;
+    ph.q = (1.0 - theta) / theta;
+    const double bscale = AMER ? 1.0 : theta;     // the linear march solves for R / p
+    ph.cA = (lane == 0) ? A_L * bscale : ((lane == 31) ? A_U * bscale : 0.0);
+    ph.cB = (lane == 0) ? B_L * bscale : ((lane == 31) ? B_U * bscale : 0.0);
+
+    double *tab = T.tab;
+    __syncwarp();
+    double den = A_C;
+    double rinv = __drcp_rn(den);
+    if (lane == 0) tab[0] = rinv;
+    int conv = n_int;                       // rows >= conv-1 share the pivot of row conv-1
+    for (int i = 1; i < n_int; ++i) {
+        const double den_i = __dsub_rn(A_C, __dmul_rn(A_L, __dmul_rn(A_U, rinv)));
+        if (den_i == den) { conv = i; break; }
+        den = den_i;
+        rinv = __drcp_rn(den);
+        if (lane == 0) tab[i] = rinv;
+    }
+    __syncwarp();
+
+    const double scale = AMER ? 1.0 : ph.p;   // linear march: p folded into the final scaling
+    double af1 = 1.0, af2 = 1.0, ab1 = 1.0, ab2 = 1.0;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const int row = lane * C + k;
+        double v_inv = 0.0, v_nm = 0.0, v_ncc = 1.0;
+        if (row < n_int) {
+            v_inv = tab[min(row, conv - 1)] * scale;
+            v_nm = (row == 0) ? 1.0 : -(A_L * tab[min(row - 1, conv - 1)]);
+            if (row < n_int - 1) v_ncc = -(A_U * tab[min(row + 1, conv - 1)]);
+        }
+        inv[k] = v_inv;
+        nm[k] = v_nm;
+        ncc[k] = v_ncc;
+        if (k < H) { af1 *= v_nm; ab2 *= v_ncc; } else { af2 *= v_nm; ab1 *= v_ncc; }
+    }
+    // forward sweep visits k = 0..H-1 (half 1) then H..C-1 (half 2); backward sweep visits
+    // k = C-1..H (half 1) then H-1..0 (half 2)
+    T.Hf[lane] = af1;  T.Hf[32 + lane] = af2;
+    T.Hb[lane] = ab1;  T.Hb[32 + lane] = ab2;
+    double af = af1 * af2, ab = ab1 * ab2;
+    const double af_lane = af, ab_lane = ab;
+    // Kogge-Stone multipliers: at level lv the incoming partial result is scaled by the product
+    // of this lane's current span; lanes without a partner at that distance get 0.
+#pragma unroll
+    for (int lv = 0; lv < SCAN_LEVELS; ++lv) {
+        const int d = 1 << lv;
+        const bool has_f = lane >= d;
+        const bool has_b = lane + d < 32;
+        T.Af[lv * 32 + lane] = has_f ? af : 0.0;
+        T.Ab[lv * 32 + lane] = has_b ? ab : 0.0;
+        const double tf = __shfl_up_sync(FULL, af, d);
+        const double tb = __shfl_down_sync(FULL, ab, d);
+        if (has_f) af *= tf;
+        if (has_b) ab *= tb;
+    }
+    // Direct carry: carry_in(l) = sum_j w_j(l) * end(l -/+ j), w_1 = 1, w_{j+1} = w_j * a(l -/+ j).
+    // The first neglected weight bounds the truncation error relative to the solution scale;
+    // 1e-20 is four orders below the rounding noise of the sweeps themselves.
+    double wf = (lane >= 1) ? 1.0 : 0.0, wb = (lane <= 30) ? 1.0 : 0.0;
+    int terms = 0;
+#pragma unroll
+    for (int j = 1; j <= DIRECT_TERMS; ++j) {
+        T.Wf[(j - 1) * 32 + lane] = wf;
+        T.Wb[(j - 1) * 32 + lane] = wb;
+        const double tf = __shfl_up_sync(FULL, af_lane, j);
+        const double tb = __shfl_down_sync(FULL, ab_lane, j);
+        wf = (lane >= j + 1) ? wf * tf : 0.0;
+        wb = (lane + j + 1 <= 31) ? wb * tb : 0.0;
+        if ((j & 1) == 0 && terms == 0 && !__any_sync(FULL, fabs(wf) > 1e-20 || fabs(wb) > 1e-20)) terms = j;
+    }
+    ph.terms = terms;
+    __syncwarp();
+}
+
+#ifdef FDM_PROFILE_CYCLES
+#define FDM_TICK(var, slot)                                             \
+    do {                                                                \
+        asm volatile("mov.b64 %0, %1;" : "=d"(var) : "d"(var));         \
+        long long t_ = clock64();                                       \
+        prof_acc[slot] += t_ - prof_t;                                  \
+        prof_t = t_;                                                    \
+    } while (0)
+#define FDM_PROF_PARAMS , long long (&prof_acc)[8], long long &prof_t
+#define FDM_PROF_ARGS , prof_acc, prof_t
+#else
+#define FDM_TICK(var, slot)
+#define FDM_PROF_PARAMS
+#define FDM_PROF_ARGS
+#endif
+
+// (a & m) | (b & ~m) and (a ^ b) & m as single LOP3s (no predicate registers involved)
+__device__ __forceinline__ int lop3_select(int a, int b, int m)
+{
+    int d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+}
+__device__ __forceinline__ int lop3_xor_and(int a, int b, int m)
+{
+    int d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+}
+
+// carry entering each lane's chunk from the lanes below (UP = true) / above (UP = false)
+template <bool UP>
+__device__ __forceinline__ double lane_carry(const double e_end, const int terms, const double *__restrict__ W,
+                                             const double *__restrict__ A, const int lane)
+{
+    if (terms) {
+        // all shuffles are independent: ~one shuffle latency instead of five dependent levels
+        double acc0, acc1;
+        {
+            const double t1 = UP ? __shfl_up_sync(FULL, e_end, 1) : __shfl_down_sync(FULL, e_end, 1);
+            const double t2 = UP ? __shfl_up_sync(FULL, e_end, 2) : __shfl_down_sync(FULL, e_end, 2);
+            acc0 = W[0 * 32 + lane] * t1;
+            acc1 = W[1 * 32 + lane] * t2;
+        }
+        if (terms > 2) {
+            const double t3 = UP ? __shfl_up_sync(FULL, e_end, 3) : __shfl_down_sync(FULL, e_end, 3);
+            const double t4 = UP ? __shfl_up_sync(FULL, e_end, 4) : __shfl_down_sync(FULL, e_end, 4);
+            acc0 = fma(W[2 * 32 + lane], t3, acc0);
+            acc1 = fma(W[3 * 32 + lane], t4, acc1);
+        }
+        if (terms > 4) {
+            const double t5 = UP ? __shfl_up_sync(FULL, e_end, 5) : __shfl_down_sync(FULL, e_end, 5);
+            const double t6 = UP ? __shfl_up_sync(FULL, e_end, 6) : __shfl_down_sync(FULL, e_end, 6);
+            acc0 = fma(W[4 * 32 + lane], t5, acc0);
+            acc1 = fma(W[5 * 32 + lane], t6, acc1);
+        }
+        return acc0 + acc1;
+    }
+    double e = e_end;
+#pragma unroll
+    for (int lv = 0; lv < SCAN_LEVELS; ++lv) {
+        const double t = UP ? __shfl_up_sync(FULL, e, 1 << lv) : __shfl_down_sync(FULL, e, 1 << lv);
+        e = fma(A[lv * 32 + lane], t, e);
+    }
+    e = UP ? __shfl_up_sync(FULL, e, 1) : __shfl_down_sync(FULL, e, 1);
+    return (UP ? lane == 0 : lane == 31) ? 0.0 : e;
+}
+
+// One theta-scheme step for the whole warp.  cin_f / cin_b: boundary contribution entering row 0
+// (non-zero on lane 0 only) and the top row (non-zero on lane 31 only, through the padded rows).
+// Each lane's chunk is swept as two independent half-chains to halve the dependent-FMA latency.
+template <int C, bool AMER>
+__device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const double (&phi)[C],
+                                           const double (&nm)[C], const double (&ncc)[C],
+                                           const double (&inv)[C], const double p, const double q,
+                                           const double cin_f, const double cin_b, const int terms,
+                                           const WarpTables<C> &T, const int lane FDM_PROF_PARAMS)
+{
+    constexpr int H = (C + 1) / 2;
+    // subtrahend G = q V + L and right-hand side R = p V + L = G + V (p - q = 1 for every theta)
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        if (AMER) {
+            const double g = fma(q, V[k], L[k]);
+            V[k] = g + V[k];
+            L[k] = g;
+        } else {
+            L[k] = q * V[k];          // p is folded into inv[] for the linear (European) march
+        }
+    }
+    // ---- forward elimination: u_i = R_i - m_i u_{i-1} ------------------------------------------
+    double e1 = cin_f, e2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < H; ++k) e1 = fma(nm[k], e1, V[k]);
+#pragma unroll
+    for (int k = H; k < C; ++k) e2 = fma(nm[k], e2, V[k]);
+    double e_end = fma(T.Hf[32 + lane], e1, e2);
+    FDM_TICK(e_end, 0);
+    double cs = lane_carry<true>(e_end, terms, T.Wf, T.Af, lane);
+    FDM_TICK(cs, 1);
+    {
+        double c1 = cs + cin_f;                       // carry into half 1
+        double c2 = fma(T.Hf[lane], cs, e1);          // carry into half 2 = true end of half 1
+#pragma unroll
+        for (int k = 0; k < H; ++k) { c1 = fma(nm[k], c1, V[k]); V[k] = c1; }
+#pragma unroll
+        for (int k = H; k < C; ++k) { c2 = fma(nm[k], c2, V[k]); V[k] = c2; }
+        FDM_TICK(c2, 2);
+    }
+    // ---- back substitution on xs_i = den_i x_i: xs_i = u_i - cc_i xs_{i+1} ----------------------
+    e1 = cin_b;
+    e2 = 0.0;
+#pragma unroll
+    for (int k = C - 1; k >= H; --k) e1 = fma(ncc[k], e1, V[k]);
+#pragma unroll
+    for (int k = H - 1; k >= 0; --k) e2 = fma(ncc[k], e2, V[k]);
+    e_end = fma(T.Hb[32 + lane], e1, e2);
+    FDM_TICK(e_end, 3);
+    cs = lane_carry<false>(e_end, terms, T.Wb, T.Ab, lane);
+    FDM_TICK(cs, 4);
+    double c1 = cs + cin_b;
+    double c2 = fma(T.Hb[lane], cs, e1);
+    // the two half-chains advance together: node C-1-i of half 1 with node H-1-i of half 2
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int k = half == 0 ? C - 1 - i : H - 1 - i;
+            if (half == 0 && k < H) continue;
+            double xs;
+            if (half == 0) { c1 = fma(ncc[k], c1, V[k]); xs = c1; }
+            else           { c2 = fma(ncc[k], c2, V[k]); xs = c2; }
+            const double vc = fma(inv[k], xs, -L[k]);
+            if (AMER) {
+                // ex = phi > vc (fd_american_option_pricer.py:496); V = ex ? phi : vc;
+                // dt*lambda_new = ex ? phi - vc : 0 (:498-500), selected on the sign bit of vc - phi
+                const double nd = vc - phi[k];
+                const int nd_hi = __double2hiint(nd);
+                const int msk = nd_hi >> 31;
+                V[k] = __hiloint2double(lop3_select(__double2hiint(phi[k]), __double2hiint(vc), msk),
+                                        lop3_select(__double2loint(phi[k]), __double2loint(vc), msk));
+                L[k] = __hiloint2double(lop3_xor_and(nd_hi, (int)0x80000000, msk), __double2loint(nd) & msk);
+            } else {
+                V[k] = vc;
+            }
+        }
+    }
+    FDM_TICK(V[0], 5);
+}
+
+// value at node j (0..n) from the distributed vector
+template <int C>
+__device__ __forceinline__ double node_value(const double (&V)[C], double V0, double VN, int j, int n, int lane)
+{
+    const int row = j - 1;
+    const int src = (row >= 0 && row < 32 * C) ? row / C : 0;
+    const int kk = row - src * C;
+    double mine = 0.0;
+#pragma unroll
+    for (int k = 0; k < C; ++k) mine = (k == kk) ? V[k] : mine;
+    double v = __shfl_sync(FULL, mine, src);
+    if (j <= 0) v = V0;
+    if (j >= n) v = VN;
+    return v;
+}
+
+// first-minimum argmin of |s_j - level| over all nodes j = 0..n (fd_american_option_pricer.py:253)
+// or over interior nodes only (discrete_barrier_fdm_pricer_cn.py:335).
+template <int C>
+__device__ __forceinline__ int argmin_node(const double (&s)[C], double s0, double sn, double level,
+                                           int n, int lane, bool interior_only)
+{
+    double best = INFINITY;
+    int bidx = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const int j = lane * C + k + 1;
+        const double v = fabs(__dsub_rn(s[k], level));
+        if (j <= n - 1 && v < best) { best = v; bidx = j; }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const double ov = __shfl_xor_sync(FULL, best, d);
+        const int oi = __shfl_xor_sync(FULL, bidx, d);
+        if (ov < best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    if (!interior_only) {
+        const double v0 = fabs(__dsub_rn(s0, level));
+        if (v0 <= best) { best = v0; bidx = 0; }
+        const double vn = fabs(__dsub_rn(sn, level));
+        if (vn < best) { best = vn; bidx = n; }
+    }
+    return bidx;
+}
+
+// Natural cubic spline through (s_j, V_j) and the ex-dividend jump V(S) <- V(S - D):
+// fd_american_option_pricer.py:321-386 and :517-548, same operation order (no FMA).
+// xs, ys, mu, cz: shared-memory arrays of n+1 doubles.  Lane 0 runs the two serial sweeps.
+template <int C>
+__device__ __forceinline__ void dividend_jump(double (&V)[C], double &V0, double &VN, const double (&phi)[C],
+                                           double phi0, double phin, double cash, bool is_call, int n,
+                                           int lane, double x_min, double dx,
+                                           double *xs, double *ys, double *mu, double *cz)
+{
+    const int nn = n + 1;   // number of knots
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const int j = lane * C + k + 1;
+        if (j <= n - 1) { xs[j] = node_s(x_min, dx, j); ys[j] = V[k]; }
+    }
+    if (lane == 0) {
+        xs[0] = node_s(x_min, dx, 0); ys[0] = V0;
+        xs[n] = node_s(x_min, dx, n); ys[n] = VN;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        // forward sweep :349-352 (l, mu, z), alpha from :339-343
+        mu[0] = 0.0;
+        cz[0] = 0.0;
+        double mu_prev = 0.0, z_prev = 0.0;
+        for (int i = 1; i < nn - 1; ++i) {
+            const double h_i = __dsub_rn(xs[i + 1], xs[i]);
+            const double h_im1 = __dsub_rn(xs[i], xs[i - 1]);
+            const double alpha = __dsub_rn(
+                __dmul_rn(3.0 / h_i, __dsub_rn(ys[i + 1], ys[i])),
+                __dmul_rn(3.0 / h_im1, __dsub_rn(ys[i], ys[i - 1])));
+            const double l = __dsub_rn(__dmul_rn(2.0, __dsub_rn(xs[i + 1], xs[i - 1])),
+                                       __dmul_rn(h_im1, mu_prev));
+            mu_prev = h_i / l;
+            z_prev = __dsub_rn(alpha, __dmul_rn(h_im1, z_prev)) / l;
+            mu[i] = mu_prev;
+            cz[i] = z_prev;
+        }
+        // back sweep :358-359: c[j] = z[j] - mu[j] * c[j+1], c[n-1] = 0
+        double c_next = 0.0;
+        cz[nn - 1] = 0.0;
+        for (int j = nn - 2; j >= 0; --j) {
+            c_next = __dsub_rn(cz[j], __dmul_rn(mu[j], c_next));
+            cz[j] = c_next;
+        }
+    }
+    __syncwarp();
+    const double s_lo = xs[0], s_hi = xs[n];
+    auto eval = [&](double Sj, double phi_j) -> double {
+        const double Sq = __dsub_rn(Sj, cash);
+        double cont;
+        if (Sq <= s_lo) cont = ys[0];
+        else if (Sq >= s_hi) cont = ys[n];
+        else {
+            int lo = 0, hi = nn - 1;                       // :375-382
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (Sq < xs[mid]) hi = mid; else lo = mid;
+            }
+            const int j = lo;
+            const double h = __dsub_rn(xs[j + 1], xs[j]);
+            const double cj = cz[j], cj1 = cz[j + 1];
+            // :360-364
+            const double bj = __dsub_rn(__dsub_rn(ys[j + 1], ys[j]) / h,
+                                        __dmul_rn(h, __dadd_rn(cj1, __dmul_rn(2.0, cj))) / 3.0);
+            const double dj = __dsub_rn(cj1, cj) / __dmul_rn(3.0, h);
+            const double dq = __dsub_rn(Sq, xs[j]);
+            // :384  a + b*dx + c*dx*dx + d*dx*dx*dx, left to right
+            double acc = __dadd_rn(ys[j], __dmul_rn(bj, dq));
+            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(cj, dq), dq));
+            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(__dmul_rn(dj, dq), dq), dq));
+            cont = acc;
+        }
+        if (is_call) cont = cont > phi_j ? cont : phi_j;   // :542-544
+        return cont;
+    };
+    double newV[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const int j = lane * C + k + 1;
+        newV[k] = (j <= n - 1) ? eval(xs[j], phi[k]) : 0.0;
+    }
+    const double n0 = eval(s_lo, phi0);
+    const double nN = eval(s_hi, phin);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < C; ++k) V[k] = newV[k];
+    V0 = n0;
+    VN = nN;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the solve kernel: one warp (one CTA of 32 threads) per PDE solve
+// ---------------------------------------------------------------------------------------------
+
+// resident warps per SM the register allocation is sized for
+#ifndef FDM_MINB
+#define FDM_MINB 0
+#endif
+template <int C, bool AMER>
+constexpr int min_blocks()
+{
+    return FDM_MINB ? FDM_MINB : (C <= 4 ? 16 : C <= 8 ? 12 : 8);
+}
+
+template <int C, bool AMER, bool TRACE>
+__global__ void __launch_bounds__(32, min_blocks<C, AMER>())
+fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int want_american,
+                const int div_smem)
+{
+    extern __shared__ double smem[];
+    const WarpTables<C> T(smem);
+    double *divbuf = T.end();
+
+    const int64_t sid = first + blockIdx.x;
+    if (sid >= B.n_solves) return;
+    const int flags = B.flags[sid];
+    // each launch handles one family (American / linear); the other family's solves are skipped
+    if (((flags & FDM_FLAG_AMERICAN) != 0) != (want_american != 0)) return;
+
+    const int lane = threadIdx.x;
+    const int n = B.n_space[sid];
+    const int n_int = n - 1;
+    const bool is_call = flags & FDM_FLAG_CALL;
+    const bool b76 = flags & FDM_FLAG_BLACK76;
+    const bool snap = flags & FDM_FLAG_SNAP;
+    const int ko = (flags & FDM_FLAG_KO_DOWN) ? 1 : ((flags & FDM_FLAG_KO_UP) ? 2 : 0);
+
+    const double x_min = B.x_min[sid];
+    const double dx = B.dx[sid];
+    const double sigma = B.sigma[sid];
+    const double r = B.r[sid];
+    const double bcar = B.b[sid];
+    const double spot = B.spot[sid];
+    const double strike = B.strike[sid];
+    const double barrier = (ko && B.barrier) ? B.barrier[sid] : 0.0;
+    const double rebate = (ko && B.rebate) ? B.rebate[sid] : 0.0;
+    const int rannacher = B.rannacher[sid];
+
+    // ---- grid, snapping, payoff -------------------------------------------------------------
+    double V[C], L[C], phi[C], nm[C], ncc[C], inv[C];
+    const double s0 = node_s(x_min, dx, 0);
+    const double sn = node_s(x_min, dx, n);
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const int j = lane * C + k + 1;
+        phi[k] = (j <= n - 1) ? node_s(x_min, dx, j) : 0.0;     // node prices, for now
+    }
+    int spot_idx = 0, strike_idx = 0;
+    double k_eff = strike;
+    if (snap) {
+        spot_idx = argmin_node<C>(phi, s0, sn, spot, n, lane, false);
+        strike_idx = argmin_node<C>(phi, s0, sn, strike, n, lane, false);
+        k_eff = node_s(x_min, dx, strike_idx);                  // fd_american_option_pricer.py:272-275
+    }
+    // KO region as a node index interval [ko_lo, ko_hi]
+    int ko_lo = 1, ko_hi = 0;
+    if (ko) {
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int j = lane * C + k + 1;
+            if (j <= n - 1) cnt += (ko == 1) ? (phi[k] <= barrier) : (phi[k] >= barrier);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+        if (ko == 1) {      // nodes with s <= B: 0 .. (count-1), s is increasing
+            const int c0 = (s0 <= barrier) + cnt + (sn <= barrier);
+            ko_lo = 0; ko_hi = c0 - 1;
+        } else {            // nodes with s >= B: n-count+1 .. n
+            const int c0 = (s0 >= barrier) + cnt + (sn >= barrier);
+            ko_lo = n - c0 + 1; ko_hi = n;
+        }
+    }
+    const double phi0 = payoff(s0, k_eff, is_call);
+    const double phin = payoff(sn, k_eff, is_call);
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const int j = lane * C + k + 1;
+        const double pv = (j <= n - 1) ? payoff(phi[k], k_eff, is_call) : 0.0;
+        phi[k] = pv;
+        V[k] = pv;                                              // terminal condition, :558
+        L[k] = 0.0;
+    }
+    // boundary node values live on the lane that owns the adjacent row: V[0] on lane 0, V[n] on lane 31
+    double Vb = (lane == 0) ? phi0 : ((lane == 31) ? phin : 0.0);
+    const bool bdry_lane = is_call ? (lane == 31) : (lane == 0);
+
+    // ---- operator coefficients, fd_american_option_pricer.py:413-426 -------------------------
+    const double sig2 = __dmul_rn(sigma, sigma);
+    const double mu_x = b76 ? __dmul_rn(-0.5, sig2) : __dsub_rn(bcar, __dmul_rn(0.5, sig2));
+    const double alpha = __dmul_rn(0.5, sig2) / __dmul_rn(dx, dx);
+    const double beta = mu_x / __dmul_rn(2.0, dx);
+    const double ca = __dsub_rn(alpha, beta);
+    const double cc = __dadd_rn(alpha, beta);
+    const double bcoef = __dsub_rn(__dmul_rn(-2.0, alpha), r);
+
+    // ---- time march ---------------------------------------------------------------------------
+    const int seg_b = B.seg_begin[sid], seg_e = B.seg_begin[sid + 1];
+    int mon_i = 0, mon_e = 0;
+    if (ko && B.mon_begin) { mon_i = B.mon_begin[sid]; mon_e = B.mon_begin[sid + 1]; }
+    int next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
+    int gstep = 0;                                              // steps marched so far (all segments)
+#ifdef FDM_PROFILE_CYCLES
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long prof_start = clock64();
+    long long prof_t = prof_start;
+#endif
+    int32_t *trace = (TRACE && O.ex_trace) ? O.ex_trace + sid * O.ex_trace_stride : nullptr;
+
+    for (int seg = seg_b; seg < seg_e; ++seg) {
+        const int n_steps = B.seg_steps[seg];
+        const double dt = B.seg_dt[seg];
+        const double tau0 = B.seg_tau0[seg];
+        const int base_ran = B.seg_restart[seg] ? rannacher : 0;   // :464
+        const double cash = B.seg_div[seg];
+        if (AMER) {
+#pragma unroll
+            for (int k = 0; k < C; ++k) L[k] = 0.0;             // lambda restarts every segment, :463
+        }
+        int m = 0;
+        // Boundary values.  A call has V_min = 0 and a put V_max = 0 at every tau (:286-298), so one
+        // sequence w(tau) describes the moving boundary.  Every 32 steps each lane evaluates the
+        // exponentials of one future step (tau = tau_start + (m+1) dt); a shuffle hands them out.
+        double my_w = 0.0;
+        int fill_base = -64;                                     // forces a refill at the first fetch
+        auto fetch_boundary = [&](int step) -> double {
+            if (step - fill_base >= 32 || step < fill_base) {
+                fill_base = step;
+                const double tau = fma((double)(step + lane + 1), dt, tau0);
+                double vmin, vmax;
+                boundary_values(is_call, b76, r, bcar, k_eff, sn, tau, vmin, vmax);
+                my_w = is_call ? vmax : vmin;
+            }
+            const double w = __shfl_sync(FULL, my_w, step - fill_base);
+            return bdry_lane ? w : 0.0;                          // value on this lane's boundary node
+        };
+        while (m < n_steps) {
+            const bool implicit_phase = m < base_ran;
+            const int m_end = implicit_phase ? min(base_ran, n_steps) : n_steps;
+            PhaseScalars ph;
+            setup_phase<C, AMER>(implicit_phase ? 1.0 : 0.5, dt, ca, cc, bcoef, n_int, lane, nm, ncc, inv, T, ph);
+            double w_next = fetch_boundary(m);
+            double cin = ph.cB * Vb - ph.cA * w_next;            // non-zero on lanes 0 and 31 only
+            for (; m < m_end; ++m) {
+                const double w_now = w_next;
+                // the following step's boundary value is fetched early: its latency hides behind this step
+                w_next = fetch_boundary(m + 1);
+                double cin_n = ph.cB * w_now - ph.cA * w_next;
+                march_step<C, AMER>(V, L, phi, nm, ncc, inv, ph.p, ph.q, (lane == 0) ? cin : 0.0,
+                                    (lane == 31) ? cin : 0.0, ph.terms, T, lane FDM_PROF_ARGS);
+                Vb = w_now;                                     // V[0] = V_min, V[-1] = V_max, :505-506
+                ++gstep;
+                if (TRACE && trace) {
+                    int lo = 0x7fffffff, hi = -1;
+#pragma unroll
+                    for (int k = 0; k < C; ++k) {
+                        const int row = lane * C + k;
+                        if (AMER && row < n_int && L[k] > 0.0) { lo = min(lo, row); hi = max(hi, row); }
+                    }
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) {
+                        lo = min(lo, __shfl_xor_sync(FULL, lo, d));
+                        hi = max(hi, __shfl_xor_sync(FULL, hi, d));
+                    }
+                    if (lane == 0 && 2 * (int64_t)gstep <= O.ex_trace_stride) {
+                        trace[2 * (gstep - 1)] = (hi < 0) ? -1 : lo;
+                        trace[2 * (gstep - 1) + 1] = hi;
+                    }
+                }
+                if (gstep == next_mon) {                        // discrete_barrier_fdm_pricer_cn.py:299-300
+#pragma unroll
+                    for (int k = 0; k < C; ++k) {
+                        const int j = lane * C + k + 1;
+                        if (j <= n - 1 && j >= ko_lo && j <= ko_hi) V[k] = rebate;
+                    }
+                    if (lane == 0 && ko_lo <= 0 && 0 <= ko_hi) Vb = rebate;
+                    if (lane == 31 && ko_lo <= n && n <= ko_hi) Vb = rebate;
+                    ++mon_i;
+                    next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
+                    cin_n = ph.cB * Vb - ph.cA * w_next;
+                }
+                cin = cin_n;
+            }
+        }
+        if (cash != 0.0) {
+            if (div_smem) {
+                double *xs = divbuf;
+                double *ys = xs + (32 * C + 2);
+                double *mu = ys + (32 * C + 2);
+                double *cz = mu + (32 * C + 2);
+                double V0 = __shfl_sync(FULL, Vb, 0), VN = __shfl_sync(FULL, Vb, 31);
+                dividend_jump<C>(V, V0, VN, phi, phi0, phin, cash, is_call, n, lane, x_min, dx, xs, ys, mu, cz);
+                Vb = (lane == 0) ? V0 : ((lane == 31) ? VN : 0.0);
+            } else {
+#pragma unroll
+                for (int k = 0; k < C; ++k) V[k] = NAN;         // launch without dividend scratch: flag it
+            }
+        }
+    }
+
+#ifdef FDM_PROFILE_CYCLES
+    if (blockIdx.x == 0 && lane == 0) {
+        const long long tot = clock64() - prof_start;
+        printf("C=%d AMER=%d steps=%d total=%lld cyc/step=%.1f | rg+fwd1 %.1f carry1 %.1f fwd2 %.1f bwd1 %.1f carry2 %.1f bwd2+proj %.1f\n",
+               C, (int)AMER, gstep, tot, (double)tot / gstep, (double)prof_acc[0] / gstep, (double)prof_acc[1] / gstep,
+               (double)prof_acc[2] / gstep, (double)prof_acc[3] / gstep, (double)prof_acc[4] / gstep, (double)prof_acc[5] / gstep);
+    }
+#endif
+    // ---- read-out -------------------------------------------------------------------------------
+    const double V0 = __shfl_sync(FULL, Vb, 0), VN = __shfl_sync(FULL, Vb, 31);
+    int ex_lo = -1, ex_hi = -1;
+    if (AMER) {
+        int lo = 0x7fffffff, hi = -1;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int row = lane * C + k;
+            if (row < n_int && L[k] > 0.0) { lo = min(lo, row); hi = max(hi, row); }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            lo = min(lo, __shfl_xor_sync(FULL, lo, d));
+            hi = max(hi, __shfl_xor_sync(FULL, hi, d));
+        }
+        if (hi >= 0) { ex_lo = lo; ex_hi = hi; }
+    }
+
+    if (O.v_dump) {
+        double *dst = O.v_dump + sid * O.v_dump_stride;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int j = lane * C + k + 1;
+            if (j <= n - 1 && j < O.v_dump_stride) dst[j] = V[k];
+        }
+        if (lane == 0) {
+            dst[0] = V0;
+            if (n < O.v_dump_stride) dst[n] = VN;
+        }
+    }
+
+    double price, delta, gamma;
+    double sv[4], ss[4];
+    int idx_a, idx_b;
+    if (snap) {
+        // _interp_price at the snapped spot is V at that node; _local_cubic_delta_gamma,
+        // fd_american_option_pricer.py:632-653
+        int i_near = min(max(spot_idx, 1), n - 2);
+        const double Sx = node_s(x_min, dx, spot_idx);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int j = i_near - 1 + t;
+            sv[t] = node_value<C>(V, V0, VN, j, n, lane);
+            ss[t] = node_s(x_min, dx, j);
+        }
+        price = node_value<C>(V, V0, VN, spot_idx, n, lane);
+        // cubic through the four points in Newton form, derivatives at z = 0 (z = S - Sx)
+        const double z0 = ss[0] - Sx, z1 = ss[1] - Sx, z2 = ss[2] - Sx, z3 = ss[3] - Sx;
+        const double f01 = (sv[1] - sv[0]) / (z1 - z0);
+        const double f12 = (sv[2] - sv[1]) / (z2 - z1);
+        const double f23 = (sv[3] - sv[2]) / (z3 - z2);
+        const double f012 = (f12 - f01) / (z2 - z0);
+        const double f123 = (f23 - f12) / (z3 - z1);
+        const double f0123 = (f123 - f012) / (z3 - z0);
+        delta = f01 + f012 * (-(z0 + z1)) + f0123 * (z0 * z1 + z0 * z2 + z1 * z2);
+        gamma = 2.0 * f012 - 2.0 * f0123 * (z0 + z1 + z2);
+        idx_a = spot_idx;
+        idx_b = strike_idx;
+    } else {
+        // discrete_barrier_fdm_pricer_cn.py:308-353
+        double sl[C];
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int j = lane * C + k + 1;
+            sl[k] = (j <= n - 1) ? node_s(x_min, dx, j) : 0.0;
+            if (j <= n - 1 && sl[k] <= spot) ++cnt;
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+        int lo = cnt;                        // largest j with s_j <= spot, given s_0 <= spot
+        if (spot <= s0) { price = V0; lo = 0; }
+        else if (spot >= sn) { price = VN; lo = n; }
+        else {
+            const double s_lo = node_s(x_min, dx, lo), s_hi = node_s(x_min, dx, lo + 1);
+            const double v_lo = node_value<C>(V, V0, VN, lo, n, lane);
+            const double v_hi = node_value<C>(V, V0, VN, lo + 1, n, lane);
+            const double w = __dsub_rn(spot, s_lo) / __dsub_rn(s_hi, s_lo);
+            price = __dadd_rn(__dmul_rn(__dsub_rn(1.0, w), v_lo), __dmul_rn(w, v_hi));
+        }
+        const int gi = argmin_node<C>(sl, s0, sn, spot, n, lane, true);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            sv[t] = node_value<C>(V, V0, VN, gi - 1 + t, n, lane);
+            ss[t] = node_s(x_min, dx, gi - 1 + t);
+        }
+        sv[3] = 0.0;
+        ss[3] = 0.0;
+        const double h1 = __dsub_rn(ss[1], ss[0]);
+        const double h2 = __dsub_rn(ss[2], ss[1]);
+        const double h12 = __dadd_rn(h1, h2);
+        delta = __dadd_rn(__dadd_rn(__dmul_rn(-h2 / __dmul_rn(h1, h12), sv[0]),
+                                    __dmul_rn(__dsub_rn(h2, h1) / __dmul_rn(h1, h2), sv[1])),
+                          __dmul_rn(h1 / __dmul_rn(h2, h12), sv[2]));
+        gamma = __dmul_rn(2.0, __dadd_rn(__dsub_rn(sv[0] / __dmul_rn(h1, h12), sv[1] / __dmul_rn(h1, h2)),
+                                         sv[2] / __dmul_rn(h2, h12)));
+        idx_a = lo;
+        idx_b = gi;
+    }
+
+    if (lane == 0) {
+        O.price[sid] = price;
+        if (O.delta) O.delta[sid] = delta;
+        if (O.gamma) O.gamma[sid] = gamma;
+        if (O.stencil_v) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) O.stencil_v[4 * sid + t] = sv[t];
+        }
+        if (O.stencil_s) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) O.stencil_s[4 * sid + t] = ss[t];
+        }
+        if (O.idx) {
+            O.idx[4 * sid + 0] = idx_a;
+            O.idx[4 * sid + 1] = idx_b;
+            O.idx[4 * sid + 2] = ex_lo;
+            O.idx[4 * sid + 3] = ex_hi;
+        }
+        if (O.status) O.status[sid] = isfinite(price) ? 0 : 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 pipe micro-benchmark
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[blockIdx.x] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+
+template <int C>
+int launch_variant(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american, bool any_linear,
+                   bool any_div, int32_t *n_launches)
+{
+    const bool trace = o.ex_trace != nullptr;
+    const int base = warp_smem_doubles<C>();
+    const int div_doubles = any_div ? 4 * (32 * C + 2) : 0;
+    const size_t smem = (size_t)(base + div_doubles) * sizeof(double);
+    const int64_t max_grid = 0x7fffffff;
+    int launches = 0;
+    for (int64_t first = 0; first < b.n_solves; first += max_grid) {
+        const int64_t count = (b.n_solves - first < max_grid) ? (b.n_solves - first) : max_grid;
+        const dim3 grid((unsigned)count), block(32);
+        if (any_american) {
+            if (trace) fdm_warp_kernel<C, true, true><<<grid, block, smem, st>>>(b, o, first, 1, any_div);
+            else       fdm_warp_kernel<C, true, false><<<grid, block, smem, st>>>(b, o, first, 1, any_div);
+            ++launches;
+        }
+        if (any_linear) {
+            fdm_warp_kernel<C, false, false><<<grid, block, smem, st>>>(b, o, first, 0, any_div);
+            ++launches;
+        }
+        FDM_CUDA(cudaGetLastError());
+    }
+    if (n_launches) *n_launches += launches;
+    return FDM_OK;
+}
+
+int validate(const FdmBatch *b, const FdmOut *o)
+{
+    if (!b || !o) return fail(FDM_ERR_INVALID, "batch / out is NULL%s");
+    if (b->n_solves < 0) return fail(FDM_ERR_INVALID, "n_solves < 0%s");
+    if (b->n_solves == 0) return FDM_OK;
+    if (!b->x_min || !b->dx || !b->sigma || !b->r || !b->b || !b->spot || !b->strike || !b->n_space ||
+        !b->flags || !b->rannacher || !b->seg_begin || !b->seg_steps || !b->seg_dt || !b->seg_tau0 ||
+        !b->seg_restart || !b->seg_div)
+        return fail(FDM_ERR_INVALID, "a required FdmBatch array is NULL%s");
+    if (!o->price) return fail(FDM_ERR_INVALID, "FdmOut.price is NULL%s");
+    if (b->n_space_max < 3) return fail(FDM_ERR_INVALID, "n_space_max < 3%s");
+    if (b->n_space_max > FDM_MAX_N_SPACE)
+        return fail(FDM_ERR_UNSUPPORTED, "n_space_max exceeds FDM_MAX_N_SPACE (513)%s");
+    if (b->n_mon_total > 0 && (!b->mon_begin || !b->mon_step))
+        return fail(FDM_ERR_INVALID, "monitor tables missing%s");
+    return FDM_OK;
+}
+
+// flags of the whole call: bit0 any american, bit1 any linear, bit2 any dividend
+int launch(const FdmBatch &b, const FdmOut &o, cudaStream_t st, int family_mask, int32_t *n_launches)
+{
+    const bool am = family_mask & 1, lin = family_mask & 2, dv = family_mask & 4;
+    const int rows = b.n_space_max - 1;
+    if (rows <= 32 * 4) return launch_variant<4>(b, o, st, am, lin, dv, n_launches);
+    if (rows <= 32 * 8) return launch_variant<8>(b, o, st, am, lin, dv, n_launches);
+    if (rows <= 32 * 13) return launch_variant<13>(b, o, st, am, lin, dv, n_launches);
+    return launch_variant<16>(b, o, st, am, lin, dv, n_launches);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fdm_version(void) { return FDM_ABI_VERSION; }
+
+const char *fdm_last_error(void) { return g_err; }
+
+int fdm_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(FDM_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+// Device-pointer entry.  The family mask cannot be derived without reading device memory, so
+// `reserved` carries it: bit0 any American solve, bit1 any linear (European / barrier) solve,
+// bit2 any dividend jump.  0 means "unknown": launch both families with dividend scratch.
+int fdm_solve_batch(const FdmBatch *batch, const FdmOut *out, void *stream, int32_t *n_launches)
+{
+    g_err[0] = 0;
+    if (n_launches) *n_launches = 0;
+    int rc = validate(batch, out);
+    if (rc != FDM_OK || batch->n_solves == 0) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(FDM_ERR_NO_DEVICE, "no CUDA device; libfdm_b200 has no CPU fallback%s");
+    int mask = batch->reserved & 7;
+    if ((mask & 3) == 0) mask = 7;
+    return launch(*batch, *out, (cudaStream_t)stream, mask, n_launches);
+}
+
+int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launches, float *kernel_ms)
+{
+    g_err[0] = 0;
+    if (n_launches) *n_launches = 0;
+    if (kernel_ms) *kernel_ms = 0.f;
+    int rc = validate(hb, ho);
+    if (rc != FDM_OK || hb->n_solves == 0) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(FDM_ERR_NO_DEVICE, "no CUDA device; libfdm_b200 has no CPU fallback%s");
+
+    const int64_t n = hb->n_solves;
+    const int64_t nseg = hb->seg_begin[n];
+    const int64_t nmon = (hb->mon_begin && hb->n_mon_total > 0) ? hb->mon_begin[n] : 0;
+    const bool has_ko = hb->barrier && hb->rebate;
+
+    int mask = 0;
+    for (int64_t i = 0; i < n; ++i) mask |= (hb->flags[i] & FDM_FLAG_AMERICAN) ? 1 : 2;
+    for (int64_t i = 0; i < nseg; ++i) if (hb->seg_div[i] != 0.0) { mask |= 4; break; }
+
+    // one device arena for descriptors and results
+    auto up8 = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += up8(bytes); return o; };
+    const size_t o_d[9] = {take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8),
+                           take(n * 8), take(has_ko ? n * 8 : 0), take(has_ko ? n * 8 : 0)};
+    const size_t o_nspace = take(n * 4), o_flags = take(n * 4), o_ran = take(n * 4);
+    const size_t o_segb = take((n + 1) * 4), o_monb = take(nmon ? (n + 1) * 4 : 0);
+    const size_t o_ssteps = take(nseg * 4), o_sdt = take(nseg * 8), o_stau = take(nseg * 8);
+    const size_t o_srst = take(nseg * 4), o_sdiv = take(nseg * 8), o_mon = take(nmon * 4);
+    const size_t in_bytes = off;
+    const size_t r_price = take(n * 8), r_delta = take(n * 8), r_gamma = take(n * 8);
+    const size_t r_sv = take(n * 32), r_ss = take(n * 32), r_idx = take(n * 16), r_status = take(n * 4);
+    const size_t r_dump = take(ho->v_dump ? (size_t)n * ho->v_dump_stride * 8 : 0);
+    const size_t r_trace = take(ho->ex_trace ? (size_t)n * ho->ex_trace_stride * 4 : 0);
+    (void)in_bytes;
+
+    char *arena = nullptr;
+    FDM_CUDA(cudaMalloc((void **)&arena, off));
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    rc = FDM_OK;
+#define FDM_TRY(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess && rc == FDM_OK)                                             \
+            rc = fail(FDM_ERR_CUDA, #call ": %s", cudaGetErrorString(e_));                 \
+    } while (0)
+    FDM_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    FDM_TRY(cudaEventCreate(&e0));
+    FDM_TRY(cudaEventCreate(&e1));
+    auto h2d = [&](size_t o, const void *src, size_t bytes) {
+        if (bytes && src) FDM_TRY(cudaMemcpyAsync(arena + o, src, bytes, cudaMemcpyHostToDevice, st));
+    };
+    const double *hd[9] = {hb->x_min, hb->dx, hb->sigma, hb->r, hb->b, hb->spot, hb->strike,
+                           has_ko ? hb->barrier : nullptr, has_ko ? hb->rebate : nullptr};
+    for (int i = 0; i < 9; ++i) h2d(o_d[i], hd[i], n * 8);
+    h2d(o_nspace, hb->n_space, n * 4);
+    h2d(o_flags, hb->flags, n * 4);
+    h2d(o_ran, hb->rannacher, n * 4);
+    h2d(o_segb, hb->seg_begin, (n + 1) * 4);
+    if (nmon) h2d(o_monb, hb->mon_begin, (n + 1) * 4);
+    h2d(o_ssteps, hb->seg_steps, nseg * 4);
+    h2d(o_sdt, hb->seg_dt, nseg * 8);
+    h2d(o_stau, hb->seg_tau0, nseg * 8);
+    h2d(o_srst, hb->seg_restart, nseg * 4);
+    h2d(o_sdiv, hb->seg_div, nseg * 8);
+    if (nmon) h2d(o_mon, hb->mon_step, nmon * 4);
+
+    FdmBatch db = *hb;
+    db.x_min = (const double *)(arena + o_d[0]);
+    db.dx = (const double *)(arena + o_d[1]);
+    db.sigma = (const double *)(arena + o_d[2]);
+    db.r = (const double *)(arena + o_d[3]);
+    db.b = (const double *)(arena + o_d[4]);
+    db.spot = (const double *)(arena + o_d[5]);
+    db.strike = (const double *)(arena + o_d[6]);
+    db.barrier = has_ko ? (const double *)(arena + o_d[7]) : nullptr;
+    db.rebate = has_ko ? (const double *)(arena + o_d[8]) : nullptr;
+    db.n_space = (const int32_t *)(arena + o_nspace);
+    db.flags = (const int32_t *)(arena + o_flags);
+    db.rannacher = (const int32_t *)(arena + o_ran);
+    db.seg_begin = (const int32_t *)(arena + o_segb);
+    db.mon_begin = nmon ? (const int32_t *)(arena + o_monb) : nullptr;
+    db.seg_steps = (const int32_t *)(arena + o_ssteps);
+    db.seg_dt = (const double *)(arena + o_sdt);
+    db.seg_tau0 = (const double *)(arena + o_stau);
+    db.seg_restart = (const int32_t *)(arena + o_srst);
+    db.seg_div = (const double *)(arena + o_sdiv);
+    db.mon_step = nmon ? (const int32_t *)(arena + o_mon) : nullptr;
+
+    FdmOut dout = *ho;
+    dout.price = (double *)(arena + r_price);
+    dout.delta = (double *)(arena + r_delta);
+    dout.gamma = (double *)(arena + r_gamma);
+    dout.stencil_v = (double *)(arena + r_sv);
+    dout.stencil_s = (double *)(arena + r_ss);
+    dout.idx = (int32_t *)(arena + r_idx);
+    dout.status = (int32_t *)(arena + r_status);
+    dout.v_dump = ho->v_dump ? (double *)(arena + r_dump) : nullptr;
+    dout.ex_trace = ho->ex_trace ? (int32_t *)(arena + r_trace) : nullptr;
+    if (ho->ex_trace) FDM_TRY(cudaMemsetAsync(arena + r_trace, 0xff, (size_t)n * ho->ex_trace_stride * 4, st));
+    if (ho->v_dump) FDM_TRY(cudaMemsetAsync(arena + r_dump, 0, (size_t)n * ho->v_dump_stride * 8, st));
+
+    if (rc == FDM_OK) {
+        FDM_TRY(cudaEventRecord(e0, st));
+        int lrc = launch(db, dout, st, mask, n_launches);
+        if (lrc != FDM_OK) rc = lrc;
+        FDM_TRY(cudaEventRecord(e1, st));
+    }
+    auto d2h = [&](void *dst, size_t o, size_t bytes) {
+        if (dst && bytes) FDM_TRY(cudaMemcpyAsync(dst, arena + o, bytes, cudaMemcpyDeviceToHost, st));
+    };
+    if (rc == FDM_OK) {
+        d2h(ho->price, r_price, n * 8);
+        d2h(ho->delta, r_delta, n * 8);
+        d2h(ho->gamma, r_gamma, n * 8);
+        d2h(ho->stencil_v, r_sv, n * 32);
+        d2h(ho->stencil_s, r_ss, n * 32);
+        d2h(ho->idx, r_idx, n * 16);
+        d2h(ho->status, r_status, n * 4);
+        if (ho->v_dump) d2h(ho->v_dump, r_dump, (size_t)n * ho->v_dump_stride * 8);
+        if (ho->ex_trace) d2h(ho->ex_trace, r_trace, (size_t)n * ho->ex_trace_stride * 4);
+        FDM_TRY(cudaStreamSynchronize(st));
+        if (kernel_ms && rc == FDM_OK) FDM_TRY(cudaEventElapsedTime(kernel_ms, e0, e1));
+    }
+#undef FDM_TRY
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    cudaFree(arena);
+    return rc;
+}
+
+int fdm_fp64_peak(double *tflops_out, float *ms_out)
+{
+    g_err[0] = 0;
+    if (!tflops_out) return fail(FDM_ERR_INVALID, "tflops_out is NULL%s");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(FDM_ERR_NO_DEVICE, "no CUDA device%s");
+    int dev = 0, sms = 0;
+    FDM_CUDA(cudaGetDevice(&dev));
+    FDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *sink = nullptr;
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    FDM_CUDA(cudaMalloc((void **)&sink, blocks * sizeof(double)));
+    cudaEvent_t e0, e1;
+    FDM_CUDA(cudaEventCreate(&e0));
+    FDM_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        FDM_CUDA(cudaEventRecord(e0));
+        fp64_peak_kernel<<<blocks, threads>>>(sink, iters, 1.0 + rep);
+        FDM_CUDA(cudaEventRecord(e1));
+        FDM_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        FDM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    const double flops = 2.0 * 64.0 * (double)iters * (double)threads * (double)blocks;
+    *tflops_out = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return FDM_OK;
+}
+
+}  // extern "C"

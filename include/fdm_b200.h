@@ -1,0 +1,151 @@
+/*
+ * fdm_b200.h -- C ABI of the B200 batched finite-difference PDE engine (libfdm_b200.so).
+ *
+ * The reference (rwx-gigaba-sonwabo/Finite_Difference) is pure Python and has no FFI.  The
+ * natural cut is its `_solve_grid` method: one call = one 1-D log-space theta/Crank-Nicolson
+ * PDE solve returning the value vector at valuation, from which the pricer classes read a
+ * price and a small stencil:
+ *
+ *   fd_american_option_pricer.py:554-602   AmericanFDMPricer._solve_grid(N_time)
+ *   fd_american_equity.py:778-843          AmericanFDMPricer._solve_grid(n_time)
+ *   fd_american_black76.py:450-472         AmericanFwdFDMPricer._solve_grid(N_time)
+ *   discrete_barrier_fdm_pricer_cn.py:219-302, fd_discrete_barrier_option.py:182-262
+ *                                          DiscreteBarrierCrankNicolsonLog._solve_grid(apply_KO)
+ *
+ * `fdm_solve_batch*` replaces a batch of those calls plus the read-out that follows them
+ * (`_interp_price` / `_local_cubic_delta_gamma`, fd_american_option_pricer.py:613-653;
+ * `_interp_price_from_grid` / `_delta_gamma_from_grid`,
+ * discrete_barrier_fdm_pricer_cn.py:308-353).  Everything above `_solve_grid` (dates, curves,
+ * Richardson and bump fan-out, knock-in parity) stays in the host language and only builds
+ * the descriptors below.
+ *
+ * Plain C, plain pointers and sizes: bindable from ctypes / cffi / cgo / JNI alike.
+ * All functions return FDM_OK (0) or a negative error code, never throw, and set a
+ * thread-local message readable through fdm_last_error().
+ */
+#ifndef FDM_B200_H
+#define FDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDM_ABI_VERSION 1
+
+/* error codes */
+#define FDM_OK                0
+#define FDM_ERR_INVALID      -1   /* bad argument (NULL pointer, n_space < 3, ...)          */
+#define FDM_ERR_CUDA         -2   /* a CUDA runtime call failed; see fdm_last_error()       */
+#define FDM_ERR_UNSUPPORTED  -3   /* grid larger than any compiled kernel variant           */
+#define FDM_ERR_NO_DEVICE    -4   /* no CUDA device: there is NO CPU fallback               */
+
+/* per-solve flags */
+#define FDM_FLAG_CALL      0x01   /* payoff max(S-K,0); else put                            */
+#define FDM_FLAG_AMERICAN  0x02   /* Ikonen-Toivanen projection, fd_american_option_pricer.py:490-503 */
+#define FDM_FLAG_BLACK76   0x04   /* drift -sigma^2/2 and Black-76 boundaries, fd_american_black76.py:291-314,:351 */
+#define FDM_FLAG_SNAP      0x08   /* snap spot and strike to the nearest node, fd_american_option_pricer.py:246-266;
+                                     price = V[spot node], 4-point stencil.  Without it (barrier dataclass):
+                                     raw strike, linear interpolation at spot, 3-point stencil              */
+#define FDM_FLAG_KO_DOWN   0x10   /* down-and-out projection at monitor steps, discrete_barrier_fdm_pricer_cn.py:203-207 */
+#define FDM_FLAG_KO_UP     0x20   /* up-and-out projection, discrete_barrier_fdm_pricer_cn.py:209-213 */
+
+/* largest num_space_nodes any compiled kernel variant handles */
+#define FDM_MAX_N_SPACE 513
+
+/*
+ * A batch of PDE solves, structure-of-arrays.  Every pointer addresses `n_solves` elements
+ * unless noted.  For fdm_solve_batch() all pointers are DEVICE pointers owned by the caller;
+ * for fdm_solve_batch_host() they are HOST pointers.
+ */
+typedef struct FdmBatch {
+    int64_t n_solves;
+    int32_t n_space_max;   /* upper bound of n_space[] in this call: selects the kernel variant */
+    int32_t n_seg_total;   /* length of the seg_* tables  */
+    int32_t n_mon_total;   /* length of mon_step (0 if none) */
+    int32_t reserved;
+
+    const double *x_min;   /* log(S_min) of the grid, fd_american_option_pricer.py:233 */
+    const double *dx;      /* (log S_max - log S_min)/n_space, :237 */
+    const double *sigma;   /* :413 */
+    const double *r;       /* discount rate (NACC), :415 */
+    const double *b;       /* carry rate (NACC), :416; ignored with FDM_FLAG_BLACK76 */
+    const double *spot;    /* :73 / S0 */
+    const double *strike;  /* :74 / K  */
+    const double *barrier; /* KO level; may be NULL if no solve has a KO flag */
+    const double *rebate;  /* undiscounted rebate, discrete_barrier_fdm_pricer_cn.py:207; may be NULL */
+    const int32_t *n_space;    /* num_space_nodes >= 3 */
+    const int32_t *flags;      /* FDM_FLAG_* */
+    const int32_t *rannacher;  /* rannacher_steps >= 0, :464 */
+    const int32_t *seg_begin;  /* CSR, n_solves+1 entries into seg_* */
+    const int32_t *mon_begin;  /* CSR, n_solves+1 entries into mon_step; NULL if n_mon_total == 0 */
+
+    /* time segments, fd_american_option_pricer.py:565-600 (one per solve when there are no dividends) */
+    const int32_t *seg_steps;    /* n_steps >= 1 */
+    const double *seg_dt;        /* (tau_end - tau_start)/n_steps, :412 */
+    const double *seg_tau0;      /* tau_start */
+    const int32_t *seg_restart;  /* restart_rannacher, :583-586 */
+    const double *seg_div;       /* cash dividend applied AFTER the segment (spline jump, :517-548); 0 = none */
+
+    /* KO monitor steps, discrete_barrier_fdm_pricer_cn.py:177-193: 1-based global step index k,
+       strictly ascending per solve; projection runs after step k */
+    const int32_t *mon_step;
+} FdmBatch;
+
+/*
+ * Results, structure-of-arrays, `n_solves` elements each (stencils: 4 per solve).
+ * Optional pointers may be NULL.
+ */
+typedef struct FdmOut {
+    double *price;      /* SNAP: V[spot node]; else linear interpolation at spot */
+    double *delta;      /* SNAP: cubic through the 4-point stencil at the snapped spot; else 3-point formula */
+    double *gamma;
+    double *stencil_v;  /* [4*n_solves] V at the stencil nodes (3 used without SNAP) */
+    double *stencil_s;  /* [4*n_solves] S at the stencil nodes */
+    int32_t *idx;       /* [4*n_solves]: {spot node (SNAP) or lower bracket node, strike node (SNAP) or
+                           stencil centre node, ex_lo, ex_hi}.  ex_lo/ex_hi: first/last interior index k
+                           (node k+1) in the exercise set after the last step, -1 if empty / not American */
+    int32_t *status;    /* 0 ok, 1 non-finite price */
+    double *v_dump;     /* optional: full value vector, v_dump_stride doubles per solve */
+    int64_t v_dump_stride;
+    int32_t *ex_trace;  /* optional: (lo,hi) per marched step, ex_trace_stride int32 per solve */
+    int64_t ex_trace_stride;
+} FdmOut;
+
+/* ABI version of the loaded library (== FDM_ABI_VERSION of the header it was built from). */
+int fdm_version(void);
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char *fdm_last_error(void);
+
+/* Number of visible CUDA devices, or a negative error code. */
+int fdm_device_count(void);
+
+/*
+ * Launch all solves of `batch` on the current CUDA device, asynchronously on `stream`
+ * (a cudaStream_t passed as void*; NULL = default stream).  Device pointers in, device
+ * pointers out; no allocation, no synchronisation.  `n_launches`, if not NULL, receives the
+ * number of kernels launched.
+ */
+int fdm_solve_batch(const FdmBatch *batch, const FdmOut *out, void *stream, int32_t *n_launches);
+
+/*
+ * Host-buffer entry point: copies the descriptors to the device, solves, copies the results
+ * back and synchronises.  `batch` and `out` hold HOST pointers.  `kernel_ms`, if not NULL,
+ * receives the device time of the solve kernels alone (CUDA events).
+ */
+int fdm_solve_batch_host(const FdmBatch *batch, const FdmOut *out, int32_t *n_launches, float *kernel_ms);
+
+/*
+ * Register-resident dependent/independent DFMA micro-benchmark: the FP64 roofline
+ * denominator MEASURED_PEAKS.json lacks.  Writes achieved TFLOP/s (FMA = 2 flops).
+ */
+int fdm_fp64_peak(double *tflops_out, float *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* FDM_B200_H */
