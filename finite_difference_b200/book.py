@@ -1,0 +1,330 @@
+"""Books of options: the batch API above the PDE solves.
+
+The reference prices one option object at a time; every public method of its pricer classes is
+a small fan-out of ``_solve_grid`` calls followed by a scalar epilogue:
+
+* ``price_log`` / ``price_log2`` / ``greeks_log2`` -- fd_american_option_pricer.py:659-751,
+  fd_american_equity.py:913-1068, fd_american_black76.py:533-625 (1 / 2 / 6 solves),
+* ``price`` / ``greeks`` of ``DiscreteBarrierCrankNicolsonLog`` --
+  discrete_barrier_fdm_pricer_cn.py:429-537 (3 solves; knock-in by parity),
+* the scenario runner calls ``price_log2()`` then ``greeks_log2()`` per CSV row
+  (run_american_scenarios.py:144-172): 8 solves per option.
+
+Here the fan-out of a whole book becomes ONE batch of solves (one C-ABI call), and the
+epilogues are numpy expressions over the per-solve outputs, written in the reference's
+operation order.  Every executed solve is kept (the runner's repeated N / 2N solves are not
+de-duplicated unless ``dedupe=True``), so the node-step count equals the reference's.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import hostlogic
+from .batch import DeviceBatch, SolveBatch, SolveResults, solve_host
+
+__all__ = ["AmericanBook", "BarrierBook", "norm_cdf"]
+
+
+def _f64(v, n=None):
+    a = np.ascontiguousarray(np.asarray(v, dtype=np.float64))
+    if a.ndim == 0:
+        a = a.reshape(1)
+    if n is not None and a.shape[0] != n:
+        a = np.ascontiguousarray(np.broadcast_to(a, (n,)))
+    return a
+
+
+# --------------------------------------------------------------------------------------
+# American books
+# --------------------------------------------------------------------------------------
+
+@dataclass
+class _Layout:
+    """Which solves of the flat batch belong to which role.  The flat batch is role-major:
+    solves [k*n_opt, (k+1)*n_opt) hold role k of every option."""
+    roles: Sequence[str]
+    n_opt: int
+
+    def sl(self, role: str) -> slice:
+        k = list(self.roles).index(role)
+        return slice(k * self.n_opt, (k + 1) * self.n_opt)
+
+
+class AmericanBook:
+    """A book of American options priced by the theta/CN + Ikonen-Toivanen solver.
+
+    Parameters mirror the scalars the reference constructors derive
+    (fd_american_option_pricer.py:117-149): ``T`` = time_to_expiry, ``r`` = discount_rate_nacc,
+    ``b`` = carry_rate_nacc.  ``black76=True`` selects ``AmericanFwdFDMPricer`` semantics
+    (``spot`` is the forward).  ``richardson_2n_space=True`` reproduces the two equity classes'
+    ``price_log2``, which uses ``2*num_space_nodes`` time steps for the fine solve
+    (fd_american_option_pricer.py:671, fd_american_equity.py:950); Black-76 uses
+    ``2*num_time_steps`` (fd_american_black76.py:545).
+    ``div_taus``: per option, [(tau_div, cash)] ascending in tau as ``_div_times_tau`` returns
+    (fd_american_option_pricer.py:304-315).
+    """
+
+    def __init__(self, spot, strike, T, sigma, r, b, is_call, num_space_nodes=400, num_time_steps=400,
+                 rannacher_steps=2, black76=False, s_max_mult=4.5, div_taus: Optional[Sequence] = None):
+        self.spot = _f64(spot)
+        n = self.n_opt = len(self.spot)
+        self.strike, self.T, self.sigma, self.r, self.b = (_f64(v, n) for v in (strike, T, sigma, r, b))
+        self.is_call = np.ascontiguousarray(np.broadcast_to(np.asarray(is_call, dtype=bool), (n,)))
+        self.n_space = np.maximum(np.broadcast_to(np.asarray(num_space_nodes, dtype=np.int64), (n,)), 3)   # :142
+        self.n_time = np.maximum(np.broadcast_to(np.asarray(num_time_steps, dtype=np.int64), (n,)), 4)     # :143
+        self.rannacher = np.maximum(np.broadcast_to(np.asarray(rannacher_steps, dtype=np.int64), (n,)), 0)
+        self.black76 = np.ascontiguousarray(np.broadcast_to(np.asarray(black76, dtype=bool), (n,)))
+        self.s_max_mult = float(s_max_mult)
+        self.div_taus = div_taus
+
+    # ---- fan-out -----------------------------------------------------------------------
+    def _solves(self, n_time, sigma) -> SolveBatch:
+        return hostlogic.build_american_batch(
+            self.spot, self.strike, self.T, sigma, self.r, self.b, self.is_call, self.n_space, n_time,
+            self.rannacher, self.black76, self.s_max_mult, div_taus=self.div_taus)
+
+    def _fine_steps_price_log2(self):
+        return np.where(self.black76, 2 * self.n_time, 2 * self.n_space)
+
+    def fanout(self, what: str, dv_sigma: float = 0.01, use_richardson: bool = True, dedupe: bool = False):
+        """Flat batch of every ``_solve_grid`` call behind ``what``:
+
+        ``"price_log"`` 1 solve, ``"price_log2"`` 2, ``"greeks_log2"`` 6 (3 without Richardson),
+        ``"scenario"`` = ``price_log2`` then ``greeks_log2`` as run_american_scenarios.py:144-172
+        (8 solves; ``dedupe=True`` drops the repeated N solve and, where the two fine step
+        counts agree, the repeated 2N solve).
+        """
+        h = float(dv_sigma)
+        s0 = self.sigma
+        parts, roles = [], []
+
+        def add(role, n_time, sigma):
+            roles.append(role)
+            parts.append(self._solves(n_time, sigma))
+
+        if what == "price_log":
+            add("N", self.n_time, s0)
+        if what in ("price_log2", "scenario"):
+            add("p_N", self.n_time, s0)
+            if use_richardson:
+                add("p_2N", self._fine_steps_price_log2(), s0)
+        if what in ("greeks_log2", "scenario"):
+            same_n = dedupe and what == "scenario"
+            if not same_n:
+                add("g_N", self.n_time, s0)
+            if use_richardson:
+                same_2n = same_n and bool(np.all(self._fine_steps_price_log2() == 2 * self.n_time))
+                if not same_2n:
+                    add("g_2N", 2 * self.n_time, s0)                         # :700
+                add("up_h", self.n_time, s0 + h)                             # :717-723
+                add("dn_h", self.n_time, s0 - h)
+                add("up_2h", self.n_time, s0 + 2.0 * h)
+                add("dn_2h", self.n_time, s0 - 2.0 * h)
+            else:
+                add("up_h", self.n_time, s0 + h)                             # :727-729
+                add("dn_h", self.n_time, s0 - h)
+        if not parts:
+            raise ValueError(f"unknown fan-out {what!r}")
+        return SolveBatch.concat(parts), _Layout(roles, self.n_opt)
+
+    # ---- epilogues -----------------------------------------------------------------------
+    def _combine(self, what, lay: _Layout, price, delta, gamma, dv_sigma, use_richardson) -> Dict[str, np.ndarray]:
+        h = float(dv_sigma)
+        out: Dict[str, np.ndarray] = {}
+        roles = list(lay.roles)
+        if what == "price_log":
+            out["price"] = price[lay.sl("N")]
+            out["delta"], out["gamma"] = delta[lay.sl("N")], gamma[lay.sl("N")]
+            return out
+        if what in ("price_log2", "scenario"):
+            pN = price[lay.sl("p_N")]
+            out["price_log2"] = (4.0 * price[lay.sl("p_2N")] - pN) / 3.0 if use_richardson else pN   # :670-672
+        if what in ("greeks_log2", "scenario"):
+            rN = "g_N" if "g_N" in roles else "p_N"
+            r2 = "g_2N" if "g_2N" in roles else "p_2N"
+            if use_richardson:
+                p = (4.0 * price[lay.sl(r2)] - price[lay.sl(rN)]) / 3.0      # :704-706
+                d = (4.0 * delta[lay.sl(r2)] - delta[lay.sl(rN)]) / 3.0
+                g = (4.0 * gamma[lay.sl(r2)] - gamma[lay.sl(rN)]) / 3.0
+                D_h = (price[lay.sl("up_h")] - price[lay.sl("dn_h")]) / (2.0 * h)
+                D_2h = (price[lay.sl("up_2h")] - price[lay.sl("dn_2h")]) / (4.0 * h)
+                dV = (4.0 * D_h - D_2h) / 3.0                                # :725
+            else:
+                p, d, g = price[lay.sl(rN)], delta[lay.sl(rN)], gamma[lay.sl(rN)]
+                dV = (price[lay.sl("up_h")] - price[lay.sl("dn_h")]) / (2.0 * h)
+            s0, S0 = self.sigma, self.spot
+            # :737-743 (q = 0) and fd_american_black76.py:614-617; the unsnapped spot is used
+            carry = np.where(self.black76, 0.0, (self.b - 0.0) * S0 * d)
+            theta = -(0.5 * s0 * s0 * S0 * S0 * g + carry - self.r * p)
+            out.update(price=p, delta=d, gamma=g, vega=dV / 100.0, theta=theta)
+        return out
+
+    # ---- public ----------------------------------------------------------------------------
+    def run(self, what: str = "scenario", dv_sigma: float = 0.01, use_richardson: bool = True,
+            dedupe: bool = False) -> Dict[str, np.ndarray]:
+        """Host-buffer path: one ``fdm_solve_batch_host`` call for the whole fan-out."""
+        batch, lay = self.fanout(what, dv_sigma, use_richardson, dedupe)
+        res = solve_host(batch)
+        out = self._combine(what, lay, res.price, res.delta, res.gamma, dv_sigma, use_richardson)
+        first = lay.sl(lay.roles[0])
+        out["ex_lo"], out["ex_hi"] = res.idx[first, 2], res.idx[first, 3]
+        out["status"] = np.maximum.reduce([res.status[lay.sl(r)] for r in lay.roles])
+        out["node_steps"] = batch.node_steps()
+        out["n_solves"] = batch.n_solves
+        out["kernel_ms"] = res.kernel_ms
+        out["n_launches"] = res.n_launches
+        return out
+
+    def price_log(self):
+        return self.run("price_log")["price"]
+
+    def price_log2(self, use_richardson: bool = True):
+        return self.run("price_log2", use_richardson=use_richardson)["price_log2"]
+
+    def greeks_log2(self, dv_sigma: float = 0.01, use_richardson: bool = True):
+        o = self.run("greeks_log2", dv_sigma, use_richardson)
+        return {k: o[k] for k in ("price", "delta", "gamma", "vega", "theta")}
+
+
+# --------------------------------------------------------------------------------------
+# Barrier books (DiscreteBarrierCrankNicolsonLog)
+# --------------------------------------------------------------------------------------
+
+def norm_cdf(x):
+    """discrete_barrier_fdm_pricer_cn.py:16-18."""
+    return 0.5 * (1.0 + math.erf(x / math.sqrt(2.0)))
+
+
+_OUT_OF = {"down-and-in": "down-and-out", "up-and-in": "up-and-out"}
+
+
+class BarrierBook:
+    """A book of discretely monitored barrier options (``DiscreteBarrierCrankNicolsonLog``,
+    discrete_barrier_fdm_pricer_cn.py:25-537).  ``N_space`` / ``N_time`` ``None`` = the
+    reference's auto-configuration (:92-118), frozen at the base volatility like the
+    reference's first ``configure_grid`` call.
+    """
+
+    def __init__(self, S0, K, T, sigma, r_disc, b_carry, option_type, barrier_type, lower_barrier=None,
+                 upper_barrier=None, rebate=0.0, monitor_times=None, N_space=None, N_time=None):
+        self.S0 = _f64(S0)
+        n = self.n_opt = len(self.S0)
+        self.K, self.T, self.sigma, self.r_disc, self.b_carry, self.rebate = (
+            _f64(v, n) for v in (K, T, sigma, r_disc, b_carry, rebate))
+
+        def strs(v):
+            return [v] * n if isinstance(v, str) else list(v)
+
+        def opt(v):
+            if v is None:
+                return [None] * n
+            if np.isscalar(v):
+                return [float(v)] * n
+            return [None if (x is None or (isinstance(x, float) and math.isnan(x))) else float(x) for x in v]
+
+        self.option_type = [s.lower() for s in strs(option_type)]
+        self.barrier_type = [s.lower() for s in strs(barrier_type)]
+        for bt in self.barrier_type:
+            if bt not in ("none", "down-and-out", "up-and-out", "down-and-in", "up-and-in"):
+                raise ValueError(f"Unsupported barrier_type: {bt}")        # :502
+        self.lower, self.upper = opt(lower_barrier), opt(upper_barrier)
+        if monitor_times is None:
+            monitor_times = [[] for _ in range(n)]
+        elif len(monitor_times) and np.isscalar(monitor_times[0]):
+            monitor_times = [list(monitor_times)] * n
+        self.monitor_times = [list(m) if m is not None else [] for m in monitor_times]
+        self.N_space, self.N_time = self._configure(N_space, N_time)
+        self.is_call = np.array([o == "call" for o in self.option_type])
+
+    def _configure(self, N_space, N_time):
+        n = self.n_opt
+        if N_space is not None and N_time is not None:
+            return (np.broadcast_to(np.asarray(N_space, dtype=np.int64), (n,)).copy(),
+                    np.broadcast_to(np.asarray(N_time, dtype=np.int64), (n,)).copy())
+        ns = np.empty(n, dtype=np.int64)
+        nt = np.empty(n, dtype=np.int64)
+        Nsp = np.broadcast_to(np.asarray(-1 if N_space is None else N_space, dtype=np.int64), (n,))
+        Nti = np.broadcast_to(np.asarray(-1 if N_time is None else N_time, dtype=np.int64), (n,))
+        for i in range(n):
+            _, _, ns[i], nt[i] = hostlogic.barrier_configure(
+                float(self.S0[i]), float(self.K[i]), float(self.T[i]), float(self.sigma[i]), self.lower[i],
+                self.upper[i], self.monitor_times[i], None if Nsp[i] < 0 else int(Nsp[i]),
+                None if Nti[i] < 0 else int(Nti[i]))
+        return ns, nt
+
+    def _solves(self, sigma, apply_ko: bool = True) -> SolveBatch:
+        ko = [_OUT_OF.get(bt, bt) if apply_ko else "none" for bt in self.barrier_type]
+        return hostlogic.build_barrier_batch(self.S0, self.K, self.T, sigma, self.r_disc, self.b_carry,
+                                             self.is_call, ko, self.lower, self.upper, self.rebate,
+                                             self.monitor_times, self.N_space, self.N_time)
+
+    def fanout(self, what: str = "greeks", dv_sigma: float = 1e-3):
+        """``"solve"`` = one KO solve per option; ``"greeks"`` = base, sigma+dv, sigma-dv
+        (``_pde_price_and_greeks``, discrete_barrier_fdm_pricer_cn.py:429-466)."""
+        if what == "solve":
+            return self._solves(self.sigma), _Layout(["base"], self.n_opt)
+        if what != "greeks":
+            raise ValueError(f"unknown fan-out {what!r}")
+        parts = [self._solves(self.sigma), self._solves(self.sigma + dv_sigma), self._solves(self.sigma - dv_sigma)]
+        return SolveBatch.concat(parts), _Layout(["base", "up", "dn"], self.n_opt)
+
+    def _vanilla_bs(self):
+        """``_vanilla_bs_price_and_greeks`` (discrete_barrier_fdm_pricer_cn.py:359-423), per option."""
+        n = self.n_opt
+        out = {k: np.empty(n) for k in ("price", "delta", "gamma", "vega", "theta")}
+        for i in range(n):
+            S, K, T, sig, r, b = (float(v[i]) for v in (self.S0, self.K, self.T, self.sigma, self.r_disc, self.b_carry))
+            sqrtT = math.sqrt(T)
+            d1 = (math.log(S / K) + (b + 0.5 * sig * sig) * T) / (sig * sqrtT)
+            d2 = d1 - sig * sqrtT
+            df_r = math.exp(-r * T)
+            df_b = math.exp((b - r) * T)
+            pdf = math.exp(-0.5 * d1 * d1) / math.sqrt(2.0 * math.pi)
+            if self.is_call[i]:
+                price = S * df_b * norm_cdf(d1) - K * df_r * norm_cdf(d2)
+                delta = df_b * norm_cdf(d1)
+            else:
+                price = K * df_r * norm_cdf(-d2) - S * df_b * norm_cdf(-d1)
+                delta = df_b * (norm_cdf(d1) - 1.0)
+            gamma = df_b * pdf / (S * sig * sqrtT)
+            vega = S * df_b * pdf * sqrtT
+            theta = -(0.5 * sig * sig * S * S * gamma + b * S * delta - r * price)
+            for k, v in zip(("price", "delta", "gamma", "vega", "theta"), (price, delta, gamma, vega, theta)):
+                out[k][i] = v
+        return out
+
+    def run(self, what: str = "greeks", dv_sigma: float = 1e-3) -> Dict[str, np.ndarray]:
+        """``_cn.py`` semantics (discrete_barrier_fdm_pricer_cn.py:472-537): ``none`` -> closed-form BS,
+        knock-out -> PDE, knock-in -> BS minus knock-out, component-wise."""
+        batch, lay = self.fanout(what, dv_sigma)
+        res = solve_host(batch)
+        base = lay.sl("base")
+        p, d, g = res.price[base].copy(), res.delta[base].copy(), res.gamma[base].copy()
+        out = dict(price=p, delta=d, gamma=g, node_steps=batch.node_steps(), n_solves=batch.n_solves,
+                   kernel_ms=res.kernel_ms, n_launches=res.n_launches, status=res.status[base])
+        if what == "greeks":
+            vega = (res.price[lay.sl("up")] - res.price[lay.sl("dn")]) / (2.0 * dv_sigma)       # :457
+            theta = -(0.5 * self.sigma * self.sigma * self.S0 * self.S0 * g
+                      + self.b_carry * self.S0 * d - self.r_disc * p)                            # :460-464
+            out.update(vega=vega, theta=theta)
+        kinds = np.array(self.barrier_type)
+        needs_bs = np.isin(kinds, ("none", "down-and-in", "up-and-in"))
+        if needs_bs.any():
+            bs = self._vanilla_bs()
+            none = kinds == "none"
+            ki = needs_bs & ~none
+            for k in ("price", "delta", "gamma", "vega", "theta"):
+                if k in out:
+                    out[k] = np.where(none, bs[k], np.where(ki, bs[k] - out[k], out[k]))         # :489-500, :522-535
+        return out
+
+    def price(self):
+        return self.run("greeks")["price"]          # the reference's price() runs all three solves, :486-487
+
+    def greeks(self, dv_sigma: float = 1e-3):
+        o = self.run("greeks", dv_sigma)
+        return {k: o[k] for k in ("price", "delta", "gamma", "vega", "theta")}

@@ -207,6 +207,39 @@ def american_batch_prices(params: Sequence[dict], n_threads: int = 0):
     return price, lo, hi
 
 
+def _struct_dtype(struct) -> np.dtype:
+    """numpy structured dtype with the exact layout of a ctypes Structure (pointers as u8)."""
+    names, formats, offsets = [], [], []
+    for name, typ in struct._fields_:
+        f = getattr(struct, name)
+        names.append(name)
+        offsets.append(f.offset)
+        formats.append({C.c_double: "f8", C.c_int32: "i4"}.get(typ, "u8"))
+    return np.dtype(dict(names=names, formats=formats, offsets=offsets, itemsize=C.sizeof(struct)))
+
+
+def american_batch_prices_arrays(spot, strike, T, sigma, r, b, is_call, model, n_space, n_time,
+                                 rannacher=2, s_max_mult=4.5, n_threads: int = 0):
+    """OpenMP batch of dividend-free American solves from broadcastable arrays (CPU baseline)."""
+    arrs = np.broadcast_arrays(*[np.asarray(v) for v in (spot, strike, T, sigma, r, b, is_call, model,
+                                                         n_space, n_time, rannacher)])
+    n = len(arrs[0])
+    rec = np.zeros(n, dtype=_struct_dtype(_FdoAmerican))
+    for name, a in zip(("spot", "strike", "T", "sigma", "r", "b", "is_call", "model", "n_space", "n_time",
+                        "rannacher"), arrs):
+        rec[name] = a
+    rec["s_max_mult"] = s_max_mult
+    price = np.empty(n, dtype=np.float64)
+    lo = np.empty(n, dtype=np.int32)
+    hi = np.empty(n, dtype=np.int32)
+    rc = lib().fdo_american_batch(n, C.cast(rec.ctypes.data, C.POINTER(_FdoAmerican)), _dptr(price),
+                                  lo.ctypes.data_as(C.POINTER(C.c_int32)),
+                                  hi.ctypes.data_as(C.POINTER(C.c_int32)), int(n_threads))
+    if rc != 0:
+        raise ValueError("fdo_american_batch: at least one solve failed")
+    return price, lo, hi
+
+
 # --------------------------------------------------------------------------------------
 # Barrier
 # --------------------------------------------------------------------------------------

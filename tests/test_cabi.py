@@ -1,0 +1,59 @@
+"""The C-ABI library builds, loads and exports every symbol include/fdm_b200.h declares.
+No compute calls here (no GPU in the CPU tier); the error path without a device is checked."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from finite_difference_b200 import _lib, build as fdm_build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "fdm_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"^\s*(?:const\s+)?(?:int|char|size_t|void)\s*\*?\s*(fdm_\w+)\s*\(", src, flags=re.M)))
+
+
+def test_header_declares_the_binding_exports():
+    assert declared_functions() == sorted(_lib.EXPORTS)
+
+
+def test_library_builds_and_exports_every_symbol():
+    path = fdm_build.build()
+    assert os.path.exists(path)
+    L = C.CDLL(path)
+    for name in declared_functions():
+        assert hasattr(L, name), name
+    assert _lib.load().fdm_version() == _lib.ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    # FdmBatch: int64 + 4 x int32 + 20 pointers; FdmOut: 7 pointers + (ptr, int64) x 2
+    assert C.sizeof(_lib.FdmBatch) == 8 + 16 + 20 * 8
+    assert C.sizeof(_lib.FdmOut) == 7 * 8 + 4 * 8
+
+
+def test_invalid_arguments_are_reported_not_thrown():
+    L = _lib.load()
+    assert L.fdm_solve_batch(None, None, None, None) == -1
+    assert b"NULL" in L.fdm_last_error()
+
+
+def test_no_device_fails_loudly():
+    """Without a CUDA device every solve entry returns an error: there is no CPU fallback."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from finite_difference_b200 import hostlogic, solve_host
+    b = hostlogic.build_american_batch([100.0], [100.0], [1.0], [0.2], [0.05], [0.05], [False], [50], [50])
+    with pytest.raises(_lib.FdmError) as ei:
+        solve_host(b)
+    assert ei.value.code in (-4, -2)
+    from finite_difference_b200 import DeviceBatch
+    with pytest.raises(_lib.FdmError):
+        DeviceBatch(b)
