@@ -26,7 +26,7 @@ import numpy as np
 from . import hostlogic
 from .batch import DeviceBatch, SolveBatch, SolveResults, solve_host
 
-__all__ = ["AmericanBook", "BarrierBook", "norm_cdf"]
+__all__ = ["AmericanBook", "BarrierBook", "norm_cdf", "lapack_delta_gamma"]
 
 
 def _f64(v, n=None):
@@ -36,6 +36,18 @@ def _f64(v, n=None):
     if n is not None and a.shape[0] != n:
         a = np.ascontiguousarray(np.broadcast_to(a, (n,)))
     return a
+
+
+def lapack_delta_gamma(stencil_s, stencil_v, spot_idx, n_space):
+    """``_local_cubic_delta_gamma`` (fd_american_option_pricer.py:632-653) over a batch: solve
+    ``[z^3 z^2 z 1] coef = V`` with ``z = s - S_snapped`` per row; delta = coef[2], gamma = 2 coef[1]."""
+    i_near = np.clip(spot_idx, 1, np.asarray(n_space) - 2)
+    pos = (spot_idx - i_near + 1).astype(np.int64)
+    Sx = np.take_along_axis(stencil_s, pos[:, None], axis=1)
+    z = stencil_s - Sx
+    M = np.stack([z ** 3, z ** 2, z, np.ones_like(z)], axis=2)
+    coef = np.linalg.solve(M, stencil_v[:, :, None])[:, :, 0]
+    return coef[:, 2], 2.0 * coef[:, 1]
 
 
 # --------------------------------------------------------------------------------------
@@ -165,11 +177,19 @@ class AmericanBook:
 
     # ---- public ----------------------------------------------------------------------------
     def run(self, what: str = "scenario", dv_sigma: float = 0.01, use_richardson: bool = True,
-            dedupe: bool = False) -> Dict[str, np.ndarray]:
-        """Host-buffer path: one ``fdm_solve_batch_host`` call for the whole fan-out."""
+            dedupe: bool = False, lapack_greeks: bool = False) -> Dict[str, np.ndarray]:
+        """Host-buffer path: one ``fdm_solve_batch_host`` call for the whole fan-out.
+
+        ``lapack_greeks=True`` recomputes delta / gamma on the host from the exported 4-point
+        stencils with the reference's own method, a LAPACK solve of the cubic's Vandermonde
+        system (fd_american_option_pricer.py:642-653), instead of the in-kernel divided differences
+        (the two agree to ~1e-9 relative; the system is ill-conditioned on fine grids)."""
         batch, lay = self.fanout(what, dv_sigma, use_richardson, dedupe)
         res = solve_host(batch)
-        out = self._combine(what, lay, res.price, res.delta, res.gamma, dv_sigma, use_richardson)
+        delta, gamma = res.delta, res.gamma
+        if lapack_greeks:
+            delta, gamma = lapack_delta_gamma(res.stencil_s, res.stencil_v, res.idx[:, 0], batch.n_space)
+        out = self._combine(what, lay, res.price, delta, gamma, dv_sigma, use_richardson)
         first = lay.sl(lay.roles[0])
         out["ex_lo"], out["ex_hi"] = res.idx[first, 2], res.idx[first, 3]
         out["status"] = np.maximum.reduce([res.status[lay.sl(r)] for r in lay.roles])
