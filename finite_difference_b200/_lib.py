@@ -20,7 +20,8 @@ FLAG_SNAP = 0x08
 FLAG_KO_DOWN = 0x10
 FLAG_KO_UP = 0x20
 
-MAX_N_SPACE = 513
+MAX_N_SPACE = 8193
+WARP_MAX_N_SPACE = 513
 
 ERR_NAMES = {0: "FDM_OK", -1: "FDM_ERR_INVALID", -2: "FDM_ERR_CUDA", -3: "FDM_ERR_UNSUPPORTED",
              -4: "FDM_ERR_NO_DEVICE"}

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (FLAG_AMERICAN, FLAG_BLACK76, FLAG_CALL, FLAG_KO_DOWN, FLAG_KO_UP, FLAG_SNAP,
-                   MAX_N_SPACE, FdmBatch, FdmOut)
+                   MAX_N_SPACE, WARP_MAX_N_SPACE, FdmBatch, FdmOut)
 
 _F64 = ("x_min", "dx", "sigma", "r", "b", "spot", "strike", "barrier", "rebate")
 _I32 = ("n_space", "flags", "rannacher")
@@ -113,6 +113,11 @@ class SolveBatch:
             m |= 2
         if np.any(self.seg_div != 0.0):
             m |= 4
+        small = self.n_space <= WARP_MAX_N_SPACE
+        if small.any():
+            m |= 8 | (int(self.n_space[small].max()) << 8)
+        if (~small).any():
+            m |= 16
         return m
 
     def take(self, sel) -> "SolveBatch":
@@ -218,7 +223,7 @@ class SolveResults:
 def _check_sizes(batch: SolveBatch):
     if batch.n_space_max > MAX_N_SPACE:
         raise _lib.FdmError(-3, f"num_space_nodes={batch.n_space_max} exceeds the largest compiled kernel "
-                                f"variant ({MAX_N_SPACE}); larger grids are not built yet")
+                                f"variant ({MAX_N_SPACE})")
 
 
 def solve_host(batch: SolveBatch, dump: bool = False, trace: bool = False) -> SolveResults:

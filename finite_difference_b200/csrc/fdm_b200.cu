@@ -90,12 +90,91 @@ __device__ __forceinline__ void boundary_values(bool is_call, bool b76, double r
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// matching the reference's discrete growth factor
+// ---------------------------------------------------------------------------------------------
+// In the row sums of A = I - theta dt L and B = I + (1-theta) dt L the large terms +-alpha dt cancel and
+// leave 1 + O(r dt).  Any LU representation stores its factors rounded to 2^-53 relative, i.e. it solves
+// with a matrix whose row sum is off by ~ulp(alpha dt); per step that scales smooth solution components
+// by 1 + O(alpha dt 2^-53), and over the march by alpha*T*2^-53 (2e-10 at 8192 nodes).  The reference's
+// Thomas sweep (fd_american_option_pricer.py:438-457) has such a bias too -- a different one.  Both are
+// fixed numbers, known once the steady-state factors are known, so the difference is folded into the
+// coefficient of V in the right-hand side:
+//     reference, smooth component:  x = S_B / S_ref * V         S_ref = (A_L + den)(1 + c')   [den, c' = its factors]
+//     here:                         x = (pd + q) / S_our * V - q V,   S_our = (1 - nm)(1 - ncc) / inv
+//     =>  pd = S_our (q + S_B / S_ref) - q
+// evaluated in double-double arithmetic.  pd = 1 + O(alpha dt 2^-53).
+
+struct dd { double hi, lo; };
+
+__device__ __forceinline__ dd dd_two_sum(double a, double b)
+{
+    const double s = __dadd_rn(a, b);
+    const double bb = __dsub_rn(s, a);
+    const double e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+    return {s, e};
+}
+__device__ __forceinline__ dd dd_two_prod(double a, double b)
+{
+    const double p = __dmul_rn(a, b);
+    return {p, __fma_rn(a, b, -p)};
+}
+__device__ __forceinline__ dd dd_add(dd a, dd b)
+{
+    dd s = dd_two_sum(a.hi, b.hi);
+    const double lo = __dadd_rn(s.lo, __dadd_rn(a.lo, b.lo));
+    return dd_two_sum(s.hi, lo);
+}
+__device__ __forceinline__ dd dd_mul(dd a, dd b)
+{
+    dd p = dd_two_prod(a.hi, b.hi);
+    const double lo = __dadd_rn(p.lo, __dadd_rn(__dmul_rn(a.hi, b.lo), __dmul_rn(a.lo, b.hi)));
+    return dd_two_sum(p.hi, lo);
+}
+__device__ __forceinline__ dd dd_neg(dd a) { return {-a.hi, -a.lo}; }
+__device__ __forceinline__ dd dd_div(dd a, dd b)
+{
+    const double q1 = a.hi / b.hi;
+    dd r = dd_add(a, dd_neg(dd_mul(b, dd{q1, 0.0})));
+    const double q2 = r.hi / b.hi;
+    r = dd_add(r, dd_neg(dd_mul(b, dd{q2, 0.0})));
+    const double q3 = r.hi / b.hi;
+    return dd_add(dd_two_sum(q1, q2), dd{q3, 0.0});
+}
+
+// rinv_inf: this engine's converged pivot reciprocal.  Returns pd.
+__device__ __noinline__ double growth_matched_pd(double A_L, double A_C, double A_U, double B_L, double B_C,
+                                                 double B_U, double q, double rinv_inf, int max_rows)
+{
+    // the reference's factors at their fixed point: c'_0 = A_U/A_C, den_i = A_C - A_L c'_{i-1}, c'_i = A_U/den_i
+    // Grids too short for either recurrence to reach its fixed point have no steady rows to match
+    // (and alpha dt is small there): pd = 1.
+    double den = A_C, cp = A_U / A_C;
+    bool fixed = false;
+    for (int i = 1; i < max_rows && !fixed; ++i) {
+        const double den_i = __dsub_rn(A_C, __dmul_rn(A_L, cp));
+        const double cp_i = A_U / den_i;
+        fixed = (den_i == den) && (cp_i == cp);
+        den = den_i;
+        cp = cp_i;
+    }
+    if (!fixed) return 1.0;
+    const double nm = -__dmul_rn(A_L, rinv_inf), ncc = -__dmul_rn(A_U, rinv_inf);
+    const dd S_ref = dd_mul(dd_two_sum(A_L, den), dd_two_sum(1.0, cp));
+    const dd S_our = dd_div(dd_mul(dd_two_sum(1.0, -nm), dd_two_sum(1.0, -ncc)), dd{rinv_inf, 0.0});
+    const dd S_B = dd_add(dd_two_sum(B_L, B_C), dd{B_U, 0.0});
+    const dd g = dd_add(dd{q, 0.0}, dd_div(S_B, S_ref));
+    const dd pd = dd_add(dd_mul(S_our, g), dd{-q, 0.0});
+    return pd.hi + pd.lo;
+}
+
 struct PhaseScalars {
     // Boundary term of this lane: lane 0 owns row 0 (V_min side), lane 31 the top row (V_max side).
     // carry = cB * V_bdry(now) - cA * V_bdry(next step): rhs -= A * V_next (:482-483) plus the
     // boundary column of the explicit operator B (:476-480); zero on every other lane.
     double cA, cB;
     double p, q;                 // 1/theta, (1-theta)/theta
+    double pd;                   // 1 + delta: coefficient of V in R = G + pd V (see setup_phase)
     int terms;                   // carries: 2/4/6-term direct weighted sum; 0 = Kogge-Stone scan
 };
 
@@ -141,9 +220,7 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
     const double B_U = __dmul_rn(__dmul_rn(__dsub_rn(1.0, theta), dt), c);
     ph.p = 1.0 / theta;
     ph.q = (1.0 - theta) / theta;
-    const double bscale = AMER ? 1.0 : theta;     // the linear march solves for R / p
-    ph.cA = (lane == 0) ? A_L * bscale : ((lane == 31) ? A_U * bscale : 0.0);
-    ph.cB = (lane == 0) ? B_L * bscale : ((lane == 31) ? B_U * bscale : 0.0);
+    const double B_C = __dadd_rn(1.0, __dmul_rn(__dmul_rn(__dsub_rn(1.0, theta), dt), bcoef));
 
     double *tab = T.tab;
     __syncwarp();
@@ -159,8 +236,14 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
         if (lane == 0) tab[i] = rinv;
     }
     __syncwarp();
+    // growth-factor matching (see growth_matched_pd): pd = 1 + delta is the coefficient of V in R = G + pd V
+    ph.pd = (conv < n_int) ? growth_matched_pd(A_L, A_C, A_U, B_L, B_C, B_U, ph.q, rinv, n_int) : 1.0;
+    const double delta = ph.pd - 1.0;
+    const double bscale = AMER ? 1.0 : 1.0 / (ph.p + delta);     // the linear march solves for R / (p + delta)
+    ph.cA = (lane == 0) ? A_L * bscale : ((lane == 31) ? A_U * bscale : 0.0);
+    ph.cB = (lane == 0) ? B_L * bscale : ((lane == 31) ? B_U * bscale : 0.0);
 
-    const double scale = AMER ? 1.0 : ph.p;   // linear march: p folded into the final scaling
+    const double scale = AMER ? 1.0 : ph.p + delta;   // linear march: p folded into the final scaling
     double af1 = 1.0, af2 = 1.0, ab1 = 1.0, ab2 = 1.0;
 #pragma unroll
     for (int k = 0; k < C; ++k) {
@@ -289,17 +372,17 @@ __device__ __forceinline__ double lane_carry(const double e_end, const int terms
 template <int C, bool AMER>
 __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const double (&phi)[C],
                                            const double (&nm)[C], const double (&ncc)[C],
-                                           const double (&inv)[C], const double p, const double q,
+                                           const double (&inv)[C], const double pd, const double q,
                                            const double cin_f, const double cin_b, const int terms,
                                            const WarpTables<C> &T, const int lane FDM_PROF_PARAMS)
 {
     constexpr int H = (C + 1) / 2;
-    // subtrahend G = q V + L and right-hand side R = p V + L = G + V (p - q = 1 for every theta)
+    // subtrahend G = q V + L and right-hand side R = (p + delta) V + L = G + pd V (p - q = 1 for every theta)
 #pragma unroll
     for (int k = 0; k < C; ++k) {
         if (AMER) {
             const double g = fma(q, V[k], L[k]);
-            V[k] = g + V[k];
+            V[k] = fma(pd, V[k], g);
             L[k] = g;
         } else {
             L[k] = q * V[k];          // p is folded into inv[] for the linear (European) march
@@ -533,6 +616,7 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
 
     const int lane = threadIdx.x;
     const int n = B.n_space[sid];
+    if (n > FDM_WARP_MAX_N_SPACE) return;                       // larger grids: fdm_cta_kernel
     const int n_int = n - 1;
     const bool is_call = flags & FDM_FLAG_CALL;
     const bool b76 = flags & FDM_FLAG_BLACK76;
@@ -660,7 +744,7 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
                 // the following step's boundary value is fetched early: its latency hides behind this step
                 w_next = fetch_boundary(m + 1);
                 double cin_n = ph.cB * w_now - ph.cA * w_next;
-                march_step<C, AMER>(V, L, phi, nm, ncc, inv, ph.p, ph.q, (lane == 0) ? cin : 0.0,
+                march_step<C, AMER>(V, L, phi, nm, ncc, inv, ph.pd, ph.q, (lane == 0) ? cin : 0.0,
                                     (lane == 31) ? cin : 0.0, ph.terms, T, lane FDM_PROF_ARGS);
                 Vb = w_now;                                     // V[0] = V_min, V[-1] = V_max, :505-506
                 ++gstep;
@@ -842,6 +926,12 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
     }
 }
 
+}  // namespace
+
+#include "fdm_cta.cuh"
+
+namespace {
+
 // ---------------------------------------------------------------------------------------------
 // FP64 pipe micro-benchmark
 // ---------------------------------------------------------------------------------------------
@@ -906,21 +996,73 @@ int validate(const FdmBatch *b, const FdmOut *o)
     if (!o->price) return fail(FDM_ERR_INVALID, "FdmOut.price is NULL%s");
     if (b->n_space_max < 3) return fail(FDM_ERR_INVALID, "n_space_max < 3%s");
     if (b->n_space_max > FDM_MAX_N_SPACE)
-        return fail(FDM_ERR_UNSUPPORTED, "n_space_max exceeds FDM_MAX_N_SPACE (513)%s");
+        return fail(FDM_ERR_UNSUPPORTED, "n_space_max exceeds FDM_MAX_N_SPACE (8193)%s");
     if (b->n_mon_total > 0 && (!b->mon_begin || !b->mon_step))
         return fail(FDM_ERR_INVALID, "monitor tables missing%s");
     return FDM_OK;
 }
 
-// flags of the whole call: bit0 any american, bit1 any linear, bit2 any dividend
+template <int C, int WARPS>
+int launch_cta_variant(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american, bool any_linear,
+                       bool any_div, int32_t *n_launches)
+{
+    const bool trace = o.ex_trace != nullptr;
+    const size_t smem = (size_t)cta::smem_doubles<C, WARPS>(any_div) * sizeof(double);
+    auto k_am = cta::fdm_cta_kernel<C, WARPS, true, false>;
+    auto k_amt = cta::fdm_cta_kernel<C, WARPS, true, true>;
+    auto k_lin = cta::fdm_cta_kernel<C, WARPS, false, false>;
+    FDM_CUDA(cudaFuncSetAttribute(k_am, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FDM_CUDA(cudaFuncSetAttribute(k_amt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FDM_CUDA(cudaFuncSetAttribute(k_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t max_grid = 0x7fffffff;
+    int launches = 0;
+    for (int64_t first = 0; first < b.n_solves; first += max_grid) {
+        const int64_t count = (b.n_solves - first < max_grid) ? (b.n_solves - first) : max_grid;
+        const dim3 grid((unsigned)count), block(32 * WARPS);
+        if (any_american) {
+            if (trace) k_amt<<<grid, block, smem, st>>>(b, o, first, 1, any_div, FDM_WARP_MAX_N_SPACE);
+            else       k_am<<<grid, block, smem, st>>>(b, o, first, 1, any_div, FDM_WARP_MAX_N_SPACE);
+            ++launches;
+        }
+        if (any_linear) {
+            k_lin<<<grid, block, smem, st>>>(b, o, first, 0, any_div, FDM_WARP_MAX_N_SPACE);
+            ++launches;
+        }
+        FDM_CUDA(cudaGetLastError());
+    }
+    if (n_launches) *n_launches += launches;
+    return FDM_OK;
+}
+
+// flags of the whole call (FdmBatch.reserved): bit0 any american, bit1 any linear, bit2 any dividend,
+// bit3 any solve with n_space <= FDM_WARP_MAX_N_SPACE, bit4 any larger solve,
+// bits 8..19 the largest n_space of the small class (0 = unknown)
 int launch(const FdmBatch &b, const FdmOut &o, cudaStream_t st, int family_mask, int32_t *n_launches)
 {
     const bool am = family_mask & 1, lin = family_mask & 2, dv = family_mask & 4;
-    const int rows = b.n_space_max - 1;
-    if (rows <= 32 * 4) return launch_variant<4>(b, o, st, am, lin, dv, n_launches);
-    if (rows <= 32 * 8) return launch_variant<8>(b, o, st, am, lin, dv, n_launches);
-    if (rows <= 32 * 13) return launch_variant<13>(b, o, st, am, lin, dv, n_launches);
-    return launch_variant<16>(b, o, st, am, lin, dv, n_launches);
+    bool small = family_mask & 8, large = family_mask & 16;
+    if (!small && !large) {
+        large = b.n_space_max > FDM_WARP_MAX_N_SPACE;
+        small = true;                                   // unknown mix: the warp kernel skips what it cannot hold
+    }
+    if (b.n_space_max <= FDM_WARP_MAX_N_SPACE) large = false;
+    int rc = FDM_OK;
+    if (small) {
+        int small_max = (family_mask >> 8) & 0xfff;
+        if (small_max == 0 || small_max > FDM_WARP_MAX_N_SPACE)
+            small_max = b.n_space_max < FDM_WARP_MAX_N_SPACE ? b.n_space_max : FDM_WARP_MAX_N_SPACE;
+        const int rows = small_max - 1;
+        if (rows <= 32 * 4) rc = launch_variant<4>(b, o, st, am, lin, dv, n_launches);
+        else if (rows <= 32 * 8) rc = launch_variant<8>(b, o, st, am, lin, dv, n_launches);
+        else if (rows <= 32 * 13) rc = launch_variant<13>(b, o, st, am, lin, dv, n_launches);
+        else rc = launch_variant<16>(b, o, st, am, lin, dv, n_launches);
+        if (rc != FDM_OK) return rc;
+    }
+    if (large) {
+        if (b.n_space_max - 1 <= 32 * 4 * 16) rc = launch_cta_variant<16, 4>(b, o, st, am, lin, dv, n_launches);
+        else rc = launch_cta_variant<16, 16>(b, o, st, am, lin, dv, n_launches);
+    }
+    return rc;
 }
 
 }  // namespace
@@ -951,8 +1093,8 @@ int fdm_solve_batch(const FdmBatch *batch, const FdmOut *out, void *stream, int3
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(FDM_ERR_NO_DEVICE, "no CUDA device; libfdm_b200 has no CPU fallback%s");
-    int mask = batch->reserved & 7;
-    if ((mask & 3) == 0) mask = 7;
+    int mask = batch->reserved;
+    if ((mask & 3) == 0) mask |= 7;
     return launch(*batch, *out, (cudaStream_t)stream, mask, n_launches);
 }
 
@@ -972,8 +1114,17 @@ int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launch
     const int64_t nmon = (hb->mon_begin && hb->n_mon_total > 0) ? hb->mon_begin[n] : 0;
     const bool has_ko = hb->barrier && hb->rebate;
 
-    int mask = 0;
-    for (int64_t i = 0; i < n; ++i) mask |= (hb->flags[i] & FDM_FLAG_AMERICAN) ? 1 : 2;
+    int mask = 0, small_max = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        mask |= (hb->flags[i] & FDM_FLAG_AMERICAN) ? 1 : 2;
+        if (hb->n_space[i] <= FDM_WARP_MAX_N_SPACE) {
+            mask |= 8;
+            if (hb->n_space[i] > small_max) small_max = hb->n_space[i];
+        } else {
+            mask |= 16;
+        }
+    }
+    mask |= small_max << 8;
     for (int64_t i = 0; i < nseg; ++i) if (hb->seg_div[i] != 0.0) { mask |= 4; break; }
 
     // one device arena for descriptors and results

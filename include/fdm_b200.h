@@ -52,8 +52,10 @@ extern "C" {
 #define FDM_FLAG_KO_DOWN   0x10   /* down-and-out projection at monitor steps, discrete_barrier_fdm_pricer_cn.py:203-207 */
 #define FDM_FLAG_KO_UP     0x20   /* up-and-out projection, discrete_barrier_fdm_pricer_cn.py:209-213 */
 
-/* largest num_space_nodes any compiled kernel variant handles */
-#define FDM_MAX_N_SPACE 513
+/* largest num_space_nodes any compiled kernel variant handles (one CTA per solve above
+   FDM_WARP_MAX_N_SPACE, one warp per solve up to it) */
+#define FDM_MAX_N_SPACE 8193
+#define FDM_WARP_MAX_N_SPACE 513
 
 /*
  * A batch of PDE solves, structure-of-arrays.  Every pointer addresses `n_solves` elements
@@ -65,7 +67,9 @@ typedef struct FdmBatch {
     int32_t n_space_max;   /* upper bound of n_space[] in this call: selects the kernel variant */
     int32_t n_seg_total;   /* length of the seg_* tables  */
     int32_t n_mon_total;   /* length of mon_step (0 if none) */
-    int32_t reserved;
+    int32_t reserved;      /* optional launch hints, 0 = derive: bit0 any American solve, bit1 any linear solve,
+                              bit2 any dividend, bit3 any n_space <= FDM_WARP_MAX_N_SPACE, bit4 any larger,
+                              bits 8..19 the largest n_space not above FDM_WARP_MAX_N_SPACE */
 
     const double *x_min;   /* log(S_min) of the grid, fd_american_option_pricer.py:233 */
     const double *dx;      /* (log S_max - log S_min)/n_space, :237 */
