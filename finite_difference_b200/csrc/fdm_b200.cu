@@ -16,8 +16,8 @@
 //                                                   xs_i = u_i - cc_i xs_{i+1}          cc_i = A_U / den_{i+1}
 //                                                   Vt_i = inv_i xs_i                   inv_i = 1 / den_i
 //                                                with den_i the reference's pivots (same recurrence, :443-451)
-//   vc  = Vt - dt*lam ; V = max(phi, vc)         vc = inv*xs - (q V + L) ; ex = phi > vc ; V = ex ? phi : vc
-//   lam = max(0, lam + (phi - Vt)/dt)            L  = ex ? phi - vc : 0     (identical in exact arithmetic)
+//   vc  = Vt - dt*lam ; V = max(phi, vc)         vc = inv*xs - (q V + L) ; L = max(phi - vc, 0) ; V = vc + L
+//   lam = max(0, lam + (phi - Vt)/dt)            (identical in exact arithmetic; V = phi up to one rounding when exercised)
 //
 // The two first-order recurrences run across the warp as (local pass, 5-level shuffle scan of
 // affine maps, local pass with the carry).  Dirichlet boundary terms enter as the carries of
@@ -314,20 +314,6 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
 #define FDM_PROF_ARGS
 #endif
 
-// (a & m) | (b & ~m) and (a ^ b) & m as single LOP3s (no predicate registers involved)
-__device__ __forceinline__ int lop3_select(int a, int b, int m)
-{
-    int d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
-    return d;
-}
-__device__ __forceinline__ int lop3_xor_and(int a, int b, int m)
-{
-    int d;
-    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
-    return d;
-}
-
 // carry entering each lane's chunk from the lanes below (UP = true) / above (UP = false)
 template <bool UP>
 __device__ __forceinline__ double lane_carry(const double e_end, const int terms, const double *__restrict__ W,
@@ -433,13 +419,13 @@ __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const
             const double vc = fma(inv[k], xs, -L[k]);
             if (AMER) {
                 // ex = phi > vc (fd_american_option_pricer.py:496); V = ex ? phi : vc;
-                // dt*lambda_new = ex ? phi - vc : 0 (:498-500), selected on the sign bit of vc - phi
-                const double nd = vc - phi[k];
-                const int nd_hi = __double2hiint(nd);
-                const int msk = nd_hi >> 31;
-                V[k] = __hiloint2double(lop3_select(__double2hiint(phi[k]), __double2hiint(vc), msk),
-                                        lop3_select(__double2loint(phi[k]), __double2loint(vc), msk));
-                L[k] = __hiloint2double(lop3_xor_and(nd_hi, (int)0x80000000, msk), __double2loint(nd) & msk);
+                // dt*lambda_new = ex ? phi - vc : 0 (:498-500)
+                // relu on the sign mask (integer pipe), V = vc + dt*lambda_new (FP64 pipe).  Measured against an
+                // all-LOP3 select, predicated moves and an all-FP64 (d + |d|)/2 form: this one is the fastest.
+                const double d = phi[k] - vc;
+                const int msk = ~(__double2hiint(d) >> 31);
+                L[k] = __hiloint2double(__double2hiint(d) & msk, __double2loint(d) & msk);
+                V[k] = vc + L[k];
             } else {
                 V[k] = vc;
             }

@@ -157,6 +157,9 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
     ph.NM = T.nm[P]; ph.NCC = T.ncc[P]; ph.INV = T.inv[P];
     const int wfirst = w * 32 * C, wlast = wfirst + 32 * C - 1;
     ph.tbl = (wfirst < P) || (wlast >= n_int - 1);
+#ifdef FDM_CTA_FORCE_CONST
+    ph.tbl = false;     // timing experiment only: wrong results
+#endif
 
     double f1 = 1.0, f2 = 1.0, b1 = 1.0, b2 = 1.0;
 #pragma unroll
@@ -312,13 +315,11 @@ __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const dou
             else           { c2 = fma(TBL ? T.ncc[ci] : ph.NCC, c2, V[k]); xs = c2; }
             const double vc = fma(TBL ? T.inv[ci] : ph.INV, xs, -L[k]);
             if (AMER) {
-                const double phi = phi_s[k * NT + t];
-                const double nd = vc - phi;                       // exercise iff phi > vc (:496)
-                const int nd_hi = __double2hiint(nd);
-                const int msk = nd_hi >> 31;
-                V[k] = __hiloint2double(lop3_select(__double2hiint(phi), __double2hiint(vc), msk),
-                                        lop3_select(__double2loint(phi), __double2loint(vc), msk));
-                L[k] = __hiloint2double(lop3_xor_and(nd_hi, (int)0x80000000, msk), __double2loint(nd) & msk);
+                // exercise iff phi > vc (:496): dt*lambda_new = max(phi - vc, 0) on the sign mask, V = vc + dt*lambda_new
+                const double d = phi_s[k * NT + t] - vc;
+                const int msk = ~(__double2hiint(d) >> 31);
+                L[k] = __hiloint2double(__double2hiint(d) & msk, __double2loint(d) & msk);
+                V[k] = vc + L[k];
             } else {
                 V[k] = vc;
             }
