@@ -12,9 +12,9 @@ during the solve, one result all-gather per step).
 One "step" = one pass of the hot path over the rank's shard.
 
 * ``value``: device-resident descriptors (already in HBM), CUDA events on the launching stream.
-* ``e2e``: the same sweep through the public host API (``AmericanBook.run``): numpy option
-  arrays -> descriptors -> ``fdm_solve_batch_host`` (H2D, kernels, D2H inside) -> Richardson /
-  vega epilogue on the host.
+* ``e2e``: the same sweep through the public host API (``AmericanBook.run_fused`` ->
+  ``fdm_american_book_host``): numpy option arrays in host memory -> H2D of the per-option
+  scalars -> fan-out, solves and Richardson / vega epilogue on the device -> D2H of the results.
 * ``roofline``: FP64 (DFMA pipe) -- algorithmic flops (22 per American node-step)
   over the kernel's event time against the FP64 peak measured live by ``fdm_fp64_peak``.
 * ``cpu_baseline``: the C oracle (a port of the reference's Python arithmetic) on the host
@@ -260,13 +260,17 @@ def run_b200(args):
     value = total_node_steps * args.steps / (step_ms_max * 1e-3)
 
     # ---- end to end through the public host API ----------------------------------------------
-    res = book.run("scenario")                       # warm-up (also the GPU results for the parity gate)
+    res = book.run_fused("scenario")                 # warm-up
     barrier()
     torch.cuda.synchronize(dev)
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, args.steps)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        out = book.run("scenario")
+        t_it = time.perf_counter()
+        out = book.run_fused("scenario")
+        if os.environ.get("FDM_BENCH_DEBUG"):
+            print(f"[debug] e2e iteration wall {1e3 * (time.perf_counter() - t_it):.1f} ms kernel {out['kernel_ms']:.1f} ms",
+                  file=sys.stderr, flush=True)
         if world > 1:
             shard.gather_results({k: out[k] for k in ("price_log2", "price", "delta", "gamma", "vega", "theta")},
                                  mine, n_total, device=dev)
@@ -275,10 +279,11 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = total_node_steps * e2e_steps / (float(e2e_ms.item()) * 1e-3)
-    h2d = sum(getattr(batch, f).nbytes for f in
-              ("x_min", "dx", "sigma", "r", "b", "spot", "strike", "n_space", "flags", "rannacher", "seg_begin",
-               "seg_steps", "seg_dt", "seg_tau0", "seg_restart", "seg_div"))
-    d2h = batch.n_solves * (3 * 8 + 2 * 32 + 16 + 4)
+    h2d, d2h = out["h2d_bytes"], out["d2h_bytes"]                      # per-option scalars in, per-option results out
+    desc_bytes = sum(getattr(batch, f).nbytes for f in
+                     ("x_min", "dx", "sigma", "r", "b", "spot", "strike", "n_space", "flags", "rannacher", "seg_begin",
+                      "seg_steps", "seg_dt", "seg_tau0", "seg_restart", "seg_div"))
+    res_bytes = batch.n_solves * (3 * 8 + 2 * 32 + 16 + 4)
 
     if rank != 0:
         return 0
@@ -307,10 +312,10 @@ def run_b200(args):
                                "(MEASURED_PEAKS.json has no FP64 entry)",
                 "flops_per_node_step": FLOPS_PER_NODE_STEP_AMERICAN, "kernel": "fdm_warp_kernel<16,true,false>",
                 "kernel_ms_per_launch": kern_ms / args.steps,
-                "hbm": {"algorithmic_bytes_per_launch": h2d + d2h,
-                        "achieved_gbs": (h2d + d2h) / kern_s / 1e9, "peak_gbs": hbm_peak,
+                "hbm": {"algorithmic_bytes_per_launch": desc_bytes + res_bytes,
+                        "achieved_gbs": (desc_bytes + res_bytes) / kern_s / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                        "frac": (h2d + d2h) / kern_s / 1e9 / hbm_peak}}
+                        "frac": (desc_bytes + res_bytes) / kern_s / 1e9 / hbm_peak}}
 
     # ---- CPU baseline + parity gate (rank 0, N = 1 only) ----------------------------------------
     cpu = None
@@ -345,7 +350,8 @@ def run_b200(args):
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": float(e2e_ms.item()) / e2e_steps,
-                    "path": "AmericanBook.run('scenario'): numpy descriptor build + fdm_solve_batch_host + host epilogue"},
+                    "path": "AmericanBook.run_fused('scenario') -> fdm_american_book_host: per-option scalars H2D, "
+                            "fan-out + solves + Richardson/bump epilogue on the device, per-option results D2H"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "wall_ms_timed_region": wall_ms_max,

@@ -52,8 +52,25 @@ class FdmOut(C.Structure):
     ]
 
 
+class FdmAmericanBook(C.Structure):
+    _fields_ = [
+        ("n_options", C.c_int64),
+        ("spot", C.c_void_p), ("strike", C.c_void_p), ("T", C.c_void_p), ("sigma", C.c_void_p),
+        ("r", C.c_void_p), ("b", C.c_void_p), ("flags", C.c_void_p), ("n_space", C.c_void_p),
+        ("n_time", C.c_void_p), ("rannacher", C.c_void_p),
+        ("s_max_mult", C.c_double), ("dv_sigma", C.c_double), ("what", C.c_int32), ("use_richardson", C.c_int32),
+    ]
+
+
+class FdmBookOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("price_log2", "price", "delta", "gamma", "vega", "theta",
+                                          "ex_lo", "ex_hi", "status")]
+
+
+BOOK_PRICE_LOG, BOOK_PRICE_LOG2, BOOK_GREEKS_LOG2, BOOK_SCENARIO = 0, 1, 2, 3
+
 EXPORTS = ("fdm_version", "fdm_last_error", "fdm_device_count", "fdm_solve_batch",
-           "fdm_solve_batch_host", "fdm_fp64_peak")
+           "fdm_solve_batch_host", "fdm_book_solves_per_option", "fdm_american_book_host", "fdm_release_workspace", "fdm_fp64_peak")
 
 
 class FdmError(RuntimeError):
@@ -87,6 +104,11 @@ def load(path: str | None = None):
     L.fdm_solve_batch.argtypes = [C.POINTER(FdmBatch), C.POINTER(FdmOut), C.c_void_p, _pi]
     L.fdm_solve_batch_host.restype = C.c_int
     L.fdm_solve_batch_host.argtypes = [C.POINTER(FdmBatch), C.POINTER(FdmOut), _pi, C.POINTER(C.c_float)]
+    L.fdm_book_solves_per_option.restype = C.c_int
+    L.fdm_book_solves_per_option.argtypes = [C.c_int32, C.c_int32]
+    L.fdm_american_book_host.restype = C.c_int
+    L.fdm_american_book_host.argtypes = [C.POINTER(FdmAmericanBook), C.POINTER(FdmBookOut), C.POINTER(C.c_int64),
+                                         _pi, C.POINTER(C.c_float)]
     L.fdm_fp64_peak.restype = C.c_int
     L.fdm_fp64_peak.argtypes = [_pd, C.POINTER(C.c_float)]
     if L.fdm_version() != ABI_VERSION:

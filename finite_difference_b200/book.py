@@ -176,6 +176,50 @@ class AmericanBook:
         return out
 
     # ---- public ----------------------------------------------------------------------------
+    _WHAT = {"price_log": 0, "price_log2": 1, "greeks_log2": 2, "scenario": 3}
+
+    def run_fused(self, what: str = "scenario", dv_sigma: float = 0.01, use_richardson: bool = True) -> Dict[str, np.ndarray]:
+        """One ``fdm_american_book_host`` call: per-option scalars go to the device (~56 B each), the
+        fan-out into solves, the solves and the Richardson / bump epilogue all run there, and only the
+        per-option results come back.  Dividend-free books only.  The grid bounds are evaluated with the
+        device's exp/log (<= 1 ulp from libm), so prices agree with :meth:`run` to ~1e-14 relative."""
+        import ctypes as C
+        from . import _lib
+        if self.div_taus is not None and any(self.div_taus):
+            raise ValueError("run_fused handles dividend-free books; use run()")
+        L = _lib.load()
+        n = self.n_opt
+        f64 = {k: np.ascontiguousarray(getattr(self, k), dtype=np.float64) for k in ("spot", "strike", "T", "sigma", "r", "b")}
+        flags = np.ascontiguousarray(np.where(self.is_call, _lib.FLAG_CALL, 0) + np.where(self.black76, _lib.FLAG_BLACK76, 0),
+                                     dtype=np.int32)
+        i32 = {"n_space": self.n_space, "n_time": self.n_time, "rannacher": self.rannacher}
+        i32 = {k: np.ascontiguousarray(v, dtype=np.int32) for k, v in i32.items()}
+        bk = _lib.FdmAmericanBook()
+        bk.n_options = n
+        for k, v in f64.items():
+            setattr(bk, k, v.ctypes.data)
+        bk.flags = flags.ctypes.data
+        for k, v in i32.items():
+            setattr(bk, k, v.ctypes.data)
+        bk.s_max_mult, bk.dv_sigma = self.s_max_mult, float(dv_sigma)
+        bk.what, bk.use_richardson = self._WHAT[what], int(bool(use_richardson))
+        res = {k: np.empty(n) for k in ("price_log2", "price", "delta", "gamma", "vega", "theta")}
+        res.update({k: np.empty(n, dtype=np.int32) for k in ("ex_lo", "ex_hi", "status")})
+        out = _lib.FdmBookOut()
+        for k, v in res.items():
+            setattr(out, k, v.ctypes.data)
+        ns, nl, ms = C.c_int64(0), C.c_int32(0), C.c_float(0.0)
+        _lib.check(L.fdm_american_book_host(C.byref(bk), C.byref(out), C.byref(ns), C.byref(nl), C.byref(ms)))
+        if what in ("price_log", "price_log2"):
+            for k in (("vega", "theta") if what == "price_log" else ("price", "delta", "gamma", "vega", "theta")):
+                res.pop(k)
+        if what == "greeks_log2":
+            res.pop("price_log2")
+        res.update(node_steps=int(ns.value), n_solves=n * int(L.fdm_book_solves_per_option(bk.what, bk.use_richardson)),
+                   kernel_ms=float(ms.value), n_launches=int(nl.value),
+                   h2d_bytes=n * (6 * 8 + 4 * 4), d2h_bytes=n * (6 * 8 + 3 * 4))
+        return res
+
     def run(self, what: str = "scenario", dv_sigma: float = 0.01, use_richardson: bool = True,
             dedupe: bool = False, lapack_greeks: bool = False) -> Dict[str, np.ndarray]:
         """Host-buffer path: one ``fdm_solve_batch_host`` call for the whole fan-out.

@@ -32,6 +32,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "fdm_b200.h"
 
 namespace {
@@ -46,6 +48,34 @@ int fail(int code, const char *fmt, const char *detail = "")
 {
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;
+}
+
+// Device workspace of the host-buffer entry points: grow-only, one per process, reused across calls
+// (cudaMalloc/cudaFree cost milliseconds and synchronise the device).  Guarded by g_arena_mu; the host
+// entries are synchronous, so holding the lock for the whole call serialises them.
+std::mutex g_arena_mu;
+char *g_arena = nullptr;
+size_t g_arena_bytes = 0;
+int g_arena_dev = -1;
+
+cudaError_t arena_get(size_t bytes, char **out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (g_arena && (dev != g_arena_dev || bytes > g_arena_bytes)) {
+        cudaFree(g_arena);
+        g_arena = nullptr;
+        g_arena_bytes = 0;
+    }
+    if (!g_arena) {
+        e = cudaMalloc((void **)&g_arena, bytes);
+        if (e != cudaSuccess) { g_arena = nullptr; return e; }
+        g_arena_bytes = bytes;
+        g_arena_dev = dev;
+    }
+    *out = g_arena;
+    return cudaSuccess;
 }
 
 #define FDM_CUDA(call)                                                                \
@@ -915,6 +945,7 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
 }  // namespace
 
 #include "fdm_cta.cuh"
+#include "fdm_book.cuh"
 
 namespace {
 
@@ -1130,8 +1161,9 @@ int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launch
     const size_t r_trace = take(ho->ex_trace ? (size_t)n * ho->ex_trace_stride * 4 : 0);
     (void)in_bytes;
 
+    std::lock_guard<std::mutex> arena_lock(g_arena_mu);
     char *arena = nullptr;
-    FDM_CUDA(cudaMalloc((void **)&arena, off));
+    FDM_CUDA(arena_get(off, &arena));
     cudaStream_t st = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     rc = FDM_OK;
@@ -1223,8 +1255,166 @@ int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launch
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (st) cudaStreamDestroy(st);
-    cudaFree(arena);
     return rc;
+}
+
+int fdm_book_solves_per_option(int32_t what, int32_t use_richardson)
+{
+    book::Role r[8];
+    if (what < 0 || what > FDM_BOOK_SCENARIO) return fail(FDM_ERR_INVALID, "unknown book fan-out%s");
+    return book::roles_of(what, use_richardson != 0, r);
+}
+
+int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int64_t *node_steps,
+                           int32_t *n_launches, float *kernel_ms)
+{
+    g_err[0] = 0;
+    if (n_launches) *n_launches = 0;
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (node_steps) *node_steps = 0;
+    if (!hb || !ho) return fail(FDM_ERR_INVALID, "book / out is NULL%s");
+    if (hb->n_options < 0) return fail(FDM_ERR_INVALID, "n_options < 0%s");
+    if (hb->what < 0 || hb->what > FDM_BOOK_SCENARIO) return fail(FDM_ERR_INVALID, "unknown book fan-out%s");
+    const int64_t n = hb->n_options;
+    if (n == 0) return FDM_OK;
+    if (!hb->spot || !hb->strike || !hb->T || !hb->sigma || !hb->r || !hb->b || !hb->flags || !hb->n_space ||
+        !hb->n_time || !hb->rannacher)
+        return fail(FDM_ERR_INVALID, "a required FdmAmericanBook array is NULL%s");
+    book::RoleTable roles;
+    roles.n = book::roles_of(hb->what, hb->use_richardson != 0, roles.r);
+    // host-side validation (the reference raises ValueError, fd_american_option_pricer.py:68-69, :123-124)
+    int n_space_max = 3, small_max = 0, mask = 1;
+    int64_t ns_total = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (!(hb->spot[i] > 0.0) || !(hb->strike[i] > 0.0) || !(hb->T[i] > 0.0))
+            return fail(FDM_ERR_INVALID, "spot, strike and time_to_expiry must be positive%s");
+        const int ns = hb->n_space[i] < 3 ? 3 : hb->n_space[i];
+        const int nt = hb->n_time[i] < 4 ? 4 : hb->n_time[i];
+        if (ns > FDM_MAX_N_SPACE) return fail(FDM_ERR_UNSUPPORTED, "n_space exceeds FDM_MAX_N_SPACE (8193)%s");
+        if (ns > n_space_max) n_space_max = ns;
+        if (ns <= FDM_WARP_MAX_N_SPACE) { mask |= 8; if (ns > small_max) small_max = ns; } else mask |= 16;
+        for (int k = 0; k < roles.n; ++k) {
+            const double sg = hb->sigma[i] + roles.r[k].bump * hb->dv_sigma;
+            if (!(sg > 0.0)) return fail(FDM_ERR_INVALID, "sigma (after bumps) must be positive%s");
+            int steps = nt;
+            if (roles.r[k].fine == 1) steps = (hb->flags[i] & FDM_FLAG_BLACK76) ? 2 * nt : 2 * ns;
+            if (roles.r[k].fine == 2) steps = 2 * nt;
+            ns_total += (int64_t)ns * steps;
+        }
+    }
+    mask |= small_max << 8;
+    if (node_steps) *node_steps = ns_total;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(FDM_ERR_NO_DEVICE, "no CUDA device; libfdm_b200 has no CPU fallback%s");
+
+    const int64_t m = n * roles.n;                   // solves
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += up(bytes); return o; };
+    // option inputs
+    const size_t i_d[6] = {take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8)};
+    const size_t i_fl = take(n * 4), i_ns = take(n * 4), i_nt = take(n * 4), i_rn = take(n * 4);
+    // expanded descriptors
+    const size_t s_d[7] = {take(m * 8), take(m * 8), take(m * 8), take(m * 8), take(m * 8), take(m * 8), take(m * 8)};
+    const size_t s_ns = take(m * 4), s_fl = take(m * 4), s_rn = take(m * 4), s_sb = take((m + 1) * 4);
+    const size_t s_st = take(m * 4), s_dt = take(m * 8), s_t0 = take(m * 8), s_rs = take(m * 4), s_dv = take(m * 8);
+    // per-solve results
+    const size_t r_p = take(m * 8), r_d = take(m * 8), r_g = take(m * 8), r_idx = take(m * 16), r_st = take(m * 4);
+    // per-option outputs
+    const size_t o_d[6] = {take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8)};
+    const size_t o_lo = take(n * 4), o_hi = take(n * 4), o_st = take(n * 4);
+
+    std::lock_guard<std::mutex> arena_lock(g_arena_mu);
+    char *arena = nullptr;
+    FDM_CUDA(arena_get(off, &arena));
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = FDM_OK;
+#define FDM_TRY(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess && rc == FDM_OK)                                             \
+            rc = fail(FDM_ERR_CUDA, #call ": %s", cudaGetErrorString(e_));                 \
+    } while (0)
+    FDM_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    FDM_TRY(cudaEventCreate(&e0));
+    FDM_TRY(cudaEventCreate(&e1));
+    const double *hd[6] = {hb->spot, hb->strike, hb->T, hb->sigma, hb->r, hb->b};
+    for (int i = 0; i < 6; ++i) FDM_TRY(cudaMemcpyAsync(arena + i_d[i], hd[i], n * 8, cudaMemcpyHostToDevice, st));
+    FDM_TRY(cudaMemcpyAsync(arena + i_fl, hb->flags, n * 4, cudaMemcpyHostToDevice, st));
+    FDM_TRY(cudaMemcpyAsync(arena + i_ns, hb->n_space, n * 4, cudaMemcpyHostToDevice, st));
+    FDM_TRY(cudaMemcpyAsync(arena + i_nt, hb->n_time, n * 4, cudaMemcpyHostToDevice, st));
+    FDM_TRY(cudaMemcpyAsync(arena + i_rn, hb->rannacher, n * 4, cudaMemcpyHostToDevice, st));
+
+    FdmAmericanBook db = *hb;
+    db.spot = (const double *)(arena + i_d[0]); db.strike = (const double *)(arena + i_d[1]);
+    db.T = (const double *)(arena + i_d[2]); db.sigma = (const double *)(arena + i_d[3]);
+    db.r = (const double *)(arena + i_d[4]); db.b = (const double *)(arena + i_d[5]);
+    db.flags = (const int32_t *)(arena + i_fl); db.n_space = (const int32_t *)(arena + i_ns);
+    db.n_time = (const int32_t *)(arena + i_nt); db.rannacher = (const int32_t *)(arena + i_rn);
+
+    FdmBatch sb;
+    memset(&sb, 0, sizeof(sb));
+    sb.n_solves = m; sb.n_space_max = n_space_max; sb.n_seg_total = (int32_t)m; sb.reserved = mask;
+    sb.x_min = (const double *)(arena + s_d[0]); sb.dx = (const double *)(arena + s_d[1]);
+    sb.sigma = (const double *)(arena + s_d[2]); sb.r = (const double *)(arena + s_d[3]);
+    sb.b = (const double *)(arena + s_d[4]); sb.spot = (const double *)(arena + s_d[5]);
+    sb.strike = (const double *)(arena + s_d[6]);
+    sb.n_space = (const int32_t *)(arena + s_ns); sb.flags = (const int32_t *)(arena + s_fl);
+    sb.rannacher = (const int32_t *)(arena + s_rn); sb.seg_begin = (const int32_t *)(arena + s_sb);
+    sb.seg_steps = (const int32_t *)(arena + s_st); sb.seg_dt = (const double *)(arena + s_dt);
+    sb.seg_tau0 = (const double *)(arena + s_t0); sb.seg_restart = (const int32_t *)(arena + s_rs);
+    sb.seg_div = (const double *)(arena + s_dv);
+
+    FdmOut so;
+    memset(&so, 0, sizeof(so));
+    so.price = (double *)(arena + r_p); so.delta = (double *)(arena + r_d); so.gamma = (double *)(arena + r_g);
+    so.idx = (int32_t *)(arena + r_idx); so.status = (int32_t *)(arena + r_st);
+
+    FdmBookOut dbo;
+    dbo.price_log2 = (double *)(arena + o_d[0]); dbo.price = (double *)(arena + o_d[1]);
+    dbo.delta = (double *)(arena + o_d[2]); dbo.gamma = (double *)(arena + o_d[3]);
+    dbo.vega = (double *)(arena + o_d[4]); dbo.theta = (double *)(arena + o_d[5]);
+    dbo.ex_lo = (int32_t *)(arena + o_lo); dbo.ex_hi = (int32_t *)(arena + o_hi); dbo.status = (int32_t *)(arena + o_st);
+
+    if (rc == FDM_OK) {
+        FDM_TRY(cudaMemsetAsync(arena + o_d[0], 0, o_st + up(n * 4) - o_d[0], st));
+        FDM_TRY(cudaEventRecord(e0, st));
+        const int threads = 256;
+        book::expand_kernel<<<(unsigned)((m + threads - 1) / threads), threads, 0, st>>>(db, sb, roles);
+        int lrc = launch(sb, so, st, mask, n_launches);
+        if (lrc != FDM_OK) rc = lrc;
+        book::combine_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(db, so, dbo, roles.n);
+        FDM_TRY(cudaGetLastError());
+        if (n_launches) *n_launches += 2;
+        FDM_TRY(cudaEventRecord(e1, st));
+    }
+    auto d2h = [&](void *dst, size_t o, size_t bytes) {
+        if (dst && bytes) FDM_TRY(cudaMemcpyAsync(dst, arena + o, bytes, cudaMemcpyDeviceToHost, st));
+    };
+    if (rc == FDM_OK) {
+        d2h(ho->price_log2, o_d[0], n * 8); d2h(ho->price, o_d[1], n * 8); d2h(ho->delta, o_d[2], n * 8);
+        d2h(ho->gamma, o_d[3], n * 8); d2h(ho->vega, o_d[4], n * 8); d2h(ho->theta, o_d[5], n * 8);
+        d2h(ho->ex_lo, o_lo, n * 4); d2h(ho->ex_hi, o_hi, n * 4); d2h(ho->status, o_st, n * 4);
+        FDM_TRY(cudaStreamSynchronize(st));
+        if (kernel_ms && rc == FDM_OK) FDM_TRY(cudaEventElapsedTime(kernel_ms, e0, e1));
+    }
+#undef FDM_TRY
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    return rc;
+}
+
+int fdm_release_workspace(void)
+{
+    std::lock_guard<std::mutex> arena_lock(g_arena_mu);
+    if (g_arena) cudaFree(g_arena);
+    g_arena = nullptr;
+    g_arena_bytes = 0;
+    g_arena_dev = -1;
+    return FDM_OK;
 }
 
 int fdm_fp64_peak(double *tflops_out, float *ms_out)

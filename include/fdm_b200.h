@@ -142,6 +142,54 @@ int fdm_solve_batch(const FdmBatch *batch, const FdmOut *out, void *stream, int3
  */
 int fdm_solve_batch_host(const FdmBatch *batch, const FdmOut *out, int32_t *n_launches, float *kernel_ms);
 
+/* ------------------------------------------------------------------------------------------------
+ * Books: the fan-out behind the pricer classes' public methods, expanded and combined on the device.
+ * Replaces N x { price_log2(); greeks_log2() } (run_american_scenarios.py:144-172) -- or any one of
+ * price_log / price_log2 / greeks_log2 (fd_american_option_pricer.py:659-751; Black-76:
+ * fd_american_black76.py:533-625) -- for N dividend-free options.  Per-option inputs are the scalars
+ * the reference constructor derives (:117-149): T = time_to_expiry, r = discount_rate_nacc,
+ * b = carry_rate_nacc.
+ */
+#define FDM_BOOK_PRICE_LOG   0   /* 1 solve  */
+#define FDM_BOOK_PRICE_LOG2  1   /* 2 solves (1 without Richardson) */
+#define FDM_BOOK_GREEKS_LOG2 2   /* 6 solves (3 without Richardson) */
+#define FDM_BOOK_SCENARIO    3   /* price_log2 then greeks_log2: 8 solves (4 without Richardson) */
+
+typedef struct FdmAmericanBook {
+    int64_t n_options;
+    const double *spot, *strike, *T, *sigma, *r, *b;
+    const int32_t *flags;        /* FDM_FLAG_CALL | FDM_FLAG_BLACK76 per option */
+    const int32_t *n_space, *n_time, *rannacher;
+    double s_max_mult;           /* 4.5 in the reference */
+    double dv_sigma;             /* volatility bump h of greeks_log2 (0.01) */
+    int32_t what;                /* FDM_BOOK_* */
+    int32_t use_richardson;
+} FdmAmericanBook;
+
+typedef struct FdmBookOut {      /* n_options entries each; any pointer may be NULL */
+    double *price_log2;          /* price_log() / price_log2() (what = 0, 1, 3) */
+    double *price, *delta, *gamma, *vega, *theta;   /* greeks_log2() (what = 2, 3; what = 0: price/delta/gamma) */
+    int32_t *ex_lo, *ex_hi;      /* exercise interval of the base solve after its last step */
+    int32_t *status;             /* max over the option's solves */
+} FdmBookOut;
+
+/* solves per option for (what, use_richardson) */
+int fdm_book_solves_per_option(int32_t what, int32_t use_richardson);
+
+/*
+ * HOST pointers in `book` and `out`.  Copies ~56 B per option to the device, expands, solves, combines,
+ * copies the results back and synchronises.  `node_steps` (optional) receives the metric unit
+ * sum(num_space_nodes x time steps) over all executed solves.
+ */
+int fdm_american_book_host(const FdmAmericanBook *book, const FdmBookOut *out, int64_t *node_steps,
+                           int32_t *n_launches, float *kernel_ms);
+
+/*
+ * The host-buffer entry points keep one grow-only device workspace per process (no cudaMalloc per call).
+ * This releases it.
+ */
+int fdm_release_workspace(void);
+
 /*
  * Register-resident dependent/independent DFMA micro-benchmark: the FP64 roofline
  * denominator MEASURED_PEAKS.json lacks.  Writes achieved TFLOP/s (FMA = 2 flops).

@@ -152,3 +152,25 @@ def test_full_size_properties_cfg2():
     assert np.all(p_ko <= p_van + 1e-9)
     assert np.all(p_ko_reb >= p_ko - 1e-9)
     assert np.max(np.abs(p_scaled - 2.0 * p_ko) / np.maximum(np.abs(p_ko), 1e-3)) < 1e-9
+
+
+def test_fused_book_path_matches_host_built_batch():
+    """fdm_american_book_host (device-side fan-out + epilogue) == AmericanBook.run (host-built descriptors)."""
+    from finite_difference_b200.book import AmericanBook
+    rng = np.random.default_rng(11)
+    n = 96
+    K = rng.uniform(180, 280, n); sig = rng.uniform(0.15, 0.45, n); r = np.log1p(rng.uniform(0.03, 0.10, n))
+    call = rng.uniform(size=n) < 0.5; b76 = rng.uniform(size=n) < 0.5
+    book = AmericanBook(np.full(n, 229.74), K, rng.uniform(0.05, 1.5, n), sig, r, r * rng.uniform(0.5, 1.0, n), call,
+                        rng.choice([100, 257, 400, 500], n), rng.choice([50, 120, 200], n), rng.integers(0, 4, n), black76=b76)
+    for what, rich in (("scenario", True), ("scenario", False), ("greeks_log2", True), ("price_log2", True), ("price_log", True)):
+        a = book.run(what, use_richardson=rich)
+        f = book.run_fused(what, use_richardson=rich)
+        assert f["node_steps"] == a["node_steps"] and f["n_solves"] == a["n_solves"]
+        assert np.all(f["status"] == 0)
+        for k in ("price_log2", "price", "delta", "gamma", "vega", "theta"):
+            if k in a and k in f:
+                tol = {"price_log2": 1e-12, "price": 1e-12, "delta": 1e-9, "gamma": 1e-8, "vega": 1e-9, "theta": 1e-8}[k]
+                err = np.max(np.abs(f[k] - a[k]) / np.maximum(np.abs(a[k]), 1e-6))
+                assert err <= tol, (what, rich, k, err)
+        assert np.array_equal(f["ex_lo"], a["ex_lo"]) and np.array_equal(f["ex_hi"], a["ex_hi"])
