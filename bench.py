@@ -94,6 +94,23 @@ def oracle_scenario(w, sel, n_threads=0):
     return dt, int(np.sum(nt_all) * N_SPACE), price, lo, hi
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def host_threads() -> int:
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm ignores it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -101,15 +118,15 @@ def run_reference(args):
         return 0
     from oracle import oracle
     oracle.build()
-    threads = oracle.max_threads()
+    threads = host_threads()
     n_sample = args.cpu_options or max(16, 16 * threads)
     w = workload(n_sample)
     sel = np.arange(n_sample)
     for _ in range(args.warmup):
-        oracle_scenario(w, sel[: max(threads, 8)])
+        oracle_scenario(w, sel[: max(threads, 8)], threads)
     total_t, total_ns = 0.0, 0
     for _ in range(args.steps):
-        dt, ns, *_ = oracle_scenario(w, sel)
+        dt, ns, *_ = oracle_scenario(w, sel, threads)
         total_t += dt
         total_ns += ns
     value = total_ns / total_t
@@ -121,7 +138,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -323,11 +340,11 @@ def run_b200(args):
     if world == 1 and not args.no_cpu:
         from oracle import oracle
         oracle.build()
-        threads = oracle.max_threads()
+        threads = host_threads()
         n_sample = args.cpu_options or max(16, 16 * threads)
         n_sample = min(n_sample, len(mine))
         sel = np.arange(n_sample)
-        dt, ns_cpu, p_cpu, lo_cpu, hi_cpu = oracle_scenario(w, mine[sel])
+        dt, ns_cpu, p_cpu, lo_cpu, hi_cpu = oracle_scenario(w, mine[sel], threads)
         cpu = {"value": ns_cpu / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"first {n_sample} options x 8 solves of the workload ({dt:.1f} s wall), C oracle port of "
                          "the reference's Python arithmetic, OpenMP"}
@@ -340,7 +357,7 @@ def run_b200(args):
         parity = {"n_solves": int(len(p_cpu)), "max_rel_err_price": float(rel.max()), "tolerance": 1e-10,
                   "exercise_intervals_identical": same_ex}
         if not (rel.max() <= 1e-10 and same_ex):
-            print(json.dumps({"error": "parity gate failed", "parity": parity}), flush=True)
+            emit({"error": "parity gate failed", "parity": parity})
             return 1
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -360,13 +377,19 @@ def run_b200(args):
     if cpu is not None:
         line["cpu_baseline"] = cpu
         line["parity"] = parity
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
 def main():
+    # the JSON line must be the only thing on stdout (NCCL prints its version banner there): everything
+    # else goes to stderr, the line is written to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

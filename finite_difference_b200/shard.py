@@ -92,28 +92,42 @@ def gather_results(local: Dict[str, "np.ndarray"], owned: np.ndarray, n_total: i
     world = dist.get_world_size()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    n_loc = torch.tensor([len(owned)], dtype=torch.int64, device=device)
-    counts = [torch.zeros_like(n_loc) for _ in range(world)]
-    dist.all_gather(counts, n_loc)
-    counts = [int(c.item()) for c in counts]
-    width = max(counts)
-
-    def padded(a, dtype):
-        t = torch.zeros((width,) + tuple(a.shape[1:]), dtype=dtype, device=device)
-        if len(a):
-            t[: len(a)] = torch.as_tensor(np.ascontiguousarray(a), device=device)
-        return t
-
-    idx_parts = [torch.zeros(width, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(idx_parts, padded(np.asarray(owned, dtype=np.int64), torch.int64))
-    out = {}
+    # shard sizes differ by at most one option: pad to ceil(n_total / world) without a size exchange
+    width = -(-n_total // world) if n_total else 0
+    if len(owned) > width:
+        raise ValueError("shards must come from shard.partition (balanced to within one option)")
+    # one collective per dtype: columns of equal dtype are packed side by side, the option index rides along
+    groups: Dict[str, list] = {}
     for k, v in local.items():
         v = np.asarray(v)
-        tdt = torch.from_numpy(np.zeros(0, dtype=v.dtype)).dtype
-        parts = [torch.zeros((width,) + tuple(v.shape[1:]), dtype=tdt, device=device) for _ in range(world)]
-        dist.all_gather(parts, padded(v, tdt))
-        full = np.empty((n_total,) + v.shape[1:], dtype=v.dtype)
-        for r in range(world):
-            full[idx_parts[r][: counts[r]].cpu().numpy()] = parts[r][: counts[r]].cpu().numpy()
-        out[k] = full
+        groups.setdefault(v.dtype.str, []).append((k, v.reshape(len(owned), -1)))
+    idx_col = np.full((width, 1), -1, dtype=np.int64)
+    idx_col[: len(owned), 0] = owned
+    groups.setdefault(np.dtype(np.int64).str, []).append(("__idx__", idx_col[: len(owned)]))
+    gathered = {}
+    for dt, cols in groups.items():
+        packed = np.zeros((width, sum(c.shape[1] for _, c in cols)), dtype=np.dtype(dt))
+        if dt == np.dtype(np.int64).str:
+            packed[:, -1] = -1                          # padding rows carry index -1
+        off = 0
+        for _, c in cols:
+            packed[: len(owned), off: off + c.shape[1]] = c
+            off += c.shape[1]
+        src = torch.from_numpy(packed).to(device)
+        dst = torch.empty((world * width, packed.shape[1]), dtype=src.dtype, device=device)
+        dist.all_gather_into_tensor(dst, src)
+        gathered[dt] = dst.cpu().numpy()
+    idx_all = gathered[np.dtype(np.int64).str][:, -1]
+    valid = idx_all >= 0
+    out = {}
+    for dt, cols in groups.items():
+        off = 0
+        for k, c in cols:
+            w = c.shape[1]
+            if k != "__idx__":
+                v = np.asarray(local[k])
+                full = np.empty((n_total,) + v.shape[1:], dtype=v.dtype)
+                full[idx_all[valid]] = gathered[dt][valid, off: off + w].reshape((-1,) + v.shape[1:])
+                out[k] = full
+            off += w
     return out
