@@ -1024,7 +1024,7 @@ int launch_cta_variant(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool
                        bool any_div, int32_t *n_launches)
 {
     const bool trace = o.ex_trace != nullptr;
-    const size_t smem = (size_t)cta::smem_doubles<C, WARPS>(any_div) * sizeof(double);
+    const size_t smem = (size_t)cta::smem_doubles<C, WARPS>() * sizeof(double);
     auto k_am = cta::fdm_cta_kernel<C, WARPS, true, false>;
     auto k_amt = cta::fdm_cta_kernel<C, WARPS, true, true>;
     auto k_lin = cta::fdm_cta_kernel<C, WARPS, false, false>;
@@ -1037,12 +1037,12 @@ int launch_cta_variant(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool
         const int64_t count = (b.n_solves - first < max_grid) ? (b.n_solves - first) : max_grid;
         const dim3 grid((unsigned)count), block(32 * WARPS);
         if (any_american) {
-            if (trace) k_amt<<<grid, block, smem, st>>>(b, o, first, 1, any_div, FDM_WARP_MAX_N_SPACE);
-            else       k_am<<<grid, block, smem, st>>>(b, o, first, 1, any_div, FDM_WARP_MAX_N_SPACE);
+            if (trace) k_amt<<<grid, block, smem, st>>>(b, o, first, 1, FDM_WARP_MAX_N_SPACE);
+            else       k_am<<<grid, block, smem, st>>>(b, o, first, 1, FDM_WARP_MAX_N_SPACE);
             ++launches;
         }
         if (any_linear) {
-            k_lin<<<grid, block, smem, st>>>(b, o, first, 0, any_div, FDM_WARP_MAX_N_SPACE);
+            k_lin<<<grid, block, smem, st>>>(b, o, first, 0, FDM_WARP_MAX_N_SPACE);
             ++launches;
         }
         FDM_CUDA(cudaGetLastError());

@@ -2,12 +2,13 @@
 // (514 .. 8193 space nodes; BASELINE config 4 is 8192 nodes x 10 000 steps).
 //
 // Same step algebra as fdm_warp_kernel (see the header of fdm_b200.cu), different residency:
-//   * thread t of the CTA owns the C contiguous interior rows [t*C, (t+1)*C); V and dt*lambda stay
-//     in registers, the payoff lives in shared memory ([k][t] layout, conflict-free);
+//   * thread t of the CTA owns C contiguous slots; slot s holds interior row s - pad, so the padding
+//     sits BELOW row 0 and the last slot of the last thread is the top row.  V and dt*lambda stay in
+//     registers, the payoff lives in shared memory ([k][t] layout, conflict-free);
 //   * the LU pivots of the Toeplitz matrix converge bit-wise after a few hundred rows at most, so
-//     only the warps that contain the first P rows (or the top boundary row / padding) read
-//     per-row coefficients from a small shared-memory table; every other warp runs with three
-//     scalar coefficients.  The choice is warp-uniform: no divergence;
+//     only the warps that hold padding or the first P rows read per-slot coefficients (staged per
+//     thread in shared memory); every other warp runs with three scalar coefficients, and warps that
+//     hold nothing but padding only keep the barriers.  The choice is warp-uniform: no divergence;
 //   * each first-order recurrence runs as  local pass -> intra-warp shuffle scan -> one
 //     __syncthreads -> short Horner sum over the preceding warps' totals -> local pass.
 //     The warp-to-warp multipliers decay like |c'|^(32 C) (1e-17 at C = 16), so the Horner sum is
@@ -68,140 +69,177 @@ __device__ __forceinline__ int first_node_ge(double x_min, double dx, int n, dou
     return j;
 }
 
-struct Tables {
-    // coefficient tables of one (theta, dt) phase, index = row class:
-    //   [0, P)  head rows (pivots still changing), [P] steady state, [P+1] the top real row
-    //   (ncc = 1 so the Dirichlet carry passes), [P+2] padding rows above the grid (inert).
-    double *nm, *ncc, *inv;
-    int P, n_int;
-    __device__ __forceinline__ int cls(int row) const
-    {
-        return row >= n_int ? P + 2 : (row == n_int - 1 ? P + 1 : min(row, P));
-    }
+template <int C, int WARPS>
+struct Layout {
+    static constexpr int NT = 32 * WARPS;
+    static constexpr int NP = NT * C + 2;
+    // warps that may carry per-slot coefficients: 6 x 512 slots hold the padding plus a head of up to ~3000
+    // rows (alpha*dt up to ~4e4 at 8193 nodes); stiffer solves are flagged with status 2
+    static constexpr int SLOTS = WARPS <= 4 ? WARPS : 6;
+    static constexpr int SLOT_DOUBLES = 3 * C * 32 + 8 * 32;         // nm, ncc, inv [k][lane] + 8 per-lane constants
+    static constexpr int R2 = NP > SLOTS * SLOT_DOUBLES ? NP : SLOTS * SLOT_DOUBLES;
+    static constexpr int SMALL = 4 * WARPS + 16 + 64 + 32 + 8;       // part, cst, PAc, wb, ishare
+    static constexpr int TOTAL = 2 * NP + R2 + SMALL;
 };
 
-struct Phase {
-    double p, q, pd;
-    double cAf, cBf, cAb, cBb;       // boundary carry coefficients (thread 0 / last thread)
-    double NM, NCC, INV;             // steady-state coefficients
-    double aF, aB;                   // product of the chunk's multipliers (forward / backward)
-    double hF1, hF2, hB1, hB2;       // half-chunk products
-    double PAf, PAb;                 // product over the lanes before (fwd) / after (bwd) this lane in the warp
-    int Kf, Kb;                      // terms of the warp-to-warp Horner sums
-    bool tbl;                        // this warp reads per-row coefficients from the tables
+struct Sm {
+    double *r0;     // payoff by slot [k*NT + t]                      | dividend jump: cz
+    double *r1;     // pivot tables of the phase                      | dividend jump: ys; read-out: V by node
+    double *r2;     // per-slot coefficients of the table warps       | dividend jump: mu
+    double *part;   // pE_f, pA_f, pE_b, pA_b [WARPS]
+    double *cst;    // phase constants of the scalar-coefficient warps: NM NCC INV aF aB hF1 hF2 hB1 hB2 top_mult pd
+    double *PAc;    // [64] exclusive lane products of those warps, forward / backward
+    double *wb;     // [32] moving Dirichlet values of the next 32 steps
+    int *ish;       // [0] P [1] spot node [2] strike node [3,4] KO range [5] status [6,7] ex lo/hi [8] Kf [9] Kb
+                    // [10] first table warp [11] last table warp
+};
+
+enum { CST_NM = 0, CST_NCC, CST_INV, CST_AF, CST_AB, CST_HF1, CST_HF2, CST_HB1, CST_HB2, CST_TOP, CST_PD };
+enum { LC_AF = 0, LC_AB, LC_HF1, LC_HF2, LC_HB1, LC_HB2, LC_PAF, LC_PAB };
+
+struct Ph {
+    double q, pd, NM, NCC, INV;
+    double cA, cB;          // boundary coefficients of this thread (row-0 owner: A_L, B_L; last thread: A_U, B_U)
+    int Kf, Kb;             // terms of the warp-to-warp Horner sums
+    int cls;                // 0 padding only, 1 scalar coefficients, 2 per-slot coefficients
+    const double *slot;     // this warp's coefficient block (cls == 2)
 };
 
 template <int C, int WARPS, bool AMER>
-__device__ __forceinline__ void setup_phase(double theta, double dt, double a, double c, double bcoef,
-                                            int n_int, double *tab_base, int tab_cap, double *part,
-                                            int *status_flag, Phase &ph, Tables &T)
+__device__ __forceinline__ void setup_phase(double theta, double dt, double a, double c, double bcoef, int n_int,
+                                            int pad, const Sm &sm, Ph &ph)
 {
-    constexpr int NT = 32 * WARPS;
+    using LY = Layout<C, WARPS>;
     constexpr int H = C / 2;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const double A_L = __dmul_rn(__dmul_rn(-theta, dt), a);
     const double A_C = __dsub_rn(1.0, __dmul_rn(__dmul_rn(theta, dt), bcoef));
     const double A_U = __dmul_rn(__dmul_rn(-theta, dt), c);
     const double B_L = __dmul_rn(__dmul_rn(__dsub_rn(1.0, theta), dt), a);
-    const double B_U = __dmul_rn(__dmul_rn(__dsub_rn(1.0, theta), dt), c);
-    ph.p = 1.0 / theta;
-    ph.q = (1.0 - theta) / theta;
     const double B_C = __dadd_rn(1.0, __dmul_rn(__dmul_rn(__dsub_rn(1.0, theta), dt), bcoef));
-
-    const int cap = tab_cap / 3 - 3;               // head rows the tables can hold
-    T.nm = tab_base;
-    T.ncc = tab_base + (cap + 3);
-    T.inv = tab_base + 2 * (cap + 3);
-    T.n_int = n_int;
-    int *ishare = (int *)(part + 4 * WARPS);
+    const double B_U = __dmul_rn(__dmul_rn(__dsub_rn(1.0, theta), dt), c);
+    const double p = 1.0 / theta;
+    ph.q = (1.0 - theta) / theta;
+    const int cap = LY::NP / 3 - 2;                     // head rows the pivot tables can hold
+    double *pv_nm = sm.r1, *pv_ncc = sm.r1 + (cap + 1), *pv_inv = sm.r1 + 2 * (cap + 1);
     __syncthreads();
     if (t == 0) {
-        // pivots: den_0 = A_C, den_i = A_C - A_L*A_U/den_{i-1} (fd_american_option_pricer.py:443-451)
+        // pivots: den_0 = A_C, den_i = A_C - A_L*A_U/den_{i-1} (fd_american_option_pricer.py:443-451);
+        // entry i < P is row i, entry P the steady state
         double r_prev = 0.0, r_cur = __drcp_rn(A_C);
         int P = -1;
         for (int i = 0; i < cap; ++i) {
             const double den_next = __dsub_rn(A_C, __dmul_rn(A_L, __dmul_rn(A_U, r_cur)));
             const double r_next = __drcp_rn(den_next);
-            T.inv[i] = r_cur;
-            T.nm[i] = (i == 0) ? 1.0 : -(A_L * r_prev);
-            T.ncc[i] = -(A_U * r_next);
-            if (i > 0 && r_cur == r_prev && r_next == r_cur) { P = i; break; }   // row i is already steady
+            pv_inv[i] = r_cur;
+            pv_nm[i] = (i == 0) ? 0.0 : -(A_L * r_prev);            // row 0 has no lower neighbour
+            pv_ncc[i] = -(A_U * r_next);
+            if (i > 0 && r_cur == r_prev && r_next == r_cur) { P = i; break; }
             r_prev = r_cur;
             r_cur = r_next;
         }
-        if (P < 0) { P = cap; *status_flag = 2; }   // pivots not converged within the table: flagged
-        // steady state = entry P (written by the loop when it broke at i == P)
-        if (P == cap) {
-            T.inv[P] = r_cur; T.nm[P] = -(A_L * r_cur); T.ncc[P] = -(A_U * r_cur);
+        if (P < 0) {                                    // not converged within the table: flagged, best effort
+            P = cap;
+            sm.ish[5] = 2;
+            pv_inv[P] = r_cur; pv_nm[P] = -(A_L * r_cur); pv_ncc[P] = -(A_U * r_cur);
         }
-        const int top = n_int - 1;
-        const int tc = min(top, P);
-        T.inv[P + 1] = T.inv[tc]; T.nm[P + 1] = T.nm[tc]; T.ncc[P + 1] = 1.0;
-        T.inv[P + 2] = 0.0; T.nm[P + 2] = 0.0; T.ncc[P + 2] = 1.0;
         // growth-factor matching (fdm_b200.cu, growth_matched_pd); the linear march folds p + delta into inv
-        const double pd = (P < cap && P < n_int) ? growth_matched_pd(A_L, A_C, A_U, B_L, B_C, B_U, ph.q, T.inv[P], n_int) : 1.0;
-        part[4 * WARPS + 4] = pd;
+        const double pd = (P < cap && P < n_int) ? growth_matched_pd(A_L, A_C, A_U, B_L, B_C, B_U, ph.q, pv_inv[P], n_int) : 1.0;
         if (!AMER) {
-            const double scale = ph.p + (pd - 1.0);
-            for (int i = 0; i <= P + 1; ++i) T.inv[i] *= scale;
+            const double scale = p + (pd - 1.0);
+            for (int i = 0; i <= P; ++i) pv_inv[i] *= scale;
         }
-        ishare[0] = P;
+        const int wf = pad / (32 * C);                              // warp that holds row 0
+        const int wl = min((pad + P - 1) / (32 * C), WARPS - 1);    // last warp with a head row
+        if (wl - wf + 1 > LY::SLOTS) sm.ish[5] = 2;                 // more table warps than staged slots
+        sm.ish[0] = P; sm.ish[10] = wf; sm.ish[11] = min(wl, wf + LY::SLOTS - 1);
+        sm.cst[CST_NM] = pv_nm[P]; sm.cst[CST_NCC] = pv_ncc[P]; sm.cst[CST_INV] = pv_inv[P];
+        sm.cst[CST_TOP] = (sm.ish[11] == WARPS - 1) ? 1.0 : 1.0 / pv_ncc[P];
+        sm.cst[CST_PD] = pd;
     }
     __syncthreads();
-    T.P = ishare[0];
-    const int P = T.P;
-    ph.pd = part[4 * WARPS + 4];
-    const double bscale = AMER ? 1.0 : 1.0 / (ph.p + (ph.pd - 1.0));   // the linear march solves for R / (p + delta)
-    ph.cAf = A_L * bscale; ph.cBf = B_L * bscale;
-    ph.cAb = A_U * bscale; ph.cBb = B_U * bscale;
-    ph.NM = T.nm[P]; ph.NCC = T.ncc[P]; ph.INV = T.inv[P];
-    const int wfirst = w * 32 * C, wlast = wfirst + 32 * C - 1;
-    ph.tbl = (wfirst < P) || (wlast >= n_int - 1);
-#ifdef FDM_CTA_FORCE_CONST
-    ph.tbl = false;     // timing experiment only: wrong results
-#endif
+    const int P = sm.ish[0], wf = sm.ish[10], wl = sm.ish[11];
+    ph.NM = sm.cst[CST_NM]; ph.NCC = sm.cst[CST_NCC]; ph.INV = sm.cst[CST_INV]; ph.pd = sm.cst[CST_PD];
+    const double bscale = AMER ? 1.0 : 1.0 / (p + (ph.pd - 1.0));   // the linear march solves for R / (p + delta)
+    const bool owner0 = (t == pad / C);
+    ph.cA = owner0 ? A_L * bscale : ((t == LY::NT - 1) ? A_U * bscale : 0.0);
+    ph.cB = owner0 ? B_L * bscale : ((t == LY::NT - 1) ? B_U * bscale : 0.0);
+    ph.cls = (w < wf) ? 0 : (w <= wl ? 2 : 1);
+    ph.slot = sm.r2 + (size_t)max(w - wf, 0) * LY::SLOT_DOUBLES;
 
-    double f1 = 1.0, f2 = 1.0, b1 = 1.0, b2 = 1.0;
+    if (ph.cls != 0) {
+        double f1 = 1.0, f2 = 1.0, b1 = 1.0, b2 = 1.0;
 #pragma unroll
-    for (int k = 0; k < C; ++k) {
-        const int ci = T.cls(t * C + k);
-        const double vnm = ph.tbl ? T.nm[ci] : ph.NM;
-        const double vncc = ph.tbl ? T.ncc[ci] : ph.NCC;
-        if (k < H) { f1 *= vnm; b2 *= vncc; } else { f2 *= vnm; b1 *= vncc; }
-    }
-    ph.hF1 = f1; ph.hF2 = f2; ph.hB1 = b1; ph.hB2 = b2;
-    ph.aF = f1 * f2; ph.aB = b1 * b2;
-    // exclusive products across the warp (forward: lanes below, backward: lanes above)
-    double pf = ph.aF, pb = ph.aB;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double tf = __shfl_up_sync(FULL, pf, d);
-        const double tb = __shfl_down_sync(FULL, pb, d);
-        if (lane >= d) pf *= tf;
-        if (lane + d < 32) pb *= tb;
-    }
-    // pf / pb are inclusive; the warp totals go to shared memory, the exclusive ones stay in registers
-    if (lane == 31) part[1 * WARPS + w] = pf;      // pA_f
-    if (lane == 0) part[3 * WARPS + w] = pb;       // pA_b
-    double ef = __shfl_up_sync(FULL, pf, 1), eb = __shfl_down_sync(FULL, pb, 1);
-    ph.PAf = (lane == 0) ? 1.0 : ef;
-    ph.PAb = (lane == 31) ? 1.0 : eb;
-    __syncthreads();
-    // terms of the warp-to-warp sums: smallest K whose neglected weight is below TRUNC_EPS for every warp
-    int Kf = WARPS - 1, Kb = WARPS - 1;
-    for (int K = 1; K < WARPS; ++K) {
-        double worst_f = 0.0, worst_b = 0.0;
-        for (int s = 0; s + K <= WARPS; ++s) {
-            double qf = 1.0, qb = 1.0;
-            for (int u = s; u < s + K; ++u) { qf *= part[1 * WARPS + u]; qb *= part[3 * WARPS + u]; }
-            worst_f = fmax(worst_f, fabs(qf));
-            worst_b = fmax(worst_b, fabs(qb));
+        for (int k = 0; k < C; ++k) {
+            double vnm = ph.NM, vncc = ph.NCC;
+            if (ph.cls == 2) {
+                const int row = t * C + k - pad;
+                double vinv = 0.0;
+                vnm = 0.0; vncc = 0.0;                               // padding slots are inert
+                if (row >= 0) {
+                    const int ci = min(row, P);
+                    vnm = pv_nm[ci];
+                    vncc = (row == n_int - 1) ? 1.0 : pv_ncc[ci];    // top row inside a table warp: carry passes
+                    vinv = pv_inv[ci];
+                }
+                double *sl = sm.r2 + (size_t)(w - wf) * LY::SLOT_DOUBLES;
+                sl[k * 32 + lane] = vnm;
+                sl[C * 32 + k * 32 + lane] = vncc;
+                sl[2 * C * 32 + k * 32 + lane] = vinv;
+            }
+            if (k < H) { f1 *= vnm; b2 *= vncc; } else { f2 *= vnm; b1 *= vncc; }
         }
-        if (worst_f < TRUNC_EPS && Kf == WARPS - 1) Kf = K;
-        if (worst_b < TRUNC_EPS && Kb == WARPS - 1) Kb = K;
+        const double aF = f1 * f2, aB = b1 * b2;
+        double pf = aF, pb = aB;                         // inclusive lane products, then exclusive
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double tf = __shfl_up_sync(FULL, pf, d);
+            const double tb = __shfl_down_sync(FULL, pb, d);
+            if (lane >= d) pf *= tf;
+            if (lane + d < 32) pb *= tb;
+        }
+        if (lane == 31) sm.part[1 * WARPS + w] = pf;     // pA_f
+        if (lane == 0) sm.part[3 * WARPS + w] = pb;      // pA_b
+        const double ef = __shfl_up_sync(FULL, pf, 1), eb = __shfl_down_sync(FULL, pb, 1);
+        const double PAf = (lane == 0) ? 1.0 : ef, PAb = (lane == 31) ? 1.0 : eb;
+        if (ph.cls == 2) {
+            double *lc = sm.r2 + (size_t)(w - wf) * LY::SLOT_DOUBLES + 3 * C * 32;
+            lc[LC_AF * 32 + lane] = aF;   lc[LC_AB * 32 + lane] = aB;
+            lc[LC_HF1 * 32 + lane] = f1;  lc[LC_HF2 * 32 + lane] = f2;
+            lc[LC_HB1 * 32 + lane] = b1;  lc[LC_HB2 * 32 + lane] = b2;
+            lc[LC_PAF * 32 + lane] = PAf; lc[LC_PAB * 32 + lane] = PAb;
+        } else if (w == wl + 1) {                        // every scalar warp has the same constants
+            if (lane == 0) {
+                sm.cst[CST_AF] = aF; sm.cst[CST_AB] = aB; sm.cst[CST_HF1] = f1; sm.cst[CST_HF2] = f2;
+                sm.cst[CST_HB1] = b1; sm.cst[CST_HB2] = b2;
+            }
+            sm.PAc[lane] = PAf;
+            sm.PAc[32 + lane] = PAb;
+        }
+    } else if (lane == 0) {
+        sm.part[0 * WARPS + w] = 0.0; sm.part[1 * WARPS + w] = 0.0;
+        sm.part[2 * WARPS + w] = 0.0; sm.part[3 * WARPS + w] = 0.0;
     }
-    ph.Kf = Kf; ph.Kb = Kb;
-    (void)NT;
+    __syncthreads();
+    if (t == 0) {
+        // terms of the warp-to-warp sums: smallest K whose neglected weight is below TRUNC_EPS for every warp
+        int Kf = WARPS - 1, Kb = WARPS - 1;
+        bool got_f = false, got_b = false;
+        for (int K = 1; K < WARPS && !(got_f && got_b); ++K) {
+            double worst_f = 0.0, worst_b = 0.0;
+            for (int s0 = wf; s0 + K <= WARPS; ++s0) {
+                double qf = 1.0, qb = 1.0;
+                for (int u = s0; u < s0 + K; ++u) { qf *= sm.part[1 * WARPS + u]; qb *= sm.part[3 * WARPS + u]; }
+                worst_f = fmax(worst_f, fabs(qf));
+                worst_b = fmax(worst_b, fabs(qb));
+            }
+            if (!got_f && worst_f < TRUNC_EPS) { Kf = K; got_f = true; }
+            if (!got_b && worst_b < TRUNC_EPS) { Kb = K; got_b = true; }
+        }
+        sm.ish[8] = Kf; sm.ish[9] = Kb;
+    }
+    __syncthreads();
+    ph.Kf = sm.ish[8]; ph.Kb = sm.ish[9];
 }
 
 // inclusive scan of affine maps across the warp; returns the inclusive end value E_l (zero carry
@@ -227,12 +265,16 @@ __device__ __forceinline__ double warp_scan(double e, double a, int lane)
 
 // ---- the three phases of one time step (barriers sit between them, outside any branch) -----------
 
+// RHS, forward local pass, intra-warp scan.  k0 >= 0 on the thread that owns row 0: its Dirichlet term
+// is added to R there.
 template <int C, int WARPS, bool AMER, bool TBL>
-__device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Phase &ph, const Tables &T,
-                                       const double cin_f, double *part, double &e1_keep, double &Eprev)
+__device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph &ph, const Sm &sm, const int k0,
+                                       const double cin_f, double &e1_keep, double &Eprev)
 {
     constexpr int H = C / 2;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const double *nm = ph.slot;
+    const double *lc = ph.slot + 3 * C * 32;
 #pragma unroll
     for (int k = 0; k < C; ++k) {
         if (AMER) {
@@ -243,80 +285,83 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Pha
             L[k] = ph.q * V[k];
         }
     }
-    double e1 = cin_f, e2 = 0.0;
+    if (TBL && k0 >= 0) {
 #pragma unroll
-    for (int k = 0; k < H; ++k) e1 = fma(TBL ? T.nm[T.cls(t * C + k)] : ph.NM, e1, V[k]);
+        for (int k = 0; k < C; ++k) if (k == k0) V[k] += cin_f;
+    }
+    double e1 = 0.0, e2 = 0.0;
 #pragma unroll
-    for (int k = H; k < C; ++k) e2 = fma(TBL ? T.nm[T.cls(t * C + k)] : ph.NM, e2, V[k]);
-    const double e_end = fma(ph.hF2, e1, e2);
-    const double E = warp_scan<TBL, true>(e_end, ph.aF, lane);
-    if (lane == 31) part[0 * WARPS + w] = E;          // pE_f
+    for (int k = 0; k < H; ++k) e1 = fma(TBL ? nm[k * 32 + lane] : ph.NM, e1, V[k]);
+#pragma unroll
+    for (int k = H; k < C; ++k) e2 = fma(TBL ? nm[k * 32 + lane] : ph.NM, e2, V[k]);
+    const double e_end = fma(TBL ? lc[LC_HF2 * 32 + lane] : sm.cst[CST_HF2], e1, e2);
+    const double E = warp_scan<TBL, true>(e_end, TBL ? lc[LC_AF * 32 + lane] : sm.cst[CST_AF], lane);
+    if (lane == 31) sm.part[0 * WARPS + w] = E;           // pE_f
     const double up = __shfl_up_sync(FULL, E, 1);
     Eprev = (lane == 0) ? 0.0 : up;
     e1_keep = e1;
 }
 
 template <int C, int WARPS, bool AMER, bool TBL>
-__device__ __forceinline__ void step_b(double (&V)[C], const Phase &ph, const Tables &T, const double cin_f,
-                                       const double cin_b, double *part, const double e1_fwd, const double Eprev,
-                                       double &e1_keep, double &Enext)
+__device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &sm, const int wf, const double cin_b,
+                                       const double e1_fwd, const double Eprev, double &e1_keep, double &Enext)
 {
     constexpr int H = C / 2;
-    constexpr int NT = 32 * WARPS;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const double *nm = ph.slot, *ncc = ph.slot + C * 32;
+    const double *lc = ph.slot + 3 * C * 32;
     // carry into this warp from the warps below (truncated Horner sum)
     double S = 0.0;
-    for (int v = max(0, w - ph.Kf); v < w; ++v) S = fma(part[1 * WARPS + v], S, part[0 * WARPS + v]);
-    const double cs = fma(ph.PAf, S, Eprev);           // carry into this thread's chunk, excluding cin_f
+    for (int v = max(wf, w - ph.Kf); v < w; ++v) S = fma(sm.part[1 * WARPS + v], S, sm.part[0 * WARPS + v]);
+    const double cs = fma(TBL ? lc[LC_PAF * 32 + lane] : sm.PAc[lane], S, Eprev);
     {
-        double c1 = cs + cin_f;
-        double c2 = fma(ph.hF1, cs, e1_fwd);
+        double c1 = cs;
+        double c2 = fma(TBL ? lc[LC_HF1 * 32 + lane] : sm.cst[CST_HF1], cs, e1_fwd);
 #pragma unroll
-        for (int k = 0; k < H; ++k) { c1 = fma(TBL ? T.nm[T.cls(t * C + k)] : ph.NM, c1, V[k]); V[k] = c1; }
+        for (int k = 0; k < H; ++k) { c1 = fma(TBL ? nm[k * 32 + lane] : ph.NM, c1, V[k]); V[k] = c1; }
 #pragma unroll
-        for (int k = H; k < C; ++k) { c2 = fma(TBL ? T.nm[T.cls(t * C + k)] : ph.NM, c2, V[k]); V[k] = c2; }
+        for (int k = H; k < C; ++k) { c2 = fma(TBL ? nm[k * 32 + lane] : ph.NM, c2, V[k]); V[k] = c2; }
     }
     // back substitution, local pass: upper half (k = C-1..H) then lower half (H-1..0)
     double e1 = cin_b, e2 = 0.0;
 #pragma unroll
-    for (int k = C - 1; k >= H; --k) e1 = fma(TBL ? T.ncc[T.cls(t * C + k)] : ph.NCC, e1, V[k]);
+    for (int k = C - 1; k >= H; --k) e1 = fma(TBL ? ncc[k * 32 + lane] : ph.NCC, e1, V[k]);
 #pragma unroll
-    for (int k = H - 1; k >= 0; --k) e2 = fma(TBL ? T.ncc[T.cls(t * C + k)] : ph.NCC, e2, V[k]);
-    const double e_end = fma(ph.hB2, e1, e2);
-    const double E = warp_scan<TBL, false>(e_end, ph.aB, lane);
-    if (lane == 0) part[2 * WARPS + w] = E;           // pE_b
+    for (int k = H - 1; k >= 0; --k) e2 = fma(TBL ? ncc[k * 32 + lane] : ph.NCC, e2, V[k]);
+    const double e_end = fma(TBL ? lc[LC_HB2 * 32 + lane] : sm.cst[CST_HB2], e1, e2);
+    const double E = warp_scan<TBL, false>(e_end, TBL ? lc[LC_AB * 32 + lane] : sm.cst[CST_AB], lane);
+    if (lane == 0) sm.part[2 * WARPS + w] = E;            // pE_b
     const double dn = __shfl_down_sync(FULL, E, 1);
     Enext = (lane == 31) ? 0.0 : dn;
     e1_keep = e1;
-    (void)NT;
 }
 
 template <int C, int WARPS, bool AMER, bool TBL>
-__device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const double *__restrict__ phi_s,
-                                       const Phase &ph, const Tables &T, const double cin_b, double *part,
+__device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph &ph, const Sm &sm, const double cin_b,
                                        const double e1_bwd, const double Enext)
 {
     constexpr int H = C / 2;
     constexpr int NT = 32 * WARPS;
-    const int t = threadIdx.x, w = t >> 5;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const double *ncc = ph.slot + C * 32, *inv = ph.slot + 2 * C * 32;
+    const double *lc = ph.slot + 3 * C * 32;
     double S = 0.0;
-    for (int v = min(WARPS - 1, w + ph.Kb); v > w; --v) S = fma(part[3 * WARPS + v], S, part[2 * WARPS + v]);
-    const double cs = fma(ph.PAb, S, Enext);
+    for (int v = min(WARPS - 1, w + ph.Kb); v > w; --v) S = fma(sm.part[3 * WARPS + v], S, sm.part[2 * WARPS + v]);
+    const double cs = fma(TBL ? lc[LC_PAB * 32 + lane] : sm.PAc[32 + lane], S, Enext);
     double c1 = cs + cin_b;
-    double c2 = fma(ph.hB1, cs, e1_bwd);
+    double c2 = fma(TBL ? lc[LC_HB1 * 32 + lane] : sm.cst[CST_HB1], cs, e1_bwd);
 #pragma unroll
     for (int i = 0; i < H; ++i) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int k = half == 0 ? C - 1 - i : H - 1 - i;
-            const int ci = TBL ? T.cls(t * C + k) : 0;
             double xs;
-            if (half == 0) { c1 = fma(TBL ? T.ncc[ci] : ph.NCC, c1, V[k]); xs = c1; }
-            else           { c2 = fma(TBL ? T.ncc[ci] : ph.NCC, c2, V[k]); xs = c2; }
-            const double vc = fma(TBL ? T.inv[ci] : ph.INV, xs, -L[k]);
+            if (half == 0) { c1 = fma(TBL ? ncc[k * 32 + lane] : ph.NCC, c1, V[k]); xs = c1; }
+            else           { c2 = fma(TBL ? ncc[k * 32 + lane] : ph.NCC, c2, V[k]); xs = c2; }
+            const double vc = fma(TBL ? inv[k * 32 + lane] : ph.INV, xs, -L[k]);
             if (AMER) {
                 // exercise iff phi > vc (:496): dt*lambda_new = max(phi - vc, 0) on the sign mask, V = vc + dt*lambda_new
-                const double d = phi_s[k * NT + t] - vc;
+                const double d = sm.r0[k * NT + t] - vc;
                 const int msk = ~(__double2hiint(d) >> 31);
                 L[k] = __hiloint2double(__double2hiint(d) & msk, __double2loint(d) & msk);
                 V[k] = vc + L[k];
@@ -332,18 +377,19 @@ __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const dou
 // in place by the forward sweep; thread 0 runs the two serial sweeps in the reference's order.
 template <int C, int WARPS>
 __device__ __forceinline__ void dividend_jump(double (&V)[C], double &Vb, double cash, bool is_call, double k_eff,
-                                              int n, double x_min, double dx, double *ys, double *mu, double *cz)
+                                              int n, int pad, double x_min, double dx, double *ys, double *mu, double *cz)
 {
     constexpr int NT = 32 * WARPS;
     const int t = threadIdx.x;
     const int nn = n + 1;
+    const bool owner0 = (t == pad / C);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-        const int j = t * C + k + 1;
-        if (j <= n - 1) { ys[j] = V[k]; mu[j] = node_s(x_min, dx, j); }
+        const int j = t * C + k - pad + 1;
+        if (j >= 1) { ys[j] = V[k]; mu[j] = node_s(x_min, dx, j); }
     }
-    if (t == 0) { ys[0] = Vb; mu[0] = node_s(x_min, dx, 0); }
+    if (owner0) { ys[0] = Vb; mu[0] = node_s(x_min, dx, 0); }
     if (t == NT - 1) { ys[n] = Vb; mu[n] = node_s(x_min, dx, n); }
     __syncthreads();
     if (t == 0) {
@@ -404,11 +450,11 @@ __device__ __forceinline__ void dividend_jump(double (&V)[C], double &Vb, double
     double newV[C];
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-        const int j = t * C + k + 1;
-        newV[k] = (j <= n - 1) ? eval(j) : 0.0;
+        const int j = t * C + k - pad + 1;
+        newV[k] = (j >= 1) ? eval(j) : 0.0;
     }
     double nb = Vb;
-    if (t == 0) nb = eval(0);
+    if (owner0) nb = eval(0);
     if (t == NT - 1) nb = eval(n);
     __syncthreads();
 #pragma unroll
@@ -419,24 +465,25 @@ __device__ __forceinline__ void dividend_jump(double (&V)[C], double &Vb, double
 // ---- the kernel ------------------------------------------------------------------------------------
 
 template <int C, int WARPS>
-constexpr int smem_doubles(bool with_div)
-{
-    return (with_div ? 3 : 2) * (32 * WARPS * C + 2) + 4 * WARPS + 16;
-}
+constexpr int smem_doubles() { return Layout<C, WARPS>::TOTAL; }
 
 template <int C, int WARPS, bool AMER, bool TRACE>
 __global__ void __launch_bounds__(32 * WARPS, 1)
-fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int want_american, const int div_smem,
-               const int n_lo)
+fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int want_american, const int n_lo)
 {
-    constexpr int NT = 32 * WARPS;
-    constexpr int NP = NT * C + 2;
+    using LY = Layout<C, WARPS>;
+    constexpr int NT = LY::NT;
+    constexpr int NP = LY::NP;
     extern __shared__ double smem[];
-    double *r0 = smem;                 // payoff [k*NT + t]          | dividend jump: cz
-    double *r1 = r0 + NP;              // coefficient tables         | dividend jump: ys; read-out: V by node
-    double *r2 = r1 + NP;              // dividend jump: mu (only allocated when div_smem)
-    double *part = div_smem ? r2 + NP : r1 + NP;     // pE_f, pA_f, pE_b, pA_b [WARPS] + scratch
-    int *ishare = (int *)(part + 4 * WARPS);         // [0] P, [1..4] snapping / KO indices, [5] status, [6,7] ex lo/hi
+    Sm sm;
+    sm.r0 = smem;
+    sm.r1 = sm.r0 + NP;
+    sm.r2 = sm.r1 + NP;
+    sm.part = sm.r2 + LY::R2;
+    sm.cst = sm.part + 4 * WARPS;
+    sm.PAc = sm.cst + 16;
+    sm.wb = sm.PAc + 64;
+    sm.ish = (int *)(sm.wb + 32);
 
     const int64_t sid = first + blockIdx.x;
     if (sid >= B.n_solves) return;
@@ -445,6 +492,7 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
     const int n = B.n_space[sid];
     if (n <= n_lo || n - 1 > NT * C) return;           // other size classes are other launches
     const int n_int = n - 1;
+    const int pad = NT * C - n_int;                    // slots below row 0
 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const bool is_call = flags & FDM_FLAG_CALL;
@@ -456,6 +504,8 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
     const double barrier = (ko && B.barrier) ? B.barrier[sid] : 0.0;
     const double rebate = (ko && B.rebate) ? B.rebate[sid] : 0.0;
     const int rannacher = B.rannacher[sid];
+    const int t0 = pad / C;                            // thread that owns row 0 (and boundary node 0)
+    const int k0 = (t == t0) ? pad % C : -1;
 
     if (t == 0) {
         int spot_idx = 0, strike_idx = 0, klo = 1, khi = 0;
@@ -465,11 +515,11 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
         }
         if (ko == 1) { klo = 0; khi = last_node_le(x_min, dx, n, barrier); }
         if (ko == 2) { klo = first_node_ge(x_min, dx, n, barrier); khi = n; }
-        ishare[1] = spot_idx; ishare[2] = strike_idx; ishare[3] = klo; ishare[4] = khi;
-        ishare[5] = 0; ishare[6] = 0x7fffffff; ishare[7] = -1;
+        sm.ish[1] = spot_idx; sm.ish[2] = strike_idx; sm.ish[3] = klo; sm.ish[4] = khi;
+        sm.ish[5] = 0; sm.ish[6] = 0x7fffffff; sm.ish[7] = -1;
     }
     __syncthreads();
-    const int spot_idx = ishare[1], strike_idx = ishare[2], ko_lo = ishare[3], ko_hi = ishare[4];
+    const int spot_idx = sm.ish[1], strike_idx = sm.ish[2], ko_lo = sm.ish[3], ko_hi = sm.ish[4];
     const double k_eff = snap ? node_s(x_min, dx, strike_idx) : strike;
     const double sn = node_s(x_min, dx, n);
 
@@ -477,18 +527,18 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
     auto fill_payoff = [&](bool set_v) {
 #pragma unroll
         for (int k = 0; k < C; ++k) {
-            const int j = t * C + k + 1;
-            const double pv = (j <= n - 1) ? payoff(node_s(x_min, dx, j), k_eff, is_call) : 0.0;
-            r0[k * NT + t] = pv;
+            const int j = t * C + k - pad + 1;
+            const double pv = (j >= 1) ? payoff(node_s(x_min, dx, j), k_eff, is_call) : 0.0;
+            sm.r0[k * NT + t] = pv;
             if (set_v) { V[k] = pv; L[k] = 0.0; }
         }
     };
     fill_payoff(true);
-    // boundary node values: V[0] on thread 0, V[n] on the last thread
-    double Vb = (t == 0) ? payoff(node_s(x_min, dx, 0), k_eff, is_call)
-                         : ((t == NT - 1) ? payoff(sn, k_eff, is_call) : 0.0);
-    const bool bdry_thread = is_call ? (t == NT - 1) : (t == 0);
-    const bool bdry_warp = is_call ? (w == WARPS - 1) : (w == 0);
+    // boundary node values: V[0] on the owner of row 0, V[n] on the last thread
+    double Vb = (t == t0) ? payoff(node_s(x_min, dx, 0), k_eff, is_call)
+                          : ((t == NT - 1) ? payoff(sn, k_eff, is_call) : 0.0);
+    const bool bdry_thread = is_call ? (t == NT - 1) : (t == t0);
+    const bool bdry_warp = is_call ? (w == WARPS - 1) : (w == t0 / 32);
 
     const double sig2 = __dmul_rn(sigma, sigma);
     const double mu_x = b76 ? __dmul_rn(-0.5, sig2) : __dsub_rn(bcar, __dmul_rn(0.5, sig2));
@@ -516,9 +566,9 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
             for (int k = 0; k < C; ++k) L[k] = 0.0;             // :463
         }
         int m = 0;
-        double my_w = 0.0;
         int fill_base = -64;
-        // moving Dirichlet value: computed 32 steps at a time by the warp that owns that boundary
+        // moving Dirichlet value: 32 steps at a time, one exponential per lane of the warp that owns the
+        // boundary, parked in shared memory (only that warp touches wb[])
         auto fetch_boundary = [&](int step) -> double {
             if (!bdry_warp) return 0.0;
             if (step - fill_base >= 32 || step < fill_base) {
@@ -526,102 +576,96 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                 const double tau = fma((double)(step + lane + 1), dt, tau0);
                 double vmin, vmax;
                 boundary_values(is_call, b76, r, bcar, k_eff, sn, tau, vmin, vmax);
-                my_w = is_call ? vmax : vmin;
+                __syncwarp();
+                sm.wb[lane] = is_call ? vmax : vmin;
+                __syncwarp();
             }
-            const double wv = __shfl_sync(FULL, my_w, step - fill_base);
-            return bdry_thread ? wv : 0.0;
+            return bdry_thread ? sm.wb[step - fill_base] : 0.0;
         };
         while (m < n_steps) {
             const bool implicit_phase = m < base_ran;
             const int m_end = implicit_phase ? min(base_ran, n_steps) : n_steps;
-            Phase ph;
-            Tables T;
-            setup_phase<C, WARPS, AMER>(implicit_phase ? 1.0 : 0.5, dt, ca, cc, bcoef, n_int, r1, NP, part,
-                                        &ishare[5], ph, T);
-            const double cA = (t == 0) ? ph.cAf : ((t == NT - 1) ? ph.cAb : 0.0);
-            const double cB = (t == 0) ? ph.cBf : ((t == NT - 1) ? ph.cBb : 0.0);
+            Ph ph;
+            setup_phase<C, WARPS, AMER>(implicit_phase ? 1.0 : 0.5, dt, ca, cc, bcoef, n_int, pad, sm, ph);
+            const int wf = sm.ish[10];
+            const double top_mult = (t == NT - 1) ? sm.cst[CST_TOP] : 0.0;
             double w_next = fetch_boundary(m);
-            double cin = cB * Vb - cA * w_next;                 // non-zero on the two boundary threads only
+            double cin = ph.cB * Vb - ph.cA * w_next;           // non-zero on the two boundary threads only
             for (; m < m_end; ++m) {
                 const double w_now = w_next;
                 w_next = fetch_boundary(m + 1);
-                double cin_n = cB * w_now - cA * w_next;
-                const double cin_f = (t == 0) ? cin : 0.0;
-                const double cin_b = (t == NT - 1) ? cin : 0.0;
-                double e1f, Eprev, e1b, Enext;
-                if (ph.tbl) step_a<C, WARPS, AMER, true>(V, L, ph, T, cin_f, part, e1f, Eprev);
-                else        step_a<C, WARPS, AMER, false>(V, L, ph, T, cin_f, part, e1f, Eprev);
+                double cin_n = ph.cB * w_now - ph.cA * w_next;
+                const double cin_b = cin * top_mult;            // enters the top row through its ncc
+                double e1f = 0.0, Eprev = 0.0, e1b = 0.0, Enext = 0.0;
+                if (ph.cls == 2) step_a<C, WARPS, AMER, true>(V, L, ph, sm, k0, cin, e1f, Eprev);
+                else if (ph.cls == 1) step_a<C, WARPS, AMER, false>(V, L, ph, sm, -1, 0.0, e1f, Eprev);
                 __syncthreads();
-                if (ph.tbl) step_b<C, WARPS, AMER, true>(V, ph, T, cin_f, cin_b, part, e1f, Eprev, e1b, Enext);
-                else        step_b<C, WARPS, AMER, false>(V, ph, T, cin_f, cin_b, part, e1f, Eprev, e1b, Enext);
+                if (ph.cls == 2) step_b<C, WARPS, AMER, true>(V, ph, sm, wf, cin_b, e1f, Eprev, e1b, Enext);
+                else if (ph.cls == 1) step_b<C, WARPS, AMER, false>(V, ph, sm, wf, cin_b, e1f, Eprev, e1b, Enext);
                 __syncthreads();
-                if (ph.tbl) step_c<C, WARPS, AMER, true>(V, L, r0, ph, T, cin_b, part, e1b, Enext);
-                else        step_c<C, WARPS, AMER, false>(V, L, r0, ph, T, cin_b, part, e1b, Enext);
+                if (ph.cls == 2) step_c<C, WARPS, AMER, true>(V, L, ph, sm, cin_b, e1b, Enext);
+                else if (ph.cls == 1) step_c<C, WARPS, AMER, false>(V, L, ph, sm, cin_b, e1b, Enext);
                 Vb = w_now;                                     // V[0] = V_min, V[-1] = V_max (:505-506)
                 ++gstep;
                 if (TRACE && trace) {
                     int lo = 0x7fffffff, hi = -1;
 #pragma unroll
                     for (int k = 0; k < C; ++k) {
-                        const int row = t * C + k;
-                        if (AMER && row < n_int && L[k] > 0.0) { lo = min(lo, row); hi = max(hi, row); }
+                        const int row = t * C + k - pad;
+                        if (AMER && row >= 0 && L[k] > 0.0) { lo = min(lo, row); hi = max(hi, row); }
                     }
                     __syncthreads();
-                    if (t == 0) { ishare[6] = 0x7fffffff; ishare[7] = -1; }
+                    if (t == 0) { sm.ish[6] = 0x7fffffff; sm.ish[7] = -1; }
                     __syncthreads();
-                    if (hi >= 0) { atomicMin(&ishare[6], lo); atomicMax(&ishare[7], hi); }
+                    if (hi >= 0) { atomicMin(&sm.ish[6], lo); atomicMax(&sm.ish[7], hi); }
                     __syncthreads();
                     if (t == 0 && 2 * (int64_t)gstep <= O.ex_trace_stride) {
-                        trace[2 * (gstep - 1)] = (ishare[7] < 0) ? -1 : ishare[6];
-                        trace[2 * (gstep - 1) + 1] = ishare[7];
+                        trace[2 * (gstep - 1)] = (sm.ish[7] < 0) ? -1 : sm.ish[6];
+                        trace[2 * (gstep - 1) + 1] = sm.ish[7];
                     }
                 }
                 if (gstep == next_mon) {                        // discrete_barrier_fdm_pricer_cn.py:299-300
 #pragma unroll
                     for (int k = 0; k < C; ++k) {
-                        const int j = t * C + k + 1;
-                        if (j <= n - 1 && j >= ko_lo && j <= ko_hi) V[k] = rebate;
+                        const int j = t * C + k - pad + 1;
+                        if (j >= 1 && j >= ko_lo && j <= ko_hi) V[k] = rebate;
                     }
-                    if (t == 0 && ko_lo <= 0 && 0 <= ko_hi) Vb = rebate;
+                    if (t == t0 && ko_lo <= 0 && 0 <= ko_hi) Vb = rebate;
                     if (t == NT - 1 && ko_lo <= n && n <= ko_hi) Vb = rebate;
                     ++mon_i;
                     next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
-                    cin_n = cB * Vb - cA * w_next;
+                    cin_n = ph.cB * Vb - ph.cA * w_next;
                 }
                 cin = cin_n;
             }
         }
         if (cash != 0.0) {
-            if (div_smem) {
-                dividend_jump<C, WARPS>(V, Vb, cash, is_call, k_eff, n, x_min, dx, r1, r2, r0);
-                __syncthreads();
-                fill_payoff(false);                             // r0 held cz during the jump
-            } else {
-#pragma unroll
-                for (int k = 0; k < C; ++k) V[k] = NAN;
-            }
+            dividend_jump<C, WARPS>(V, Vb, cash, is_call, k_eff, n, pad, x_min, dx, sm.r1, sm.r2, sm.r0);
+            __syncthreads();
+            fill_payoff(false);                                 // r0 held cz during the jump
         }
     }
 
     // ---- read-out: stage the value vector by node in shared memory, thread 0 finishes -------------
     __syncthreads();
-    double *Vs = r1;
+    double *Vs = sm.r1;
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-        const int j = t * C + k + 1;
-        if (j <= n - 1) Vs[j] = V[k];
+        const int j = t * C + k - pad + 1;
+        if (j >= 1) Vs[j] = V[k];
     }
-    if (t == 0) { Vs[0] = Vb; ishare[6] = 0x7fffffff; ishare[7] = -1; }
+    if (t == t0) Vs[0] = Vb;
     if (t == NT - 1) Vs[n] = Vb;
+    if (t == 0) { sm.ish[6] = 0x7fffffff; sm.ish[7] = -1; }
     __syncthreads();
     if (AMER) {
         int lo = 0x7fffffff, hi = -1;
 #pragma unroll
         for (int k = 0; k < C; ++k) {
-            const int row = t * C + k;
-            if (row < n_int && L[k] > 0.0) { lo = min(lo, row); hi = max(hi, row); }
+            const int row = t * C + k - pad;
+            if (row >= 0 && L[k] > 0.0) { lo = min(lo, row); hi = max(hi, row); }
         }
-        if (hi >= 0) { atomicMin(&ishare[6], lo); atomicMax(&ishare[7], hi); }
+        if (hi >= 0) { atomicMin(&sm.ish[6], lo); atomicMax(&sm.ish[7], hi); }
     }
     if (O.v_dump) {
         double *dst = O.v_dump + sid * O.v_dump_stride;
@@ -629,6 +673,7 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
     }
     __syncthreads();
     if (t != 0) return;
+    int *ishare = sm.ish;
 
     const int ex_lo = (AMER && ishare[7] >= 0) ? ishare[6] : -1;
     const int ex_hi = (AMER && ishare[7] >= 0) ? ishare[7] : -1;
