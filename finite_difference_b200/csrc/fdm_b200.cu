@@ -511,7 +511,7 @@ __device__ __forceinline__ int argmin_node(const double (&s)[C], double s0, doub
 
 // Natural cubic spline through (s_j, V_j) and the ex-dividend jump V(S) <- V(S - D):
 // fd_american_option_pricer.py:321-386 and :517-548, same operation order (no FMA).
-// xs, ys, mu, cz: shared-memory arrays of n+1 doubles.  Lane 0 runs the two serial sweeps.
+// xs, ys, mu, cz: shared-memory arrays of n+1 doubles.
 template <int C>
 __device__ __forceinline__ void dividend_jump(double (&V)[C], double &V0, double &VN, const double (&phi)[C],
                                            double phi0, double phin, double cash, bool is_call, int n,
@@ -530,12 +530,17 @@ __device__ __forceinline__ void dividend_jump(double (&V)[C], double &V0, double
         xs[n] = node_s(x_min, dx, n); ys[n] = VN;
     }
     __syncwarp();
-    if (lane == 0) {
-        // forward sweep :349-352 (l, mu, z), alpha from :339-343
-        mu[0] = 0.0;
-        cz[0] = 0.0;
+    // The spline's tridiagonal system (:338-359) is diagonally dominant: its forward recurrences forget their
+    // start like 0.27^k, and so does the back substitution.  Each lane warm-starts G rows outside its own
+    // rows (exactly at the true ends) and keeps only its own: all rows are eliminated in parallel, in the
+    // reference's operation order, to within 0.27^G of the serial sweep.
+    constexpr int G = 40;
+    const int j_first = lane * C + 1;                       // this lane's interior knots [j_first, j_last]
+    const int j_last = min(lane * C + C, n - 1);
+    const bool has_rows = j_first <= n - 1;
+    if (has_rows) {
         double mu_prev = 0.0, z_prev = 0.0;
-        for (int i = 1; i < nn - 1; ++i) {
+        for (int i = max(1, j_first - G); i <= j_last; ++i) {
             const double h_i = __dsub_rn(xs[i + 1], xs[i]);
             const double h_im1 = __dsub_rn(xs[i], xs[i - 1]);
             const double alpha = __dsub_rn(
@@ -545,16 +550,26 @@ __device__ __forceinline__ void dividend_jump(double (&V)[C], double &V0, double
                                        __dmul_rn(h_im1, mu_prev));
             mu_prev = h_i / l;
             z_prev = __dsub_rn(alpha, __dmul_rn(h_im1, z_prev)) / l;
-            mu[i] = mu_prev;
-            cz[i] = z_prev;
+            if (i >= j_first) { mu[i] = mu_prev; cz[i] = z_prev; }
         }
-        // back sweep :358-359: c[j] = z[j] - mu[j] * c[j+1], c[n-1] = 0
+    }
+    if (lane == 0) { mu[0] = 0.0; cz[0] = 0.0; cz[nn - 1] = 0.0; }
+    __syncwarp();
+    // back substitution c[j] = z[j] - mu[j] c[j+1] (:358-359); results parked in V until every lane has read z
+    if (has_rows) {
         double c_next = 0.0;
-        cz[nn - 1] = 0.0;
-        for (int j = nn - 2; j >= 0; --j) {
-            c_next = __dsub_rn(cz[j], __dmul_rn(mu[j], c_next));
-            cz[j] = c_next;
+        for (int j = min(n - 1, j_last + G); j > j_last; --j) c_next = __dsub_rn(cz[j], __dmul_rn(mu[j], c_next));
+#pragma unroll
+        for (int k = C - 1; k >= 0; --k) {
+            const int j = lane * C + k + 1;
+            if (j <= n - 1) { c_next = __dsub_rn(cz[j], __dmul_rn(mu[j], c_next)); V[k] = c_next; }
         }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const int j = lane * C + k + 1;
+        if (j <= n - 1) cz[j] = V[k];
     }
     __syncwarp();
     const double s_lo = xs[0], s_hi = xs[n];

@@ -373,32 +373,35 @@ __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph 
 }
 
 // ---- dividend jump (fd_american_option_pricer.py:321-386, :517-548) ------------------------------
-// ys, mu, cz: shared arrays of n+1 doubles.  The knot abscissae are staged in mu[] and overwritten
-// in place by the forward sweep; thread 0 runs the two serial sweeps in the reference's order.
+// ys, mu, cz: shared arrays of n+1 doubles.
+// Works on shared memory only (value vector in ys[], result returned in mu[]) and is not inlined, so its
+// registers do not weigh on the time loop.  Returns the new boundary node value of this thread.
 template <int C, int WARPS>
-__device__ __forceinline__ void dividend_jump(double (&V)[C], double &Vb, double cash, bool is_call, double k_eff,
-                                              int n, int pad, double x_min, double dx, double *ys, double *mu, double *cz)
+__device__ __noinline__ double dividend_jump(double Vb, double cash, bool is_call, double k_eff, int n, int pad,
+                                             double x_min, double dx, double *ys, double *mu, double *cz)
 {
+    double V[C];
     constexpr int NT = 32 * WARPS;
     const int t = threadIdx.x;
     const int nn = n + 1;
     const bool owner0 = (t == pad / C);
+    if (owner0) ys[0] = Vb;
+    if (t == NT - 1) ys[n] = Vb;
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < C; ++k) {
-        const int j = t * C + k - pad + 1;
-        if (j >= 1) { ys[j] = V[k]; mu[j] = node_s(x_min, dx, j); }
-    }
-    if (owner0) { ys[0] = Vb; mu[0] = node_s(x_min, dx, 0); }
-    if (t == NT - 1) { ys[n] = Vb; mu[n] = node_s(x_min, dx, n); }
-    __syncthreads();
-    if (t == 0) {
-        double x_im1 = mu[0], x_i = mu[1];
+    // The spline's tridiagonal system (:338-359) is diagonally dominant: the forward recurrences forget
+    // their start like 0.27^k and so does the back substitution.  Every thread therefore warm-starts
+    // G rows outside its own rows (exactly at the true ends) and keeps only its own rows: all rows are
+    // eliminated in parallel, in the reference's operation order, to within 0.27^G of the serial sweep.
+    constexpr int G = 40;
+    const int j_first = max(t * C - pad + 1, 1);           // this thread's interior knots [j_first, j_last]
+    const int j_last = t * C + C - pad;
+    const bool has_rows = j_last >= 1;
+    if (has_rows) {
+        const int i0 = max(1, j_first - G);
+        double x_im1 = node_s(x_min, dx, i0 - 1), x_i = node_s(x_min, dx, i0);
         double mu_prev = 0.0, z_prev = 0.0;
-        mu[0] = 0.0;
-        cz[0] = 0.0;
-        for (int i = 1; i < nn - 1; ++i) {
-            const double x_ip1 = mu[i + 1];
+        for (int i = i0; i <= j_last; ++i) {
+            const double x_ip1 = node_s(x_min, dx, i + 1);
             const double h_i = __dsub_rn(x_ip1, x_i);
             const double h_im1 = __dsub_rn(x_i, x_im1);
             const double alpha = __dsub_rn(__dmul_rn(3.0 / h_i, __dsub_rn(ys[i + 1], ys[i])),
@@ -406,17 +409,30 @@ __device__ __forceinline__ void dividend_jump(double (&V)[C], double &Vb, double
             const double l = __dsub_rn(__dmul_rn(2.0, __dsub_rn(x_ip1, x_im1)), __dmul_rn(h_im1, mu_prev));
             mu_prev = h_i / l;
             z_prev = __dsub_rn(alpha, __dmul_rn(h_im1, z_prev)) / l;
-            mu[i] = mu_prev;
-            cz[i] = z_prev;
+            if (i >= j_first) { mu[i] = mu_prev; cz[i] = z_prev; }
             x_im1 = x_i;
             x_i = x_ip1;
         }
+    }
+    if (owner0) { mu[0] = 0.0; cz[0] = 0.0; }
+    if (t == NT - 1) cz[nn - 1] = 0.0;
+    __syncthreads();
+    // back substitution c[j] = z[j] - mu[j] c[j+1] (:358-359); results parked in V until every thread has read z
+    if (has_rows) {
+        const int i1 = min(n - 1, j_last + G);
         double c_next = 0.0;
-        cz[nn - 1] = 0.0;
-        for (int j = nn - 2; j >= 0; --j) {
-            c_next = __dsub_rn(cz[j], __dmul_rn(mu[j], c_next));
-            cz[j] = c_next;
+        for (int j = i1; j > j_last; --j) c_next = __dsub_rn(cz[j], __dmul_rn(mu[j], c_next));
+#pragma unroll
+        for (int k = C - 1; k >= 0; --k) {
+            const int j = t * C + k - pad + 1;
+            if (j >= 1) { c_next = __dsub_rn(cz[j], __dmul_rn(mu[j], c_next)); V[k] = c_next; }
         }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const int j = t * C + k - pad + 1;
+        if (j >= 1) cz[j] = V[k];
     }
     __syncthreads();
     const double s_lo = node_s(x_min, dx, 0), s_hi = node_s(x_min, dx, n);
@@ -447,19 +463,17 @@ __device__ __forceinline__ void dividend_jump(double (&V)[C], double &Vb, double
         }
         return cont;
     };
-    double newV[C];
+    // mu[] is free once cz[] holds the spline's c coefficients: the jumped values go there
 #pragma unroll
     for (int k = 0; k < C; ++k) {
         const int j = t * C + k - pad + 1;
-        newV[k] = (j >= 1) ? eval(j) : 0.0;
+        if (j >= 1) mu[j] = eval(j);
     }
     double nb = Vb;
     if (owner0) nb = eval(0);
     if (t == NT - 1) nb = eval(n);
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < C; ++k) V[k] = newV[k];
-    Vb = nb;
+    return nb;
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
@@ -640,7 +654,18 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
             }
         }
         if (cash != 0.0) {
-            dividend_jump<C, WARPS>(V, Vb, cash, is_call, k_eff, n, pad, x_min, dx, sm.r1, sm.r2, sm.r0);
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                const int j = t * C + k - pad + 1;
+                if (j >= 1) sm.r1[j] = V[k];
+            }
+            Vb = dividend_jump<C, WARPS>(Vb, cash, is_call, k_eff, n, pad, x_min, dx, sm.r1, sm.r2, sm.r0);
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                const int j = t * C + k - pad + 1;
+                V[k] = (j >= 1) ? sm.r2[j] : 0.0;
+            }
             __syncthreads();
             fill_payoff(false);                                 // r0 held cz during the jump
         }

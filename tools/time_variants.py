@@ -31,6 +31,15 @@ def timeit(name, batch, reps=3):
     print(f"{name}: {batch.n_solves} solves, {ns:.3e} node-steps, {best:.2f} ms -> {ns / best * 1e3:.3e} node-steps/s", flush=True)
     return ns / best * 1e3
 
+def american_div(n_opt, n, m, seed=5):
+    rng = np.random.default_rng(seed)
+    K = rng.uniform(180, 280, n_opt); sig = rng.uniform(0.15, 0.45, n_opt)
+    r = np.log1p(rng.uniform(0.03, 0.10, n_opt)); call = rng.uniform(size=n_opt) < 0.5
+    cash = rng.uniform(2, 9, (n_opt, 2))
+    dts = [[(109.0 / 365.0, float(cash[i, 1])), (319.0 / 365.0, float(cash[i, 0]))] for i in range(n_opt)]
+    return hostlogic.build_american_batch(np.full(n_opt, 229.74), K, 1.0, sig, r, r, call, n, m, 2, False, div_taus=dts)
+
+
 if __name__ == "__main__":
     print("lib", _lib.lib_path())
     tf, ms = _lib.fp64_peak_tflops()
@@ -41,5 +50,6 @@ if __name__ == "__main__":
     timeit("american eq 256x256", american(nopt, 256, 256, False))
     timeit("american eq 128x128", american(nopt, 128, 128, False))
     timeit("barrier 400x400", barrier(nopt, 400, 400))
+    timeit("american eq 500x500, 2 dividends", american_div(nopt // 4, 500, 500))
     tf, ms = _lib.fp64_peak_tflops()
     print(f"fp64 peak microbench (after): {tf:.2f} TFLOP/s ({ms:.3f} ms)")
