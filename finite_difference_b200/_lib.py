@@ -70,7 +70,7 @@ class FdmBookOut(C.Structure):
 BOOK_PRICE_LOG, BOOK_PRICE_LOG2, BOOK_GREEKS_LOG2, BOOK_SCENARIO = 0, 1, 2, 3
 
 EXPORTS = ("fdm_version", "fdm_last_error", "fdm_device_count", "fdm_solve_batch",
-           "fdm_solve_batch_host", "fdm_book_solves_per_option", "fdm_american_book_host", "fdm_release_workspace", "fdm_fp64_peak")
+           "fdm_solve_batch_host", "fdm_launch_hints", "fdm_book_solves_per_option", "fdm_american_book_host", "fdm_release_workspace", "fdm_fp64_peak")
 
 
 class FdmError(RuntimeError):
@@ -104,6 +104,8 @@ def load(path: str | None = None):
     L.fdm_solve_batch.argtypes = [C.POINTER(FdmBatch), C.POINTER(FdmOut), C.c_void_p, _pi]
     L.fdm_solve_batch_host.restype = C.c_int
     L.fdm_solve_batch_host.argtypes = [C.POINTER(FdmBatch), C.POINTER(FdmOut), _pi, C.POINTER(C.c_float)]
+    L.fdm_launch_hints.restype = C.c_int
+    L.fdm_launch_hints.argtypes = [_pi, _pi, C.c_int64, _pd, C.c_int64]
     L.fdm_book_solves_per_option.restype = C.c_int
     L.fdm_book_solves_per_option.argtypes = [C.c_int32, C.c_int32]
     L.fdm_american_book_host.restype = C.c_int

@@ -105,20 +105,15 @@ class SolveBatch:
         return int(np.sum(self.n_space.astype(np.int64) * self.steps_per_solve()))
 
     def family_mask(self) -> int:
-        m = 0
-        am = (self.flags & FLAG_AMERICAN) != 0
-        if am.any():
-            m |= 1
-        if (~am).any():
-            m |= 2
-        if np.any(self.seg_div != 0.0):
-            m |= 4
-        small = self.n_space <= WARP_MAX_N_SPACE
-        if small.any():
-            m |= 8 | (int(self.n_space[small].max()) << 8)
-        if (~small).any():
-            m |= 16
-        return m
+        """Launch hints (FdmBatch.reserved): kernel families and grid-size classes present, fdm_launch_hints()."""
+        if self.n_solves == 0:
+            return 0
+        n_space = np.ascontiguousarray(self.n_space, dtype=np.int32)
+        flags = np.ascontiguousarray(self.flags, dtype=np.int32)
+        seg_div = np.ascontiguousarray(self.seg_div, dtype=np.float64)
+        return int(_lib.load().fdm_launch_hints(
+            n_space.ctypes.data_as(_lib._pi), flags.ctypes.data_as(_lib._pi), int(self.n_solves),
+            seg_div.ctypes.data_as(_lib._pd), int(seg_div.size)))
 
     def take(self, sel) -> "SolveBatch":
         """Sub-batch of the selected solves (index array or boolean mask), CSR tables rebuilt."""

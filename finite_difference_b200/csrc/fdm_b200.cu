@@ -30,6 +30,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -464,13 +465,36 @@ __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const
     FDM_TICK(V[0], 5);
 }
 
+// How the n-1 interior rows are dealt to the 32 lanes of a warp: lane l holds rows row0 .. row0+cnt-1 in slots
+// 0 .. cnt-1 of its C-slot register arrays.
+//   uniform(C): every lane C slots, rows beyond n-2 are padding            (fdm_warp_kernel)
+//   packed(n_int): lane l holds base + (l < extra) rows, no padding        (fdm_lean_kernel)
+struct RowLayout {
+    int row0, cnt;       // this lane
+    int base, extra;     // base rows per lane; the first `extra` lanes hold one more
+    __device__ static RowLayout uniform(int C, int lane) { return {lane * C, C, C, 0}; }
+    __device__ static RowLayout packed(int n_int, int lane)
+    {
+        const int base = n_int >> 5, extra = n_int & 31;
+        return {lane * base + min(lane, extra), base + (lane < extra ? 1 : 0), base, extra};
+    }
+    __device__ void owner(int row, int &src, int &kk) const
+    {
+        const int head = extra * (base + 1);
+        if (row < head) { src = row / (base + 1); kk = row - src * (base + 1); }
+        else { const int r2 = row - head; const int d = r2 / base; src = extra + d; kk = r2 - d * base; }
+        if (src > 31) { src = 31; kk = -1; }
+    }
+};
+
 // value at node j (0..n) from the distributed vector
 template <int C>
-__device__ __forceinline__ double node_value(const double (&V)[C], double V0, double VN, int j, int n, int lane)
+__device__ __forceinline__ double node_value(const double (&V)[C], double V0, double VN, int j, int n,
+                                             const RowLayout &ly)
 {
     const int row = j - 1;
-    const int src = (row >= 0 && row < 32 * C) ? row / C : 0;
-    const int kk = row - src * C;
+    int src = 0, kk = -1;
+    if (row >= 0 && row < n - 1) ly.owner(row, src, kk);
     double mine = 0.0;
 #pragma unroll
     for (int k = 0; k < C; ++k) mine = (k == kk) ? V[k] : mine;
@@ -484,15 +508,15 @@ __device__ __forceinline__ double node_value(const double (&V)[C], double V0, do
 // or over interior nodes only (discrete_barrier_fdm_pricer_cn.py:335).
 template <int C>
 __device__ __forceinline__ int argmin_node(const double (&s)[C], double s0, double sn, double level,
-                                           int n, int lane, bool interior_only)
+                                           int n, const RowLayout &ly, bool interior_only)
 {
     double best = INFINITY;
     int bidx = 0x7fffffff;
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-        const int j = lane * C + k + 1;
+        const int j = ly.row0 + k + 1;
         const double v = fabs(__dsub_rn(s[k], level));
-        if (j <= n - 1 && v < best) { best = v; bidx = j; }
+        if (k < ly.cnt && j <= n - 1 && v < best) { best = v; bidx = j; }
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
@@ -512,18 +536,18 @@ __device__ __forceinline__ int argmin_node(const double (&s)[C], double s0, doub
 // Natural cubic spline through (s_j, V_j) and the ex-dividend jump V(S) <- V(S - D):
 // fd_american_option_pricer.py:321-386 and :517-548, same operation order (no FMA).
 // xs, ys, mu, cz: shared-memory arrays of n+1 doubles.
-template <int C>
-__device__ __forceinline__ void dividend_jump(double (&V)[C], double &V0, double &VN, const double (&phi)[C],
+template <int C, class PhiAt>
+__device__ __forceinline__ void dividend_jump(double (&V)[C], double &V0, double &VN, const PhiAt &phi,
                                            double phi0, double phin, double cash, bool is_call, int n,
-                                           int lane, double x_min, double dx,
+                                           int lane, const RowLayout &ly, double x_min, double dx,
                                            double *xs, double *ys, double *mu, double *cz)
 {
     const int nn = n + 1;   // number of knots
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-        const int j = lane * C + k + 1;
-        if (j <= n - 1) { xs[j] = node_s(x_min, dx, j); ys[j] = V[k]; }
+        const int j = ly.row0 + k + 1;
+        if (k < ly.cnt && j <= n - 1) { xs[j] = node_s(x_min, dx, j); ys[j] = V[k]; }
     }
     if (lane == 0) {
         xs[0] = node_s(x_min, dx, 0); ys[0] = V0;
@@ -535,9 +559,9 @@ __device__ __forceinline__ void dividend_jump(double (&V)[C], double &V0, double
     // rows (exactly at the true ends) and keeps only its own: all rows are eliminated in parallel, in the
     // reference's operation order, to within 0.27^G of the serial sweep.
     constexpr int G = 40;
-    const int j_first = lane * C + 1;                       // this lane's interior knots [j_first, j_last]
-    const int j_last = min(lane * C + C, n - 1);
-    const bool has_rows = j_first <= n - 1;
+    const int j_first = ly.row0 + 1;                       // this lane's interior knots [j_first, j_last]
+    const int j_last = min(ly.row0 + ly.cnt, n - 1);
+    const bool has_rows = ly.cnt > 0 && j_first <= n - 1;
     if (has_rows) {
         double mu_prev = 0.0, z_prev = 0.0;
         for (int i = max(1, j_first - G); i <= j_last; ++i) {
@@ -561,15 +585,15 @@ __device__ __forceinline__ void dividend_jump(double (&V)[C], double &V0, double
         for (int j = min(n - 1, j_last + G); j > j_last; --j) c_next = __dsub_rn(cz[j], __dmul_rn(mu[j], c_next));
 #pragma unroll
         for (int k = C - 1; k >= 0; --k) {
-            const int j = lane * C + k + 1;
-            if (j <= n - 1) { c_next = __dsub_rn(cz[j], __dmul_rn(mu[j], c_next)); V[k] = c_next; }
+            const int j = ly.row0 + k + 1;
+            if (k < ly.cnt && j <= n - 1) { c_next = __dsub_rn(cz[j], __dmul_rn(mu[j], c_next)); V[k] = c_next; }
         }
     }
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-        const int j = lane * C + k + 1;
-        if (j <= n - 1) cz[j] = V[k];
+        const int j = ly.row0 + k + 1;
+        if (k < ly.cnt && j <= n - 1) cz[j] = V[k];
     }
     __syncwarp();
     const double s_lo = xs[0], s_hi = xs[n];
@@ -604,8 +628,8 @@ __device__ __forceinline__ void dividend_jump(double (&V)[C], double &V0, double
     double newV[C];
 #pragma unroll
     for (int k = 0; k < C; ++k) {
-        const int j = lane * C + k + 1;
-        newV[k] = (j <= n - 1) ? eval(xs[j], phi[k]) : 0.0;
+        const int j = ly.row0 + k + 1;
+        newV[k] = (k < ly.cnt && j <= n - 1) ? eval(xs[j], phi(k)) : 0.0;
     }
     const double n0 = eval(s_lo, phi0);
     const double nN = eval(s_hi, phin);
@@ -630,10 +654,17 @@ constexpr int min_blocks()
     return FDM_MINB ? FDM_MINB : (C <= 4 ? 16 : C <= 8 ? 12 : 8);
 }
 
+}  // namespace
+
+#include "fdm_lean.cuh"
+
+namespace {
+
+// only_rest != 0: solve only what fdm_lean_kernel left -- sizes outside its classes and solves it marked for retry
 template <int C, bool AMER, bool TRACE>
 __global__ void __launch_bounds__(32, min_blocks<C, AMER>())
 fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int want_american,
-                const int div_smem)
+                const int div_smem, const int only_rest)
 {
     extern __shared__ double smem[];
     const WarpTables<C> T(smem);
@@ -648,6 +679,9 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
     const int lane = threadIdx.x;
     const int n = B.n_space[sid];
     if (n > FDM_WARP_MAX_N_SPACE) return;                       // larger grids: fdm_cta_kernel
+    if (only_rest && lean::class_of(n - 1) != 0 &&
+        (unsigned long long)__double_as_longlong(O.price[sid]) != lean::RETRY_BITS) return;
+    const RowLayout ly = RowLayout::uniform(C, lane);
     const int n_int = n - 1;
     const bool is_call = flags & FDM_FLAG_CALL;
     const bool b76 = flags & FDM_FLAG_BLACK76;
@@ -677,8 +711,8 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
     int spot_idx = 0, strike_idx = 0;
     double k_eff = strike;
     if (snap) {
-        spot_idx = argmin_node<C>(phi, s0, sn, spot, n, lane, false);
-        strike_idx = argmin_node<C>(phi, s0, sn, strike, n, lane, false);
+        spot_idx = argmin_node<C>(phi, s0, sn, spot, n, ly, false);
+        strike_idx = argmin_node<C>(phi, s0, sn, strike, n, ly, false);
         k_eff = node_s(x_min, dx, strike_idx);                  // fd_american_option_pricer.py:272-275
     }
     // KO region as a node index interval [ko_lo, ko_hi]
@@ -818,7 +852,10 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
                 double *mu = ys + (32 * C + 2);
                 double *cz = mu + (32 * C + 2);
                 double V0 = __shfl_sync(FULL, Vb, 0), VN = __shfl_sync(FULL, Vb, 31);
-                dividend_jump<C>(V, V0, VN, phi, phi0, phin, cash, is_call, n, lane, x_min, dx, xs, ys, mu, cz);
+                dividend_jump<C>(V, V0, VN, [&](int k) { double v = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < C; ++kk) v = (kk == k) ? phi[kk] : v;
+                    return v; }, phi0, phin, cash, is_call, n, lane, ly, x_min, dx, xs, ys, mu, cz);
                 Vb = (lane == 0) ? V0 : ((lane == 31) ? VN : 0.0);
             } else {
 #pragma unroll
@@ -877,10 +914,10 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int j = i_near - 1 + t;
-            sv[t] = node_value<C>(V, V0, VN, j, n, lane);
+            sv[t] = node_value<C>(V, V0, VN, j, n, ly);
             ss[t] = node_s(x_min, dx, j);
         }
-        price = node_value<C>(V, V0, VN, spot_idx, n, lane);
+        price = node_value<C>(V, V0, VN, spot_idx, n, ly);
         // cubic through the four points in Newton form, derivatives at z = 0 (z = S - Sx)
         const double z0 = ss[0] - Sx, z1 = ss[1] - Sx, z2 = ss[2] - Sx, z3 = ss[3] - Sx;
         const double f01 = (sv[1] - sv[0]) / (z1 - z0);
@@ -910,15 +947,15 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
         else if (spot >= sn) { price = VN; lo = n; }
         else {
             const double s_lo = node_s(x_min, dx, lo), s_hi = node_s(x_min, dx, lo + 1);
-            const double v_lo = node_value<C>(V, V0, VN, lo, n, lane);
-            const double v_hi = node_value<C>(V, V0, VN, lo + 1, n, lane);
+            const double v_lo = node_value<C>(V, V0, VN, lo, n, ly);
+            const double v_hi = node_value<C>(V, V0, VN, lo + 1, n, ly);
             const double w = __dsub_rn(spot, s_lo) / __dsub_rn(s_hi, s_lo);
             price = __dadd_rn(__dmul_rn(__dsub_rn(1.0, w), v_lo), __dmul_rn(w, v_hi));
         }
-        const int gi = argmin_node<C>(sl, s0, sn, spot, n, lane, true);
+        const int gi = argmin_node<C>(sl, s0, sn, spot, n, ly, true);
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-            sv[t] = node_value<C>(V, V0, VN, gi - 1 + t, n, lane);
+            sv[t] = node_value<C>(V, V0, VN, gi - 1 + t, n, ly);
             ss[t] = node_s(x_min, dx, gi - 1 + t);
         }
         sv[3] = 0.0;
@@ -990,7 +1027,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters,
 
 template <int C>
 int launch_variant(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american, bool any_linear,
-                   bool any_div, int32_t *n_launches)
+                   bool any_div, int only_rest, int32_t *n_launches)
 {
     const bool trace = o.ex_trace != nullptr;
     const int base = warp_smem_doubles<C>();
@@ -1002,12 +1039,12 @@ int launch_variant(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any
         const int64_t count = (b.n_solves - first < max_grid) ? (b.n_solves - first) : max_grid;
         const dim3 grid((unsigned)count), block(32);
         if (any_american) {
-            if (trace) fdm_warp_kernel<C, true, true><<<grid, block, smem, st>>>(b, o, first, 1, any_div);
-            else       fdm_warp_kernel<C, true, false><<<grid, block, smem, st>>>(b, o, first, 1, any_div);
+            if (trace) fdm_warp_kernel<C, true, true><<<grid, block, smem, st>>>(b, o, first, 1, any_div, only_rest);
+            else       fdm_warp_kernel<C, true, false><<<grid, block, smem, st>>>(b, o, first, 1, any_div, only_rest);
             ++launches;
         }
         if (any_linear) {
-            fdm_warp_kernel<C, false, false><<<grid, block, smem, st>>>(b, o, first, 0, any_div);
+            fdm_warp_kernel<C, false, false><<<grid, block, smem, st>>>(b, o, first, 0, any_div, only_rest);
             ++launches;
         }
         FDM_CUDA(cudaGetLastError());
@@ -1015,6 +1052,72 @@ int launch_variant(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any
     if (n_launches) *n_launches += launches;
     return FDM_OK;
 }
+
+// the register-lean kernel of one size class (fdm_lean.cuh); solves of other classes exit at once
+template <int C>
+int launch_lean_class(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american, bool any_linear,
+                      bool any_div, int32_t *n_launches)
+{
+    const bool trace = o.ex_trace != nullptr;
+    const int div_doubles = any_div ? 4 * (32 * C + 2) : 0;
+    const size_t smem = (size_t)(lean::smem_doubles<C>() + div_doubles) * sizeof(double);
+    auto k_am = lean::fdm_lean_kernel<C, true, false>;
+    auto k_amt = lean::fdm_lean_kernel<C, true, true>;
+    auto k_lin = lean::fdm_lean_kernel<C, false, false>;
+    if (smem > 48 * 1024) {
+        FDM_CUDA(cudaFuncSetAttribute(k_am, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FDM_CUDA(cudaFuncSetAttribute(k_amt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FDM_CUDA(cudaFuncSetAttribute(k_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    const int64_t max_grid = 0x7fffffff;
+    int launches = 0;
+    for (int64_t first = 0; first < b.n_solves; first += max_grid) {
+        const int64_t count = (b.n_solves - first < max_grid) ? (b.n_solves - first) : max_grid;
+        const dim3 grid((unsigned)count), block(32);
+        if (any_american) {
+            if (trace) k_amt<<<grid, block, smem, st>>>(b, o, first, 1, any_div);
+            else       k_am<<<grid, block, smem, st>>>(b, o, first, 1, any_div);
+            ++launches;
+        }
+        if (any_linear) {
+            k_lin<<<grid, block, smem, st>>>(b, o, first, 0, any_div);
+            ++launches;
+        }
+        FDM_CUDA(cudaGetLastError());
+    }
+    if (n_launches) *n_launches += launches;
+    return FDM_OK;
+}
+
+template <int I>
+int launch_lean_all(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool am, bool lin, bool dv, int class_mask,
+                    int32_t *n_launches)
+{
+    constexpr lean::ClassList cl = lean::class_list();
+    if constexpr (I < cl.n) {
+        if (class_mask & (1 << I)) {
+            const int rc = launch_lean_class<cl.c[I]>(b, o, st, am, lin, dv, n_launches);
+            if (rc != FDM_OK) return rc;
+        }
+        return launch_lean_all<I + 1>(b, o, st, am, lin, dv, class_mask, n_launches);
+    } else {
+        return FDM_OK;
+    }
+}
+
+// launch hints of the size classes present in a call (FdmBatch.reserved bits 20..29):
+// bit 20+i: class i of lean::class_list() is present; bit 28: a warp-sized grid outside every class is present;
+// bit 29: these hints are valid
+int lean_hint_bits(int n_space)
+{
+    if (n_space > FDM_WARP_MAX_N_SPACE) return 0;
+    constexpr lean::ClassList cl = lean::class_list();
+    const int c = lean::class_of(n_space - 1);
+    if (c == 0) return 1 << 28;
+    for (int i = 0; i < cl.n; ++i) if (cl.c[i] == c) return 1 << (20 + i);
+    return 1 << 28;
+}
+constexpr int LEAN_HINTS_VALID = 1 << 29;
 
 int validate(const FdmBatch *b, const FdmOut *o)
 {
@@ -1084,10 +1187,23 @@ int launch(const FdmBatch &b, const FdmOut &o, cudaStream_t st, int family_mask,
         if (small_max == 0 || small_max > FDM_WARP_MAX_N_SPACE)
             small_max = b.n_space_max < FDM_WARP_MAX_N_SPACE ? b.n_space_max : FDM_WARP_MAX_N_SPACE;
         const int rows = small_max - 1;
-        if (rows <= 32 * 4) rc = launch_variant<4>(b, o, st, am, lin, dv, n_launches);
-        else if (rows <= 32 * 8) rc = launch_variant<8>(b, o, st, am, lin, dv, n_launches);
-        else if (rows <= 32 * 13) rc = launch_variant<13>(b, o, st, am, lin, dv, n_launches);
-        else rc = launch_variant<16>(b, o, st, am, lin, dv, n_launches);
+        // register-lean kernels first (one launch per size class present), then fdm_warp_kernel for the rest:
+        // sizes outside the classes and the solves the lean kernel handed back
+        static const bool no_lean = getenv("FDM_B200_NO_LEAN") != nullptr;
+        int only_rest = 0;
+        bool need_general = true;
+        if (!no_lean) {
+            const bool hinted = family_mask & LEAN_HINTS_VALID;
+            const int class_mask = hinted ? (family_mask >> 20) & 0xff : 0xff;
+            rc = launch_lean_all<0>(b, o, st, am, lin, dv, class_mask, n_launches);
+            if (rc != FDM_OK) return rc;
+            only_rest = 1;
+            (void)need_general;
+        }
+        if (rows <= 32 * 4) rc = launch_variant<4>(b, o, st, am, lin, dv, only_rest, n_launches);
+        else if (rows <= 32 * 8) rc = launch_variant<8>(b, o, st, am, lin, dv, only_rest, n_launches);
+        else if (rows <= 32 * 13) rc = launch_variant<13>(b, o, st, am, lin, dv, only_rest, n_launches);
+        else rc = launch_variant<16>(b, o, st, am, lin, dv, only_rest, n_launches);
         if (rc != FDM_OK) return rc;
     }
     if (large) {
@@ -1146,18 +1262,7 @@ int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launch
     const int64_t nmon = (hb->mon_begin && hb->n_mon_total > 0) ? hb->mon_begin[n] : 0;
     const bool has_ko = hb->barrier && hb->rebate;
 
-    int mask = 0, small_max = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        mask |= (hb->flags[i] & FDM_FLAG_AMERICAN) ? 1 : 2;
-        if (hb->n_space[i] <= FDM_WARP_MAX_N_SPACE) {
-            mask |= 8;
-            if (hb->n_space[i] > small_max) small_max = hb->n_space[i];
-        } else {
-            mask |= 16;
-        }
-    }
-    mask |= small_max << 8;
-    for (int64_t i = 0; i < nseg; ++i) if (hb->seg_div[i] != 0.0) { mask |= 4; break; }
+    const int mask = fdm_launch_hints(hb->n_space, hb->flags, n, hb->seg_div, nseg);
 
     // one device arena for descriptors and results
     auto up8 = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -1307,7 +1412,10 @@ int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int6
         const int nt = hb->n_time[i] < 4 ? 4 : hb->n_time[i];
         if (ns > FDM_MAX_N_SPACE) return fail(FDM_ERR_UNSUPPORTED, "n_space exceeds FDM_MAX_N_SPACE (8193)%s");
         if (ns > n_space_max) n_space_max = ns;
-        if (ns <= FDM_WARP_MAX_N_SPACE) { mask |= 8; if (ns > small_max) small_max = ns; } else mask |= 16;
+        if (ns <= FDM_WARP_MAX_N_SPACE) {
+            mask |= 8 | LEAN_HINTS_VALID | lean_hint_bits(ns);
+            if (ns > small_max) small_max = ns;
+        } else mask |= 16;
         for (int k = 0; k < roles.n; ++k) {
             const double sg = hb->sigma[i] + roles.r[k].bump * hb->dv_sigma;
             if (!(sg > 0.0)) return fail(FDM_ERR_INVALID, "sigma (after bumps) must be positive%s");
@@ -1420,6 +1528,29 @@ int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int6
     if (e1) cudaEventDestroy(e1);
     if (st) cudaStreamDestroy(st);
     return rc;
+}
+
+int fdm_launch_hints(const int32_t *n_space, const int32_t *flags, int64_t n_solves, const double *seg_div,
+                     int64_t n_seg)
+{
+    if (!n_space || !flags || n_solves < 0) return 0;
+    int mask = 0, small_max = 0;
+    for (int64_t i = 0; i < n_solves; ++i) {
+        mask |= (flags[i] & FDM_FLAG_AMERICAN) ? 1 : 2;
+        if (n_space[i] <= FDM_WARP_MAX_N_SPACE) {
+            mask |= 8 | LEAN_HINTS_VALID | lean_hint_bits(n_space[i]);
+            if (n_space[i] > small_max) small_max = n_space[i];
+        } else {
+            mask |= 16;
+        }
+    }
+    mask |= small_max << 8;
+    if (seg_div) {
+        for (int64_t i = 0; i < n_seg; ++i) if (seg_div[i] != 0.0) { mask |= 4; break; }
+    } else {
+        mask |= 4;
+    }
+    return mask;
 }
 
 int fdm_release_workspace(void)

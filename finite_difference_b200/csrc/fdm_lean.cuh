@@ -1,0 +1,656 @@
+// fdm_lean.cuh -- the register-lean warp-per-solve kernel: same step algebra as fdm_warp_kernel (see the header
+// of fdm_b200.cu), but NO per-row coefficient registers, so 12-16 solves are resident per SM instead of 8.
+// fdm_warp_kernel is latency-bound at two warps per scheduler (a lone warp needs ~1270 cycles per time step for
+// ~290 cycles of FP64 pipe work); this kernel buys the missing warps with registers.
+//
+//   * Constant-coefficient LU.  The pivots of the Toeplitz matrix A converge to a fixed point den_inf; the
+//     factors built from it, L_inf U_inf = A_inf, reproduce A except for entry (0,0) = den_inf instead of A_C.
+//     Sherman-Morrison puts the missing delta = A_C - den_inf back exactly:
+//         A = A_inf + delta e0 e0^T   =>   x = y - gamma z,  y = A_inf^-1 R,  z = A_inf^-1 e0,
+//                                          gamma = delta y_0 / (1 + delta z_0)
+//     z (decays like |m|^i away from row 0) is solved once per (theta, dt) phase and kept in registers; per step
+//     the correction is one FMA per node folded into the subtrahend: vc = inv xs - (G + gamma z).
+//   * No padding.  Lane l holds base + (l < extra) rows (base = n_int / 32): only the last slot of a lane is
+//     optional and it is predicated, so three scalars (nm, ncc, inv) serve every slot of every lane.
+//     A kernel compiled for C slots serves 32 (C-1) <= n_int <= 32 C.
+//   * The payoff lives in shared memory (one conflict-free LDS per node and step), scaled by 3 (below).
+//   * American state is (vc, 3 dt lambda) instead of (V, dt lambda): with V = vc + dt lambda,
+//         theta = 1/2:  R = 2 V + L = 2 vc + Ls          G = V + L = vc + (2/3) Ls
+//         theta = 1  :  R =   V + L =   vc + (2/3) Ls    G =     L =      (1/3) Ls          (Ls = 3 L)
+//     and Ls_new = relu(3 phi - 3 vc): one FP64 instruction fewer per node than carrying V.  Where a node is
+//     exercised, V = phi exactly (fd_american_option_pricer.py:497), rebuilt as phi3 / 3 at read-out.
+//     The growth-factor matching of fdm_b200.cu (pd) is folded into inv, as the linear march always did.
+//
+// Solves this kernel cannot take (pivots not converged within MAX_PIVOT_ITERS rows, a zero off-diagonal) are
+// marked by a NaN payload in price[] and solved by fdm_warp_kernel in a following launch.
+//
+// Included by fdm_b200.cu (single translation unit); uses its helpers.
+
+#pragma once
+
+namespace lean {
+
+constexpr unsigned long long RETRY_BITS = 0x7ff8b200dead0001ull;   // quiet NaN: "solve me with fdm_warp_kernel"
+constexpr int MAX_PIVOT_ITERS = 4096;
+
+// Compiled size classes: a kernel with C slots per lane serves 32 (C-1) <= n_int <= 32 C interior rows
+// (400 nodes -> 13, 500 -> 16, 300 -> 10, 256 -> 8, 200 -> 7, 128 -> 4).  Other sizes: fdm_warp_kernel.
+#ifdef FDM_LEAN_DEV                       // development builds: two classes compile faster
+#define FDM_LEAN_CLASSES {13, 16}
+#else
+#define FDM_LEAN_CLASSES {4, 7, 8, 10, 13, 16}
+#endif
+constexpr int N_CLASSES_MAX = 8;
+struct ClassList { int c[N_CLASSES_MAX]; int n; };
+__host__ __device__ constexpr ClassList class_list()
+{
+    constexpr int src[] = FDM_LEAN_CLASSES;
+    ClassList l = {{0, 0, 0, 0, 0, 0, 0, 0}, (int)(sizeof(src) / sizeof(int))};
+    for (int i = 0; i < l.n; ++i) l.c[i] = src[i];
+    return l;
+}
+// slots per lane of the class that owns a grid with n_int interior rows (the smallest that fits); 0 = none
+__host__ __device__ constexpr int class_of(int n_int)
+{
+    constexpr ClassList l = class_list();
+    for (int i = 0; i < l.n; ++i)
+        if (n_int >= 32 * (l.c[i] - 1) && n_int <= 32 * l.c[i]) return l.c[i];
+    return 0;
+}
+
+// shared-memory tables of one warp (doubles): phi3 [C][32] | Wf, Wb [DIRECT_TERMS][32] | Af, Ab [SCAN_LEVELS][32]
+template <int C>
+struct Tables {
+    double *phi3, *Wf, *Wb, *Af, *Ab, *par;
+    __device__ explicit Tables(double *base)
+    {
+        phi3 = base;
+        Wf = phi3 + 32 * C;
+        Wb = Wf + DIRECT_TERMS * 32;
+        Af = Wb + DIRECT_TERMS * 32;
+        Ab = Af + SCAN_LEVELS * 32;
+        par = Ab + SCAN_LEVELS * 32;        // [0] k_eff [1] s_n: inputs of the boundary refill, parked out of registers
+    }
+    __device__ double *end() const { return par + 4; }
+};
+template <int C>
+constexpr int smem_doubles() { return 32 * C + 2 * DIRECT_TERMS * 32 + 2 * SCAN_LEVELS * 32 + 4; }
+
+struct Ph {
+    double NM, NCC, INV;      // -A_L/den_inf, -A_U/den_inf, scale/den_inf
+    double cA, cB;            // boundary coefficients of this lane, already divided by NM (lane 0) / NCC (lane 31)
+    double q;                 // (1-theta)/theta  (linear march)
+    double kap;               // gamma = kap * xs_0
+    double af1, af2, ab1, ab2;   // half-chain products: NM^H, NM^(cnt-H), NCC^(cnt-H), NCC^H
+    double abl;               // NCC^cnt
+    int terms;                // direct carry terms (0: Kogge-Stone scan)
+    bool half;                // theta == 1/2
+};
+
+__device__ __forceinline__ double ipow(double a, int n)
+{
+    double r = 1.0;
+    for (int i = 0; i < n; ++i) r *= a;
+    return r;
+}
+
+// Sweeps of the constant-coefficient factors on a register vector with exact Kogge-Stone carries: on return V
+// holds xs (den_inf * A_inf^-1 V).  Used once per phase for z; not on the per-step path.
+// nmL / nccL: multipliers of the optional last slot (NM / NCC where the lane holds it, else 1 with V[C-1] = 0).
+template <int C>
+__device__ __forceinline__ void const_sweeps(double (&V)[C], const bool last, const int cnt, const double NM,
+                                             const double NCC, const int lane)
+{
+    const double nmL = last ? NM : 1.0, nccL = last ? NCC : 1.0;
+    double e = 0.0;
+#pragma unroll
+    for (int k = 0; k < C; ++k) e = fma(k < C - 1 ? NM : nmL, e, V[k]);
+    double E = e, A = ipow(NM, cnt);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double tE = __shfl_up_sync(FULL, E, d), tA = __shfl_up_sync(FULL, A, d);
+        const bool has = lane >= d;
+        E = fma(has ? A : 0.0, tE, E);
+        A *= has ? tA : 1.0;
+    }
+    double c = __shfl_up_sync(FULL, E, 1);
+    c = (lane == 0) ? 0.0 : c;
+#pragma unroll
+    for (int k = 0; k < C; ++k) { c = fma(k < C - 1 ? NM : nmL, c, V[k]); V[k] = (k < C - 1 || last) ? c : 0.0; }
+    e = 0.0;
+#pragma unroll
+    for (int k = C - 1; k >= 0; --k) e = fma(k < C - 1 ? NCC : nccL, e, V[k]);
+    E = e;
+    A = ipow(NCC, cnt);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double tE = __shfl_down_sync(FULL, E, d), tA = __shfl_down_sync(FULL, A, d);
+        const bool has = lane + d < 32;
+        E = fma(has ? A : 0.0, tE, E);
+        A *= has ? tA : 1.0;
+    }
+    c = __shfl_down_sync(FULL, E, 1);
+    c = (lane == 31) ? 0.0 : c;
+#pragma unroll
+    for (int k = C - 1; k >= 0; --k) { c = fma(k < C - 1 ? NCC : nccL, c, V[k]); V[k] = (k < C - 1 || last) ? c : 0.0; }
+}
+
+// Phase constants, carry tables and the Sherman-Morrison vector z.  Returns false if this solve has to go to
+// fdm_warp_kernel.
+template <int C, bool AMER>
+__device__ __forceinline__ bool setup_phase(double theta, double dt, double a, double c, double bcoef, int n_int,
+                                            int lane, const RowLayout &ly, double (&z)[C], const Tables<C> &T, Ph &ph)
+{
+    constexpr int H = C / 2;
+    const bool last = ly.cnt == C;
+    const double A_L = __dmul_rn(__dmul_rn(-theta, dt), a);
+    const double A_C = __dsub_rn(1.0, __dmul_rn(__dmul_rn(theta, dt), bcoef));
+    const double A_U = __dmul_rn(__dmul_rn(-theta, dt), c);
+    const double B_L = __dmul_rn(__dmul_rn(__dsub_rn(1.0, theta), dt), a);
+    const double B_C = __dadd_rn(1.0, __dmul_rn(__dmul_rn(__dsub_rn(1.0, theta), dt), bcoef));
+    const double B_U = __dmul_rn(__dmul_rn(__dsub_rn(1.0, theta), dt), c);
+    const double p = 1.0 / theta;
+    ph.q = (1.0 - theta) / theta;
+    ph.half = theta == 0.5;
+
+    // pivots of the reference's recurrence (fd_american_option_pricer.py:443-451) to their bit-wise fixed point
+    double den = A_C, rinv = __drcp_rn(den);
+    bool conv = false;
+    for (int i = 1; i < MAX_PIVOT_ITERS; ++i) {
+        const double den_i = __dsub_rn(A_C, __dmul_rn(A_L, __dmul_rn(A_U, rinv)));
+        if (den_i == den) { conv = true; break; }
+        den = den_i;
+        rinv = __drcp_rn(den);
+    }
+    const double NM = -(A_L * rinv), NCC = -(A_U * rinv);
+    // the verdict is taken by a warp vote at the end, so that the compiler sees uniform control flow around it
+    const bool bad = !conv || !(fabs(NM) > 0.0) || !(fabs(NCC) > 0.0) || !isfinite(rinv);
+    const double delta_sm = __dmul_rn(A_L, __dmul_rn(A_U, rinv));       // A_C - den_inf, as the recurrence forms it
+
+    // growth-factor matching (fdm_b200.cu): the V coefficient p + q = 1 + 2q... carries 1 + delta; folded into inv
+    const double pd = growth_matched_pd(A_L, A_C, A_U, B_L, B_C, B_U, ph.q, rinv, n_int);
+    const double scale = AMER ? 1.0 + (pd - 1.0) / (1.0 + ph.q) : p + (pd - 1.0);
+    const double bscale = 1.0 / scale;
+    ph.NM = NM;
+    ph.NCC = NCC;
+    ph.INV = rinv * scale;
+    ph.cA = (lane == 0) ? A_L * bscale / NM : ((lane == 31) ? A_U * bscale / NCC : 0.0);
+    ph.cB = (lane == 0) ? B_L * bscale / NM : ((lane == 31) ? B_U * bscale / NCC : 0.0);
+
+    ph.af1 = ipow(NM, H);
+    ph.af2 = ipow(NM, ly.cnt - H);
+    ph.ab1 = ipow(NCC, ly.cnt - H);
+    ph.ab2 = ipow(NCC, H);
+    const double af_lane = ph.af1 * ph.af2, ab_lane = ph.ab1 * ph.ab2;
+    ph.abl = ab_lane;
+
+    __syncwarp();
+    // Kogge-Stone multipliers and direct-carry weights, as in fdm_warp_kernel's setup_phase
+    double af = af_lane, ab = ab_lane;
+#pragma unroll
+    for (int lv = 0; lv < SCAN_LEVELS; ++lv) {
+        const int d = 1 << lv;
+        const bool has_f = lane >= d, has_b = lane + d < 32;
+        T.Af[lv * 32 + lane] = has_f ? af : 0.0;
+        T.Ab[lv * 32 + lane] = has_b ? ab : 0.0;
+        const double tf = __shfl_up_sync(FULL, af, d), tb = __shfl_down_sync(FULL, ab, d);
+        if (has_f) af *= tf;
+        if (has_b) ab *= tb;
+    }
+    double wf = (lane >= 1) ? 1.0 : 0.0, wb = (lane <= 30) ? 1.0 : 0.0;
+    int terms = 0;
+#pragma unroll
+    for (int j = 1; j <= DIRECT_TERMS; ++j) {
+        T.Wf[(j - 1) * 32 + lane] = wf;
+        T.Wb[(j - 1) * 32 + lane] = wb;
+        const double tf = __shfl_up_sync(FULL, af_lane, j), tb = __shfl_down_sync(FULL, ab_lane, j);
+        wf = (lane >= j + 1) ? wf * tf : 0.0;
+        wb = (lane + j + 1 <= 31) ? wb * tb : 0.0;
+        if ((j & 1) == 0 && terms == 0 && !__any_sync(FULL, fabs(wf) > 1e-20 || fabs(wb) > 1e-20)) terms = j;
+    }
+    ph.terms = terms;
+    __syncwarp();
+
+    // z = A_inf^-1 e0, in the units of the final value: z_k = INV * xs_k(e0)
+#pragma unroll
+    for (int k = 0; k < C; ++k) z[k] = (lane == 0 && k == 0) ? 1.0 : 0.0;
+    const_sweeps<C>(z, last, ly.cnt, NM, NCC, lane);
+    const double xs00 = __shfl_sync(FULL, z[0], 0);
+    const double zx0 = rinv * xs00;                                     // (A_inf^-1 e0)_0
+    ph.kap = delta_sm * rinv / (1.0 + delta_sm * zx0);
+    // Entries below 1e-30 of z_0 are dropped: the direct carries neglect terms below 1e-20 as well, and where they
+    // leave an exact zero (far out-of-the-money rows in the first steps) the correction must not turn it negative
+    // -- the reference's exercise test phi > vc (:496) is strict.
+    const double z_floor = 1e-30 * fabs(xs00);
+#pragma unroll
+    for (int k = 0; k < C; ++k) z[k] = (fabs(z[k]) > z_floor) ? ph.INV * z[k] : 0.0;
+    return !__any_sync(FULL, bad);
+}
+
+// One theta-scheme step.  V: vc (American) / V (linear) on entry and exit; L: 3 dt lambda (American) / scratch.
+// The optional last slot is handled without branches: on lanes that do not hold it its multipliers are 1 and its
+// V, L stay 0, which makes it the identity in both sweeps.
+template <int C, bool AMER>
+__device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const double (&z)[C], const Ph &ph,
+                                           const double cin_f, const double cin_b, const bool last,
+                                           const Tables<C> &T, const int lane)
+{
+    constexpr int H = C / 2;
+    const double NM = ph.NM, NCC = ph.NCC;
+    const double nmL = last ? NM : 1.0, nccL = last ? NCC : 1.0;
+    // right-hand side R (into V) and subtrahend G (into L)
+    if (AMER) {
+        if (ph.half) {
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                const double g = fma(2.0 / 3.0, L[k], V[k]);
+                V[k] = fma(2.0, V[k], L[k]);
+                L[k] = g;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                const double g = (1.0 / 3.0) * L[k];
+                V[k] = fma(2.0 / 3.0, L[k], V[k]);
+                L[k] = g;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < C; ++k) L[k] = ph.q * V[k];
+    }
+    // ---- forward elimination --------------------------------------------------------------------
+    double e1 = cin_f, e2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < H; ++k) e1 = fma(NM, e1, V[k]);
+#pragma unroll
+    for (int k = H; k < C; ++k) e2 = fma(k < C - 1 ? NM : nmL, e2, V[k]);
+    double e_end = fma(ph.af2, e1, e2);
+    double cs = lane_carry<true>(e_end, ph.terms, T.Wf, T.Af, lane);
+    {
+        double c1 = cs + cin_f;
+        double c2 = fma(ph.af1, cs, e1);
+#pragma unroll
+        for (int k = 0; k < H; ++k) { c1 = fma(NM, c1, V[k]); V[k] = c1; }
+#pragma unroll
+        for (int k = H; k < C - 1; ++k) { c2 = fma(NM, c2, V[k]); V[k] = c2; }
+        c2 = fma(nmL, c2, V[C - 1]);
+        V[C - 1] = last ? c2 : 0.0;
+    }
+    // ---- back substitution -------------------------------------------------------------------------
+    e1 = cin_b;
+    e2 = 0.0;
+#pragma unroll
+    for (int k = C - 1; k >= H; --k) e1 = fma(k < C - 1 ? NCC : nccL, e1, V[k]);
+#pragma unroll
+    for (int k = H - 1; k >= 0; --k) e2 = fma(NCC, e2, V[k]);
+    e_end = fma(ph.ab2, e1, e2);
+    cs = lane_carry<false>(e_end, ph.terms, T.Wb, T.Ab, lane);
+    // Sherman-Morrison: xs_0 is lane 0's inclusive end value
+    const double gamma = ph.kap * __shfl_sync(FULL, fma(ph.abl, cs, e_end), 0);
+    double c1 = cs + cin_b;
+    double c2 = fma(ph.ab1, cs, e1);
+    // slots in the order the two half-chains reach them: C-1, then (C-2, H-1), (C-3, H-2), ...
+    auto slot_of = [](const int i) -> int {
+        if (i == 0) return C - 1;
+        const int j = (i - 1) >> 1;
+        const bool upper_exists = C - 2 - j >= H;
+        if (!upper_exists) return H - 1 - ((i - 1) - (C - 1 - H));      // only the lower chain is left
+        return ((i - 1) & 1) == 0 ? C - 2 - j : H - 1 - j;
+    };
+    // the payoff of slot order[i + PF] is fetched while slot order[i] is finished (LDS latency off the chain)
+    constexpr int PF = 4;
+    double pf[C + PF];
+    if (AMER) {
+#pragma unroll
+        for (int i = 0; i < PF; ++i) pf[i] = T.phi3[slot_of(i < C ? i : C - 1) * 32 + lane];
+    }
+    auto finish = [&](const int i, const int k, const double xs, const bool keep) {
+        const double gp = fma(gamma, z[k], L[k]);
+        const double vc = fma(ph.INV, xs, -gp);
+        if (AMER) {
+            if (i + PF < C) pf[i + PF] = T.phi3[slot_of(i + PF) * 32 + lane];
+            // exercise iff phi > vc (fd_american_option_pricer.py:496); Ls = 3 dt lambda_new = relu(3 phi - 3 vc)
+            const double d = fma(-3.0, vc, pf[i]);
+            const int msk = keep ? ~(__double2hiint(d) >> 31) : 0;
+            L[k] = __hiloint2double(__double2hiint(d) & msk, __double2loint(d) & msk);
+        }
+        V[k] = keep ? vc : 0.0;
+    };
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        const int k = slot_of(i);
+        if (k >= H) {
+            c1 = fma(k < C - 1 ? NCC : nccL, c1, V[k]);
+            finish(i, k, c1, k < C - 1 ? true : last);
+        } else {
+            c2 = fma(NCC, c2, V[k]);
+            finish(i, k, c2, true);
+        }
+    }
+}
+
+#ifndef FDM_LEAN_MINB
+#define FDM_LEAN_MINB 0
+#endif
+template <int C>
+constexpr int min_blocks() { return FDM_LEAN_MINB ? FDM_LEAN_MINB : (C <= 8 ? 16 : 12); }
+
+template <int C, bool AMER, bool TRACE>
+__global__ void __launch_bounds__(32, min_blocks<C>())
+fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int want_american, const int div_smem)
+{
+    extern __shared__ double smem[];
+    const Tables<C> T(smem);
+    double *divbuf = T.end();
+
+    const int64_t sid = first + blockIdx.x;
+    if (sid >= B.n_solves) return;
+    const int flags = B.flags[sid];
+    if (((flags & FDM_FLAG_AMERICAN) != 0) != (want_american != 0)) return;
+    const int lane = threadIdx.x;
+    const int n = B.n_space[sid];
+    const int n_int = n - 1;
+    if (class_of(n_int) != C) return;                           // another size class, or fdm_warp_kernel's
+    const RowLayout ly = RowLayout::packed(n_int, lane);
+    const bool last = ly.cnt == C;
+    const bool is_call = flags & FDM_FLAG_CALL;
+    const bool b76 = flags & FDM_FLAG_BLACK76;
+    const bool snap = flags & FDM_FLAG_SNAP;
+    const int ko = (flags & FDM_FLAG_KO_DOWN) ? 1 : ((flags & FDM_FLAG_KO_UP) ? 2 : 0);
+
+    const double x_min = B.x_min[sid], dx = B.dx[sid], sigma = B.sigma[sid], r = B.r[sid], bcar = B.b[sid];
+    const double spot = B.spot[sid], strike = B.strike[sid];
+    const double barrier = (ko && B.barrier) ? B.barrier[sid] : 0.0;
+    const double rebate = (ko && B.rebate) ? B.rebate[sid] : 0.0;
+    const int rannacher = B.rannacher[sid];
+
+    // ---- grid, snapping, payoff -------------------------------------------------------------
+    double V[C], L[C], z[C];
+    const double s0 = node_s(x_min, dx, 0);
+    const double sn = node_s(x_min, dx, n);
+#pragma unroll
+    for (int k = 0; k < C; ++k) V[k] = (k < ly.cnt) ? node_s(x_min, dx, ly.row0 + k + 1) : 0.0;   // node prices, for now
+    int spot_idx = 0, strike_idx = 0;
+    double k_eff = strike;
+    if (snap) {
+        spot_idx = argmin_node<C>(V, s0, sn, spot, n, ly, false);
+        strike_idx = argmin_node<C>(V, s0, sn, strike, n, ly, false);
+        k_eff = node_s(x_min, dx, strike_idx);                  // fd_american_option_pricer.py:272-275
+    }
+    int ko_lo = 1, ko_hi = 0;
+    if (ko) {
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+            if (k < ly.cnt) cnt += (ko == 1) ? (V[k] <= barrier) : (V[k] >= barrier);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+        if (ko == 1) { ko_lo = 0; ko_hi = (s0 <= barrier) + cnt + (sn <= barrier) - 1; }
+        else         { ko_lo = n - ((s0 >= barrier) + cnt + (sn >= barrier)) + 1; ko_hi = n; }
+    }
+    const double phi0 = payoff(s0, k_eff, is_call);
+    const double phin = payoff(sn, k_eff, is_call);
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const double pv = (k < ly.cnt) ? payoff(V[k], k_eff, is_call) : 0.0;
+        T.phi3[k * 32 + lane] = 3.0 * pv;
+        V[k] = pv;                                              // terminal condition, :558
+        L[k] = 0.0;
+    }
+    // payoff of slot k to within one ulp (rare uses: dividend jump, read-out)
+    auto phi_at = [&](int k) -> double { return T.phi3[k * 32 + lane] * (1.0 / 3.0); };
+    // value vector from the (vc, 3 dt lambda) state: V = phi where exercised (:497)
+    auto materialise = [&]() {
+        if (AMER) {
+#pragma unroll
+            for (int k = 0; k < C; ++k) if (L[k] > 0.0) V[k] = phi_at(k);
+        }
+    };
+    double Vb = (lane == 0) ? phi0 : ((lane == 31) ? phin : 0.0);
+    const bool bdry_lane = is_call ? (lane == 31) : (lane == 0);
+    if (lane == 0) { T.par[0] = k_eff; T.par[1] = sn; }
+    __syncwarp();
+
+    // ---- operator coefficients, fd_american_option_pricer.py:413-426 -------------------------
+    const double sig2 = __dmul_rn(sigma, sigma);
+    const double mu_x = b76 ? __dmul_rn(-0.5, sig2) : __dsub_rn(bcar, __dmul_rn(0.5, sig2));
+    const double alpha = __dmul_rn(0.5, sig2) / __dmul_rn(dx, dx);
+    const double beta = mu_x / __dmul_rn(2.0, dx);
+    const double ca = __dsub_rn(alpha, beta);
+    const double cc = __dadd_rn(alpha, beta);
+    const double bcoef = __dsub_rn(__dmul_rn(-2.0, alpha), r);
+
+    const int seg_b = B.seg_begin[sid], seg_e = B.seg_begin[sid + 1];
+    int mon_i = 0, mon_e = 0;
+    if (ko && B.mon_begin) { mon_i = B.mon_begin[sid]; mon_e = B.mon_begin[sid + 1]; }
+    int next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
+    int gstep = 0;
+    int32_t *trace = (TRACE && O.ex_trace) ? O.ex_trace + sid * O.ex_trace_stride : nullptr;
+    bool retry = false;
+
+    for (int seg = seg_b; seg < seg_e && !retry; ++seg) {
+        const int n_steps = B.seg_steps[seg];
+        const double dt = B.seg_dt[seg];
+        const double tau0 = B.seg_tau0[seg];
+        const int base_ran = B.seg_restart[seg] ? rannacher : 0;   // :464
+        const double cash = B.seg_div[seg];
+        if (AMER) {
+#pragma unroll
+            for (int k = 0; k < C; ++k) L[k] = 0.0;             // lambda restarts every segment, :463
+        }
+        int m = 0;
+        double my_w = 0.0;
+        int fill_base = -64;
+        auto fetch_boundary = [&](int step) -> double {
+            if (step - fill_base >= 32 || step < fill_base) {
+                // once per 32 steps: the inputs are re-read (global / shared) instead of living in registers
+                fill_base = step;
+                const double dt_ = *(volatile const double *)&B.seg_dt[seg];
+                const double tau0_ = *(volatile const double *)&B.seg_tau0[seg];
+                const double r_ = *(volatile const double *)&B.r[sid];
+                const double b_ = *(volatile const double *)&B.b[sid];
+                const double tau = fma((double)(step + lane + 1), dt_, tau0_);
+                double vmin, vmax;
+                boundary_values(is_call, b76, r_, b_, ((volatile double *)T.par)[0], ((volatile double *)T.par)[1], tau,
+                                vmin, vmax);
+                my_w = is_call ? vmax : vmin;
+            }
+            const double w = __shfl_sync(FULL, my_w, step - fill_base);
+            return bdry_lane ? w : 0.0;
+        };
+        while (m < n_steps) {
+            const bool implicit_phase = m < base_ran;
+            const int m_end = implicit_phase ? min(base_ran, n_steps) : n_steps;
+            Ph ph;
+            if (!setup_phase<C, AMER>(implicit_phase ? 1.0 : 0.5, dt, ca, cc, bcoef, n_int, lane, ly, z, T, ph)) {
+                retry = true;
+                break;
+            }
+            double w_next = fetch_boundary(m);
+            double cin = ph.cB * Vb - ph.cA * w_next;            // non-zero on lanes 0 and 31 only
+            for (; m < m_end; ++m) {
+                const double w_now = w_next;
+                w_next = fetch_boundary(m + 1);
+                double cin_n = ph.cB * w_now - ph.cA * w_next;
+                march_step<C, AMER>(V, L, z, ph, (lane == 0) ? cin : 0.0, (lane == 31) ? cin : 0.0, last, T, lane);
+                Vb = w_now;                                     // V[0] = V_min, V[-1] = V_max, :505-506
+                ++gstep;
+                if (TRACE && trace) {
+                    int lo = 0x7fffffff, hi = -1;
+#pragma unroll
+                    for (int k = 0; k < C; ++k) {
+                        const int row = ly.row0 + k;
+                        if (AMER && k < ly.cnt && L[k] > 0.0) { lo = min(lo, row); hi = max(hi, row); }
+                    }
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) {
+                        lo = min(lo, __shfl_xor_sync(FULL, lo, d));
+                        hi = max(hi, __shfl_xor_sync(FULL, hi, d));
+                    }
+                    if (lane == 0 && 2 * (int64_t)gstep <= O.ex_trace_stride) {
+                        trace[2 * (gstep - 1)] = (hi < 0) ? -1 : lo;
+                        trace[2 * (gstep - 1) + 1] = hi;
+                    }
+                }
+                if (gstep == next_mon) {                        // discrete_barrier_fdm_pricer_cn.py:299-300
+#pragma unroll
+                    for (int k = 0; k < C; ++k) {
+                        const int j = ly.row0 + k + 1;
+                        if (k < ly.cnt && j >= ko_lo && j <= ko_hi) V[k] = rebate;
+                    }
+                    if (lane == 0 && ko_lo <= 0 && 0 <= ko_hi) Vb = rebate;
+                    if (lane == 31 && ko_lo <= n && n <= ko_hi) Vb = rebate;
+                    ++mon_i;
+                    next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
+                    cin_n = ph.cB * Vb - ph.cA * w_next;
+                }
+                cin = cin_n;
+            }
+        }
+        if (retry) break;
+        if (cash != 0.0) {
+            materialise();
+            if (div_smem) {
+                double *xs = divbuf;
+                double *ys = xs + (32 * C + 2);
+                double *mu = ys + (32 * C + 2);
+                double *cz = mu + (32 * C + 2);
+                double V0 = __shfl_sync(FULL, Vb, 0), VN = __shfl_sync(FULL, Vb, 31);
+                dividend_jump<C>(V, V0, VN, phi_at, phi0, phin, cash, is_call, n, lane, ly, x_min, dx, xs, ys, mu, cz);
+                Vb = (lane == 0) ? V0 : ((lane == 31) ? VN : 0.0);
+            } else {
+#pragma unroll
+                for (int k = 0; k < C; ++k) V[k] = NAN;
+            }
+            if (AMER) {
+#pragma unroll
+                for (int k = 0; k < C; ++k) L[k] = 0.0;
+            }
+        }
+    }
+    if (retry) {
+        if (lane == 0) O.price[sid] = __longlong_as_double((long long)RETRY_BITS);
+        return;
+    }
+
+    // ---- read-out (as fdm_warp_kernel) ------------------------------------------------------------
+    const double V0 = __shfl_sync(FULL, Vb, 0), VN = __shfl_sync(FULL, Vb, 31);
+    int ex_lo = -1, ex_hi = -1;
+    if (AMER) {
+        int lo = 0x7fffffff, hi = -1;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int row = ly.row0 + k;
+            if (k < ly.cnt && L[k] > 0.0) { lo = min(lo, row); hi = max(hi, row); }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            lo = min(lo, __shfl_xor_sync(FULL, lo, d));
+            hi = max(hi, __shfl_xor_sync(FULL, hi, d));
+        }
+        if (hi >= 0) { ex_lo = lo; ex_hi = hi; }
+    }
+    materialise();
+
+    if (O.v_dump) {
+        double *dst = O.v_dump + sid * O.v_dump_stride;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int j = ly.row0 + k + 1;
+            if (k < ly.cnt && j < O.v_dump_stride) dst[j] = V[k];
+        }
+        if (lane == 0) {
+            dst[0] = V0;
+            if (n < O.v_dump_stride) dst[n] = VN;
+        }
+    }
+
+    double price, delta, gamma;
+    double sv[4], ss[4];
+    int idx_a, idx_b;
+    if (snap) {
+        // fd_american_option_pricer.py:613-653
+        const int i_near = min(max(spot_idx, 1), n - 2);
+        const double Sx = node_s(x_min, dx, spot_idx);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int j = i_near - 1 + t;
+            sv[t] = node_value<C>(V, V0, VN, j, n, ly);
+            ss[t] = node_s(x_min, dx, j);
+        }
+        price = node_value<C>(V, V0, VN, spot_idx, n, ly);
+        const double z0 = ss[0] - Sx, z1 = ss[1] - Sx, z2 = ss[2] - Sx, z3 = ss[3] - Sx;
+        const double f01 = (sv[1] - sv[0]) / (z1 - z0);
+        const double f12 = (sv[2] - sv[1]) / (z2 - z1);
+        const double f23 = (sv[3] - sv[2]) / (z3 - z2);
+        const double f012 = (f12 - f01) / (z2 - z0);
+        const double f123 = (f23 - f12) / (z3 - z1);
+        const double f0123 = (f123 - f012) / (z3 - z0);
+        delta = f01 + f012 * (-(z0 + z1)) + f0123 * (z0 * z1 + z0 * z2 + z1 * z2);
+        gamma = 2.0 * f012 - 2.0 * f0123 * (z0 + z1 + z2);
+        idx_a = spot_idx;
+        idx_b = strike_idx;
+    } else {
+        // discrete_barrier_fdm_pricer_cn.py:308-353
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            L[k] = (k < ly.cnt) ? node_s(x_min, dx, ly.row0 + k + 1) : 0.0;    // L is free now: node prices
+            if (k < ly.cnt && L[k] <= spot) ++cnt;
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+        int lo = cnt;
+        if (spot <= s0) { price = V0; lo = 0; }
+        else if (spot >= sn) { price = VN; lo = n; }
+        else {
+            const double s_lo = node_s(x_min, dx, lo), s_hi = node_s(x_min, dx, lo + 1);
+            const double v_lo = node_value<C>(V, V0, VN, lo, n, ly);
+            const double v_hi = node_value<C>(V, V0, VN, lo + 1, n, ly);
+            const double w = __dsub_rn(spot, s_lo) / __dsub_rn(s_hi, s_lo);
+            price = __dadd_rn(__dmul_rn(__dsub_rn(1.0, w), v_lo), __dmul_rn(w, v_hi));
+        }
+        const int gi = argmin_node<C>(L, s0, sn, spot, n, ly, true);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            sv[t] = node_value<C>(V, V0, VN, gi - 1 + t, n, ly);
+            ss[t] = node_s(x_min, dx, gi - 1 + t);
+        }
+        sv[3] = 0.0;
+        ss[3] = 0.0;
+        const double h1 = __dsub_rn(ss[1], ss[0]);
+        const double h2 = __dsub_rn(ss[2], ss[1]);
+        const double h12 = __dadd_rn(h1, h2);
+        delta = __dadd_rn(__dadd_rn(__dmul_rn(-h2 / __dmul_rn(h1, h12), sv[0]),
+                                    __dmul_rn(__dsub_rn(h2, h1) / __dmul_rn(h1, h2), sv[1])),
+                          __dmul_rn(h1 / __dmul_rn(h2, h12), sv[2]));
+        gamma = __dmul_rn(2.0, __dadd_rn(__dsub_rn(sv[0] / __dmul_rn(h1, h12), sv[1] / __dmul_rn(h1, h2)),
+                                         sv[2] / __dmul_rn(h2, h12)));
+        idx_a = lo;
+        idx_b = gi;
+    }
+
+    if (lane == 0) {
+        O.price[sid] = price;
+        if (O.delta) O.delta[sid] = delta;
+        if (O.gamma) O.gamma[sid] = gamma;
+        if (O.stencil_v) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) O.stencil_v[4 * sid + t] = sv[t];
+        }
+        if (O.stencil_s) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) O.stencil_s[4 * sid + t] = ss[t];
+        }
+        if (O.idx) {
+            O.idx[4 * sid + 0] = idx_a;
+            O.idx[4 * sid + 1] = idx_b;
+            O.idx[4 * sid + 2] = ex_lo;
+            O.idx[4 * sid + 3] = ex_hi;
+        }
+        if (O.status) O.status[sid] = isfinite(price) ? 0 : 1;
+    }
+}
+
+}  // namespace lean

@@ -67,9 +67,8 @@ typedef struct FdmBatch {
     int32_t n_space_max;   /* upper bound of n_space[] in this call: selects the kernel variant */
     int32_t n_seg_total;   /* length of the seg_* tables  */
     int32_t n_mon_total;   /* length of mon_step (0 if none) */
-    int32_t reserved;      /* optional launch hints, 0 = derive: bit0 any American solve, bit1 any linear solve,
-                              bit2 any dividend, bit3 any n_space <= FDM_WARP_MAX_N_SPACE, bit4 any larger,
-                              bits 8..19 the largest n_space not above FDM_WARP_MAX_N_SPACE */
+    int32_t reserved;      /* optional launch hints from fdm_launch_hints(); 0 = unknown mix (every kernel family and
+                              size class is launched; solves that are not theirs exit at once) */
 
     const double *x_min;   /* log(S_min) of the grid, fd_american_option_pricer.py:233 */
     const double *dx;      /* (log S_max - log S_min)/n_space, :237 */
@@ -134,6 +133,14 @@ int fdm_device_count(void);
  * number of kernels launched.
  */
 int fdm_solve_batch(const FdmBatch *batch, const FdmOut *out, void *stream, int32_t *n_launches);
+
+/*
+ * Launch hints for FdmBatch.reserved, from HOST copies of n_space[], flags[] (n_solves entries) and seg_div[]
+ * (n_seg entries, may be NULL): which kernel families (American / linear, dividend scratch) and grid-size classes
+ * occur, so that fdm_solve_batch() launches only those.  Pure host function, no device needed.
+ */
+int fdm_launch_hints(const int32_t *n_space, const int32_t *flags, int64_t n_solves, const double *seg_div,
+                     int64_t n_seg);
 
 /*
  * Host-buffer entry point: copies the descriptors to the device, solves, copies the results
