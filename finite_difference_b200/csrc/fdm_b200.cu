@@ -1059,8 +1059,8 @@ int launch_lean_class(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool 
                       bool any_div, int32_t *n_launches)
 {
     const bool trace = o.ex_trace != nullptr;
-    const int div_doubles = any_div ? 4 * (32 * C + 2) : 0;
-    const size_t smem = (size_t)(lean::smem_doubles<C>() + div_doubles) * sizeof(double);
+    (void)any_div;
+    const size_t smem = (size_t)lean::smem_doubles<C>() * sizeof(double);
     auto k_am = lean::fdm_lean_kernel<C, true, false>;
     auto k_amt = lean::fdm_lean_kernel<C, true, true>;
     auto k_lin = lean::fdm_lean_kernel<C, false, false>;
@@ -1075,12 +1075,12 @@ int launch_lean_class(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool 
         const int64_t count = (b.n_solves - first < max_grid) ? (b.n_solves - first) : max_grid;
         const dim3 grid((unsigned)count), block(32);
         if (any_american) {
-            if (trace) k_amt<<<grid, block, smem, st>>>(b, o, first, 1, any_div);
-            else       k_am<<<grid, block, smem, st>>>(b, o, first, 1, any_div);
+            if (trace) k_amt<<<grid, block, smem, st>>>(b, o, first, 1);
+            else       k_am<<<grid, block, smem, st>>>(b, o, first, 1);
             ++launches;
         }
         if (any_linear) {
-            k_lin<<<grid, block, smem, st>>>(b, o, first, 0, any_div);
+            k_lin<<<grid, block, smem, st>>>(b, o, first, 0);
             ++launches;
         }
         FDM_CUDA(cudaGetLastError());
@@ -1191,14 +1191,12 @@ int launch(const FdmBatch &b, const FdmOut &o, cudaStream_t st, int family_mask,
         // sizes outside the classes and the solves the lean kernel handed back
         static const bool no_lean = getenv("FDM_B200_NO_LEAN") != nullptr;
         int only_rest = 0;
-        bool need_general = true;
         if (!no_lean) {
             const bool hinted = family_mask & LEAN_HINTS_VALID;
             const int class_mask = hinted ? (family_mask >> 20) & 0xff : 0xff;
             rc = launch_lean_all<0>(b, o, st, am, lin, dv, class_mask, n_launches);
             if (rc != FDM_OK) return rc;
             only_rest = 1;
-            (void)need_general;
         }
         if (rows <= 32 * 4) rc = launch_variant<4>(b, o, st, am, lin, dv, only_rest, n_launches);
         else if (rows <= 32 * 8) rc = launch_variant<8>(b, o, st, am, lin, dv, only_rest, n_launches);

@@ -6,10 +6,16 @@
 //   * Constant-coefficient LU.  The pivots of the Toeplitz matrix A converge to a fixed point den_inf; the
 //     factors built from it, L_inf U_inf = A_inf, reproduce A except for entry (0,0) = den_inf instead of A_C.
 //     Sherman-Morrison puts the missing delta = A_C - den_inf back exactly:
-//         A = A_inf + delta e0 e0^T   =>   x = y - gamma z,  y = A_inf^-1 R,  z = A_inf^-1 e0,
-//                                          gamma = delta y_0 / (1 + delta z_0)
-//     z (decays like |m|^i away from row 0) is solved once per (theta, dt) phase and kept in registers; per step
-//     the correction is one FMA per node folded into the subtrahend: vc = inv xs - (G + gamma z).
+//         A x = R   <=>   A_inf x = R - delta x_0 e0,     x_0 = y_0 / (1 + delta z_0),  y = A_inf^-1 R, z = A_inf^-1 e0
+//     i.e. the same sweeps with R_0 lowered by g = delta x_0.  In the forward sweep that is -g nm^i on row i --
+//     a change of every lane's carry-in by a per-lane constant times g -- and in the backward sweep -g xsz_i,
+//     again a per-lane constant on the carry-in.  So the correction costs a few scalar FMAs per step, no per-node
+//     work and no per-node registers.
+//   * Each sweep is local pass -> carries -> local pass.  Here the forward local pass stores its result u_loc and
+//     the second forward pass becomes independent FMAs  u_k = u_loc_k + nm^(k+1) carry  (powers of nm: C/2
+//     warp-uniform registers), which also lets the backward local pass run on u_loc while the forward carries
+//     are still in flight, and lets x_0 (one shuffle) be known before the last pass.
+//     Per node and step: 8 FP64 instructions American, 6 linear (fdm_warp_kernel: 9 / 6).
 //   * No padding.  Lane l holds base + (l < extra) rows (base = n_int / 32): only the last slot of a lane is
 //     optional and it is predicated, so three scalars (nm, ncc, inv) serve every slot of every lane.
 //     A kernel compiled for C slots serves 32 (C-1) <= n_int <= 32 C.
@@ -21,7 +27,8 @@
 //     exercised, V = phi exactly (fd_american_option_pricer.py:497), rebuilt as phi3 / 3 at read-out.
 //     The growth-factor matching of fdm_b200.cu (pd) is folded into inv, as the linear march always did.
 //
-// Solves this kernel cannot take (pivots not converged within MAX_PIVOT_ITERS rows, a zero off-diagonal) are
+// Solves this kernel does not take (dividend jumps, pivots not converged within MAX_PIVOT_ITERS rows, a zero
+// off-diagonal) are
 // marked by a NaN payload in price[] and solved by fdm_warp_kernel in a following launch.
 //
 // Included by fdm_b200.cu (single translation unit); uses its helpers.
@@ -34,11 +41,16 @@ constexpr unsigned long long RETRY_BITS = 0x7ff8b200dead0001ull;   // quiet NaN:
 constexpr int MAX_PIVOT_ITERS = 4096;
 
 // Compiled size classes: a kernel with C slots per lane serves 32 (C-1) <= n_int <= 32 C interior rows
-// (400 nodes -> 13, 500 -> 16, 300 -> 10, 256 -> 8, 200 -> 7, 128 -> 4).  Other sizes: fdm_warp_kernel.
-#ifdef FDM_LEAN_DEV                       // development builds: two classes compile faster
-#define FDM_LEAN_CLASSES {13, 16}
-#else
+// (400 nodes -> 13, 300 -> 10).  Other sizes: fdm_warp_kernel.
+// Measured on B200 (tools/time_variants.py): with 10..13 slots per lane the kernel fits 128 registers and 16 solves
+// per SM (400-node grids: +15 % American, +8 % barrier over fdm_warp_kernel).  16 slots (500 nodes) spill at 128
+// registers and only tie fdm_warp_kernel, and below ~250 nodes the per-phase setup outweighs the extra warps:
+// those sizes stay with fdm_warp_kernel.  Define FDM_LEAN_ALL_CLASSES to compile every class (parity tests of the
+// layout at the other sizes).
+#ifdef FDM_LEAN_ALL_CLASSES
 #define FDM_LEAN_CLASSES {4, 7, 8, 10, 13, 16}
+#else
+#define FDM_LEAN_CLASSES {10, 13}
 #endif
 constexpr int N_CLASSES_MAX = 8;
 struct ClassList { int c[N_CLASSES_MAX]; int n; };
@@ -76,13 +88,17 @@ struct Tables {
 template <int C>
 constexpr int smem_doubles() { return 32 * C + 2 * DIRECT_TERMS * 32 + 2 * SCAN_LEVELS * 32 + 4; }
 
+template <int C>
 struct Ph {
+    static constexpr int H = C / 2, PW = C - C / 2;
     double NM, NCC, INV;      // -A_L/den_inf, -A_U/den_inf, scale/den_inf
+    double P[PW + 1];         // P[j] = NM^j, j = 0..PW
     double cA, cB;            // boundary coefficients of this lane, already divided by NM (lane 0) / NCC (lane 31)
     double q;                 // (1-theta)/theta  (linear march)
-    double kap;               // gamma = kap * xs_0
-    double af1, af2, ab1, ab2;   // half-chain products: NM^H, NM^(cnt-H), NCC^(cnt-H), NCC^H
-    double abl;               // NCC^cnt
+    double kap;               // g = kap * xs_0
+    double D, Zc;             // Sherman-Morrison: forward carry-in -= g D, backward carry-in -= g Zc   (per lane)
+    double kapL, kapU;        // sum_k NCC^k NM^(k+1) over the lower / upper half of this lane
+    double ab1, ab2, abl;     // NCC^(cnt-H), NCC^H, NCC^cnt
     int terms;                // direct carry terms (0: Kogge-Stone scan)
     bool half;                // theta == 1/2
 };
@@ -135,14 +151,14 @@ __device__ __forceinline__ void const_sweeps(double (&V)[C], const bool last, co
     for (int k = C - 1; k >= 0; --k) { c = fma(k < C - 1 ? NCC : nccL, c, V[k]); V[k] = (k < C - 1 || last) ? c : 0.0; }
 }
 
-// Phase constants, carry tables and the Sherman-Morrison vector z.  Returns false if this solve has to go to
-// fdm_warp_kernel.
+// Phase constants and carry tables.  Returns false if this solve has to go to fdm_warp_kernel.
 template <int C, bool AMER>
 __device__ __forceinline__ bool setup_phase(double theta, double dt, double a, double c, double bcoef, int n_int,
-                                            int lane, const RowLayout &ly, double (&z)[C], const Tables<C> &T, Ph &ph)
+                                            int lane, const RowLayout &ly, const Tables<C> &T, Ph<C> &ph)
 {
-    constexpr int H = C / 2;
+    constexpr int H = C / 2, PW = C - H;
     const bool last = ly.cnt == C;
+    const int cntU = ly.cnt - H;
     const double A_L = __dmul_rn(__dmul_rn(-theta, dt), a);
     const double A_C = __dsub_rn(1.0, __dmul_rn(__dmul_rn(theta, dt), bcoef));
     const double A_U = __dmul_rn(__dmul_rn(-theta, dt), c);
@@ -167,7 +183,7 @@ __device__ __forceinline__ bool setup_phase(double theta, double dt, double a, d
     const bool bad = !conv || !(fabs(NM) > 0.0) || !(fabs(NCC) > 0.0) || !isfinite(rinv);
     const double delta_sm = __dmul_rn(A_L, __dmul_rn(A_U, rinv));       // A_C - den_inf, as the recurrence forms it
 
-    // growth-factor matching (fdm_b200.cu): the V coefficient p + q = 1 + 2q... carries 1 + delta; folded into inv
+    // growth-factor matching (fdm_b200.cu): the V coefficient carries 1 + delta; folded into inv
     const double pd = growth_matched_pd(A_L, A_C, A_U, B_L, B_C, B_U, ph.q, rinv, n_int);
     const double scale = AMER ? 1.0 + (pd - 1.0) / (1.0 + ph.q) : p + (pd - 1.0);
     const double bscale = 1.0 / scale;
@@ -177,12 +193,23 @@ __device__ __forceinline__ bool setup_phase(double theta, double dt, double a, d
     ph.cA = (lane == 0) ? A_L * bscale / NM : ((lane == 31) ? A_U * bscale / NCC : 0.0);
     ph.cB = (lane == 0) ? B_L * bscale / NM : ((lane == 31) ? B_U * bscale / NCC : 0.0);
 
-    ph.af1 = ipow(NM, H);
-    ph.af2 = ipow(NM, ly.cnt - H);
-    ph.ab1 = ipow(NCC, ly.cnt - H);
+    ph.P[0] = 1.0;
+#pragma unroll
+    for (int j = 1; j <= PW; ++j) ph.P[j] = ph.P[j - 1] * NM;
+    const double af1 = ipow(NM, H), af2 = ipow(NM, cntU);
+    ph.ab1 = ipow(NCC, cntU);
     ph.ab2 = ipow(NCC, H);
-    const double af_lane = ph.af1 * ph.af2, ab_lane = ph.ab1 * ph.ab2;
+    const double af_lane = af1 * af2, ab_lane = ph.ab1 * ph.ab2;
     ph.abl = ab_lane;
+    // backward local end of  NM^(k+1) carry : sum_k NCC^k NM^(k+1) over the slots of a half
+    {
+        double sL = 0.0, sU = 0.0, t = NM;
+        for (int k = 0; k < H; ++k) { sL += t; t *= NCC * NM; }
+        t = NM;
+        for (int k = 0; k < cntU; ++k) { sU += t; t *= NCC * NM; }
+        ph.kapL = sL;
+        ph.kapU = sU;
+    }
 
     __syncwarp();
     // Kogge-Stone multipliers and direct-carry weights, as in fdm_warp_kernel's setup_phase
@@ -211,31 +238,68 @@ __device__ __forceinline__ bool setup_phase(double theta, double dt, double a, d
     ph.terms = terms;
     __syncwarp();
 
-    // z = A_inf^-1 e0, in the units of the final value: z_k = INV * xs_k(e0)
+    // Sherman-Morrison constants.  xsz = sweeps of e0 (den_inf * A_inf^-1 e0), exact carries.
+    double xsz[C];
 #pragma unroll
-    for (int k = 0; k < C; ++k) z[k] = (lane == 0 && k == 0) ? 1.0 : 0.0;
-    const_sweeps<C>(z, last, ly.cnt, NM, NCC, lane);
-    const double xs00 = __shfl_sync(FULL, z[0], 0);
-    const double zx0 = rinv * xs00;                                     // (A_inf^-1 e0)_0
-    ph.kap = delta_sm * rinv / (1.0 + delta_sm * zx0);
-    // Entries below 1e-30 of z_0 are dropped: the direct carries neglect terms below 1e-20 as well, and where they
-    // leave an exact zero (far out-of-the-money rows in the first steps) the correction must not turn it negative
-    // -- the reference's exercise test phi > vc (:496) is strict.
-    const double z_floor = 1e-30 * fabs(xs00);
-#pragma unroll
-    for (int k = 0; k < C; ++k) z[k] = (fabs(z[k]) > z_floor) ? ph.INV * z[k] : 0.0;
+    for (int k = 0; k < C; ++k) xsz[k] = (lane == 0 && k == 0) ? 1.0 : 0.0;
+    const_sweeps<C>(xsz, last, ly.cnt, NM, NCC, lane);
+    const double xs00 = __shfl_sync(FULL, xsz[0], 0);
+    ph.kap = delta_sm * rinv / (1.0 + delta_sm * (rinv * xs00));       // g = delta x_0 = kap * xs_0(uncorrected)
+    // forward: rows of lane l change by -g NM^(row0 + k) = NM^(k+1) * (-g NM^(row0 - 1))
+    double Dl = (lane == 0) ? 1.0 / NM : ipow(NM, ly.row0 - 1);
+    // backward: the carry into lane l is xs of the first row of lane l+1, which changes by -g xsz there
+    double Zl = __shfl_down_sync(FULL, xsz[0], 1);
+    if (lane == 31) Zl = 0.0;
+    // Contributions below 1e-30 of the leading one are dropped: the direct carries neglect terms below 1e-20 as
+    // well, and where they leave an exact zero (far out-of-the-money rows in the first steps) the correction must
+    // not turn it negative -- the reference's exercise test phi > vc (:496) is strict.
+    if (!(fabs(Dl) > 1e-30)) Dl = 0.0;
+    if (!(fabs(Zl) > 1e-30 * fabs(xs00))) Zl = 0.0;
+    ph.D = Dl;
+    ph.Zc = Zl;
     return !__any_sync(FULL, bad);
 }
 
+// direct carry, split in two so that independent work can be issued between the shuffles and their use
+template <bool UP>
+struct CarryShf {
+    double t[DIRECT_TERMS];
+    __device__ __forceinline__ void issue(const double e_end, const int terms)
+    {
+        if (terms) {
+            t[0] = UP ? __shfl_up_sync(FULL, e_end, 1) : __shfl_down_sync(FULL, e_end, 1);
+            t[1] = UP ? __shfl_up_sync(FULL, e_end, 2) : __shfl_down_sync(FULL, e_end, 2);
+            if (terms > 2) {
+                t[2] = UP ? __shfl_up_sync(FULL, e_end, 3) : __shfl_down_sync(FULL, e_end, 3);
+                t[3] = UP ? __shfl_up_sync(FULL, e_end, 4) : __shfl_down_sync(FULL, e_end, 4);
+            }
+            if (terms > 4) {
+                t[4] = UP ? __shfl_up_sync(FULL, e_end, 5) : __shfl_down_sync(FULL, e_end, 5);
+                t[5] = UP ? __shfl_up_sync(FULL, e_end, 6) : __shfl_down_sync(FULL, e_end, 6);
+            }
+        }
+    }
+    __device__ __forceinline__ double combine(const double e_end, const int terms, const double *__restrict__ W,
+                                              const double *__restrict__ A, const int lane) const
+    {
+        if (terms) {
+            double acc0 = W[0 * 32 + lane] * t[0], acc1 = W[1 * 32 + lane] * t[1];
+            if (terms > 2) { acc0 = fma(W[2 * 32 + lane], t[2], acc0); acc1 = fma(W[3 * 32 + lane], t[3], acc1); }
+            if (terms > 4) { acc0 = fma(W[4 * 32 + lane], t[4], acc0); acc1 = fma(W[5 * 32 + lane], t[5], acc1); }
+            return acc0 + acc1;
+        }
+        return lane_carry<UP>(e_end, 0, W, A, lane);        // Kogge-Stone scan
+    }
+};
+
 // One theta-scheme step.  V: vc (American) / V (linear) on entry and exit; L: 3 dt lambda (American) / scratch.
-// The optional last slot is handled without branches: on lanes that do not hold it its multipliers are 1 and its
-// V, L stay 0, which makes it the identity in both sweeps.
+// The optional last slot is handled without branches: on lanes that do not hold it its multipliers are 1 / 0 and
+// its V, L stay 0, which makes it the identity in both sweeps.
 template <int C, bool AMER>
-__device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const double (&z)[C], const Ph &ph,
-                                           const double cin_f, const double cin_b, const bool last,
-                                           const Tables<C> &T, const int lane)
+__device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const Ph<C> &ph, const double cin_f,
+                                           const double cin_b, const bool last, const Tables<C> &T, const int lane)
 {
-    constexpr int H = C / 2;
+    constexpr int H = C / 2, PW = C - H;
     const double NM = ph.NM, NCC = ph.NCC;
     const double nmL = last ? NM : 1.0, nccL = last ? NCC : 1.0;
     // right-hand side R (into V) and subtrahend G (into L)
@@ -259,38 +323,40 @@ __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const
 #pragma unroll
         for (int k = 0; k < C; ++k) L[k] = ph.q * V[k];
     }
-    // ---- forward elimination --------------------------------------------------------------------
-    double e1 = cin_f, e2 = 0.0;
+    // ---- forward local pass (zero carry-in; the Dirichlet term of row 0 is lane 0's own start value),
+    //      result u_loc kept in V ------------------------------------------------------------------------------
+    double a = cin_f, b = 0.0;
 #pragma unroll
-    for (int k = 0; k < H; ++k) e1 = fma(NM, e1, V[k]);
+    for (int k = 0; k < H; ++k) { a = fma(NM, a, V[k]); V[k] = a; }
 #pragma unroll
-    for (int k = H; k < C; ++k) e2 = fma(k < C - 1 ? NM : nmL, e2, V[k]);
-    double e_end = fma(ph.af2, e1, e2);
-    double cs = lane_carry<true>(e_end, ph.terms, T.Wf, T.Af, lane);
-    {
-        double c1 = cs + cin_f;
-        double c2 = fma(ph.af1, cs, e1);
-#pragma unroll
-        for (int k = 0; k < H; ++k) { c1 = fma(NM, c1, V[k]); V[k] = c1; }
-#pragma unroll
-        for (int k = H; k < C - 1; ++k) { c2 = fma(NM, c2, V[k]); V[k] = c2; }
-        c2 = fma(nmL, c2, V[C - 1]);
-        V[C - 1] = last ? c2 : 0.0;
-    }
-    // ---- back substitution -------------------------------------------------------------------------
-    e1 = cin_b;
-    e2 = 0.0;
+    for (int k = H; k < C - 1; ++k) { b = fma(NM, b, V[k]); V[k] = b; }
+    b = fma(nmL, b, V[C - 1]);
+    V[C - 1] = last ? b : 0.0;
+    const double af2 = last ? ph.P[PW] : ph.P[PW - 1];
+    const double e_end = fma(af2, a, b);
+    CarryShf<true> shf_f;
+    shf_f.issue(e_end, ph.terms);
+    // ---- backward local pass on u_loc, while the forward carries are in flight ------------------------
+    double e1 = cin_b, e2 = 0.0;
 #pragma unroll
     for (int k = C - 1; k >= H; --k) e1 = fma(k < C - 1 ? NCC : nccL, e1, V[k]);
 #pragma unroll
     for (int k = H - 1; k >= 0; --k) e2 = fma(NCC, e2, V[k]);
-    e_end = fma(ph.ab2, e1, e2);
-    cs = lane_carry<false>(e_end, ph.terms, T.Wb, T.Ab, lane);
-    // Sherman-Morrison: xs_0 is lane 0's inclusive end value
-    const double gamma = ph.kap * __shfl_sync(FULL, fma(ph.abl, cs, e_end), 0);
-    double c1 = cs + cin_b;
-    double c2 = fma(ph.ab1, cs, e1);
-    // slots in the order the two half-chains reach them: C-1, then (C-2, H-1), (C-3, H-2), ...
+    const double c_in = shf_f.combine(e_end, ph.terms, T.Wf, T.Af, lane);            // carry into slot 0
+    const double c_mid = fma(ph.P[H], c_in, a);                                      // carry into slot H (= u_{H-1})
+    // true u = u_loc + NM^(k+1) carry  =>  backward local ends pick up kap * carry
+    double e_end_b = fma(ph.ab2, fma(ph.kapU, c_mid, e1), fma(ph.kapL, c_in, e2));
+    CarryShf<false> shf_b;
+    shf_b.issue(e_end_b, ph.terms);
+    double cb = shf_b.combine(e_end_b, ph.terms, T.Wb, T.Ab, lane);
+    // Sherman-Morrison: g = delta x_0 from lane 0's inclusive end value xs_0; R_0 -= g
+    const double g = ph.kap * __shfl_sync(FULL, fma(ph.abl, cb, e_end_b), 0);
+    const double c_in2 = fma(-g, ph.D, c_in);
+    const double c_mid2 = fma(ph.P[H], c_in2, a);
+    cb = fma(-g, ph.Zc, cb);
+    double c1 = cb + cin_b;                                       // xs above the top slot
+    double c2 = fma(ph.ab1, cb, fma(ph.kapU, c_mid2, e1));        // xs of slot H
+    // ---- second passes: u = u_loc + P carry (independent), xs chain, projection --------------------------
     auto slot_of = [](const int i) -> int {
         if (i == 0) return C - 1;
         const int j = (i - 1) >> 1;
@@ -298,16 +364,29 @@ __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const
         if (!upper_exists) return H - 1 - ((i - 1) - (C - 1 - H));      // only the lower chain is left
         return ((i - 1) & 1) == 0 ? C - 2 - j : H - 1 - j;
     };
-    // the payoff of slot order[i + PF] is fetched while slot order[i] is finished (LDS latency off the chain)
-    constexpr int PF = 4;
+    constexpr int PF = 4;                                         // payoff prefetch distance (LDS latency off the chain)
     double pf[C + PF];
     if (AMER) {
 #pragma unroll
         for (int i = 0; i < PF; ++i) pf[i] = T.phi3[slot_of(i < C ? i : C - 1) * 32 + lane];
     }
-    auto finish = [&](const int i, const int k, const double xs, const bool keep) {
-        const double gp = fma(gamma, z[k], L[k]);
-        const double vc = fma(ph.INV, xs, -gp);
+    const double pL = last ? ph.P[PW] : 0.0;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        const int k = slot_of(i);
+        double xs;
+        bool keep = true;
+        if (k >= H) {
+            const double u = fma(k < C - 1 ? ph.P[k - H + 1] : pL, c_mid2, V[k]);
+            c1 = fma(k < C - 1 ? NCC : nccL, c1, u);
+            xs = c1;
+            keep = k < C - 1 ? true : last;
+        } else {
+            const double u = fma(ph.P[k + 1], c_in2, V[k]);
+            c2 = fma(NCC, c2, u);
+            xs = c2;
+        }
+        const double vc = fma(ph.INV, xs, -L[k]);
         if (AMER) {
             if (i + PF < C) pf[i + PF] = T.phi3[slot_of(i + PF) * 32 + lane];
             // exercise iff phi > vc (fd_american_option_pricer.py:496); Ls = 3 dt lambda_new = relu(3 phi - 3 vc)
@@ -316,17 +395,6 @@ __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const
             L[k] = __hiloint2double(__double2hiint(d) & msk, __double2loint(d) & msk);
         }
         V[k] = keep ? vc : 0.0;
-    };
-#pragma unroll
-    for (int i = 0; i < C; ++i) {
-        const int k = slot_of(i);
-        if (k >= H) {
-            c1 = fma(k < C - 1 ? NCC : nccL, c1, V[k]);
-            finish(i, k, c1, k < C - 1 ? true : last);
-        } else {
-            c2 = fma(NCC, c2, V[k]);
-            finish(i, k, c2, true);
-        }
     }
 }
 
@@ -334,15 +402,14 @@ __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const
 #define FDM_LEAN_MINB 0
 #endif
 template <int C>
-constexpr int min_blocks() { return FDM_LEAN_MINB ? FDM_LEAN_MINB : (C <= 8 ? 16 : 12); }
+constexpr int min_blocks() { return FDM_LEAN_MINB ? FDM_LEAN_MINB : (C <= 4 ? 24 : C <= 8 ? 20 : 16); }
 
 template <int C, bool AMER, bool TRACE>
 __global__ void __launch_bounds__(32, min_blocks<C>())
-fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int want_american, const int div_smem)
+fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int want_american)
 {
     extern __shared__ double smem[];
     const Tables<C> T(smem);
-    double *divbuf = T.end();
 
     const int64_t sid = first + blockIdx.x;
     if (sid >= B.n_solves) return;
@@ -366,7 +433,7 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
     const int rannacher = B.rannacher[sid];
 
     // ---- grid, snapping, payoff -------------------------------------------------------------
-    double V[C], L[C], z[C];
+    double V[C], L[C];
     const double s0 = node_s(x_min, dx, 0);
     const double sn = node_s(x_min, dx, n);
 #pragma unroll
@@ -398,8 +465,10 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
         V[k] = pv;                                              // terminal condition, :558
         L[k] = 0.0;
     }
-    // payoff of slot k to within one ulp (rare uses: dividend jump, read-out)
-    auto phi_at = [&](int k) -> double { return T.phi3[k * 32 + lane] * (1.0 / 3.0); };
+    // exact payoff of slot k, recomputed (rare uses: dividend jump, read-out); node_s is not inlined
+    auto phi_at = [&](int k) -> double {
+        return (k < ly.cnt) ? payoff(node_s(x_min, dx, ly.row0 + k + 1), k_eff, is_call) : 0.0;
+    };
     // value vector from the (vc, 3 dt lambda) state: V = phi where exercised (:497)
     auto materialise = [&]() {
         if (AMER) {
@@ -427,14 +496,14 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
     int next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
     int gstep = 0;
     int32_t *trace = (TRACE && O.ex_trace) ? O.ex_trace + sid * O.ex_trace_stride : nullptr;
+    // solves with a dividend jump go to fdm_warp_kernel (its spline scratch would cut this kernel's occupancy)
     bool retry = false;
+    for (int seg = seg_b; seg < seg_e; ++seg) retry |= B.seg_div[seg] != 0.0;
 
     for (int seg = seg_b; seg < seg_e && !retry; ++seg) {
         const int n_steps = B.seg_steps[seg];
         const double dt = B.seg_dt[seg];
-        const double tau0 = B.seg_tau0[seg];
         const int base_ran = B.seg_restart[seg] ? rannacher : 0;   // :464
-        const double cash = B.seg_div[seg];
         if (AMER) {
 #pragma unroll
             for (int k = 0; k < C; ++k) L[k] = 0.0;             // lambda restarts every segment, :463
@@ -462,8 +531,8 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
         while (m < n_steps) {
             const bool implicit_phase = m < base_ran;
             const int m_end = implicit_phase ? min(base_ran, n_steps) : n_steps;
-            Ph ph;
-            if (!setup_phase<C, AMER>(implicit_phase ? 1.0 : 0.5, dt, ca, cc, bcoef, n_int, lane, ly, z, T, ph)) {
+            Ph<C> ph;
+            if (!setup_phase<C, AMER>(implicit_phase ? 1.0 : 0.5, dt, ca, cc, bcoef, n_int, lane, ly, T, ph)) {
                 retry = true;
                 break;
             }
@@ -473,7 +542,7 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
                 const double w_now = w_next;
                 w_next = fetch_boundary(m + 1);
                 double cin_n = ph.cB * w_now - ph.cA * w_next;
-                march_step<C, AMER>(V, L, z, ph, (lane == 0) ? cin : 0.0, (lane == 31) ? cin : 0.0, last, T, lane);
+                march_step<C, AMER>(V, L, ph, (lane == 0) ? cin : 0.0, (lane == 31) ? cin : 0.0, last, T, lane);
                 Vb = w_now;                                     // V[0] = V_min, V[-1] = V_max, :505-506
                 ++gstep;
                 if (TRACE && trace) {
@@ -509,25 +578,6 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
             }
         }
         if (retry) break;
-        if (cash != 0.0) {
-            materialise();
-            if (div_smem) {
-                double *xs = divbuf;
-                double *ys = xs + (32 * C + 2);
-                double *mu = ys + (32 * C + 2);
-                double *cz = mu + (32 * C + 2);
-                double V0 = __shfl_sync(FULL, Vb, 0), VN = __shfl_sync(FULL, Vb, 31);
-                dividend_jump<C>(V, V0, VN, phi_at, phi0, phin, cash, is_call, n, lane, ly, x_min, dx, xs, ys, mu, cz);
-                Vb = (lane == 0) ? V0 : ((lane == 31) ? VN : 0.0);
-            } else {
-#pragma unroll
-                for (int k = 0; k < C; ++k) V[k] = NAN;
-            }
-            if (AMER) {
-#pragma unroll
-                for (int k = 0; k < C; ++k) L[k] = 0.0;
-            }
-        }
     }
     if (retry) {
         if (lane == 0) O.price[sid] = __longlong_as_double((long long)RETRY_BITS);

@@ -8,3 +8,6 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 40000
 timeit("american b76 500x500", american(n, 500, 500, True))
 timeit("american eq 400x400", american(n, 400, 400, False))
 timeit("barrier 400x400", barrier(n, 400, 400))
+timeit("american eq 300x300", american(n, 300, 300, False))
+timeit("barrier 300x544", barrier(n, 300, 544))
+timeit("american eq 320x320", american(n, 320, 320, False))
