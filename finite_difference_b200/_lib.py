@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(_HERE, "libfdm_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 FLAG_CALL = 0x01
 FLAG_AMERICAN = 0x02
@@ -19,6 +19,8 @@ FLAG_BLACK76 = 0x04
 FLAG_SNAP = 0x08
 FLAG_KO_DOWN = 0x10
 FLAG_KO_UP = 0x20
+FLAG_BDRY_TOP_NEXT = 0x40
+FLAG_PUT_BDRY_SMIN = 0x80
 
 MAX_N_SPACE = 8193
 WARP_MAX_N_SPACE = 513
@@ -40,6 +42,7 @@ class FdmBatch(C.Structure):
         ("rannacher", C.c_void_p), ("seg_begin", C.c_void_p), ("mon_begin", C.c_void_p),
         ("seg_steps", C.c_void_p), ("seg_dt", C.c_void_p), ("seg_tau0", C.c_void_p),
         ("seg_restart", C.c_void_p), ("seg_div", C.c_void_p), ("mon_step", C.c_void_p),
+        ("b_bdry", C.c_void_p), ("barrier_up", C.c_void_p), ("mon_rebate", C.c_void_p),
     ]
 
 
@@ -69,7 +72,7 @@ class FdmBookOut(C.Structure):
 
 BOOK_PRICE_LOG, BOOK_PRICE_LOG2, BOOK_GREEKS_LOG2, BOOK_SCENARIO = 0, 1, 2, 3
 
-EXPORTS = ("fdm_version", "fdm_last_error", "fdm_device_count", "fdm_solve_batch",
+EXPORTS = ("fdm_version", "fdm_sizeof", "fdm_last_error", "fdm_device_count", "fdm_solve_batch",
            "fdm_solve_batch_host", "fdm_launch_hints", "fdm_book_solves_per_option", "fdm_american_book_host", "fdm_release_workspace", "fdm_fp64_peak")
 
 
@@ -98,6 +101,8 @@ def load(path: str | None = None):
                            "(nvcc, sm_100a).  finite_difference_b200 has no CPU fallback.")
     L = C.CDLL(path)
     L.fdm_version.restype = C.c_int
+    L.fdm_sizeof.restype = C.c_int
+    L.fdm_sizeof.argtypes = [C.c_int]
     L.fdm_last_error.restype = C.c_char_p
     L.fdm_device_count.restype = C.c_int
     L.fdm_solve_batch.restype = C.c_int

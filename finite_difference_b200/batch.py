@@ -48,6 +48,10 @@ class SolveBatch:
     rebate: Optional[np.ndarray] = None
     mon_begin: Optional[np.ndarray] = None   # CSR, n+1
     mon_step: Optional[np.ndarray] = None
+    # ABI 2 (optional): carry rate inside the Dirichlet values, upper level of a double-out, per-monitor rebate value
+    b_bdry: Optional[np.ndarray] = None
+    barrier_up: Optional[np.ndarray] = None
+    mon_rebate: Optional[np.ndarray] = None
 
     def __post_init__(self):
         n = len(self.x_min)
@@ -68,6 +72,17 @@ class SolveBatch:
             self.mon_step = np.ascontiguousarray(self.mon_step, dtype=np.int32)
         if (self.barrier is None) != (self.rebate is None):
             raise ValueError("barrier and rebate must be given together")
+        for name in ("b_bdry", "barrier_up"):
+            v = getattr(self, name)
+            if v is not None:
+                v = np.ascontiguousarray(v, dtype=np.float64)
+                if len(v) != n:
+                    raise ValueError(f"{name}: expected {n} entries, got {len(v)}")
+                setattr(self, name, v)
+        if self.mon_rebate is not None:
+            self.mon_rebate = np.ascontiguousarray(self.mon_rebate, dtype=np.float64)
+            if self.mon_step is None or len(self.mon_rebate) != len(self.mon_step):
+                raise ValueError("mon_rebate needs one entry per mon_step entry")
         for name in _F64 + _I32:
             v = getattr(self, name)
             if v is not None and len(v) != n:
@@ -132,9 +147,12 @@ class SolveBatch:
 
         seg_begin, (ss, sd, st, sr, sv) = csr(self.seg_begin, self.seg_steps, self.seg_dt,
                                               self.seg_tau0, self.seg_restart, self.seg_div)
-        mon_begin = mon_step = None
+        mon_begin = mon_step = mon_rebate = None
         if self.mon_begin is not None:
-            mon_begin, (mon_step,) = csr(self.mon_begin, self.mon_step)
+            if self.mon_rebate is not None:
+                mon_begin, (mon_step, mon_rebate) = csr(self.mon_begin, self.mon_step, self.mon_rebate)
+            else:
+                mon_begin, (mon_step,) = csr(self.mon_begin, self.mon_step)
         return SolveBatch(
             x_min=self.x_min[sel], dx=self.dx[sel], sigma=self.sigma[sel], r=self.r[sel], b=self.b[sel],
             spot=self.spot[sel], strike=self.strike[sel], n_space=self.n_space[sel],
@@ -142,7 +160,9 @@ class SolveBatch:
             seg_steps=ss, seg_dt=sd, seg_tau0=st, seg_restart=sr, seg_div=sv,
             barrier=None if self.barrier is None else self.barrier[sel],
             rebate=None if self.rebate is None else self.rebate[sel],
-            mon_begin=mon_begin, mon_step=mon_step)
+            mon_begin=mon_begin, mon_step=mon_step,
+            b_bdry=None if self.b_bdry is None else self.b_bdry[sel],
+            barrier_up=None if self.barrier_up is None else self.barrier_up[sel], mon_rebate=mon_rebate)
 
     @staticmethod
     def concat(parts: Sequence["SolveBatch"]) -> "SolveBatch":
@@ -169,11 +189,29 @@ class SolveBatch:
                 off += int(bg[-1])
             return np.concatenate(out).astype(np.int32)
 
-        mon_begin = mon_step = None
+        mon_begin = mon_step = mon_rebate = None
         if has_mon:
             mon_begin = cat_csr("mon_begin", None)
             mon_step = np.concatenate([p.mon_step if p.mon_step is not None else np.zeros(0, np.int32)
                                        for p in parts])
+            if any(p.mon_rebate is not None for p in parts):
+                # parts without per-monitor values repeat their per-solve rebate
+                def per_mon(p):
+                    if p.mon_step is None:
+                        return np.zeros(0)
+                    if p.mon_rebate is not None:
+                        return p.mon_rebate
+                    reb = p.rebate if p.rebate is not None else np.zeros(p.n_solves)
+                    return np.repeat(reb, np.diff(p.mon_begin))
+                mon_rebate = np.concatenate([per_mon(p) for p in parts])
+        b_bdry = None
+        if any(p.b_bdry is not None for p in parts):
+            b_bdry = np.concatenate([p.b_bdry if p.b_bdry is not None else p.b for p in parts])
+        barrier_up = None
+        if any(p.barrier_up is not None for p in parts):
+            barrier_up = np.concatenate([p.barrier_up if p.barrier_up is not None
+                                         else (p.barrier if p.barrier is not None else np.zeros(p.n_solves))
+                                         for p in parts])
         return SolveBatch(
             x_min=cat("x_min"), dx=cat("dx"), sigma=cat("sigma"), r=cat("r"), b=cat("b"),
             spot=cat("spot"), strike=cat("strike"), n_space=cat("n_space"), flags=cat("flags"),
@@ -182,7 +220,7 @@ class SolveBatch:
             seg_restart=cat("seg_restart"), seg_div=cat("seg_div"),
             barrier=cat_opt("barrier") if has_ko else None,
             rebate=cat_opt("rebate") if has_ko else None,
-            mon_begin=mon_begin, mon_step=mon_step)
+            mon_begin=mon_begin, mon_step=mon_step, b_bdry=b_bdry, barrier_up=barrier_up, mon_rebate=mon_rebate)
 
     # ------------------------------------------------------------------
     def _struct(self, ptr) -> FdmBatch:
@@ -194,7 +232,7 @@ class SolveBatch:
         s.n_mon_total = 0 if self.mon_step is None else len(self.mon_step)
         s.reserved = self.family_mask()
         for name in _F64 + _I32 + ("seg_begin", "seg_steps", "seg_dt", "seg_tau0", "seg_restart",
-                                   "seg_div", "mon_begin", "mon_step"):
+                                   "seg_div", "mon_begin", "mon_step", "b_bdry", "barrier_up", "mon_rebate"):
             arr = getattr(self, name)
             setattr(s, name, None if arr is None else ptr(name, arr))
         return s

@@ -104,8 +104,11 @@ __device__ __forceinline__ double payoff(double s, double k, bool is_call)
 
 // Dirichlet values at time-to-maturity tau: fd_american_option_pricer.py:286-298,
 // fd_american_black76.py:291-314, discrete_barrier_fdm_pricer_cn.py:153-171.
+// put_smin: the date-aware barrier pricer's put value K e^{-r tau} * S_min * e^{(b-r) tau}
+// (discrete_barrier_fdm_pricer.py:391, evaluated left to right).
 __device__ __forceinline__ void boundary_values(bool is_call, bool b76, double r, double b, double k,
-                                                double s_top, double tau, double &vmin, double &vmax)
+                                                double s_top, double tau, double &vmin, double &vmax,
+                                                bool put_smin = false, double s_bot = 0.0)
 {
     if (b76) {
         double disc = exp(__dmul_rn(-r, tau));
@@ -117,7 +120,49 @@ __device__ __forceinline__ void boundary_values(bool is_call, bool b76, double r
                          __dmul_rn(k, exp(__dmul_rn(-r, tau))));
     } else {
         vmin = __dmul_rn(k, exp(__dmul_rn(-r, tau)));
+        if (put_smin) vmin = __dmul_rn(__dmul_rn(vmin, s_bot), exp(__dmul_rn(__dsub_rn(b, r), tau)));
         vmax = 0.0;
+    }
+}
+
+// largest node index j in [-1, n] with s_j <= level (-1: none)
+__device__ __forceinline__ int last_node_le(double x_min, double dx, int n, double level)
+{
+    if (!(level > 0.0)) return -1;
+    double xj = (log(level) - x_min) / dx;
+    if (xj < -2.0) return -1;
+    if (xj > (double)n + 2.0) return n;
+    int j = min(max((int)floor(xj), -1), n);
+    while (j + 1 <= n && node_s(x_min, dx, j + 1) <= level) ++j;
+    while (j >= 0 && node_s(x_min, dx, j) > level) --j;
+    return j;
+}
+
+// smallest node index j in [0, n+1] with s_j >= level (n+1: none)
+__device__ __forceinline__ int first_node_ge(double x_min, double dx, int n, double level)
+{
+    if (!(level > 0.0)) return 0;
+    double xj = (log(level) - x_min) / dx;
+    if (xj < -2.0) return 0;
+    if (xj > (double)n + 2.0) return n + 1;
+    int j = min(max((int)ceil(xj), 0), n + 1);
+    while (j - 1 >= 0 && node_s(x_min, dx, j - 1) >= level) --j;
+    while (j <= n && node_s(x_min, dx, j) < level) ++j;
+    return j;
+}
+
+// Knock-out set of a solve as two thresholds: node j is knocked out iff j <= ko_a or j >= ko_b
+// (discrete_barrier_fdm_pricer_cn.py:203-213; double-out: discrete_barrier_fdm_pricer.py:433-435).
+__device__ __forceinline__ void ko_thresholds(const FdmBatch &B, int64_t sid, int flags, double x_min, double dx, int n,
+                                              int &ko_a, int &ko_b)
+{
+    ko_a = -1;
+    ko_b = n + 1;
+    const bool dn = flags & FDM_FLAG_KO_DOWN, up = flags & FDM_FLAG_KO_UP;
+    if (dn && B.barrier) ko_a = last_node_le(x_min, dx, n, B.barrier[sid]);
+    if (up) {
+        const double *lv = (dn && B.barrier_up) ? B.barrier_up : B.barrier;
+        if (lv) ko_b = first_node_ge(x_min, dx, n, lv[sid]);
     }
 }
 
@@ -686,7 +731,7 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
     const bool is_call = flags & FDM_FLAG_CALL;
     const bool b76 = flags & FDM_FLAG_BLACK76;
     const bool snap = flags & FDM_FLAG_SNAP;
-    const int ko = (flags & FDM_FLAG_KO_DOWN) ? 1 : ((flags & FDM_FLAG_KO_UP) ? 2 : 0);
+    const bool ko = flags & (FDM_FLAG_KO_DOWN | FDM_FLAG_KO_UP);
 
     const double x_min = B.x_min[sid];
     const double dx = B.dx[sid];
@@ -695,7 +740,6 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
     const double bcar = B.b[sid];
     const double spot = B.spot[sid];
     const double strike = B.strike[sid];
-    const double barrier = (ko && B.barrier) ? B.barrier[sid] : 0.0;
     const double rebate = (ko && B.rebate) ? B.rebate[sid] : 0.0;
     const int rannacher = B.rannacher[sid];
 
@@ -715,25 +759,11 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
         strike_idx = argmin_node<C>(phi, s0, sn, strike, n, ly, false);
         k_eff = node_s(x_min, dx, strike_idx);                  // fd_american_option_pricer.py:272-275
     }
-    // KO region as a node index interval [ko_lo, ko_hi]
-    int ko_lo = 1, ko_hi = 0;
-    if (ko) {
-        int cnt = 0;
-#pragma unroll
-        for (int k = 0; k < C; ++k) {
-            const int j = lane * C + k + 1;
-            if (j <= n - 1) cnt += (ko == 1) ? (phi[k] <= barrier) : (phi[k] >= barrier);
-        }
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
-        if (ko == 1) {      // nodes with s <= B: 0 .. (count-1), s is increasing
-            const int c0 = (s0 <= barrier) + cnt + (sn <= barrier);
-            ko_lo = 0; ko_hi = c0 - 1;
-        } else {            // nodes with s >= B: n-count+1 .. n
-            const int c0 = (s0 >= barrier) + cnt + (sn >= barrier);
-            ko_lo = n - c0 + 1; ko_hi = n;
-        }
-    }
+    int ko_a, ko_b;
+    ko_thresholds(B, sid, flags, x_min, dx, n, ko_a, ko_b);
+    const bool put_smin = flags & FDM_FLAG_PUT_BDRY_SMIN;
+    const double sn_bdry = (flags & FDM_FLAG_BDRY_TOP_NEXT) ? node_s(x_min, dx, n + 1) : sn;
+    const double b_bdry = B.b_bdry ? B.b_bdry[sid] : bcar;
     const double phi0 = payoff(s0, k_eff, is_call);
     const double phin = payoff(sn, k_eff, is_call);
 #pragma unroll
@@ -791,7 +821,7 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
                 fill_base = step;
                 const double tau = fma((double)(step + lane + 1), dt, tau0);
                 double vmin, vmax;
-                boundary_values(is_call, b76, r, bcar, k_eff, sn, tau, vmin, vmax);
+                boundary_values(is_call, b76, r, b_bdry, k_eff, sn_bdry, tau, vmin, vmax, put_smin, s0);
                 my_w = is_call ? vmax : vmin;
             }
             const double w = __shfl_sync(FULL, my_w, step - fill_base);
@@ -831,13 +861,14 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
                     }
                 }
                 if (gstep == next_mon) {                        // discrete_barrier_fdm_pricer_cn.py:299-300
+                    const double reb = B.mon_rebate ? B.mon_rebate[mon_i] : rebate;
 #pragma unroll
                     for (int k = 0; k < C; ++k) {
                         const int j = lane * C + k + 1;
-                        if (j <= n - 1 && j >= ko_lo && j <= ko_hi) V[k] = rebate;
+                        if (j <= n - 1 && (j <= ko_a || j >= ko_b)) V[k] = reb;
                     }
-                    if (lane == 0 && ko_lo <= 0 && 0 <= ko_hi) Vb = rebate;
-                    if (lane == 31 && ko_lo <= n && n <= ko_hi) Vb = rebate;
+                    if (lane == 0 && 0 <= ko_a) Vb = reb;
+                    if (lane == 31 && n >= ko_b) Vb = reb;
                     ++mon_i;
                     next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
                     cin_n = ph.cB * Vb - ph.cA * w_next;
@@ -1217,6 +1248,17 @@ extern "C" {
 
 int fdm_version(void) { return FDM_ABI_VERSION; }
 
+int fdm_sizeof(int which)
+{
+    switch (which) {
+    case 0: return (int)sizeof(FdmBatch);
+    case 1: return (int)sizeof(FdmOut);
+    case 2: return (int)sizeof(FdmAmericanBook);
+    case 3: return (int)sizeof(FdmBookOut);
+    default: return -1;
+    }
+}
+
 const char *fdm_last_error(void) { return g_err; }
 
 int fdm_device_count(void)
@@ -1272,6 +1314,8 @@ int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launch
     const size_t o_segb = take((n + 1) * 4), o_monb = take(nmon ? (n + 1) * 4 : 0);
     const size_t o_ssteps = take(nseg * 4), o_sdt = take(nseg * 8), o_stau = take(nseg * 8);
     const size_t o_srst = take(nseg * 4), o_sdiv = take(nseg * 8), o_mon = take(nmon * 4);
+    const size_t o_bb = take(hb->b_bdry ? n * 8 : 0), o_bup = take(hb->barrier_up ? n * 8 : 0);
+    const size_t o_mreb = take((hb->mon_rebate && nmon) ? nmon * 8 : 0);
     const size_t in_bytes = off;
     const size_t r_price = take(n * 8), r_delta = take(n * 8), r_gamma = take(n * 8);
     const size_t r_sv = take(n * 32), r_ss = take(n * 32), r_idx = take(n * 16), r_status = take(n * 4);
@@ -1311,6 +1355,9 @@ int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launch
     h2d(o_srst, hb->seg_restart, nseg * 4);
     h2d(o_sdiv, hb->seg_div, nseg * 8);
     if (nmon) h2d(o_mon, hb->mon_step, nmon * 4);
+    if (hb->b_bdry) h2d(o_bb, hb->b_bdry, n * 8);
+    if (hb->barrier_up) h2d(o_bup, hb->barrier_up, n * 8);
+    if (hb->mon_rebate && nmon) h2d(o_mreb, hb->mon_rebate, nmon * 8);
 
     FdmBatch db = *hb;
     db.x_min = (const double *)(arena + o_d[0]);
@@ -1333,6 +1380,9 @@ int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launch
     db.seg_restart = (const int32_t *)(arena + o_srst);
     db.seg_div = (const double *)(arena + o_sdiv);
     db.mon_step = nmon ? (const int32_t *)(arena + o_mon) : nullptr;
+    db.b_bdry = hb->b_bdry ? (const double *)(arena + o_bb) : nullptr;
+    db.barrier_up = hb->barrier_up ? (const double *)(arena + o_bup) : nullptr;
+    db.mon_rebate = (hb->mon_rebate && nmon) ? (const double *)(arena + o_mreb) : nullptr;
 
     FdmOut dout = *ho;
     dout.price = (double *)(arena + r_price);

@@ -43,32 +43,6 @@ __device__ __forceinline__ int nearest_node(double x_min, double dx, int n, doub
     return bidx;
 }
 
-// largest node index j in [-1, n] with s_j <= level (-1: none)
-__device__ __forceinline__ int last_node_le(double x_min, double dx, int n, double level)
-{
-    if (!(level > 0.0)) return -1;
-    double xj = (log(level) - x_min) / dx;
-    if (xj < -2.0) return -1;
-    if (xj > (double)n + 2.0) return n;
-    int j = min(max((int)floor(xj), -1), n);
-    while (j + 1 <= n && node_s(x_min, dx, j + 1) <= level) ++j;
-    while (j >= 0 && node_s(x_min, dx, j) > level) --j;
-    return j;
-}
-
-// smallest node index j in [0, n+1] with s_j >= level (n+1: none)
-__device__ __forceinline__ int first_node_ge(double x_min, double dx, int n, double level)
-{
-    if (!(level > 0.0)) return 0;
-    double xj = (log(level) - x_min) / dx;
-    if (xj < -2.0) return 0;
-    if (xj > (double)n + 2.0) return n + 1;
-    int j = min(max((int)ceil(xj), 0), n + 1);
-    while (j - 1 >= 0 && node_s(x_min, dx, j - 1) >= level) --j;
-    while (j <= n && node_s(x_min, dx, j) < level) ++j;
-    return j;
-}
-
 template <int C, int WARPS>
 struct Layout {
     static constexpr int NT = 32 * WARPS;
@@ -512,30 +486,31 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
     const bool is_call = flags & FDM_FLAG_CALL;
     const bool b76 = flags & FDM_FLAG_BLACK76;
     const bool snap = flags & FDM_FLAG_SNAP;
-    const int ko = (flags & FDM_FLAG_KO_DOWN) ? 1 : ((flags & FDM_FLAG_KO_UP) ? 2 : 0);
+    const bool ko = flags & (FDM_FLAG_KO_DOWN | FDM_FLAG_KO_UP);
     const double x_min = B.x_min[sid], dx = B.dx[sid], sigma = B.sigma[sid], r = B.r[sid], bcar = B.b[sid];
     const double spot = B.spot[sid], strike = B.strike[sid];
-    const double barrier = (ko && B.barrier) ? B.barrier[sid] : 0.0;
     const double rebate = (ko && B.rebate) ? B.rebate[sid] : 0.0;
     const int rannacher = B.rannacher[sid];
     const int t0 = pad / C;                            // thread that owns row 0 (and boundary node 0)
     const int k0 = (t == t0) ? pad % C : -1;
 
     if (t == 0) {
-        int spot_idx = 0, strike_idx = 0, klo = 1, khi = 0;
+        int spot_idx = 0, strike_idx = 0, ka, kb;
         if (snap) {
             spot_idx = nearest_node(x_min, dx, n, spot, false);
             strike_idx = nearest_node(x_min, dx, n, strike, false);
         }
-        if (ko == 1) { klo = 0; khi = last_node_le(x_min, dx, n, barrier); }
-        if (ko == 2) { klo = first_node_ge(x_min, dx, n, barrier); khi = n; }
-        sm.ish[1] = spot_idx; sm.ish[2] = strike_idx; sm.ish[3] = klo; sm.ish[4] = khi;
+        ko_thresholds(B, sid, flags, x_min, dx, n, ka, kb);
+        sm.ish[1] = spot_idx; sm.ish[2] = strike_idx; sm.ish[3] = ka; sm.ish[4] = kb;
         sm.ish[5] = 0; sm.ish[6] = 0x7fffffff; sm.ish[7] = -1;
     }
     __syncthreads();
-    const int spot_idx = sm.ish[1], strike_idx = sm.ish[2], ko_lo = sm.ish[3], ko_hi = sm.ish[4];
+    const int spot_idx = sm.ish[1], strike_idx = sm.ish[2], ko_a = sm.ish[3], ko_b = sm.ish[4];
     const double k_eff = snap ? node_s(x_min, dx, strike_idx) : strike;
     const double sn = node_s(x_min, dx, n);
+    const bool put_smin = flags & FDM_FLAG_PUT_BDRY_SMIN;
+    const double sn_bdry = (flags & FDM_FLAG_BDRY_TOP_NEXT) ? node_s(x_min, dx, n + 1) : sn;
+    const double b_bdry = B.b_bdry ? B.b_bdry[sid] : bcar;
 
     double V[C], L[C];
     auto fill_payoff = [&](bool set_v) {
@@ -589,7 +564,7 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                 fill_base = step;
                 const double tau = fma((double)(step + lane + 1), dt, tau0);
                 double vmin, vmax;
-                boundary_values(is_call, b76, r, bcar, k_eff, sn, tau, vmin, vmax);
+                boundary_values(is_call, b76, r, b_bdry, k_eff, sn_bdry, tau, vmin, vmax, put_smin, node_s(x_min, dx, 0));
                 __syncwarp();
                 sm.wb[lane] = is_call ? vmax : vmin;
                 __syncwarp();
@@ -639,13 +614,14 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                     }
                 }
                 if (gstep == next_mon) {                        // discrete_barrier_fdm_pricer_cn.py:299-300
+                    const double reb = B.mon_rebate ? B.mon_rebate[mon_i] : rebate;
 #pragma unroll
                     for (int k = 0; k < C; ++k) {
                         const int j = t * C + k - pad + 1;
-                        if (j >= 1 && j >= ko_lo && j <= ko_hi) V[k] = rebate;
+                        if (j >= 1 && (j <= ko_a || j >= ko_b)) V[k] = reb;
                     }
-                    if (t == t0 && ko_lo <= 0 && 0 <= ko_hi) Vb = rebate;
-                    if (t == NT - 1 && ko_lo <= n && n <= ko_hi) Vb = rebate;
+                    if (t == t0 && 0 <= ko_a) Vb = reb;
+                    if (t == NT - 1 && n >= ko_b) Vb = reb;
                     ++mon_i;
                     next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
                     cin_n = ph.cB * Vb - ph.cA * w_next;

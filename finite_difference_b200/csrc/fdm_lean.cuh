@@ -424,11 +424,10 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
     const bool is_call = flags & FDM_FLAG_CALL;
     const bool b76 = flags & FDM_FLAG_BLACK76;
     const bool snap = flags & FDM_FLAG_SNAP;
-    const int ko = (flags & FDM_FLAG_KO_DOWN) ? 1 : ((flags & FDM_FLAG_KO_UP) ? 2 : 0);
+    const bool ko = flags & (FDM_FLAG_KO_DOWN | FDM_FLAG_KO_UP);
 
     const double x_min = B.x_min[sid], dx = B.dx[sid], sigma = B.sigma[sid], r = B.r[sid], bcar = B.b[sid];
     const double spot = B.spot[sid], strike = B.strike[sid];
-    const double barrier = (ko && B.barrier) ? B.barrier[sid] : 0.0;
     const double rebate = (ko && B.rebate) ? B.rebate[sid] : 0.0;
     const int rannacher = B.rannacher[sid];
 
@@ -445,17 +444,9 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
         strike_idx = argmin_node<C>(V, s0, sn, strike, n, ly, false);
         k_eff = node_s(x_min, dx, strike_idx);                  // fd_american_option_pricer.py:272-275
     }
-    int ko_lo = 1, ko_hi = 0;
-    if (ko) {
-        int cnt = 0;
-#pragma unroll
-        for (int k = 0; k < C; ++k)
-            if (k < ly.cnt) cnt += (ko == 1) ? (V[k] <= barrier) : (V[k] >= barrier);
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
-        if (ko == 1) { ko_lo = 0; ko_hi = (s0 <= barrier) + cnt + (sn <= barrier) - 1; }
-        else         { ko_lo = n - ((s0 >= barrier) + cnt + (sn >= barrier)) + 1; ko_hi = n; }
-    }
+    int ko_a, ko_b;
+    ko_thresholds(B, sid, flags, x_min, dx, n, ko_a, ko_b);
+    const bool put_smin = flags & FDM_FLAG_PUT_BDRY_SMIN;
     const double phi0 = payoff(s0, k_eff, is_call);
     const double phin = payoff(sn, k_eff, is_call);
 #pragma unroll
@@ -478,7 +469,11 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
     };
     double Vb = (lane == 0) ? phi0 : ((lane == 31) ? phin : 0.0);
     const bool bdry_lane = is_call ? (lane == 31) : (lane == 0);
-    if (lane == 0) { T.par[0] = k_eff; T.par[1] = sn; }
+    if (lane == 0) {
+        T.par[0] = k_eff;
+        T.par[1] = (flags & FDM_FLAG_BDRY_TOP_NEXT) ? node_s(x_min, dx, n + 1) : sn;
+        T.par[2] = s0;
+    }
     __syncwarp();
 
     // ---- operator coefficients, fd_american_option_pricer.py:413-426 -------------------------
@@ -518,11 +513,11 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
                 const double dt_ = *(volatile const double *)&B.seg_dt[seg];
                 const double tau0_ = *(volatile const double *)&B.seg_tau0[seg];
                 const double r_ = *(volatile const double *)&B.r[sid];
-                const double b_ = *(volatile const double *)&B.b[sid];
+                const double b_ = B.b_bdry ? *(volatile const double *)&B.b_bdry[sid] : *(volatile const double *)&B.b[sid];
                 const double tau = fma((double)(step + lane + 1), dt_, tau0_);
                 double vmin, vmax;
                 boundary_values(is_call, b76, r_, b_, ((volatile double *)T.par)[0], ((volatile double *)T.par)[1], tau,
-                                vmin, vmax);
+                                vmin, vmax, put_smin, ((volatile double *)T.par)[2]);
                 my_w = is_call ? vmax : vmin;
             }
             const double w = __shfl_sync(FULL, my_w, step - fill_base);
@@ -563,13 +558,14 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
                     }
                 }
                 if (gstep == next_mon) {                        // discrete_barrier_fdm_pricer_cn.py:299-300
+                    const double reb = B.mon_rebate ? B.mon_rebate[mon_i] : rebate;
 #pragma unroll
                     for (int k = 0; k < C; ++k) {
                         const int j = ly.row0 + k + 1;
-                        if (k < ly.cnt && j >= ko_lo && j <= ko_hi) V[k] = rebate;
+                        if (k < ly.cnt && (j <= ko_a || j >= ko_b)) V[k] = reb;
                     }
-                    if (lane == 0 && ko_lo <= 0 && 0 <= ko_hi) Vb = rebate;
-                    if (lane == 31 && ko_lo <= n && n <= ko_hi) Vb = rebate;
+                    if (lane == 0 && 0 <= ko_a) Vb = reb;
+                    if (lane == 31 && n >= ko_b) Vb = reb;
                     ++mon_i;
                     next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
                     cin_n = ph.cB * Vb - ph.cA * w_next;

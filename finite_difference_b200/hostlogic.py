@@ -4,7 +4,7 @@ constructor and the time loop, restated as (a) scalar functions that follow the 
 numpy-vectorised builders for large batches.
 
 Reference line numbers: AM = fd_american_option_pricer.py, B76 = fd_american_black76.py,
-BAR = discrete_barrier_fdm_pricer_cn.py (lines 1-537).
+BAR = discrete_barrier_fdm_pricer_cn.py (lines 1-537), DBF = discrete_barrier_fdm_pricer.py (lines 1-745, 883-1027).
 """
 from __future__ import annotations
 
@@ -13,7 +13,8 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from ._lib import FLAG_AMERICAN, FLAG_BLACK76, FLAG_CALL, FLAG_KO_DOWN, FLAG_KO_UP, FLAG_SNAP
+from ._lib import (FLAG_AMERICAN, FLAG_BLACK76, FLAG_BDRY_TOP_NEXT, FLAG_CALL, FLAG_KO_DOWN, FLAG_KO_UP,
+                   FLAG_PUT_BDRY_SMIN, FLAG_SNAP)
 from .batch import SolveBatch
 
 # --------------------------------------------------------------------------------------
@@ -316,3 +317,107 @@ def build_barrier_batch(S0, K, T, sigma, r_disc, b_carry, is_call, ko_type: Sequ
         seg_begin=np.arange(n + 1, dtype=np.int32), seg_steps=N_time.astype(np.int32),
         seg_dt=T / N_time, seg_tau0=np.zeros(n), seg_restart=np.zeros(n, dtype=np.int32),
         seg_div=np.zeros(n), barrier=level, rebate=rebate, mon_begin=mon_begin, mon_step=mon_step)
+
+
+# --------------------------------------------------------------------------------------
+# Date/curve-aware barrier pricer DiscreteBarrierFDMPricer (DBF)
+# --------------------------------------------------------------------------------------
+
+
+def dbfp_grid_parameters(S0: float, K: float, lower_barrier, upper_barrier, T: float, sigma: float, N_time: int,
+                         k_ppf: float) -> Tuple[int, int, float, float]:
+    """``choose_grid_parameters`` (DBF:270-320): ``(N_space, N_time, S_min, S_max)``.  ``k_ppf`` is
+    ``scipy.stats.norm.ppf(0.99999)``; ``T`` is ``time_to_expiry``."""
+    candidates = [S0, K]
+    if lower_barrier is not None and lower_barrier > 0.0:
+        candidates.append(lower_barrier)
+    if upper_barrier is not None and upper_barrier > 0.0:
+        candidates.append(upper_barrier)
+    s_low = min(candidates)
+    s_high = max(candidates)
+    domain_width = 2.0 * k_ppf * sigma * math.sqrt(T)
+    s_c = math.sqrt(s_low * s_high)
+    x_c = math.log(s_c)
+    x_min = x_c - 0.5 * domain_width
+    x_max = x_c + 0.5 * domain_width
+    S_min = math.exp(x_min)
+    S_max = math.exp(x_max)
+    S_min = min(S_min, 0.5 * s_low)
+    S_max = max(S_max, 2 * s_high)
+    N_space = math.ceil((domain_width * N_time) / (2 * sigma * math.sqrt(T)))
+    return N_space, N_time, S_min, S_max
+
+
+def dbfp_monitor_steps(T: float, dt: float, num_time_steps: int, monitor_times) -> List[int]:
+    """``_monitor_indices_tau`` (DBF:395-411), sorted: floor mapping clamped to [1, num_time_steps]."""
+    idx = set()
+    for t_mon in (monitor_times or []):
+        if t_mon <= 0.0 or t_mon > T:
+            continue
+        tau_mon = T - t_mon
+        k = int(math.floor(tau_mon / dt + 1e-9))
+        idx.add(max(1, min(num_time_steps, k)))
+    return sorted(idx)
+
+
+_DBFP_KO = {"none": 0, "down-and-out": FLAG_KO_DOWN, "up-and-out": FLAG_KO_UP, "double-out": FLAG_KO_DOWN | FLAG_KO_UP}
+
+
+def build_dbfp_batch(S0_eff, K, T, sigma, r, b, q, is_call, ko_type: Sequence[str], lower_barrier, upper_barrier,
+                     rebate_amount, rebate_at_hit, monitor_times: Sequence, num_space_nodes, num_time_steps,
+                     rannacher_steps, S_min, S_max, n_march=None) -> SolveBatch:
+    """Descriptors for ``DiscreteBarrierFDMPricer._solve_grid`` (DBF:442-547), one entry per solve.
+
+    ``ko_type[i]``: the projection actually applied ("none" for knock-in types or ``apply_KO=False``, DBF:415-416).
+    The kernel grid has ``num_space_nodes - 1`` intervals (DBF:448 with :540), the top Dirichlet value is taken one
+    node above it, the drift carries ``b - q`` and the boundaries ``b``; rebates not paid at hit are discounted per
+    monitor step (DBF:421-424).  ``num_space_nodes`` / ``S_min`` / ``S_max`` come from :func:`dbfp_grid_parameters`.
+    """
+    n = len(S0_eff)
+    f = lambda v: np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (n,)))
+    S0_eff, K, T, sigma, r, b, q, rebate_amount, S_min, S_max = (f(v) for v in (S0_eff, K, T, sigma, r, b, q,
+                                                                                 rebate_amount, S_min, S_max))
+    ns = np.ascontiguousarray(np.broadcast_to(np.asarray(num_space_nodes, dtype=np.int64), (n,)))
+    nt = np.ascontiguousarray(np.broadcast_to(np.asarray(num_time_steps, dtype=np.int64), (n,)))
+    march = nt if n_march is None else np.ascontiguousarray(np.broadcast_to(np.asarray(n_march, dtype=np.int64), (n,)))
+    ran = np.ascontiguousarray(np.broadcast_to(np.asarray(rannacher_steps, dtype=np.int64), (n,)))
+    at_hit = np.broadcast_to(np.asarray(rebate_at_hit, dtype=bool), (n,))
+    call = np.broadcast_to(np.asarray(is_call, dtype=bool), (n,))
+    if np.any(ns < 4):
+        raise ValueError("num_space_nodes must be >= 4")
+    x_min = np.log(S_min)
+    dx = (np.log(S_max) - x_min) / ns                                           # DBF:349-354
+    dt = T / nt                                                                 # DBF:451
+    low = np.array([np.nan if v is None else float(v) for v in lower_barrier], dtype=np.float64)
+    up = np.array([np.nan if v is None else float(v) for v in upper_barrier], dtype=np.float64)
+    ko = np.array([_DBFP_KO[k] for k in ko_type], dtype=np.int64)
+    # DBF:428-435: a side whose level is None never knocks out
+    ko = np.where(np.isnan(low), ko & ~FLAG_KO_DOWN, ko)
+    ko = np.where(np.isnan(up), ko & ~FLAG_KO_UP, ko)
+    both = (ko & (FLAG_KO_DOWN | FLAG_KO_UP)) == (FLAG_KO_DOWN | FLAG_KO_UP)
+    level = np.where((ko & FLAG_KO_DOWN) != 0, low, np.where((ko & FLAG_KO_UP) != 0, up, 0.0))
+    level_up = np.where(both, up, 0.0)
+    flags = ko | np.where(call, FLAG_CALL, 0) | FLAG_BDRY_TOP_NEXT | FLAG_PUT_BDRY_SMIN
+
+    mon_begin = [0]
+    mon_step: List[int] = []
+    mon_rebate: List[float] = []
+    for i in range(n):
+        if ko[i]:
+            steps = [k for k in dbfp_monitor_steps(float(T[i]), float(dt[i]), int(nt[i]), monitor_times[i])
+                     if k <= int(march[i])]
+            mon_step.extend(steps)
+            if at_hit[i]:
+                mon_rebate.extend([float(rebate_amount[i])] * len(steps))
+            else:                                                               # DBF:424, tau_left = (m+1) dt
+                mon_rebate.extend(float(rebate_amount[i]) * math.exp(-float(b[i]) * (k * float(dt[i]))) for k in steps)
+        mon_begin.append(len(mon_step))
+
+    return SolveBatch(
+        x_min=x_min, dx=dx, sigma=sigma, r=r, b=b - q, spot=S0_eff, strike=K,
+        n_space=(ns - 1).astype(np.int32), flags=flags.astype(np.int32), rannacher=np.maximum(ran, 0).astype(np.int32),
+        seg_begin=np.arange(n + 1, dtype=np.int32), seg_steps=march.astype(np.int32), seg_dt=dt,
+        seg_tau0=np.zeros(n), seg_restart=np.ones(n, dtype=np.int32), seg_div=np.zeros(n),
+        barrier=level, rebate=rebate_amount, mon_begin=np.asarray(mon_begin, dtype=np.int32),
+        mon_step=np.asarray(mon_step, dtype=np.int32), b_bdry=b, barrier_up=level_up,
+        mon_rebate=np.asarray(mon_rebate, dtype=np.float64))

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FDM_ABI_VERSION 1
+#define FDM_ABI_VERSION 2
 
 /* error codes */
 #define FDM_OK                0
@@ -50,7 +50,15 @@ extern "C" {
                                      price = V[spot node], 4-point stencil.  Without it (barrier dataclass):
                                      raw strike, linear interpolation at spot, 3-point stencil              */
 #define FDM_FLAG_KO_DOWN   0x10   /* down-and-out projection at monitor steps, discrete_barrier_fdm_pricer_cn.py:203-207 */
-#define FDM_FLAG_KO_UP     0x20   /* up-and-out projection, discrete_barrier_fdm_pricer_cn.py:209-213 */
+#define FDM_FLAG_KO_UP     0x20   /* up-and-out projection, discrete_barrier_fdm_pricer_cn.py:209-213.
+                                     KO_DOWN | KO_UP together: double-out (discrete_barrier_fdm_pricer.py:433-435),
+                                     lower level in barrier[], upper level in barrier_up[] */
+/* The date/curve-aware barrier pricer DiscreteBarrierFDMPricer (discrete_barrier_fdm_pricer.py:442-547) marches a
+   vector that is one node shorter than its s_nodes (V[1:-1] = V_int with N = num_space_nodes - 1, :448, :540):
+   the kernel grid is then n_space = num_space_nodes - 1, but the Dirichlet value at the top is still evaluated at
+   s_nodes[-1], one node ABOVE the kernel grid. */
+#define FDM_FLAG_BDRY_TOP_NEXT 0x40  /* top Dirichlet value uses S = exp(x_min + (n_space+1) dx), :378 with :540 */
+#define FDM_FLAG_PUT_BDRY_SMIN 0x80  /* put: V_min = K e^{-r tau} * S_min * e^{(b-r) tau}, discrete_barrier_fdm_pricer.py:391 */
 
 /* largest num_space_nodes any compiled kernel variant handles (one CTA per solve above
    FDM_WARP_MAX_N_SPACE, one warp per solve up to it) */
@@ -95,6 +103,13 @@ typedef struct FdmBatch {
     /* KO monitor steps, discrete_barrier_fdm_pricer_cn.py:177-193: 1-based global step index k,
        strictly ascending per solve; projection runs after step k */
     const int32_t *mon_step;
+
+    /* ABI 2 (all optional, NULL = not used) */
+    const double *b_bdry;      /* carry rate inside the Dirichlet values when it differs from the drift's b
+                                  (discrete_barrier_fdm_pricer.py:382 uses carry_rate_nacc, the drift :461 b - q) */
+    const double *barrier_up;  /* upper KO level of a double-out solve (KO_DOWN | KO_UP) */
+    const double *mon_rebate;  /* [n_mon_total] value written at knocked-out nodes at each monitor step, e.g.
+                                  rebate * exp(-b tau) (discrete_barrier_fdm_pricer.py:421-424); NULL: rebate[] */
 } FdmBatch;
 
 /*
@@ -119,6 +134,10 @@ typedef struct FdmOut {
 
 /* ABI version of the loaded library (== FDM_ABI_VERSION of the header it was built from). */
 int fdm_version(void);
+
+/* sizeof() of the ABI structs as this library was compiled: 0 FdmBatch, 1 FdmOut, 2 FdmAmericanBook, 3 FdmBookOut
+   (-1: unknown).  Lets a binding verify its own struct declarations at load time. */
+int fdm_sizeof(int which);
 
 /* Message of the last failure on the calling thread ("" if none). */
 const char *fdm_last_error(void);

@@ -650,6 +650,182 @@ int fdo_barrier_solve(const FdoBarrier *p, double *V_out, double *s_out,
     return FDO_OK;
 }
 
+
+/* ------------------------------------------------------------------------------------ */
+/* Date/curve-aware barrier pricer DiscreteBarrierFDMPricer                              */
+/* DBF = discrete_barrier_fdm_pricer.py.  The file does not parse as shipped; the class  */
+/* body used for the goldens is its lines 1-745 + 883-1027 (see oracle/ref_loader.py).    */
+
+typedef struct {
+    double S_min, S_max;        /* choose_grid_parameters, DBF:270-320 (host: needs scipy norm.ppf) */
+    double S0_eff;              /* spot - pv_divs, DBF:632 */
+    double S_greek;             /* self.spot: centre of the delta/gamma stencil, DBF:952 */
+    double K, T, sigma;
+    double r, b, q;             /* discount_rate_nacc, carry_rate_nacc, div_yield_nacc, DBF:457-459 */
+    double lower_barrier, upper_barrier;   /* NaN == None */
+    double rebate_amount;
+    int32_t rebate_at_hit;      /* DBF:421-424 */
+    int32_t is_call;
+    int32_t ko_kind;            /* 0 no projection (none / knock-in types, DBF:415-416), 1 down-and-out,
+                                   2 up-and-out, 3 double-out */
+    int32_t apply_KO;
+    int32_t num_space_nodes;    /* n: s_nodes has n+1 entries, DBF:352-357 */
+    int32_t num_time_steps;     /* dt = T / num_time_steps, DBF:451 */
+    int32_t N_time;             /* steps marched, DBF:449 */
+    int32_t rannacher_steps;    /* DBF:510-518 */
+    int32_t n_monitor;
+    const double *monitor_times;   /* self.monitor_times, DBF:257-268 */
+} FdoDbfp;
+
+typedef struct {
+    double dx, price, delta, gamma;
+    int32_t v_len;              /* length of the value vector after the march (n, see below) */
+    int32_t greek_idx;
+    int32_t n_monitor_steps;
+} FdoDbfpInfo;
+
+/* _solve_grid, DBF:442-547; _interp_price, DBF:629-646; _delta_gamma_from_grid, DBF:949-977.
+ * Note DBF:448 N = num_space_nodes - 1 and DBF:540 V[1:-1] = V_int: the slice assignment drops one
+ * element in the first step, so from then on V has n entries (nodes 0..n-1) while s_nodes keeps n+1;
+ * the top Dirichlet value (evaluated with S_max = s_nodes[n]) sits at index n-1.
+ * V_out: n+1 doubles (v_len are valid).  s_out: n+1. */
+int fdo_dbfp_solve(const FdoDbfp *p, double *V_out, double *s_out, int32_t *monitor_steps_out, FdoDbfpInfo *info)
+{
+    if (!p || !V_out || !info) return FDO_EINVAL;
+    const int n = p->num_space_nodes;
+    const int N = n - 1;                                               /* DBF:448 */
+    const int M = p->N_time;
+    if (n < 4 || M < 1 || p->num_time_steps < 1) return FDO_EINVAL;
+    const int n_nodes = n + 1;
+    double *s = (double *)malloc((size_t)n_nodes * sizeof(double));
+    double *rhs = (double *)malloc((size_t)n_nodes * sizeof(double));
+    double *xi = (double *)malloc((size_t)n_nodes * sizeof(double));
+    double *cp = (double *)malloc((size_t)n_nodes * sizeof(double));
+    double *dp = (double *)malloc((size_t)n_nodes * sizeof(double));
+    unsigned char *is_mon = (unsigned char *)calloc((size_t)p->num_time_steps + 2, 1);
+    if (!s || !rhs || !xi || !cp || !dp || !is_mon) {
+        free(s); free(rhs); free(xi); free(cp); free(dp); free(is_mon);
+        return FDO_ENOMEM;
+    }
+    const double x_min = log(p->S_min), x_max = log(p->S_max);         /* DBF:349-357 */
+    const double dx = (x_max - x_min) / n;
+    for (int i = 0; i < n_nodes; ++i) {
+        double x = x_min + i * dx;
+        s[i] = exp(x);
+    }
+    const double dt = p->T / p->num_time_steps;                        /* DBF:451 */
+    const double sig2 = p->sigma * p->sigma;
+    const double mu_x = (p->b - p->q) - 0.5 * sig2;                    /* DBF:461-462 */
+    const double alpha = 0.5 * sig2 / (dx * dx);
+    const double beta_adv = mu_x / (2.0 * dx);
+    const double a = alpha - beta_adv;
+    const double c = alpha + beta_adv;
+    const double bcoef = -2.0 * alpha - p->r;
+
+    double *V = V_out;
+    int v_len = n_nodes;
+    for (int i = 0; i < n_nodes; ++i) {                                /* DBF:366-370 */
+        double v = p->is_call ? s[i] - p->K : p->K - s[i];
+        V[i] = v > 0.0 ? v : 0.0;
+    }
+    int n_mon_steps = 0;                                               /* DBF:395-411 */
+    for (int i = 0; i < p->n_monitor; ++i) {
+        double t_mon = p->monitor_times[i];
+        if (t_mon <= 0.0 || t_mon > p->T) continue;
+        double tau_mon = p->T - t_mon;
+        long k = (long)floor(tau_mon / dt + 1e-9);
+        if (k < 1) k = 1;
+        if (k > p->num_time_steps) k = p->num_time_steps;
+        if (!is_mon[k]) ++n_mon_steps;
+        is_mon[k] = 1;
+    }
+    int rannacher_left = p->rannacher_steps;
+    const int n_int = N - 1;
+    for (int m = 0; m < M; ++m) {                                      /* DBF:513-546 */
+        double theta;
+        if (rannacher_left > 0) { theta = 1.0; --rannacher_left; } else theta = 0.5;
+        const double A_L = -theta * dt * a;                            /* DBF:475-483 */
+        const double A_C = 1.0 - theta * dt * bcoef;
+        const double A_U = -theta * dt * c;
+        const double B_L = (1.0 - theta) * dt * a;
+        const double B_C = 1.0 + (1.0 - theta) * dt * bcoef;
+        const double B_U = (1.0 - theta) * dt * c;
+        const double tau_next = (m + 1) * dt;
+        double V_min_next, V_max_next;                                 /* DBF:372-393 */
+        if (p->is_call) {
+            V_min_next = 0.0;
+            V_max_next = s[n] * exp((p->b - p->r) * tau_next) - p->K * exp(-p->r * tau_next);
+        } else {
+            V_max_next = 0.0;
+            V_min_next = p->K * exp(-p->r * tau_next) * s[0] * exp((p->b - p->r) * tau_next);
+        }
+        for (int j = 1; j < N; ++j)
+            rhs[j - 1] = B_L * V[j - 1] + B_C * V[j] + B_U * V[j + 1];
+        rhs[0] -= A_L * V_min_next;
+        rhs[n_int - 1] -= A_U * V_max_next;
+        thomas_toeplitz(A_L, A_C, A_U, rhs, xi, cp, dp, n_int);
+        V[0] = V_min_next;                                             /* DBF:538-540 */
+        memcpy(V + 1, xi, (size_t)n_int * sizeof(double));
+        V[n_int + 1] = V_max_next;
+        v_len = n_int + 2;                                             /* == n */
+        if (p->apply_KO && is_mon[m + 1] && p->ko_kind != 0) {         /* DBF:542-543, 413-440 */
+            const double rebate = p->rebate_at_hit ? p->rebate_amount
+                                                   : p->rebate_amount * exp(-p->b * tau_next);
+            const int cnt = v_len < n_nodes ? v_len : n_nodes;
+            for (int i = 0; i < cnt; ++i) {
+                int out = 0;
+                if (p->ko_kind == 1 && !isnan(p->lower_barrier) && s[i] <= p->lower_barrier) out = 1;
+                else if (p->ko_kind == 2 && !isnan(p->upper_barrier) && s[i] >= p->upper_barrier) out = 1;
+                else if (p->ko_kind == 3 && ((!isnan(p->lower_barrier) && s[i] <= p->lower_barrier) ||
+                                             (!isnan(p->upper_barrier) && s[i] >= p->upper_barrier))) out = 1;
+                if (out) V[i] = rebate;
+            }
+        }
+    }
+    /* _interp_price, DBF:629-646 (binary search over the n+1 s_nodes; V indexed alike) */
+    const double S0 = p->S0_eff;
+    double price;
+    if (S0 <= s[0]) price = V[0];
+    else if (S0 >= s[n]) price = V[v_len - 1];
+    else {
+        int lo = 0, hi = n;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) / 2;
+            if (S0 < s[mid]) hi = mid; else lo = mid;
+        }
+        if (hi >= v_len) { free(s); free(rhs); free(xi); free(cp); free(dp); free(is_mon); return FDO_EINVAL; }
+        double w = (S0 - s[lo]) / (s[hi] - s[lo]);
+        price = (1.0 - w) * V[lo] + w * V[hi];
+    }
+    /* _delta_gamma_from_grid, DBF:949-977: interior node of s_nodes (1..n-1) closest to self.spot, first minimum */
+    int idx = 1;
+    {
+        double bestv = fabs(s[1] - p->S_greek);
+        for (int i = 2; i < n; ++i) {
+            double v = fabs(s[i] - p->S_greek);
+            if (v < bestv) { bestv = v; idx = i; }
+        }
+    }
+    if (idx + 1 >= v_len) { free(s); free(rhs); free(xi); free(cp); free(dp); free(is_mon); return FDO_EINVAL; }
+    {
+        const double h1 = s[idx] - s[idx - 1];
+        const double h2 = s[idx + 1] - s[idx];
+        info->delta = -h2 / (h1 * (h1 + h2)) * V[idx - 1] + (h2 - h1) / (h1 * h2) * V[idx]
+                      + h1 / (h2 * (h1 + h2)) * V[idx + 1];
+        info->gamma = 2.0 * (V[idx - 1] / (h1 * (h1 + h2)) - V[idx] / (h1 * h2) + V[idx + 1] / (h2 * (h1 + h2)));
+        info->greek_idx = idx;
+    }
+    info->dx = dx;
+    info->price = price;
+    info->v_len = v_len;
+    info->n_monitor_steps = n_mon_steps;
+    if (s_out) memcpy(s_out, s, (size_t)n_nodes * sizeof(double));
+    if (monitor_steps_out)
+        for (int k = 0; k <= p->num_time_steps; ++k) monitor_steps_out[k] = is_mon[k];
+    free(s); free(rhs); free(xi); free(cp); free(dp); free(is_mon);
+    return FDO_OK;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* Batch drivers (OpenMP over solves) for the CPU baseline.  Results: price per solve.    */
 

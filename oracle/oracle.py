@@ -342,6 +342,65 @@ def barrier_batch_prices(params: Sequence[dict], n_threads: int = 0):
     return price, delta, gamma
 
 
+class _FdoDbfp(C.Structure):
+    _fields_ = [("S_min", C.c_double), ("S_max", C.c_double), ("S0_eff", C.c_double), ("S_greek", C.c_double),
+                ("K", C.c_double), ("T", C.c_double), ("sigma", C.c_double),
+                ("r", C.c_double), ("b", C.c_double), ("q", C.c_double),
+                ("lower_barrier", C.c_double), ("upper_barrier", C.c_double), ("rebate_amount", C.c_double),
+                ("rebate_at_hit", C.c_int32), ("is_call", C.c_int32), ("ko_kind", C.c_int32),
+                ("apply_KO", C.c_int32), ("num_space_nodes", C.c_int32), ("num_time_steps", C.c_int32),
+                ("N_time", C.c_int32), ("rannacher_steps", C.c_int32), ("n_monitor", C.c_int32),
+                ("monitor_times", C.POINTER(C.c_double))]
+
+
+class _FdoDbfpInfo(C.Structure):
+    _fields_ = [("dx", C.c_double), ("price", C.c_double), ("delta", C.c_double), ("gamma", C.c_double),
+                ("v_len", C.c_int32), ("greek_idx", C.c_int32), ("n_monitor_steps", C.c_int32)]
+
+
+@dataclass
+class DbfpResult:
+    V: np.ndarray           # value vector after the march (n entries, see fdo_dbfp_solve)
+    s: np.ndarray           # n+1 node prices
+    price: float
+    delta: float
+    gamma: float
+    dx: float
+    greek_idx: int
+    monitor_steps: np.ndarray
+
+
+DBFP_KO = {"none": 0, "down-and-in": 0, "up-and-in": 0, "double-in": 0,
+           "down-and-out": 1, "up-and-out": 2, "double-out": 3}
+
+
+def dbfp_solve(S_min, S_max, S0_eff, S_greek, K, T, sigma, r, b, q, is_call, barrier_type, lower_barrier,
+               upper_barrier, rebate_amount, rebate_at_hit, monitor_times, num_space_nodes, num_time_steps,
+               rannacher_steps, apply_KO=True, N_time=None) -> DbfpResult:
+    """DiscreteBarrierFDMPricer._solve_grid + _interp_price + _delta_gamma_from_grid
+    (discrete_barrier_fdm_pricer.py:442-547, :629-646, :949-977)."""
+    L = lib()
+    mt = np.ascontiguousarray(monitor_times, dtype=np.float64)
+    nan = float("nan")
+    p = _FdoDbfp(S_min, S_max, S0_eff, S_greek, K, T, sigma, r, b, q,
+                 nan if lower_barrier is None else float(lower_barrier),
+                 nan if upper_barrier is None else float(upper_barrier), float(rebate_amount),
+                 int(bool(rebate_at_hit)), int(bool(is_call)), DBFP_KO[barrier_type], int(bool(apply_KO)),
+                 int(num_space_nodes), int(num_time_steps), int(N_time if N_time is not None else num_time_steps),
+                 int(rannacher_steps), len(mt), mt.ctypes.data_as(C.POINTER(C.c_double)))
+    n = int(num_space_nodes)
+    V = np.zeros(n + 1)
+    s = np.zeros(n + 1)
+    mon = np.zeros(int(num_time_steps) + 1, dtype=np.int32)
+    info = _FdoDbfpInfo()
+    L.fdo_dbfp_solve.restype = C.c_int
+    rc = L.fdo_dbfp_solve(C.byref(p), _dptr(V), _dptr(s), mon.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(info))
+    if rc != 0:
+        raise RuntimeError(f"fdo_dbfp_solve failed: {rc}")
+    return DbfpResult(V=V[:info.v_len].copy(), s=s, price=info.price, delta=info.delta, gamma=info.gamma,
+                      dx=info.dx, greek_idx=info.greek_idx, monitor_steps=np.nonzero(mon)[0])
+
+
 def max_threads() -> int:
     return int(lib().fdo_max_threads())
 

@@ -19,6 +19,33 @@ def barrier_cases():
     return load("barrier")
 
 
+def dbfp_cases():
+    return load("dbfp")
+
+
+def dbfp_monitor_dates(case):
+    """Monitoring calendar of the goldens (oracle/gen_golden_dbfp.py): every weekday (or every fifth) from
+    valuation to maturity, as run_config_scenarios.py:199-222 lists them."""
+    v, m = d(case["valuation"]), d(case["maturity"])
+    days, cur = [], v
+    while cur <= m:
+        if cur.weekday() < 5:
+            days.append(cur)
+        cur += dt.timedelta(days=1)
+    return days if case["monitor"] == "weekdays" else days[::5]
+
+
+def dbfp_oracle_kwargs(case):
+    o = case["out"]
+    return dict(
+        S_min=o["S_min"], S_max=o["S_max"], S0_eff=case["spot"] - o["pv_divs"], S_greek=case["spot"], K=case["strike"],
+        T=o["T"], sigma=case["sigma"], r=o["r"], b=o["b"], q=o["q"], is_call=case["option_type"] == "call",
+        barrier_type=case["barrier_type"], lower_barrier=case["lower_barrier"], upper_barrier=case["upper_barrier"],
+        rebate_amount=case["rebate_amount"], rebate_at_hit=case["rebate_at_hit"], monitor_times=o["monitor_times"],
+        num_space_nodes=o["num_space_nodes"], num_time_steps=case["num_time_steps"],
+        rannacher_steps=case["rannacher_steps"])
+
+
 def am_model(case):
     return 1 if case["module"] == "fd_american_black76" else 0
 

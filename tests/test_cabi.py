@@ -33,9 +33,13 @@ def test_library_builds_and_exports_every_symbol():
 
 
 def test_struct_layout_matches_header():
-    # FdmBatch: int64 + 4 x int32 + 20 pointers; FdmOut: 7 pointers + (ptr, int64) x 2
-    assert C.sizeof(_lib.FdmBatch) == 8 + 16 + 20 * 8
+    # FdmBatch: int64 + 4 x int32 + 23 pointers (ABI 2); FdmOut: 7 pointers + (ptr, int64) x 2
+    assert C.sizeof(_lib.FdmBatch) == 8 + 16 + 23 * 8
     assert C.sizeof(_lib.FdmOut) == 7 * 8 + 4 * 8
+    # and the compiled library agrees with the ctypes declarations
+    L = _lib.load()
+    for which, st in enumerate((_lib.FdmBatch, _lib.FdmOut, _lib.FdmAmericanBook, _lib.FdmBookOut)):
+        assert L.fdm_sizeof(which) == C.sizeof(st), st.__name__
 
 
 def test_invalid_arguments_are_reported_not_thrown():
