@@ -426,4 +426,63 @@ class DiscreteBarrierFDMPricer:
         raise ValueError(f"Unsupported barrier_type: {self.barrier_type}")
 
 
-__all__ = ["DiscreteBarrierFDMPricer"]
+def price_and_greeks_batch(pricers: Sequence[DiscreteBarrierFDMPricer], dv_sigma: float = 0.0001):
+    """``(price_log2(), greeks_log2(dv_sigma))`` of every pricer with ALL PDE solves in one C-ABI call.
+
+    The reference executes four solves per knock-out / knock-in scenario (``price_log2`` and ``greeks_log2`` each run
+    ``_pde_price_and_greeks3``, :883-903); they are two distinct solves (sigma and sigma + dv_sigma), so two per
+    scenario are launched and shared.  Results are those of the per-object methods: the read-out is the same
+    arithmetic in the kernel epilogue (linear interpolation at ``spot - pv_divs``, 3-point stencil), except with
+    escrowed dividends, where the stencil is centred on ``spot`` (:952) and the value vector is read back instead.
+    Returns ``(prices, greeks, n_solves, node_steps)``.
+    """
+    n = len(pricers)
+    prices: List[Optional[float]] = [None] * n
+    greeks: List[Optional[Dict[str, float]]] = [None] * n
+    parts, owners = [], []
+    for i, pr in enumerate(pricers):
+        bt = pr.barrier_type.lower()
+        if bt == "none" or (bt in ("down-and-out", "up-and-out") and pr.already_hit) \
+                or (bt in ("down-and-in", "up-and-in") and pr.already_in):
+            prices[i] = pr.price_log2()
+            greeks[i] = pr.greeks_log2(dv_sigma)
+            continue
+        if bt not in ("down-and-out", "up-and-out", "down-and-in", "up-and-in"):
+            raise ValueError(f"Unsupported barrier_type: {pr.barrier_type}")
+        original_bt = pr.barrier_type
+        pr.barrier_type = {"down-and-in": "down-and-out", "up-and-in": "up-and-out"}.get(bt, bt)
+        try:
+            pr._build_log_grid()
+            parts.append(pr._solve_descriptor(True))
+            parts.append(pr._solve_descriptor(True, sigma=pr.sigma + dv_sigma))
+        finally:
+            pr.barrier_type = original_bt
+        owners.append(i)
+    n_solves = node_steps = 0
+    if parts:
+        batch = SolveBatch.concat(parts)
+        need_dump = any(pricers[i].pv_divs != 0.0 for i in owners)
+        res = solve_host(batch, dump=need_dump)
+        n_solves, node_steps = batch.n_solves, batch.node_steps()
+        for j, i in enumerate(owners):
+            pr = pricers[i]
+            bt = pr.barrier_type.lower()
+            price_base, price_up = float(res.price[2 * j]), float(res.price[2 * j + 1])
+            delta, gamma = float(res.delta[2 * j]), float(res.gamma[2 * j])
+            if pr.pv_divs != 0.0:
+                pr._build_log_grid()
+                delta, gamma = pr._delta_gamma_from_grid([float(v) for v in res.V[2 * j, :pr.num_space_nodes]])
+            vega = (price_up - price_base) / (dv_sigma * 100)
+            theta = -(0.5 * pr.sigma * pr.sigma * pr.spot * pr.spot * gamma
+                      + (pr.carry_rate_nacc - pr.div_yield_nacc) * pr.spot * delta - pr.discount_rate_nacc * price_base)
+            g_ko = {"price": price_base, "delta": delta, "gamma": gamma, "vega": vega, "theta": theta}
+            if bt in ("down-and-out", "up-and-out"):
+                prices[i], greeks[i] = price_base, g_ko
+            else:
+                prices[i] = pr._vanilla_black76_price() - price_base
+                g_van = pr._vanilla_black76_greeks_fd()
+                greeks[i] = {k: g_van[k] - g_ko[k] for k in g_van.keys()}
+    return prices, greeks, n_solves, node_steps
+
+
+__all__ = ["DiscreteBarrierFDMPricer", "price_and_greeks_batch"]

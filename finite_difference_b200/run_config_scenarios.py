@@ -1,0 +1,141 @@
+"""Drop-in for the reference's barrier scenario runner (run_config_scenarios.py): same function names, arguments,
+CSV schema (config_scenarios*.csv) and result keys (run_config_scenarios.py:9-137, :138-195).
+
+``run_scenario`` prices one row through the drop-in ``DiscreteBarrierFDMPricer``.  ``run_all_scenarios`` builds every
+row's pricer on the host and prices the whole CSV as ONE batch on the GPU (two PDE solves per knock-out / knock-in
+row; the reference runs four, serially) and can shard the rows over the GPUs of a box (``shard.py``).
+"""
+from __future__ import annotations
+
+import datetime as dt
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import pandas as pd
+
+from . import shard
+from .discrete_barrier_fdm_pricer import DiscreteBarrierFDMPricer, price_and_greeks_batch
+from .utils import create_rate_df_iso, naca_to_nacc
+
+
+def _pct_diff(model_val: float, fa_val: Optional[float]) -> float:
+    """run_config_scenarios.py:101-104."""
+    if fa_val is None or np.isnan(fa_val) or fa_val == 0.0:
+        return np.nan
+    return abs(model_val - fa_val) / abs(fa_val) * 100.0
+
+
+def _build_pricer(S0, K, sigma, rate, barrier_type, upper_barrier, lower_barrier, valuation, maturity, monitor_dates,
+                  opt_type="call", trade_number=201871103, quantity=1000, contract_size=1, position="long", divs=None,
+                  rebate_amount=0, rebate_at_hit=True, use_one_sided_greeks_near_barrier=False, already_hit=False,
+                  already_in=False, underlying_spot_days=0, option_days=0, option_settlement_days=0,
+                  day_count="ACT/365", grid_type="uniform", num_space_nodes=500, num_time_steps=500,
+                  _curve_cache: Optional[dict] = None) -> DiscreteBarrierFDMPricer:
+    """The constructor call of run_config_scenarios.py:60-94 (curves: :52-57, ISO dates)."""
+    naca_to_nacc(rate)                                   # :50, kept for its validation side effects
+    if _curve_cache is not None and rate in _curve_cache:
+        curve = _curve_cache[rate]
+    else:
+        curve = create_rate_df_iso(rate)
+        if _curve_cache is not None:
+            _curve_cache[rate] = curve
+    return DiscreteBarrierFDMPricer(
+        spot=S0, strike=K, valuation_date=valuation, maturity_date=maturity, sigma=sigma, option_type=opt_type,
+        barrier_type=barrier_type, lower_barrier=lower_barrier, upper_barrier=upper_barrier, already_in=already_in,
+        already_hit=already_hit, monitor_dates=monitor_dates, discount_curve=curve, forward_curve=curve,
+        dividend_schedule=divs or [], trade_id=trade_number, direction=position, quantity=quantity,
+        underlying_spot_days=underlying_spot_days, option_days=option_days,
+        option_settlement_days=option_settlement_days, rebate_amount=rebate_amount, rebate_at_hit=rebate_at_hit,
+        contract_multiplier=contract_size, use_one_sided_greeks_near_barrier=use_one_sided_greeks_near_barrier,
+        num_space_nodes=num_space_nodes, num_time_steps=num_time_steps, grid_type=grid_type, rannacher_steps=2,
+        restart_on_monitoring=False, mollify_final=False, mollify_band_nodes=2, day_count=day_count)
+
+
+def _result_row(scenario_name, S0, K, sigma, rate, barrier_type, upper_barrier, lower_barrier, model_price, greeks,
+                FA_price, FA_delta, FA_gamma, FA_vega) -> Dict[str, Any]:
+    """Result dictionary in the reference's key order (run_config_scenarios.py:107-133)."""
+    nan = np.nan
+    return {
+        "scenario_name": scenario_name, "S0": S0, "K": K, "sigma": sigma, "rate": rate, "barrier_type": barrier_type,
+        "upper_barrier": upper_barrier if upper_barrier is not None else nan,
+        "lower_barrier": lower_barrier if lower_barrier is not None else nan,
+        "model_price": model_price, "FA_price": FA_price if FA_price is not None else nan,
+        "price_diff": abs(model_price - FA_price) if FA_price is not None else nan,
+        "price_pct_diff": _pct_diff(model_price, FA_price),
+        "model_delta": greeks["delta"], "FA_delta": FA_delta if FA_delta is not None else nan,
+        "delta_diff": abs(greeks["delta"] - FA_delta) if FA_delta is not None else nan,
+        "delta_pct_diff": _pct_diff(greeks["delta"], FA_delta),
+        "model_gamma": greeks["gamma"], "FA_gamma": FA_gamma if FA_gamma is not None else nan,
+        "gamma_diff": abs(greeks["gamma"] - FA_gamma) if FA_gamma is not None else nan,
+        "gamma_pct_diff": _pct_diff(greeks["gamma"], FA_gamma),
+        "model_vega": greeks["vega"], "FA_vega": FA_vega if FA_vega is not None else nan,
+        "vega_diff": abs(greeks["vega"] - FA_vega) if FA_vega is not None else nan,
+        "vega_pct_diff": _pct_diff(greeks["vega"], FA_vega),
+    }
+
+
+def run_scenario(scenario_name: str, S0: float, K: float, sigma: float, rate: float, barrier_type: str,
+                 upper_barrier: Optional[float], lower_barrier: Optional[float], FA_price: Optional[float],
+                 FA_delta: Optional[float], FA_gamma: Optional[float], FA_vega: Optional[float], valuation: dt.date,
+                 maturity: dt.date, monitor_dates: list, opt_type: str = "call", trade_number: int = 201871103,
+                 quantity: int = 1000, contract_size: int = 1, position: str = "long", divs: list = None,
+                 rebate_amount: float = 0, rebate_at_hit: bool = True, use_one_sided_greeks_near_barrier: bool = False,
+                 already_hit: bool = False, already_in: bool = False, underlying_spot_days: int = 0,
+                 option_days: int = 0, option_settlement_days: int = 0, day_count: str = "ACT/365",
+                 grid_type: str = "uniform", num_space_nodes: int = 500, num_time_steps: int = 500) -> Dict[str, Any]:
+    """Run a single pricing scenario and return headline results (run_config_scenarios.py:9-137)."""
+    pricer = _build_pricer(S0, K, sigma, rate, barrier_type, upper_barrier, lower_barrier, valuation, maturity,
+                           monitor_dates, opt_type, trade_number, quantity, contract_size, position, divs,
+                           rebate_amount, rebate_at_hit, use_one_sided_greeks_near_barrier, already_hit, already_in,
+                           underlying_spot_days, option_days, option_settlement_days, day_count, grid_type,
+                           num_space_nodes, num_time_steps)
+    model_price = pricer.price_log2()
+    greeks = pricer.greeks_log2()
+    return _result_row(scenario_name, S0, K, sigma, rate, barrier_type, upper_barrier, lower_barrier, model_price,
+                       greeks, FA_price, FA_delta, FA_gamma, FA_vega)
+
+
+def _opt(v):
+    return v if pd.notna(v) else None
+
+
+def run_scenarios_frame(config_df: pd.DataFrame, base_params: Dict[str, Any], distributed: bool = False) -> pd.DataFrame:
+    """All rows of a scenario frame as one GPU batch.  With ``distributed=True`` under ``torchrun`` the rows are dealt
+    over the ranks by cost and the per-row results gathered on every rank (no other communication)."""
+    rows = [r for _, r in config_df.iterrows()]
+    cache: dict = {}
+    pricers = [_build_pricer(r["S0"], r["K"], r["sigma"], r["rate"], r["barrier_type"], _opt(r["upper_barrier"]),
+                             _opt(r["lower_barrier"]), _curve_cache=cache, **base_params) for r in rows]
+    rank, world, _ = shard.rank_world()
+    mine = np.arange(len(rows), dtype=np.int64)
+    if distributed and world > 1:
+        # cost of a row ~ space nodes x time steps of its solves; rows priced in closed form cost nothing
+        cost = np.array([0.0 if p.barrier_type.lower() == "none" else float(p.num_time_steps) ** 2 for p in pricers])
+        mine = shard.partition(cost, world)[rank]
+    prices, greeks, _, _ = price_and_greeks_batch([pricers[i] for i in mine])
+    local = np.array([[prices[j], greeks[j]["delta"], greeks[j]["gamma"], greeks[j]["vega"], greeks[j]["theta"]]
+                      for j in range(len(mine))], dtype=np.float64).reshape(len(mine), 5)
+    if distributed and world > 1:
+        vals = shard.gather_results({"vals": local}, mine, len(rows))["vals"]
+    else:
+        vals = np.empty((len(rows), 5))
+        vals[mine] = local
+    out = []
+    for i, r in enumerate(rows):
+        g = {"delta": vals[i, 1], "gamma": vals[i, 2], "vega": vals[i, 3], "theta": vals[i, 4]}
+        out.append(_result_row(r["scenario_name"], r["S0"], r["K"], r["sigma"], r["rate"], r["barrier_type"],
+                               _opt(r["upper_barrier"]), _opt(r["lower_barrier"]), vals[i, 0], g, _opt(r["FA_price"]),
+                               _opt(r["FA_delta"]), _opt(r["FA_gamma"]), _opt(r["FA_vega"])))
+    return pd.DataFrame(out)
+
+
+def run_all_scenarios(config_csv_path: str, output_csv_path: str, base_params: Dict[str, Any]) -> pd.DataFrame:
+    """Read the configuration CSV, run all scenarios, save the results CSV (run_config_scenarios.py:138-195)."""
+    config_df = pd.read_csv(config_csv_path)
+    results_df = run_scenarios_frame(config_df, base_params)
+    results_df.to_csv(output_csv_path, index=False)
+    print(f"\n✓ Results saved to {output_csv_path}")
+    return results_df
+
+
+__all__ = ["run_scenario", "run_all_scenarios", "run_scenarios_frame"]

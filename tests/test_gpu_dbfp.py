@@ -79,3 +79,33 @@ def test_gpu_matches_oracle_on_unseen_inputs():
         tol = 1e-10 * np.abs(ref.V) + 1e-12 * np.max(np.abs(ref.V))
         assert np.all(np.abs(V - ref.V) <= tol), (i, float(np.max(np.abs(V - ref.V))))
         _close(pr._interp_price(list(V)), ref.price, 1e-10, 1e-8)
+
+
+def test_run_config_scenarios_batch_equals_per_row(tmp_path):
+    """run_all_scenarios (one GPU batch for the CSV) against run_scenario (per-row drop-in class) and the goldens."""
+    import pandas as pd
+    from finite_difference_b200 import run_config_scenarios as rcs
+    cases = [c for c in DBFP if c["id"].startswith("config_scenarios_1_") and c["num_time_steps"] == 60]
+    frame = pd.DataFrame([dict(scenario_name=c["id"], S0=c["spot"], K=c["strike"], sigma=c["sigma"], rate=c["naca"],
+                               barrier_type=c["barrier_type"], upper_barrier=c["upper_barrier"],
+                               lower_barrier=c["lower_barrier"], FA_price=1.0, FA_delta=None, FA_gamma=0.0, FA_vega=2.0)
+                          for c in cases])
+    cfg, out = tmp_path / "cfg.csv", tmp_path / "res.csv"
+    frame.to_csv(cfg, index=False)
+    base = dict(valuation=_golden.d(cases[0]["valuation"]), maturity=_golden.d(cases[0]["maturity"]),
+                monitor_dates=_golden.dbfp_monitor_dates(cases[0]), opt_type="put", num_time_steps=60)
+    df = rcs.run_all_scenarios(str(cfg), str(out), base)
+    assert list(df.columns) == list(pd.read_csv(out).columns) and len(df) == len(cases)
+    for i, c in enumerate(cases):
+        ref = c["out"]["greeks_log2"]
+        gv = max(abs(ref["price"]), abs(c["out"]["solve_price"]), 1e-6)
+        _close(df.loc[i, "model_price"], c["out"]["price_log2"], 1e-10, gv)
+        row = rcs.run_scenario(c["id"], c["spot"], c["strike"], c["sigma"], c["naca"], c["barrier_type"],
+                               c["upper_barrier"], c["lower_barrier"], 1.0, None, 0.0, 2.0, **base)
+        assert list(row.keys()) == list(df.columns)
+        # the batch reads prices in the kernel epilogue (CUDA exp for the node prices), the class on the host
+        # (glibc exp): one-ulp differences of the ~29.0 legs, amplified 1e2 by the one-sided vega bump
+        _close(df.loc[i, "model_price"], row["model_price"], 1e-13, gv)
+        for k, rel in (("model_delta", 1e-9), ("model_gamma", 1e-7), ("model_vega", 1e-7)):
+            _close(df.loc[i, k], row[k], rel, max(abs(row[k]), 1e-2))
+        assert np.isnan(df.loc[i, "FA_delta"]) and np.isnan(df.loc[i, "gamma_pct_diff"])
