@@ -1170,7 +1170,7 @@ int validate(const FdmBatch *b, const FdmOut *o)
 
 template <int C, int WARPS>
 int launch_cta_variant(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american, bool any_linear,
-                       bool any_div, int32_t *n_launches)
+                       bool any_div, int n_lo, int32_t *n_launches)
 {
     const bool trace = o.ex_trace != nullptr;
     const size_t smem = (size_t)cta::smem_doubles<C, WARPS>() * sizeof(double);
@@ -1186,12 +1186,12 @@ int launch_cta_variant(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool
         const int64_t count = (b.n_solves - first < max_grid) ? (b.n_solves - first) : max_grid;
         const dim3 grid((unsigned)count), block(32 * WARPS);
         if (any_american) {
-            if (trace) k_amt<<<grid, block, smem, st>>>(b, o, first, 1, FDM_WARP_MAX_N_SPACE);
-            else       k_am<<<grid, block, smem, st>>>(b, o, first, 1, FDM_WARP_MAX_N_SPACE);
+            if (trace) k_amt<<<grid, block, smem, st>>>(b, o, first, 1, n_lo);
+            else       k_am<<<grid, block, smem, st>>>(b, o, first, 1, n_lo);
             ++launches;
         }
         if (any_linear) {
-            k_lin<<<grid, block, smem, st>>>(b, o, first, 0, FDM_WARP_MAX_N_SPACE);
+            k_lin<<<grid, block, smem, st>>>(b, o, first, 0, n_lo);
             ++launches;
         }
         FDM_CUDA(cudaGetLastError());
@@ -1236,8 +1236,14 @@ int launch(const FdmBatch &b, const FdmOut &o, cudaStream_t st, int family_mask,
         if (rc != FDM_OK) return rc;
     }
     if (large) {
-        if (b.n_space_max - 1 <= 32 * 4 * 16) rc = launch_cta_variant<16, 4>(b, o, st, am, lin, dv, n_launches);
-        else rc = launch_cta_variant<16, 16>(b, o, st, am, lin, dv, n_launches);
+        // one launch per CTA size class that can be populated: 4 / 5 / 8 / 16 warps of 16 slots per thread serve
+        // up to 2048 / 2560 / 4096 / 8192 interior rows; a solve runs in the smallest class that holds it
+        // (n_lo = largest n_space of the class below), other classes' CTAs exit at once
+        const int rows_max = b.n_space_max - 1;
+        rc = launch_cta_variant<16, 4>(b, o, st, am, lin, dv, FDM_WARP_MAX_N_SPACE, n_launches);
+        if (rc == FDM_OK && rows_max > 2048) rc = launch_cta_variant<16, 5>(b, o, st, am, lin, dv, 2049, n_launches);
+        if (rc == FDM_OK && rows_max > 2560) rc = launch_cta_variant<16, 8>(b, o, st, am, lin, dv, 2561, n_launches);
+        if (rc == FDM_OK && rows_max > 4096) rc = launch_cta_variant<16, 16>(b, o, st, am, lin, dv, 4097, n_launches);
     }
     return rc;
 }
