@@ -87,7 +87,11 @@ __device__ __forceinline__ void ring_publish(double *ring, int *prog, int ring_l
 // wait until warp v has published step `step`
 __device__ __forceinline__ void ring_wait(const int *prog, int v, int step)
 {
-    while (((const volatile int *)prog)[v] < step + 1) { }
+#ifndef FDM_CTA_SPIN_NS
+#define FDM_CTA_SPIN_NS 40
+#endif
+    // back off between polls: a busy poll loop takes issue slots from the warps it is waiting for
+    while (((const volatile int *)prog)[v] < step + 1) { if (FDM_CTA_SPIN_NS) __nanosleep(FDM_CTA_SPIN_NS); }
 }
 
 enum { CST_NM = 0, CST_NCC, CST_INV, CST_AF, CST_AB, CST_HF1, CST_HF2, CST_HB1, CST_HB2, CST_TOP, CST_PD };
