@@ -9,15 +9,15 @@
 //     only the warps that hold padding or the first P rows read per-slot coefficients (staged per
 //     thread in shared memory); every other warp runs with three scalar coefficients, and warps that
 //     hold nothing but padding only keep the barriers.  The choice is warp-uniform: no divergence;
-//   * each first-order recurrence runs as  local pass -> intra-warp shuffle scan -> short Horner sum
-//     over the preceding warps' totals -> local pass.  The warp-to-warp multipliers decay like
+//   * each first-order recurrence runs as  local pass -> intra-warp shuffle scan -> one __syncthreads ->
+//     short Horner sum over the preceding warps' totals -> local pass.  The warp-to-warp multipliers decay like
 //     |c'|^(32 C) (1e-17 at C = 16), so the Horner sum is truncated after K terms with the neglected
 //     weight below 1e-22 (K is found per phase).
-//   * NO block-wide barrier inside the time loop: a warp needs the totals of its K nearest neighbours only,
-//     so the totals travel through a shared-memory ring (slot = step mod RING) with one progress counter per
-//     warp and direction; a consumer spins on its neighbours' counters.  Warps drift apart by up to one step
-//     per warp of distance, which lets the latency-bound phases of different warps overlap (with the two
-//     __syncthreads per step this kernel spent most of its time waiting for the slowest warp).
+//   Two block-wide barriers per time step.  (Tried and dropped: passing the warp totals through a shared-memory
+//   ring with per-warp progress counters instead of the barriers -- the warps need their nearest neighbours only --
+//   measured 8..10 % slower on 2048..8192-node grids: the warps stay in lock-step anyway and the polls cost issue slots.)
+//   * size classes: 4 / 5 / 8 / 16 warps of 16 slots per thread serve up to 2048 / 2560 / 4096 / 8192 rows; a solve
+//     runs in the smallest class that holds it (2133-node barrier grids: 5 warps, two CTAs per SM).
 //
 // Included by fdm_b200.cu (single translation unit); uses its helpers.
 
@@ -56,8 +56,7 @@ struct Layout {
     static constexpr int SLOTS = WARPS <= 4 ? WARPS : (WARPS <= 5 ? 4 : 6);   // 5 warps: two CTAs per SM must fit shared memory
     static constexpr int SLOT_DOUBLES = 3 * C * 32 + 8 * 32;         // nm, ncc, inv [k][lane] + 8 per-lane constants
     static constexpr int R2 = NP > SLOTS * SLOT_DOUBLES ? NP : SLOTS * SLOT_DOUBLES;
-    static constexpr int RING = 2 * WARPS;                            // > the largest drift between two warps
-    static constexpr int SMALL = 4 * WARPS + 16 + 64 + 32 + 8 + 2 * RING * WARPS + WARPS;   // part, cst, PAc, wb, ishare, rings, progress
+    static constexpr int SMALL = 4 * WARPS + 16 + 64 + 32 + 8;       // part, cst, PAc, wb, ishare
     static constexpr int TOTAL = 2 * NP + R2 + SMALL;
 };
 
@@ -71,28 +70,7 @@ struct Sm {
     double *wb;     // [32] moving Dirichlet values of the next 32 steps
     int *ish;       // [0] P [1] spot node [2] strike node [3,4] KO range [5] status [6,7] ex lo/hi [8] Kf [9] Kb
                     // [10] first table warp [11] last table warp
-    double *ringF;  // [RING][WARPS] forward warp totals pE_f of the last RING steps
-    double *ringB;  // [RING][WARPS] backward warp totals pE_b
-    int *prog;      // [2][WARPS] steps published so far, forward / backward
 };
-
-// publish a warp total for step `step` (one lane calls this)
-__device__ __forceinline__ void ring_publish(double *ring, int *prog, int ring_len, int warps, int w, int step, double v)
-{
-    ((volatile double *)ring)[(step % ring_len) * warps + w] = v;
-    __threadfence_block();
-    ((volatile int *)prog)[w] = step + 1;
-}
-
-// wait until warp v has published step `step`
-__device__ __forceinline__ void ring_wait(const int *prog, int v, int step)
-{
-#ifndef FDM_CTA_SPIN_NS
-#define FDM_CTA_SPIN_NS 40
-#endif
-    // back off between polls: a busy poll loop takes issue slots from the warps it is waiting for
-    while (((const volatile int *)prog)[v] < step + 1) { if (FDM_CTA_SPIN_NS) __nanosleep(FDM_CTA_SPIN_NS); }
-}
 
 enum { CST_NM = 0, CST_NCC, CST_INV, CST_AF, CST_AB, CST_HF1, CST_HF2, CST_HB1, CST_HB2, CST_TOP, CST_PD };
 enum { LC_AF = 0, LC_AB, LC_HF1, LC_HF2, LC_HB1, LC_HB2, LC_PAF, LC_PAB };
@@ -269,7 +247,7 @@ __device__ __forceinline__ double warp_scan(double e, double a, int lane)
 // is added to R there.
 template <int C, int WARPS, bool AMER, bool TBL>
 __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph &ph, const Sm &sm, const int k0,
-                                       const double cin_f, double &e1_keep, double &Eprev, const int step)
+                                       const double cin_f, double &e1_keep, double &Eprev)
 {
     constexpr int H = C / 2;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -296,7 +274,7 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
     for (int k = H; k < C; ++k) e2 = fma(TBL ? nm[k * 32 + lane] : ph.NM, e2, V[k]);
     const double e_end = fma(TBL ? lc[LC_HF2 * 32 + lane] : sm.cst[CST_HF2], e1, e2);
     const double E = warp_scan<TBL, true>(e_end, TBL ? lc[LC_AF * 32 + lane] : sm.cst[CST_AF], lane);
-    if (lane == 31) ring_publish(sm.ringF, sm.prog, Layout<C, WARPS>::RING, WARPS, w, step, E);   // pE_f
+    if (lane == 31) sm.part[0 * WARPS + w] = E;           // pE_f
     const double up = __shfl_up_sync(FULL, E, 1);
     Eprev = (lane == 0) ? 0.0 : up;
     e1_keep = e1;
@@ -304,23 +282,15 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
 
 template <int C, int WARPS, bool AMER, bool TBL>
 __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &sm, const int wf, const double cin_b,
-                                       const double e1_fwd, const double Eprev, double &e1_keep, double &Enext,
-                                       const int step)
+                                       const double e1_fwd, const double Eprev, double &e1_keep, double &Enext)
 {
     constexpr int H = C / 2;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const double *nm = ph.slot, *ncc = ph.slot + C * 32;
     const double *lc = ph.slot + 3 * C * 32;
-    // carry into this warp from the warps below (truncated Horner sum over their totals of THIS step)
+    // carry into this warp from the warps below (truncated Horner sum)
     double S = 0.0;
-    {
-        constexpr int RING = Layout<C, WARPS>::RING;
-        const int v0 = max(wf, w - ph.Kf);
-        for (int v = v0; v < w; ++v) ring_wait(sm.prog, v, step);
-        __threadfence_block();
-        const volatile double *slot = (const volatile double *)sm.ringF + (step % RING) * WARPS;
-        for (int v = v0; v < w; ++v) S = fma(sm.part[1 * WARPS + v], S, slot[v]);
-    }
+    for (int v = max(wf, w - ph.Kf); v < w; ++v) S = fma(sm.part[1 * WARPS + v], S, sm.part[0 * WARPS + v]);
     const double cs = fma(TBL ? lc[LC_PAF * 32 + lane] : sm.PAc[lane], S, Eprev);
     {
         double c1 = cs;
@@ -338,7 +308,7 @@ __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &s
     for (int k = H - 1; k >= 0; --k) e2 = fma(TBL ? ncc[k * 32 + lane] : ph.NCC, e2, V[k]);
     const double e_end = fma(TBL ? lc[LC_HB2 * 32 + lane] : sm.cst[CST_HB2], e1, e2);
     const double E = warp_scan<TBL, false>(e_end, TBL ? lc[LC_AB * 32 + lane] : sm.cst[CST_AB], lane);
-    if (lane == 0) ring_publish(sm.ringB, sm.prog + WARPS, Layout<C, WARPS>::RING, WARPS, w, step, E);   // pE_b
+    if (lane == 0) sm.part[2 * WARPS + w] = E;            // pE_b
     const double dn = __shfl_down_sync(FULL, E, 1);
     Enext = (lane == 31) ? 0.0 : dn;
     e1_keep = e1;
@@ -346,7 +316,7 @@ __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &s
 
 template <int C, int WARPS, bool AMER, bool TBL>
 __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph &ph, const Sm &sm, const double cin_b,
-                                       const double e1_bwd, const double Enext, const int step)
+                                       const double e1_bwd, const double Enext)
 {
     constexpr int H = C / 2;
     constexpr int NT = 32 * WARPS;
@@ -354,14 +324,7 @@ __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph 
     const double *ncc = ph.slot + C * 32, *inv = ph.slot + 2 * C * 32;
     const double *lc = ph.slot + 3 * C * 32;
     double S = 0.0;
-    {
-        constexpr int RING = Layout<C, WARPS>::RING;
-        const int v1 = min(WARPS - 1, w + ph.Kb);
-        for (int v = v1; v > w; --v) ring_wait(sm.prog + WARPS, v, step);
-        __threadfence_block();
-        const volatile double *slot = (const volatile double *)sm.ringB + (step % RING) * WARPS;
-        for (int v = v1; v > w; --v) S = fma(sm.part[3 * WARPS + v], S, slot[v]);
-    }
+    for (int v = min(WARPS - 1, w + ph.Kb); v > w; --v) S = fma(sm.part[3 * WARPS + v], S, sm.part[2 * WARPS + v]);
     const double cs = fma(TBL ? lc[LC_PAB * 32 + lane] : sm.PAc[32 + lane], S, Enext);
     double c1 = cs + cin_b;
     double c2 = fma(TBL ? lc[LC_HB1 * 32 + lane] : sm.cst[CST_HB1], cs, e1_bwd);
@@ -517,9 +480,6 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
     sm.PAc = sm.cst + 16;
     sm.wb = sm.PAc + 64;
     sm.ish = (int *)(sm.wb + 32);
-    sm.ringF = sm.wb + 32 + 8;
-    sm.ringB = sm.ringF + LY::RING * WARPS;
-    sm.prog = (int *)(sm.ringB + LY::RING * WARPS);
 
     const int64_t sid = first + blockIdx.x;
     if (sid >= B.n_solves) return;
@@ -542,7 +502,6 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
     const int t0 = pad / C;                            // thread that owns row 0 (and boundary node 0)
     const int k0 = (t == t0) ? pad % C : -1;
 
-    if (t < 2 * WARPS) sm.prog[t] = 0;
     if (t == 0) {
         int spot_idx = 0, strike_idx = 0, ka, kb;
         if (snap) {
@@ -635,27 +594,14 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                 double cin_n = ph.cB * w_now - ph.cA * w_next;
                 const double cin_b = cin * top_mult;            // enters the top row through its ncc
                 double e1f = 0.0, Eprev = 0.0, e1b = 0.0, Enext = 0.0;
-                // no block-wide barrier: the warps exchange their totals through the rings (see the file header)
-#ifdef FDM_CTA_BARRIER_SYNC      // A/B switch: block-wide barriers between the phases (the former scheme)
-                if (ph.cls == 2) step_a<C, WARPS, AMER, true>(V, L, ph, sm, k0, cin, e1f, Eprev, gstep);
-                else if (ph.cls == 1) step_a<C, WARPS, AMER, false>(V, L, ph, sm, -1, 0.0, e1f, Eprev, gstep);
+                if (ph.cls == 2) step_a<C, WARPS, AMER, true>(V, L, ph, sm, k0, cin, e1f, Eprev);
+                else if (ph.cls == 1) step_a<C, WARPS, AMER, false>(V, L, ph, sm, -1, 0.0, e1f, Eprev);
                 __syncthreads();
-                if (ph.cls == 2) step_b<C, WARPS, AMER, true>(V, ph, sm, wf, cin_b, e1f, Eprev, e1b, Enext, gstep);
-                else if (ph.cls == 1) step_b<C, WARPS, AMER, false>(V, ph, sm, wf, cin_b, e1f, Eprev, e1b, Enext, gstep);
+                if (ph.cls == 2) step_b<C, WARPS, AMER, true>(V, ph, sm, wf, cin_b, e1f, Eprev, e1b, Enext);
+                else if (ph.cls == 1) step_b<C, WARPS, AMER, false>(V, ph, sm, wf, cin_b, e1f, Eprev, e1b, Enext);
                 __syncthreads();
-                if (ph.cls == 2) step_c<C, WARPS, AMER, true>(V, L, ph, sm, cin_b, e1b, Enext, gstep);
-                else if (ph.cls == 1) step_c<C, WARPS, AMER, false>(V, L, ph, sm, cin_b, e1b, Enext, gstep);
-#else
-                if (ph.cls == 2) {
-                    step_a<C, WARPS, AMER, true>(V, L, ph, sm, k0, cin, e1f, Eprev, gstep);
-                    step_b<C, WARPS, AMER, true>(V, ph, sm, wf, cin_b, e1f, Eprev, e1b, Enext, gstep);
-                    step_c<C, WARPS, AMER, true>(V, L, ph, sm, cin_b, e1b, Enext, gstep);
-                } else if (ph.cls == 1) {
-                    step_a<C, WARPS, AMER, false>(V, L, ph, sm, -1, 0.0, e1f, Eprev, gstep);
-                    step_b<C, WARPS, AMER, false>(V, ph, sm, wf, cin_b, e1f, Eprev, e1b, Enext, gstep);
-                    step_c<C, WARPS, AMER, false>(V, L, ph, sm, cin_b, e1b, Enext, gstep);
-                }
-#endif
+                if (ph.cls == 2) step_c<C, WARPS, AMER, true>(V, L, ph, sm, cin_b, e1b, Enext);
+                else if (ph.cls == 1) step_c<C, WARPS, AMER, false>(V, L, ph, sm, cin_b, e1b, Enext);
                 Vb = w_now;                                     // V[0] = V_min, V[-1] = V_max (:505-506)
                 ++gstep;
                 if (TRACE && trace) {

@@ -90,9 +90,16 @@ class DiscreteBarrierFDMPricer:
         self.option_days = option_days
         self.option_settlement_days = option_settlement_days
         self.calendar = SouthAfrica()
-        self.discount_curve_df = discount_curve.copy() if discount_curve is not None else None
-        self.forward_curve_df = forward_curve.copy() if forward_curve is not None else None
-        self._discount_lookup = CurveLookup(self.discount_curve_df) if self.discount_curve_df is not None else None
+        if isinstance(discount_curve, CurveLookup):
+            # internal fast path of the batch runner: one shared date -> NACA table instead of a DataFrame copy and
+            # a fresh table per pricer (the reference copies the frame, :118-119, and scans it per look-up)
+            self._discount_lookup = discount_curve
+            self.discount_curve_df = discount_curve.df
+            self.forward_curve_df = forward_curve.df if isinstance(forward_curve, CurveLookup) else forward_curve
+        else:
+            self.discount_curve_df = discount_curve.copy() if discount_curve is not None else None
+            self.forward_curve_df = forward_curve.copy() if forward_curve is not None else None
+            self._discount_lookup = CurveLookup(self.discount_curve_df) if self.discount_curve_df is not None else None
         self.dividend_schedule = sorted(dividend_schedule or [], key=lambda x: x[0])
         self.trade_id = trade_id
         self.direction = direction
@@ -262,9 +269,9 @@ class DiscreteBarrierFDMPricer:
         return set(hostlogic.dbfp_monitor_steps(self.time_to_expiry, dt, self.num_time_steps, self.monitor_times))
 
     # ---- the solve ---------------------------------------------------------------------------------------
-    def _solve_descriptor(self, apply_KO: bool, N_time: Optional[int] = None, sigma: Optional[float] = None) -> SolveBatch:
-        """Descriptor of one ``_solve_grid`` call at volatility ``sigma`` (default: ``self.sigma``).  Like the
-        reference, a bumped sigma re-runs ``configure_grid`` (the domain and ``num_space_nodes`` follow it)."""
+    def _solve_args(self, apply_KO: bool, N_time: Optional[int] = None, sigma: Optional[float] = None) -> Dict[str, Any]:
+        """Arguments of :func:`hostlogic.build_dbfp_batch` for one ``_solve_grid`` call at volatility ``sigma``
+        (default ``self.sigma``).  Like the reference, a bumped sigma re-runs ``configure_grid`` (the domain follows it)."""
         sig = self.sigma if sigma is None else sigma
         N_space, N_steps, S_min, S_max = self.choose_grid_parameters(
             S0=self.spot - self.pv_divs, K=self.strike, lower_barrier=self.lower_barrier,
@@ -272,14 +279,17 @@ class DiscreteBarrierFDMPricer:
         n_march = int(N_time) if N_time is not None else int(N_steps)
         assert n_march >= 1
         ko = self.barrier_type if (apply_KO and self.barrier_type in _KO_TYPES) else "none"
-        return hostlogic.build_dbfp_batch(
-            S0_eff=[self.spot - self.pv_divs], K=[self.strike], T=[self.time_to_expiry], sigma=[sig],
-            r=[self.discount_rate_nacc], b=[self.carry_rate_nacc], q=[self.div_yield_nacc],
-            is_call=[self.option_type == "call"], ko_type=[ko], lower_barrier=[self.lower_barrier],
-            upper_barrier=[self.upper_barrier], rebate_amount=[self.rebate_amount],
-            rebate_at_hit=[self.rebate_at_hit], monitor_times=[self.monitor_times], num_space_nodes=[N_space],
-            num_time_steps=[N_steps], rannacher_steps=[self.rannacher_steps], S_min=[S_min], S_max=[S_max],
-            n_march=[n_march])
+        return dict(
+            S0_eff=self.spot - self.pv_divs, K=self.strike, T=self.time_to_expiry, sigma=sig,
+            r=self.discount_rate_nacc, b=self.carry_rate_nacc, q=self.div_yield_nacc,
+            is_call=self.option_type == "call", ko_type=ko, lower_barrier=self.lower_barrier,
+            upper_barrier=self.upper_barrier, rebate_amount=self.rebate_amount, rebate_at_hit=self.rebate_at_hit,
+            monitor_times=self.monitor_times, num_space_nodes=N_space, num_time_steps=N_steps,
+            rannacher_steps=self.rannacher_steps, S_min=S_min, S_max=S_max, n_march=n_march)
+
+    def _solve_descriptor(self, apply_KO: bool, N_time: Optional[int] = None, sigma: Optional[float] = None) -> SolveBatch:
+        """Descriptor of one ``_solve_grid`` call."""
+        return hostlogic.build_dbfp_batch(**{k: [v] for k, v in self._solve_args(apply_KO, N_time, sigma).items()})
 
     def _solve_grid(self, apply_KO: bool, N_time: int = None) -> List[float]:
         """One PDE solve on the GPU; returns the value vector (``num_space_nodes`` entries, see module docstring)."""
@@ -439,7 +449,7 @@ def price_and_greeks_batch(pricers: Sequence[DiscreteBarrierFDMPricer], dv_sigma
     n = len(pricers)
     prices: List[Optional[float]] = [None] * n
     greeks: List[Optional[Dict[str, float]]] = [None] * n
-    parts, owners = [], []
+    args, owners = [], []
     for i, pr in enumerate(pricers):
         bt = pr.barrier_type.lower()
         if bt == "none" or (bt in ("down-and-out", "up-and-out") and pr.already_hit) \
@@ -452,15 +462,14 @@ def price_and_greeks_batch(pricers: Sequence[DiscreteBarrierFDMPricer], dv_sigma
         original_bt = pr.barrier_type
         pr.barrier_type = {"down-and-in": "down-and-out", "up-and-in": "up-and-out"}.get(bt, bt)
         try:
-            pr._build_log_grid()
-            parts.append(pr._solve_descriptor(True))
-            parts.append(pr._solve_descriptor(True, sigma=pr.sigma + dv_sigma))
+            args.append(pr._solve_args(True))
+            args.append(pr._solve_args(True, sigma=pr.sigma + dv_sigma))
         finally:
             pr.barrier_type = original_bt
         owners.append(i)
     n_solves = node_steps = 0
-    if parts:
-        batch = SolveBatch.concat(parts)
+    if args:
+        batch = hostlogic.build_dbfp_batch(**{k: [a[k] for a in args] for k in args[0]})
         need_dump = any(pricers[i].pv_divs != 0.0 for i in owners)
         res = solve_host(batch, dump=need_dump)
         n_solves, node_steps = batch.n_solves, batch.node_steps()

@@ -14,6 +14,7 @@ import numpy as np
 import pandas as pd
 
 from . import shard
+from .american import CurveLookup
 from .discrete_barrier_fdm_pricer import DiscreteBarrierFDMPricer, price_and_greeks_batch
 from .utils import create_rate_df_iso, naca_to_nacc
 
@@ -33,12 +34,13 @@ def _build_pricer(S0, K, sigma, rate, barrier_type, upper_barrier, lower_barrier
                   _curve_cache: Optional[dict] = None) -> DiscreteBarrierFDMPricer:
     """The constructor call of run_config_scenarios.py:60-94 (curves: :52-57, ISO dates)."""
     naca_to_nacc(rate)                                   # :50, kept for its validation side effects
-    if _curve_cache is not None and rate in _curve_cache:
+    if _curve_cache is not None:
+        # batch path: one date -> NACA table per distinct rate, shared by the pricers (no DataFrame copies)
+        if rate not in _curve_cache:
+            _curve_cache[rate] = CurveLookup(create_rate_df_iso(rate))
         curve = _curve_cache[rate]
     else:
         curve = create_rate_df_iso(rate)
-        if _curve_cache is not None:
-            _curve_cache[rate] = curve
     return DiscreteBarrierFDMPricer(
         spot=S0, strike=K, valuation_date=valuation, maturity_date=maturity, sigma=sigma, option_type=opt_type,
         barrier_type=barrier_type, lower_barrier=lower_barrier, upper_barrier=upper_barrier, already_in=already_in,

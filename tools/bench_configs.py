@@ -163,7 +163,55 @@ def cfg5(peak):
          "(3 grids) = one GPU's share of the 1M-option book, 400 x 400", batch, ms, flops, peak, par, {"launches": n_launch})
 
 
-ALL = {"cfg1": cfg1, "cfg2": cfg2, "am400": am400, "cfg4": cfg4, "cfg5": cfg5}
+def dbfp(peak):
+    """Barrier scenario sweep of run_config_scenarios.py on its own grid: DiscreteBarrierFDMPricer, put, valuation
+    2025-07-28, maturity 2025-08-28, weekday monitoring, num_time_steps = 500 -> 2133 space nodes; 2 PDE solves per
+    row (sigma, sigma + 1e-4).  Device-resident kernel time and the end-to-end time of the runner (host pricer
+    construction + descriptors + H2D + solves + D2H + result rows)."""
+    import datetime as dt
+    import time
+    import pandas as pd
+    from finite_difference_b200 import run_config_scenarios as rcs
+    from finite_difference_b200.discrete_barrier_fdm_pricer import price_and_greeks_batch
+    n = 4096
+    rng = np.random.default_rng(SEED + 6)
+    val, mat = dt.date(2025, 7, 28), dt.date(2025, 8, 28)
+    mons = [d for d in (val + dt.timedelta(days=i) for i in range(32)) if d.weekday() < 5]
+    down = rng.uniform(size=n) < 0.5
+    frame = pd.DataFrame(dict(
+        scenario_name=[f"s{i}" for i in range(n)], S0=229.74, K=rng.uniform(180, 280, n), sigma=rng.uniform(0.15, 0.45, n),
+        rate=rng.choice(np.round(np.linspace(0.03, 0.10, 15), 4), n), barrier_type=np.where(down, "down-and-out", "up-and-out"),
+        upper_barrier=np.where(down, np.nan, rng.uniform(240, 330, n)), lower_barrier=np.where(down, rng.uniform(150, 220, n), np.nan),
+        FA_price=np.nan, FA_delta=np.nan, FA_gamma=np.nan, FA_vega=np.nan))
+    base = dict(valuation=val, maturity=mat, monitor_dates=mons, opt_type="put", num_time_steps=500)
+    cache = {}
+    pricers = [rcs._build_pricer(r["S0"], r["K"], r["sigma"], r["rate"], r["barrier_type"], rcs._opt(r["upper_barrier"]),
+                                 rcs._opt(r["lower_barrier"]), _curve_cache=cache, **base) for _, r in frame.iterrows()]
+    args = []
+    for p in pricers:
+        args.append(p._solve_args(True)); args.append(p._solve_args(True, sigma=p.sigma + 1e-4))
+    batch = hostlogic.build_dbfp_batch(**{k: [a[k] for a in args] for k in args[0]})
+    ms, _, res = timed(batch)
+    worst = 0.0
+    for i in range(0, 16, 2):
+        a = args[i]
+        o = oracle.dbfp_solve(a["S_min"], a["S_max"], a["S0_eff"], a["S0_eff"], a["K"], a["T"], a["sigma"], a["r"], a["b"], a["q"],
+                              a["is_call"], a["ko_type"], a["lower_barrier"], a["upper_barrier"], a["rebate_amount"],
+                              a["rebate_at_hit"], a["monitor_times"], a["num_space_nodes"], a["num_time_steps"],
+                              a["rannacher_steps"])
+        worst = max(worst, abs(res.price[i] - o.price) / max(abs(o.price), 1e-2))
+    rcs.run_scenarios_frame(frame.iloc[:64], base)            # warm-up (scipy import, workspace)
+    t0 = time.perf_counter()
+    rcs.run_scenarios_frame(frame, base)
+    e2e_s = time.perf_counter() - t0
+    line("dbfp", f"barrier scenario sweep (run_config_scenarios shape, DiscreteBarrierFDMPricer): {n} rows x 2 solves, "
+         "2133 space nodes x 500 steps, daily monitoring, Rannacher 2", batch, ms, 13.0, peak,
+         {"n": 8, "max_rel_err_price": worst, "tolerance": 1e-10},
+         {"e2e_runner": {"value": batch.node_steps() / e2e_s, "unit": "node-steps/s", "seconds": e2e_s,
+                         "note": "host-bound: one Python pricer object per row (constructor + descriptors ~0.5 ms/row)"}})
+
+
+ALL = {"cfg1": cfg1, "cfg2": cfg2, "am400": am400, "cfg4": cfg4, "cfg5": cfg5, "dbfp": dbfp}
 
 if __name__ == "__main__":
     oracle.build()
