@@ -327,8 +327,10 @@ def run_b200(args):
                 "traffic": traffic,
                 "peak_source": "fdm_fp64_peak register-resident DFMA micro-benchmark, measured in this run "
                                "(MEASURED_PEAKS.json has no FP64 entry)",
-                "flops_per_node_step": FLOPS_PER_NODE_STEP_AMERICAN, "kernel": "fdm_warp_kernel<16,true,false>",
+                "flops_per_node_step": FLOPS_PER_NODE_STEP_AMERICAN, "kernel": "fdm_lean_kernel<16,true,false>",
                 "kernel_ms_per_launch": kern_ms / args.steps,
+                "launches_per_step": "fdm_lean_kernel<16,true,false> (all 800k solves) + fdm_warp_kernel<16,true,false> in "
+                                     "only_rest mode (takes what the lean kernel hands back: nothing here, exits at once)",
                 "hbm": {"algorithmic_bytes_per_launch": desc_bytes + res_bytes,
                         "achieved_gbs": (desc_bytes + res_bytes) / kern_s / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",

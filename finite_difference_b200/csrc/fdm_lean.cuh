@@ -41,16 +41,15 @@ constexpr unsigned long long RETRY_BITS = 0x7ff8b200dead0001ull;   // quiet NaN:
 constexpr int MAX_PIVOT_ITERS = 4096;
 
 // Compiled size classes: a kernel with C slots per lane serves 32 (C-1) <= n_int <= 32 C interior rows
-// (400 nodes -> 13, 300 -> 10).  Other sizes: fdm_warp_kernel.
-// Measured on B200 (tools/time_variants.py): with 10..13 slots per lane the kernel fits 128 registers and 16 solves
-// per SM (400-node grids: +15 % American, +8 % barrier over fdm_warp_kernel).  16 slots (500 nodes) spill at 128
-// registers and only tie fdm_warp_kernel, and below ~250 nodes the per-phase setup outweighs the extra warps:
-// those sizes stay with fdm_warp_kernel.  Define FDM_LEAN_ALL_CLASSES to compile every class (parity tests of the
-// layout at the other sizes).
+// (500 nodes -> 16, 400 -> 13, 300 -> 10).  Other sizes: fdm_warp_kernel.
+// Measured on B200 (tools/time_lean.py, bench.py): 10..13 slots per lane (300..416 rows) gain +15..33 % over
+// fdm_warp_kernel, 16 slots (500-node grids, cfg3) +5 %; below ~250 nodes the per-phase setup outweighs the extra
+// resident warps, so those sizes stay with fdm_warp_kernel.  Define FDM_LEAN_ALL_CLASSES to compile every class
+// (parity tests of the layout at the other sizes).
 #ifdef FDM_LEAN_ALL_CLASSES
 #define FDM_LEAN_CLASSES {4, 7, 8, 10, 13, 16}
 #else
-#define FDM_LEAN_CLASSES {10, 13}
+#define FDM_LEAN_CLASSES {10, 13, 16}
 #endif
 constexpr int N_CLASSES_MAX = 8;
 struct ClassList { int c[N_CLASSES_MAX]; int n; };
@@ -70,6 +69,9 @@ __host__ __device__ constexpr int class_of(int n_int)
     return 0;
 }
 
+enum { LC_KAP = 0, LC_KAPL, LC_KAPU, LC_D, LC_ZC, LC_AB1, LC_AB2, LC_ABL, LC_CA, LC_CB, LC_N };
+constexpr int PW_MAX = 16;      // powers of NM kept in shared memory (warp-uniform, broadcast reads)
+
 // shared-memory tables of one warp (doubles): phi3 [C][32] | Wf, Wb [DIRECT_TERMS][32] | Af, Ab [SCAN_LEVELS][32]
 template <int C>
 struct Tables {
@@ -81,18 +83,24 @@ struct Tables {
         Wb = Wf + DIRECT_TERMS * 32;
         Af = Wb + DIRECT_TERMS * 32;
         Ab = Af + SCAN_LEVELS * 32;
-        par = Ab + SCAN_LEVELS * 32;        // [0] k_eff [1] s_n: inputs of the boundary refill, parked out of registers
+        par = Ab + SCAN_LEVELS * 32;        // [0] k_eff [1] s_n [2] s_0: inputs of the boundary refill, parked out of registers
+        lc = par + 4;                       // [LC_N][32] per-lane phase constants read once per step
     }
-    __device__ double *end() const { return par + 4; }
+    __device__ double *end() const { return lc + LC_N * 32 + PW_MAX; }
+    double *lc;
+    // P[j] = NM^j, j = 0..C-C/2 for the 16-slot class.  Kept out of registers on purpose: at 128 registers the
+    // compiler would otherwise rebuild the powers with a dependent DMUL chain in every time step.
+    __device__ double pw(int j) const { return ((const volatile double *)(lc + LC_N * 32))[j]; }
 };
 template <int C>
-constexpr int smem_doubles() { return 32 * C + 2 * DIRECT_TERMS * 32 + 2 * SCAN_LEVELS * 32 + 4; }
+constexpr int smem_doubles() { return 32 * C + 2 * DIRECT_TERMS * 32 + 2 * SCAN_LEVELS * 32 + 4 + LC_N * 32 + PW_MAX; }
 
 template <int C>
 struct Ph {
     static constexpr int H = C / 2, PW = C - C / 2;
+    static constexpr bool P_SMEM = C > 13;   // where the powers of NM live (measured: registers win up to 13 slots)
     double NM, NCC, INV;      // -A_L/den_inf, -A_U/den_inf, scale/den_inf
-    double P[PW + 1];         // P[j] = NM^j, j = 0..PW
+    double P[PW + 1];         // P[j] = NM^j, j = 0..PW (registers, C <= 13; else Tables::pw)
     double cA, cB;            // boundary coefficients of this lane, already divided by NM (lane 0) / NCC (lane 31)
     double q;                 // (1-theta)/theta  (linear march)
     double kap;               // g = kap * xs_0
@@ -196,6 +204,11 @@ __device__ __forceinline__ bool setup_phase(double theta, double dt, double a, d
     ph.P[0] = 1.0;
 #pragma unroll
     for (int j = 1; j <= PW; ++j) ph.P[j] = ph.P[j - 1] * NM;
+    __syncwarp();
+    if (Ph<C>::P_SMEM && lane == 0) {
+#pragma unroll
+        for (int j = 0; j <= PW; ++j) T.lc[LC_N * 32 + j] = ph.P[j];
+    }
     const double af1 = ipow(NM, H), af2 = ipow(NM, cntU);
     ph.ab1 = ipow(NCC, cntU);
     ph.ab2 = ipow(NCC, H);
@@ -257,25 +270,40 @@ __device__ __forceinline__ bool setup_phase(double theta, double dt, double a, d
     if (!(fabs(Zl) > 1e-30 * fabs(xs00))) Zl = 0.0;
     ph.D = Dl;
     ph.Zc = Zl;
+    if (Ph<C>::P_SMEM) {
+        T.lc[LC_KAP * 32 + lane] = ph.kap;   T.lc[LC_KAPL * 32 + lane] = ph.kapL; T.lc[LC_KAPU * 32 + lane] = ph.kapU;
+        T.lc[LC_D * 32 + lane] = ph.D;       T.lc[LC_ZC * 32 + lane] = ph.Zc;     T.lc[LC_AB1 * 32 + lane] = ph.ab1;
+        T.lc[LC_AB2 * 32 + lane] = ph.ab2;   T.lc[LC_ABL * 32 + lane] = ph.abl;   T.lc[LC_CA * 32 + lane] = ph.cA;
+        T.lc[LC_CB * 32 + lane] = ph.cB;
+    }
+    __syncwarp();
     return !__any_sync(FULL, bad);
 }
+
+// Per-lane phase constants that are used once per step.  In the 16-slot class they are read from shared memory at
+// the point of use (volatile: not hoisted back into registers), which frees ~20 registers in the time loop -- there
+// it is the difference between losing to fdm_warp_kernel and beating it; with 13 slots or fewer there is room and
+// registers are faster (measured both ways).
+#define LCV(ph, T, lane, field, idx) \
+    (Ph<C>::P_SMEM ? ((const volatile double *)(T).lc)[(idx) * 32 + (lane)] : (ph).field)
 
 // direct carry, split in two so that independent work can be issued between the shuffles and their use
 template <bool UP>
 struct CarryShf {
-    double t[DIRECT_TERMS];
+    double t1, t2, t3, t4, t5, t6;       // scalars, always initialised: an array here ends up in local memory
     __device__ __forceinline__ void issue(const double e_end, const int terms)
     {
+        t1 = t2 = t3 = t4 = t5 = t6 = 0.0;
         if (terms) {
-            t[0] = UP ? __shfl_up_sync(FULL, e_end, 1) : __shfl_down_sync(FULL, e_end, 1);
-            t[1] = UP ? __shfl_up_sync(FULL, e_end, 2) : __shfl_down_sync(FULL, e_end, 2);
+            t1 = UP ? __shfl_up_sync(FULL, e_end, 1) : __shfl_down_sync(FULL, e_end, 1);
+            t2 = UP ? __shfl_up_sync(FULL, e_end, 2) : __shfl_down_sync(FULL, e_end, 2);
             if (terms > 2) {
-                t[2] = UP ? __shfl_up_sync(FULL, e_end, 3) : __shfl_down_sync(FULL, e_end, 3);
-                t[3] = UP ? __shfl_up_sync(FULL, e_end, 4) : __shfl_down_sync(FULL, e_end, 4);
+                t3 = UP ? __shfl_up_sync(FULL, e_end, 3) : __shfl_down_sync(FULL, e_end, 3);
+                t4 = UP ? __shfl_up_sync(FULL, e_end, 4) : __shfl_down_sync(FULL, e_end, 4);
             }
             if (terms > 4) {
-                t[4] = UP ? __shfl_up_sync(FULL, e_end, 5) : __shfl_down_sync(FULL, e_end, 5);
-                t[5] = UP ? __shfl_up_sync(FULL, e_end, 6) : __shfl_down_sync(FULL, e_end, 6);
+                t5 = UP ? __shfl_up_sync(FULL, e_end, 5) : __shfl_down_sync(FULL, e_end, 5);
+                t6 = UP ? __shfl_up_sync(FULL, e_end, 6) : __shfl_down_sync(FULL, e_end, 6);
             }
         }
     }
@@ -283,9 +311,9 @@ struct CarryShf {
                                               const double *__restrict__ A, const int lane) const
     {
         if (terms) {
-            double acc0 = W[0 * 32 + lane] * t[0], acc1 = W[1 * 32 + lane] * t[1];
-            if (terms > 2) { acc0 = fma(W[2 * 32 + lane], t[2], acc0); acc1 = fma(W[3 * 32 + lane], t[3], acc1); }
-            if (terms > 4) { acc0 = fma(W[4 * 32 + lane], t[4], acc0); acc1 = fma(W[5 * 32 + lane], t[5], acc1); }
+            double acc0 = W[0 * 32 + lane] * t1, acc1 = W[1 * 32 + lane] * t2;
+            if (terms > 2) { acc0 = fma(W[2 * 32 + lane], t3, acc0); acc1 = fma(W[3 * 32 + lane], t4, acc1); }
+            if (terms > 4) { acc0 = fma(W[4 * 32 + lane], t5, acc0); acc1 = fma(W[5 * 32 + lane], t6, acc1); }
             return acc0 + acc1;
         }
         return lane_carry<UP>(e_end, 0, W, A, lane);        // Kogge-Stone scan
@@ -332,7 +360,8 @@ __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const
     for (int k = H; k < C - 1; ++k) { b = fma(NM, b, V[k]); V[k] = b; }
     b = fma(nmL, b, V[C - 1]);
     V[C - 1] = last ? b : 0.0;
-    const double af2 = last ? ph.P[PW] : ph.P[PW - 1];
+    auto pw = [&](const int j) -> double { return Ph<C>::P_SMEM ? T.pw(j) : ph.P[j]; };
+    const double af2 = last ? pw(PW) : pw(PW - 1);
     const double e_end = fma(af2, a, b);
     CarryShf<true> shf_f;
     shf_f.issue(e_end, ph.terms);
@@ -343,19 +372,21 @@ __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const
 #pragma unroll
     for (int k = H - 1; k >= 0; --k) e2 = fma(NCC, e2, V[k]);
     const double c_in = shf_f.combine(e_end, ph.terms, T.Wf, T.Af, lane);            // carry into slot 0
-    const double c_mid = fma(ph.P[H], c_in, a);                                      // carry into slot H (= u_{H-1})
+    const double pH = pw(H);
+    const double c_mid = fma(pH, c_in, a);                                           // carry into slot H (= u_{H-1})
     // true u = u_loc + NM^(k+1) carry  =>  backward local ends pick up kap * carry
-    double e_end_b = fma(ph.ab2, fma(ph.kapU, c_mid, e1), fma(ph.kapL, c_in, e2));
+    const double kapU = LCV(ph, T, lane, kapU, LC_KAPU);
+    double e_end_b = fma(LCV(ph, T, lane, ab2, LC_AB2), fma(kapU, c_mid, e1), fma(LCV(ph, T, lane, kapL, LC_KAPL), c_in, e2));
     CarryShf<false> shf_b;
     shf_b.issue(e_end_b, ph.terms);
     double cb = shf_b.combine(e_end_b, ph.terms, T.Wb, T.Ab, lane);
     // Sherman-Morrison: g = delta x_0 from lane 0's inclusive end value xs_0; R_0 -= g
-    const double g = ph.kap * __shfl_sync(FULL, fma(ph.abl, cb, e_end_b), 0);
-    const double c_in2 = fma(-g, ph.D, c_in);
-    const double c_mid2 = fma(ph.P[H], c_in2, a);
-    cb = fma(-g, ph.Zc, cb);
+    const double g = LCV(ph, T, lane, kap, LC_KAP) * __shfl_sync(FULL, fma(LCV(ph, T, lane, abl, LC_ABL), cb, e_end_b), 0);
+    const double c_in2 = fma(-g, LCV(ph, T, lane, D, LC_D), c_in);
+    const double c_mid2 = fma(pH, c_in2, a);
+    cb = fma(-g, LCV(ph, T, lane, Zc, LC_ZC), cb);
     double c1 = cb + cin_b;                                       // xs above the top slot
-    double c2 = fma(ph.ab1, cb, fma(ph.kapU, c_mid2, e1));        // xs of slot H
+    double c2 = fma(LCV(ph, T, lane, ab1, LC_AB1), cb, fma(kapU, c_mid2, e1));        // xs of slot H
     // ---- second passes: u = u_loc + P carry (independent), xs chain, projection --------------------------
     auto slot_of = [](const int i) -> int {
         if (i == 0) return C - 1;
@@ -370,19 +401,19 @@ __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const
 #pragma unroll
         for (int i = 0; i < PF; ++i) pf[i] = T.phi3[slot_of(i < C ? i : C - 1) * 32 + lane];
     }
-    const double pL = last ? ph.P[PW] : 0.0;
+    const double pL = last ? pw(PW) : 0.0;
 #pragma unroll
     for (int i = 0; i < C; ++i) {
         const int k = slot_of(i);
         double xs;
         bool keep = true;
         if (k >= H) {
-            const double u = fma(k < C - 1 ? ph.P[k - H + 1] : pL, c_mid2, V[k]);
+            const double u = fma(k < C - 1 ? pw(k - H + 1) : pL, c_mid2, V[k]);
             c1 = fma(k < C - 1 ? NCC : nccL, c1, u);
             xs = c1;
             keep = k < C - 1 ? true : last;
         } else {
-            const double u = fma(ph.P[k + 1], c_in2, V[k]);
+            const double u = fma(pw(k + 1), c_in2, V[k]);
             c2 = fma(NCC, c2, u);
             xs = c2;
         }
@@ -532,11 +563,11 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
                 break;
             }
             double w_next = fetch_boundary(m);
-            double cin = ph.cB * Vb - ph.cA * w_next;            // non-zero on lanes 0 and 31 only
+            double cin = LCV(ph, T, lane, cB, LC_CB) * Vb - LCV(ph, T, lane, cA, LC_CA) * w_next;   // non-zero on lanes 0 and 31 only
             for (; m < m_end; ++m) {
                 const double w_now = w_next;
                 w_next = fetch_boundary(m + 1);
-                double cin_n = ph.cB * w_now - ph.cA * w_next;
+                double cin_n = LCV(ph, T, lane, cB, LC_CB) * w_now - LCV(ph, T, lane, cA, LC_CA) * w_next;
                 march_step<C, AMER>(V, L, ph, (lane == 0) ? cin : 0.0, (lane == 31) ? cin : 0.0, last, T, lane);
                 Vb = w_now;                                     // V[0] = V_min, V[-1] = V_max, :505-506
                 ++gstep;
@@ -568,7 +599,7 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
                     if (lane == 31 && n >= ko_b) Vb = reb;
                     ++mon_i;
                     next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
-                    cin_n = ph.cB * Vb - ph.cA * w_next;
+                    cin_n = LCV(ph, T, lane, cB, LC_CB) * Vb - LCV(ph, T, lane, cA, LC_CA) * w_next;
                 }
                 cin = cin_n;
             }
