@@ -80,3 +80,88 @@ def test_reference_exceptions():
     pr = pricer(dict(case, barrier_type="double-out"))
     with pytest.raises(ValueError, match="Unsupported barrier_type"):      # discrete_barrier_fdm_pricer.py:945
         pr.price_log2()
+
+
+def test_launch_hints_families_and_size_classes():
+    """fdm_launch_hints (pure host): kernel families, dividend flag, largest warp-sized grid, lean size classes."""
+    from finite_difference_b200 import hostlogic
+    am = hostlogic.build_american_batch([100.0] * 3, [100.0] * 3, [1.0] * 3, [0.2] * 3, [0.05] * 3, [0.05] * 3,
+                                        [False, True, False], [400, 500, 128], [50, 50, 50])
+    m = am.family_mask()
+    assert m & 1 and not m & 2 and not m & 4 and m & 8 and not m & 16          # American only, no dividends, warp-sized only
+    assert (m >> 8) & 0xfff == 500
+    assert m & (1 << 29)                                                         # size-class hints valid
+    assert m & (1 << 28)                                                         # 128 nodes: outside the lean classes
+    assert bin((m >> 20) & 0xff).count("1") == 2                                 # 400 and 500 nodes: two lean classes
+    case = next(c for c in DBFP if c["id"] == "syn_doc_put_full500")
+    pr = pricer(case)
+    pr._build_log_grid()
+    b = pr._solve_descriptor(True)
+    m = b.family_mask()
+    assert m & 2 and not m & 1 and m & 16 and not m & 8                          # linear, CTA-sized grid (2132 intervals)
+
+
+def test_abi2_arrays_survive_take_and_concat():
+    from finite_difference_b200.batch import SolveBatch
+    a = pricer(next(c for c in DBFP if c["id"] == "syn_rebate_at_expiry"))
+    a._build_log_grid()
+    b = pricer(next(c for c in DBFP if c["id"] == "syn_double_out_solve"))
+    b._build_log_grid()
+    from finite_difference_b200 import hostlogic
+    plain = hostlogic.build_barrier_batch([100.0], [100.0], [1.0], [0.2], [0.05], [0.03], [True], ["down-and-out"], [90.0],
+                                          [None], [1.25], [[0.25, 0.5, 0.75]], [200], [200])
+    cat = SolveBatch.concat([a._solve_descriptor(True), plain, b._solve_descriptor(True)])
+    assert cat.n_solves == 3 and len(cat.mon_rebate) == len(cat.mon_step)
+    lo, hi = int(cat.mon_begin[1]), int(cat.mon_begin[2])
+    np.testing.assert_array_equal(cat.mon_rebate[lo:hi], 1.25)                   # the plain solve repeats its rebate
+    assert cat.b_bdry[1] == cat.b[1] == 0.03 and cat.barrier_up[2] == 260.0
+    sub = cat.take([2, 0])
+    assert sub.barrier_up[0] == 260.0 and sub.b_bdry[1] == a.carry_rate_nacc
+    assert len(sub.mon_rebate) == len(sub.mon_step) == (int(cat.mon_begin[3]) - hi) + lo
+    np.testing.assert_array_equal(sub.mon_rebate[:int(sub.mon_begin[1])], cat.mon_rebate[hi:])
+
+
+def test_batch_runner_composition_with_oracle_solves(monkeypatch):
+    """price_and_greeks_batch / run_scenarios_frame with the GPU call replaced by the C oracle: the host composition
+    (two solves per row, one-sided vega per vol point, theta, knock-in parity) reproduces the reference's
+    price_log2 / greeks_log2 goldens."""
+    import pandas as pd
+    from oracle import oracle
+    from finite_difference_b200 import batch as batch_mod, discrete_barrier_fdm_pricer as mod, run_config_scenarios as rcs
+    cases = [c for c in DBFP if c["id"].startswith("config_scenarios_1_") and c["num_time_steps"] == 60][:6]
+    captured = {}
+
+    def fake_solve_host(b, dump=False, trace=False):
+        n = b.n_solves
+        res = batch_mod.SolveResults(price=np.empty(n), delta=np.empty(n), gamma=np.empty(n), stencil_v=np.zeros((n, 4)),
+                                     stencil_s=np.zeros((n, 4)), idx=np.zeros((n, 4), np.int32), status=np.zeros(n, np.int32))
+        for i in range(n):
+            a = captured["args"][i]
+            o = oracle.dbfp_solve(a["S_min"], a["S_max"], a["S0_eff"], a["S0_eff"], a["K"], a["T"], a["sigma"], a["r"], a["b"],
+                                  a["q"], a["is_call"], a["ko_type"], a["lower_barrier"], a["upper_barrier"],
+                                  a["rebate_amount"], a["rebate_at_hit"], a["monitor_times"], a["num_space_nodes"],
+                                  a["num_time_steps"], a["rannacher_steps"])
+            res.price[i], res.delta[i], res.gamma[i] = o.price, o.delta, o.gamma
+        return res
+
+    real_build = hostlogic.build_dbfp_batch
+
+    def spy_build(**kw):
+        captured["args"] = [{k: v[i] for k, v in kw.items()} for i in range(len(kw["K"]))]
+        return real_build(**kw)
+
+    monkeypatch.setattr(mod, "solve_host", fake_solve_host)
+    monkeypatch.setattr(mod.hostlogic, "build_dbfp_batch", spy_build)
+    frame = pd.DataFrame([dict(scenario_name=c["id"], S0=c["spot"], K=c["strike"], sigma=c["sigma"], rate=c["naca"],
+                               barrier_type=c["barrier_type"], upper_barrier=c["upper_barrier"],
+                               lower_barrier=c["lower_barrier"], FA_price=None, FA_delta=None, FA_gamma=None, FA_vega=None)
+                          for c in cases])
+    base = dict(valuation=_golden.d(cases[0]["valuation"]), maturity=_golden.d(cases[0]["maturity"]),
+                monitor_dates=_golden.dbfp_monitor_dates(cases[0]), opt_type="put", num_time_steps=60)
+    df = rcs.run_scenarios_frame(frame, base)
+    for i, c in enumerate(cases):
+        ref = c["out"]["greeks_log2"]
+        leg = max(abs(c["out"]["solve_price"]), 1e-6)
+        assert abs(df.loc[i, "model_price"] - c["out"]["price_log2"]) <= 1e-12 * leg
+        assert abs(df.loc[i, "model_delta"] - ref["delta"]) <= 1e-10 * max(abs(ref["delta"]), 1.0)
+        assert abs(df.loc[i, "model_vega"] - ref["vega"]) <= 1e-9 * max(abs(ref["vega"]), 1.0)
