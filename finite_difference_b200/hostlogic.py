@@ -365,7 +365,7 @@ _DBFP_KO = {"none": 0, "down-and-out": FLAG_KO_DOWN, "up-and-out": FLAG_KO_UP, "
 
 def build_dbfp_batch(S0_eff, K, T, sigma, r, b, q, is_call, ko_type: Sequence[str], lower_barrier, upper_barrier,
                      rebate_amount, rebate_at_hit, monitor_times: Sequence, num_space_nodes, num_time_steps,
-                     rannacher_steps, S_min, S_max, n_march=None) -> SolveBatch:
+                     rannacher_steps, S_min, S_max, n_march=None, shared_monitors: bool = False) -> SolveBatch:
     """Descriptors for ``DiscreteBarrierFDMPricer._solve_grid`` (DBF:442-547), one entry per solve.
 
     ``ko_type[i]``: the projection actually applied ("none" for knock-in types or ``apply_KO=False``, DBF:415-416).
@@ -398,6 +398,28 @@ def build_dbfp_batch(S0_eff, K, T, sigma, r, b, q, is_call, ko_type: Sequence[st
     level = np.where((ko & FLAG_KO_DOWN) != 0, low, np.where((ko & FLAG_KO_UP) != 0, up, 0.0))
     level_up = np.where(both, up, 0.0)
     flags = ko | np.where(call, FLAG_CALL, 0) | FLAG_BDRY_TOP_NEXT | FLAG_PUT_BDRY_SMIN
+
+    if shared_monitors:
+        steps = np.array([k for k in dbfp_monitor_steps(float(T[0]), float(dt[0]), int(nt[0]), monitor_times)
+                          if k <= int(march[0])], dtype=np.int32)
+        has = ko != 0
+        counts = np.where(has, len(steps), 0)
+        mon_begin = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        mon_step = np.tile(steps, int(has.sum()))
+        if len(steps):
+            tau = steps.astype(np.float64) * float(dt[0])
+            reb = np.where(at_hit[has, None], rebate_amount[has, None],
+                           rebate_amount[has, None] * np.exp(-b[has, None] * tau[None, :]))          # DBF:421-424
+            mon_rebate = reb.reshape(-1)
+        else:
+            mon_rebate = np.zeros(0)
+        return SolveBatch(
+            x_min=x_min, dx=dx, sigma=sigma, r=r, b=b - q, spot=S0_eff, strike=K,
+            n_space=(ns - 1).astype(np.int32), flags=flags.astype(np.int32), rannacher=np.maximum(ran, 0).astype(np.int32),
+            seg_begin=np.arange(n + 1, dtype=np.int32), seg_steps=march.astype(np.int32), seg_dt=dt,
+            seg_tau0=np.zeros(n), seg_restart=np.ones(n, dtype=np.int32), seg_div=np.zeros(n),
+            barrier=level, rebate=rebate_amount, mon_begin=mon_begin, mon_step=mon_step, b_bdry=b, barrier_up=level_up,
+            mon_rebate=mon_rebate)
 
     mon_begin = [0]
     mon_step: List[int] = []

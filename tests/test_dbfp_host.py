@@ -147,7 +147,16 @@ def test_batch_runner_composition_with_oracle_solves(monkeypatch):
     real_build = hostlogic.build_dbfp_batch
 
     def spy_build(**kw):
-        captured["args"] = [{k: v[i] for k, v in kw.items()} for i in range(len(kw["K"]))]
+        n = len(kw["K"])
+        shared = kw.get("shared_monitors", False)
+
+        def at(k, v, i):
+            if k == "monitor_times":
+                return v if shared else v[i]
+            if isinstance(v, (list, tuple, np.ndarray)):
+                return v[i]
+            return v
+        captured["args"] = [{k: at(k, v, i) for k, v in kw.items() if k != "shared_monitors"} for i in range(n)]
         return real_build(**kw)
 
     monkeypatch.setattr(mod, "solve_host", fake_solve_host)
@@ -158,10 +167,13 @@ def test_batch_runner_composition_with_oracle_solves(monkeypatch):
                           for c in cases])
     base = dict(valuation=_golden.d(cases[0]["valuation"]), maturity=_golden.d(cases[0]["maturity"]),
                 monitor_dates=_golden.dbfp_monitor_dates(cases[0]), opt_type="put", num_time_steps=60)
-    df = rcs.run_scenarios_frame(frame, base)
-    for i, c in enumerate(cases):
-        ref = c["out"]["greeks_log2"]
-        leg = max(abs(c["out"]["solve_price"]), 1e-6)
-        assert abs(df.loc[i, "model_price"] - c["out"]["price_log2"]) <= 1e-12 * leg
-        assert abs(df.loc[i, "model_delta"] - ref["delta"]) <= 1e-10 * max(abs(ref["delta"]), 1.0)
-        assert abs(df.loc[i, "model_vega"] - ref["vega"]) <= 1e-9 * max(abs(ref["vega"]), 1.0)
+    from finite_difference_b200 import barrier_book
+    monkeypatch.setattr(barrier_book, "solve_host", fake_solve_host)
+    for vectorised in (False, True):            # one pricer object per row / numpy over the rows
+        df = rcs.run_scenarios_frame(frame, base, vectorised=vectorised)
+        for i, c in enumerate(cases):
+            ref = c["out"]["greeks_log2"]
+            leg = max(abs(c["out"]["solve_price"]), 1e-6)
+            assert abs(df.loc[i, "model_price"] - c["out"]["price_log2"]) <= 1e-12 * leg, (vectorised, i)
+            assert abs(df.loc[i, "model_delta"] - ref["delta"]) <= 1e-10 * max(abs(ref["delta"]), 1.0)
+            assert abs(df.loc[i, "model_vega"] - ref["vega"]) <= 1e-8 * max(abs(ref["vega"]), 1.0)

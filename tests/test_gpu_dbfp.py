@@ -94,8 +94,14 @@ def test_run_config_scenarios_batch_equals_per_row(tmp_path):
     frame.to_csv(cfg, index=False)
     base = dict(valuation=_golden.d(cases[0]["valuation"]), maturity=_golden.d(cases[0]["maturity"]),
                 monitor_dates=_golden.dbfp_monitor_dates(cases[0]), opt_type="put", num_time_steps=60)
-    df = rcs.run_all_scenarios(str(cfg), str(out), base)
+    df = rcs.run_all_scenarios(str(cfg), str(out), base)                 # vectorised host path (no dividends)
     assert list(df.columns) == list(pd.read_csv(out).columns) and len(df) == len(cases)
+    df_obj = rcs.run_scenarios_frame(pd.read_csv(cfg), base, vectorised=False)      # one pricer object per row
+    assert list(df_obj.columns) == list(df.columns)
+    for k in ("model_price", "model_delta", "model_gamma", "model_vega"):
+        scale = np.maximum(np.abs(df_obj[k].to_numpy()), 30.0 if k == "model_price" else 1e-2)
+        assert np.all(np.abs(df[k].to_numpy() - df_obj[k].to_numpy()) <= 1e-7 * scale), k
+    assert np.all(np.abs(df["model_price"].to_numpy() - df_obj["model_price"].to_numpy()) <= 1e-12 * 30.0)
     for i, c in enumerate(cases):
         ref = c["out"]["greeks_log2"]
         gv = max(abs(ref["price"]), abs(c["out"]["solve_price"]), 1e-6)

@@ -202,13 +202,23 @@ def dbfp(peak):
         worst = max(worst, abs(res.price[i] - o.price) / max(abs(o.price), 1e-2))
     rcs.run_scenarios_frame(frame.iloc[:64], base)            # warm-up (scipy import, workspace)
     t0 = time.perf_counter()
-    rcs.run_scenarios_frame(frame, base)
+    df = rcs.run_scenarios_frame(frame, base)                 # vectorised host path
     e2e_s = time.perf_counter() - t0
+    rcs.run_scenarios_frame(frame.iloc[:64], base, vectorised=False)
+    t0 = time.perf_counter()
+    df_obj = rcs.run_scenarios_frame(frame, base, vectorised=False)
+    e2e_obj_s = time.perf_counter() - t0
+    worst_vec = float(np.max(np.abs(df["model_price"].to_numpy() - df_obj["model_price"].to_numpy())
+                             / np.maximum(np.abs(df_obj["model_price"].to_numpy()), 1e-2)))
     line("dbfp", f"barrier scenario sweep (run_config_scenarios shape, DiscreteBarrierFDMPricer): {n} rows x 2 solves, "
          "2133 space nodes x 500 steps, daily monitoring, Rannacher 2", batch, ms, 13.0, peak,
          {"n": 8, "max_rel_err_price": worst, "tolerance": 1e-10},
          {"e2e_runner": {"value": batch.node_steps() / e2e_s, "unit": "node-steps/s", "seconds": e2e_s,
-                         "note": "host-bound: one Python pricer object per row (constructor + descriptors ~0.5 ms/row)"}})
+                         "path": "run_config_scenarios.run_scenarios_frame -> BarrierScenarioBook (numpy over rows) -> "
+                                 "fdm_solve_batch_host -> result frame",
+                         "per_object_path": {"value": batch.node_steps() / e2e_obj_s, "seconds": e2e_obj_s,
+                                             "note": "one Python pricer object per row"},
+                         "max_rel_price_diff_between_paths": worst_vec}})
 
 
 ALL = {"cfg1": cfg1, "cfg2": cfg2, "am400": am400, "cfg4": cfg4, "cfg5": cfg5, "dbfp": dbfp}
