@@ -277,7 +277,10 @@ def run_b200(args):
     value = total_node_steps * args.steps / (step_ms_max * 1e-3)
 
     # ---- end to end through the public host API ----------------------------------------------
-    res = book.run_fused("scenario")                 # warm-up
+    res = book.run_fused("scenario")                 # warm-up (including the result gather: NCCL sets up its
+    if world > 1:                                    # point-to-point channels on first use)
+        shard.gather_results({k: res[k] for k in ("price_log2", "price", "delta", "gamma", "vega", "theta")},
+                             mine, n_total, device=dev, dst=0)
     barrier()
     torch.cuda.synchronize(dev)
     e2e_steps = max(1, args.steps)
@@ -289,8 +292,9 @@ def run_b200(args):
             print(f"[debug] e2e iteration wall {1e3 * (time.perf_counter() - t_it):.1f} ms kernel {out['kernel_ms']:.1f} ms",
                   file=sys.stderr, flush=True)
         if world > 1:
+            # the sweep's one collective: per-option results to rank 0 (the other ranks keep their shards)
             shard.gather_results({k: out[k] for k in ("price_log2", "price", "delta", "gamma", "vega", "theta")},
-                                 mine, n_total, device=dev)
+                                 mine, n_total, device=dev, dst=0)
     torch.cuda.synchronize(dev)
     e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
     if world > 1:

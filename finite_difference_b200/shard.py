@@ -73,8 +73,10 @@ def init_distributed(backend: Optional[str] = None):
     return rank, world, local
 
 
-def gather_results(local: Dict[str, "np.ndarray"], owned: np.ndarray, n_total: int, device=None) -> Dict[str, np.ndarray]:
-    """All-gather per-option result columns onto every rank, in book order.
+def gather_results(local: Dict[str, "np.ndarray"], owned: np.ndarray, n_total: int, device=None,
+                   dst: Optional[int] = None) -> Optional[Dict[str, np.ndarray]]:
+    """Gather per-option result columns in book order: onto every rank (``dst=None``, all-gather) or onto rank
+    ``dst`` only (the other ranks return ``None`` and skip the unpacking -- the final result gather of a sweep).
 
     ``local[name]`` holds this rank's values for options ``owned`` (ascending global indices).
     Shards may differ in length by one option; columns are padded to the longest shard.
@@ -114,20 +116,32 @@ def gather_results(local: Dict[str, "np.ndarray"], owned: np.ndarray, n_total: i
             packed[: len(owned), off: off + c.shape[1]] = c
             off += c.shape[1]
         src = torch.from_numpy(packed).to(device)
-        dst = torch.empty((world * width, packed.shape[1]), dtype=src.dtype, device=device)
-        dist.all_gather_into_tensor(dst, src)
-        gathered[dt] = dst.cpu().numpy()
+        if dst is None:
+            buf = torch.empty((world * width, packed.shape[1]), dtype=src.dtype, device=device)
+            dist.all_gather_into_tensor(buf, src)
+            gathered[dt] = buf.cpu().numpy()
+        else:
+            me = dist.get_rank()
+            parts = [torch.empty_like(src) for _ in range(world)] if me == dst else None
+            dist.gather(src, parts, dst=dst)
+            if me == dst:
+                gathered[dt] = torch.cat(parts, dim=0).cpu().numpy()
+    if dst is not None and dist.get_rank() != dst:
+        return None
     idx_all = gathered[np.dtype(np.int64).str][:, -1]
     valid = idx_all >= 0
+    rows = idx_all[valid]
     out = {}
     for dt, cols in groups.items():
+        # one row scatter per dtype group (not one per column); the columns are returned as views of it
+        src = gathered[dt] if valid.all() else gathered[dt][valid]
+        full_group = np.empty((n_total, src.shape[1]), dtype=src.dtype)
+        full_group[rows] = src
         off = 0
         for k, c in cols:
             w = c.shape[1]
             if k != "__idx__":
                 v = np.asarray(local[k])
-                full = np.empty((n_total,) + v.shape[1:], dtype=v.dtype)
-                full[idx_all[valid]] = gathered[dt][valid, off: off + w].reshape((-1,) + v.shape[1:])
-                out[k] = full
+                out[k] = full_group[:, off: off + w].reshape((n_total,) + v.shape[1:])
             off += w
     return out

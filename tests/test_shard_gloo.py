@@ -43,6 +43,11 @@ def _worker(rank, world, port, n_total, tmp):
     full = shard.gather_results(local, mine, n_total)
     assert np.array_equal(full["price"], np.arange(n_total) * 1.5)
     assert np.array_equal(full["idx"][:, 1], -np.arange(n_total))
+    only0 = shard.gather_results(local, mine, n_total, dst=0)            # gather onto rank 0 only
+    if rank == 0:
+        assert np.array_equal(only0["price"], np.arange(n_total) * 1.5) and np.array_equal(only0["idx"][:, 0], np.arange(n_total))
+    else:
+        assert only0 is None
     np.save(os.path.join(tmp, f"r{rank}.npy"), mine)
     dist.barrier()
     dist.destroy_process_group()
