@@ -24,8 +24,9 @@ def nvcc_path() -> str:
 
 def build(force: bool = False, out: str = OUT, extra_flags=()) -> str:
     hdr = os.path.join(ROOT, "include", "fdm_b200.h")
-    if (not force and os.path.exists(out)
-            and os.path.getmtime(out) >= max(os.path.getmtime(SRC), os.path.getmtime(hdr))):
+    csrc = os.path.dirname(SRC)
+    deps = [hdr] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".h"))]
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(d) for d in deps):
         return out
     cmd = [nvcc_path(), *NVCC_FLAGS, *extra_flags, "-I", os.path.join(ROOT, "include"), "-o", out, SRC]
     subprocess.run(cmd, check=True)

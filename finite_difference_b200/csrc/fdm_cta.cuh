@@ -25,7 +25,29 @@
 
 namespace cta {
 
+#ifdef FDM_CTA_EXP_NOSYNC           // timing experiment only (wrong results): no block barriers in the step
+#define FDM_CTA_STEP_SYNC() __syncwarp()
+#else
+#define FDM_CTA_STEP_SYNC() __syncthreads()
+#endif
+
 constexpr double TRUNC_EPS = 1e-22;
+
+// Row-0 correction (see setup_phase) instead of per-slot table warps.  The 16-warp class runs at its 128-register cap:
+// its linear variant then spills inside the time loop and the table warps stay faster (8192-node barrier grids: 5.5e11
+// with tables, 4.1e11 with the correction), so that one variant keeps the tables.  Measured gains elsewhere: 8192-node
+// American +8 %, 2133-node barrier grids +33 %.
+template <int WARPS, bool AMER>
+__host__ __device__ constexpr bool row0_mode()
+{
+#ifdef FDM_CTA_ROW0_ALL
+    return true;
+#elif defined(FDM_CTA_NO_ROW0_CORR)
+    return false;
+#else
+    return WARPS < 16 || AMER;
+#endif
+}
 
 // nearest node to `level` with the reference's first-minimum tie-break
 // (fd_american_option_pricer.py:253; interior_only: discrete_barrier_fdm_pricer_cn.py:335).
@@ -56,7 +78,7 @@ struct Layout {
     static constexpr int SLOTS = WARPS <= 4 ? WARPS : (WARPS <= 5 ? 4 : 6);   // 5 warps: two CTAs per SM must fit shared memory
     static constexpr int SLOT_DOUBLES = 3 * C * 32 + 8 * 32;         // nm, ncc, inv [k][lane] + 8 per-lane constants
     static constexpr int R2 = NP > SLOTS * SLOT_DOUBLES ? NP : SLOTS * SLOT_DOUBLES;
-    static constexpr int SMALL = 4 * WARPS + 16 + 64 + 32 + 8;       // part, cst, PAc, wb, ishare
+    static constexpr int SMALL = 4 * WARPS + 16 + 64 + 32 + 8 + C + 8;   // part, cst, PAc, wb, ishare, nmp, smv
     static constexpr int TOTAL = 2 * NP + R2 + SMALL;
 };
 
@@ -69,7 +91,10 @@ struct Sm {
     double *PAc;    // [64] exclusive lane products of those warps, forward / backward
     double *wb;     // [32] moving Dirichlet values of the next 32 steps
     int *ish;       // [0] P [1] spot node [2] strike node [3,4] KO range [5] status [6,7] ex lo/hi [8] Kf [9] Kb
-                    // [10] first table warp [11] last table warp
+                    // [10] first table warp [11] last table warp [12] last warp the row-0 correction reaches (-1: table mode)
+    double *nmp;    // [C] powers NM^k of the steady-state forward multiplier (row-0 correction)
+    double *smv;    // [0] GF NCC^-k0, factor of the row-0 correction  [1] xs at slot 0 of the owner of row 0, current step
+                    // [2] Kc: what the Dirichlet carry leaves in [1] through the k0 dead slots below row 0
 };
 
 enum { CST_NM = 0, CST_NCC, CST_INV, CST_AF, CST_AB, CST_HF1, CST_HF2, CST_HB1, CST_HB2, CST_TOP, CST_PD };
@@ -77,6 +102,11 @@ enum { LC_AF = 0, LC_AB, LC_HF1, LC_HF2, LC_HB1, LC_HB2, LC_PAF, LC_PAB };
 
 struct Ph {
     double q, pd, NM, NCC, INV;
+    double gz;              // row-0 correction weight of this thread: GF * NM^(row of slot 0), 0 where it does not reach
+    int smc;                // this warp applies the row-0 correction in step_c
+    int bar3;               // the correction reaches beyond the warp of row 0: a third block barrier per step
+    double cF;              // owner of row 0: NM^-(k0+1), turns the Dirichlet term of row 0 into a forward carry; else 0
+    const double *invw;     // warp of row 0: pivot scaling by slot and lane, 0 on the dead slots below row 0
     double cA, cB;          // boundary coefficients of this thread (row-0 owner: A_L, B_L; last thread: A_U, B_U)
     int Kf, Kb;             // terms of the warp-to-warp Horner sums
     int cls;                // 0 padding only, 1 scalar coefficients, 2 per-slot coefficients
@@ -116,11 +146,48 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
             r_prev = r_cur;
             r_cur = r_next;
         }
+        const bool converged = P >= 0;
         if (P < 0) {                                    // not converged within the table: flagged, best effort
             P = cap;
             sm.ish[5] = 2;
             pv_inv[P] = r_cur; pv_nm[P] = -(A_L * r_cur); pv_ncc[P] = -(A_U * r_cur);
         }
+        // Row-0 correction (Sherman-Morrison).  The factors built from the steady-state pivot den_inf reproduce A except
+        // for entry (0,0): A = A_inf + delta e0 e0^T, delta = A_C - den_inf = A_L A_U / den_inf.  So A x = R is
+        // A_inf x = R - g e0 with g = delta x_0, and in the sweeps' variables (u forward, xs = den_inf x backward)
+        //     xs'_i = xs_i - g kappa NM^i (1 - rho^(n-i)),  rho = NM NCC,  kappa = 1 / (1 - rho),
+        //     g = delta r_inf xs_0 / (1 + delta r_inf kappa)   =>   xs'_i = xs_i - GF xs_0 NM^i.
+        // Every warp then runs with the three scalar coefficients; the warps the NM^i tail reaches (normally only the
+        // warp of row 0) subtract it in step_c.  Used when the pivots converged and the tail dies inside the grid
+        // (rho^(n-i) term below 1e-24); otherwise the per-slot tables below stay in charge.
+        double GF = 0.0;
+        int wz = -1;
+        if (row0_mode<WARPS, AMER>() && converged) {
+            const double rinf = pv_inv[P], nmc = pv_nm[P], nccc = pv_ncc[P];
+            const double kappa = 1.0 / (1.0 - nmc * nccc);
+            const double dl = A_L * A_U * rinf * rinf;                  // delta * r_inf
+            const double gf = dl * kappa / (1.0 + dl * kappa);
+            const double anm = fabs(nmc);
+            if (anm > 1e-10 && anm < 1.0 && fabs(nccc) > 1e-10 && isfinite(gf)) {
+                const double rows = (log(1e-24) - log(fmax(fabs(gf), 1e-300))) / log(anm);
+                const int Pz = rows < 1.0 ? 1 : (rows > 1e9 ? 0x3fffffff : (int)rows + 1);
+                if (Pz < n_int) { GF = gf; wz = min((pad + Pz - 1) / (32 * C), WARPS - 1); }
+            }
+            double pw = 1.0;
+            for (int k = 0; k < C; ++k) { sm.nmp[k] = pw; pw *= nmc; }
+        }
+        {
+            // the owner of row 0 publishes xs at its slot 0 = NCC^k0 xs_0 (k0 padding slots below row 0)
+            double unw = 1.0;
+            for (int k = 0; k < pad % C; ++k) unw /= pv_ncc[P];
+            sm.smv[0] = GF * unw;
+            // dead slot j of the owner of row 0 carries u_j = NM^(j+1) carry: sum_j NCC^j u_j reaches its slot 0
+            const double nmc = pv_nm[P], rho = pv_nm[P] * pv_ncc[P];
+            double kc = 0.0, rj = 1.0;
+            for (int k = 0; k < pad % C; ++k) { kc += rj; rj *= rho; }
+            sm.smv[2] = nmc * kc;
+        }
+        sm.ish[12] = wz;
         // growth-factor matching (fdm_b200.cu, growth_matched_pd); the linear march folds p + delta into inv
         const double pd = (P < cap && P < n_int) ? growth_matched_pd(A_L, A_C, A_U, B_L, B_C, B_U, ph.q, pv_inv[P], n_int) : 1.0;
         if (!AMER) {
@@ -128,8 +195,9 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
             for (int i = 0; i <= P; ++i) pv_inv[i] *= scale;
         }
         const int wf = pad / (32 * C);                              // warp that holds row 0
-        const int wl = min((pad + P - 1) / (32 * C), WARPS - 1);    // last warp with a head row
-        if (wl - wf + 1 > LY::SLOTS) sm.ish[5] = 2;                 // more table warps than staged slots
+        int wl = min((pad + P - 1) / (32 * C), WARPS - 1);          // last warp with a head row
+        if (wz >= 0) wl = wf - 1;                                   // row-0 correction: no table warps
+        else if (wl - wf + 1 > LY::SLOTS) sm.ish[5] = 2;            // more table warps than staged slots
         sm.ish[0] = P; sm.ish[10] = wf; sm.ish[11] = min(wl, wf + LY::SLOTS - 1);
         sm.cst[CST_NM] = pv_nm[P]; sm.cst[CST_NCC] = pv_ncc[P]; sm.cst[CST_INV] = pv_inv[P];
         sm.cst[CST_TOP] = (sm.ish[11] == WARPS - 1) ? 1.0 : 1.0 / pv_ncc[P];
@@ -143,6 +211,35 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
     ph.cA = owner0 ? A_L * bscale : ((t == LY::NT - 1) ? A_U * bscale : 0.0);
     ph.cB = owner0 ? B_L * bscale : ((t == LY::NT - 1) ? B_U * bscale : 0.0);
     ph.cls = (w < wf) ? 0 : (w <= wl ? 2 : 1);
+#ifdef FDM_CTA_EXP_NOTBL          // timing experiment only (wrong results): no table warps
+    if (ph.cls == 2) ph.cls = 1;
+#endif
+    ph.gz = 0.0; ph.cF = 0.0; ph.smc = 0; ph.bar3 = 0; ph.invw = sm.r2;
+    if (row0_mode<WARPS, AMER>()) {
+        const int wz = sm.ish[12];
+        ph.smc = (wz >= 0 && w >= wf && w <= wz) ? 1 : 0;
+        ph.bar3 = (wz > wf) ? 1 : 0;
+        ph.gz = 0.0;
+        ph.cF = 0.0;
+        ph.invw = sm.r2;
+        if (wz >= 0) {
+            // dead lanes below row 0 stay at exactly zero with a zero pivot scaling (V = 0 * xs - 0); the owner of
+            // row 0 has dead AND live slots: its warp reads the scaling by slot from shared memory
+            const int t0 = pad / C, k0 = pad % C;
+            if (w == wf) {
+#pragma unroll
+                for (int k = 0; k < C; ++k) sm.r2[k * 32 + lane] = (t * C + k >= pad) ? ph.INV : 0.0;
+            }
+            if (t == t0) ph.cF = 1.0 / pow(ph.NM, (double)(k0 + 1));
+            if (t < t0) ph.INV = 0.0;
+        }
+        const int e0 = t * C - pad;                                  // row of slot 0 (negative inside the padding)
+        if (ph.smc && e0 > -C) {
+            const double nmc = ph.NM;
+            const double mag = pow(fabs(nmc), (double)e0);
+            ph.gz = sm.smv[0] * ((nmc < 0.0 && (e0 & 1)) ? -mag : mag);
+        }
+    }
     ph.slot = sm.r2 + (size_t)max(w - wf, 0) * LY::SLOT_DOUBLES;
 
     if (ph.cls != 0) {
@@ -245,9 +342,9 @@ __device__ __forceinline__ double warp_scan(double e, double a, int lane)
 
 // RHS, forward local pass, intra-warp scan.  k0 >= 0 on the thread that owns row 0: its Dirichlet term
 // is added to R there.
-template <int C, int WARPS, bool AMER, bool TBL>
+template <int C, int WARPS, bool AMER, bool TBL, bool R0>
 __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph &ph, const Sm &sm, const int k0,
-                                       const double cin_f, double &e1_keep, double &Eprev)
+                                       const double cin_f, const double carryF, double &e1_keep, double &Eprev)
 {
     constexpr int H = C / 2;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -272,7 +369,8 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
     for (int k = 0; k < H; ++k) e1 = fma(TBL ? nm[k * 32 + lane] : ph.NM, e1, V[k]);
 #pragma unroll
     for (int k = H; k < C; ++k) e2 = fma(TBL ? nm[k * 32 + lane] : ph.NM, e2, V[k]);
-    const double e_end = fma(TBL ? lc[LC_HF2 * 32 + lane] : sm.cst[CST_HF2], e1, e2);
+    double e_end = fma(TBL ? lc[LC_HF2 * 32 + lane] : sm.cst[CST_HF2], e1, e2);
+    if (!TBL && R0) e_end = fma(sm.cst[CST_AF], carryF, e_end);  // Dirichlet term of row 0 as a carry into its owner
     const double E = warp_scan<TBL, true>(e_end, TBL ? lc[LC_AF * 32 + lane] : sm.cst[CST_AF], lane);
     if (lane == 31) sm.part[0 * WARPS + w] = E;           // pE_f
     const double up = __shfl_up_sync(FULL, E, 1);
@@ -280,9 +378,10 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
     e1_keep = e1;
 }
 
-template <int C, int WARPS, bool AMER, bool TBL>
+template <int C, int WARPS, bool AMER, bool TBL, bool R0>
 __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &sm, const int wf, const double cin_b,
-                                       const double e1_fwd, const double Eprev, double &e1_keep, double &Enext)
+                                       const double e1_fwd, const double Eprev, const double carryF, double &e1_keep,
+                                       double &Enext, double &eend_keep)
 {
     constexpr int H = C / 2;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -291,7 +390,7 @@ __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &s
     // carry into this warp from the warps below (truncated Horner sum)
     double S = 0.0;
     for (int v = max(wf, w - ph.Kf); v < w; ++v) S = fma(sm.part[1 * WARPS + v], S, sm.part[0 * WARPS + v]);
-    const double cs = fma(TBL ? lc[LC_PAF * 32 + lane] : sm.PAc[lane], S, Eprev);
+    const double cs = fma(TBL ? lc[LC_PAF * 32 + lane] : sm.PAc[lane], S, Eprev) + ((TBL || !R0) ? 0.0 : carryF);
     {
         double c1 = cs;
         double c2 = fma(TBL ? lc[LC_HF1 * 32 + lane] : sm.cst[CST_HF1], cs, e1_fwd);
@@ -312,6 +411,7 @@ __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &s
     const double dn = __shfl_down_sync(FULL, E, 1);
     Enext = (lane == 31) ? 0.0 : dn;
     e1_keep = e1;
+    eend_keep = e_end;
 }
 
 template <int C, int WARPS, bool AMER, bool TBL>
@@ -339,6 +439,51 @@ __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph 
             const double vc = fma(TBL ? inv[k * 32 + lane] : ph.INV, xs, -L[k]);
             if (AMER) {
                 // exercise iff phi > vc (:496): dt*lambda_new = max(phi - vc, 0) on the sign mask, V = vc + dt*lambda_new
+                const double d = sm.r0[k * NT + t] - vc;
+                const int msk = ~(__double2hiint(d) >> 31);
+                L[k] = __hiloint2double(__double2hiint(d) & msk, __double2loint(d) & msk);
+                V[k] = vc + L[k];
+            } else {
+                V[k] = vc;
+            }
+        }
+    }
+}
+
+// step_c of a scalar-coefficient warp with the backward carry `cs` already summed (bwd_carry).  CORR: the row-0
+// correction reaches this warp: xs'_k = xs_k - gz xs_0 NM^k (one extra FMA per slot, off the recurrence chain).
+// INVT: the warp of row 0 (pivot scaling by slot, zero on the dead slots).
+template <int WARPS>
+__device__ __forceinline__ double bwd_carry(const Ph &ph, const Sm &sm, const double Enext)
+{
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    double S = 0.0;
+    for (int v = min(WARPS - 1, w + ph.Kb); v > w; --v) S = fma(sm.part[3 * WARPS + v], S, sm.part[2 * WARPS + v]);
+    return fma(sm.PAc[32 + lane], S, Enext);
+}
+
+template <int C, int WARPS, bool AMER, bool CORR, bool INVT>
+__device__ __forceinline__ void step_cs(double (&V)[C], double (&L)[C], const Ph &ph, const Sm &sm, const double cs,
+                                        const double cin_b, const double e1_bwd)
+{
+    constexpr int H = C / 2;
+    constexpr int NT = 32 * WARPS;
+    const int t = threadIdx.x;
+    double c1 = cs + cin_b;
+    double c2 = fma(sm.cst[CST_HB1], cs, e1_bwd);
+    const int lane = t & 31;
+    const double gzx = CORR ? -(ph.gz * sm.smv[1]) : 0.0;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int k = half == 0 ? C - 1 - i : H - 1 - i;
+            double xs;
+            if (half == 0) { c1 = fma(ph.NCC, c1, V[k]); xs = c1; }
+            else           { c2 = fma(ph.NCC, c2, V[k]); xs = c2; }
+            if (CORR) xs = fma(gzx, sm.nmp[k], xs);
+            const double vc = fma(INVT ? ph.invw[k * 32 + lane] : ph.INV, xs, -L[k]);
+            if (AMER) {
                 const double d = sm.r0[k * NT + t] - vc;
                 const int msk = ~(__double2hiint(d) >> 31);
                 L[k] = __hiloint2double(__double2hiint(d) & msk, __double2loint(d) & msk);
@@ -480,6 +625,8 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
     sm.PAc = sm.cst + 16;
     sm.wb = sm.PAc + 64;
     sm.ish = (int *)(sm.wb + 32);
+    sm.nmp = sm.wb + 32 + 8;
+    sm.smv = sm.nmp + C;
 
     const int64_t sid = first + blockIdx.x;
     if (sid >= B.n_solves) return;
@@ -585,6 +732,8 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
             Ph ph;
             setup_phase<C, WARPS, AMER>(implicit_phase ? 1.0 : 0.5, dt, ca, cc, bcoef, n_int, pad, sm, ph);
             const int wf = sm.ish[10];
+            constexpr bool R0 = row0_mode<WARPS, AMER>();
+            const bool row0_corr = R0 && sm.ish[12] >= 0;       // CTA-uniform
             const double top_mult = (t == NT - 1) ? sm.cst[CST_TOP] : 0.0;
             double w_next = fetch_boundary(m);
             double cin = ph.cB * Vb - ph.cA * w_next;           // non-zero on the two boundary threads only
@@ -593,15 +742,32 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                 w_next = fetch_boundary(m + 1);
                 double cin_n = ph.cB * w_now - ph.cA * w_next;
                 const double cin_b = cin * top_mult;            // enters the top row through its ncc
-                double e1f = 0.0, Eprev = 0.0, e1b = 0.0, Enext = 0.0;
-                if (ph.cls == 2) step_a<C, WARPS, AMER, true>(V, L, ph, sm, k0, cin, e1f, Eprev);
-                else if (ph.cls == 1) step_a<C, WARPS, AMER, false>(V, L, ph, sm, -1, 0.0, e1f, Eprev);
-                __syncthreads();
-                if (ph.cls == 2) step_b<C, WARPS, AMER, true>(V, ph, sm, wf, cin_b, e1f, Eprev, e1b, Enext);
-                else if (ph.cls == 1) step_b<C, WARPS, AMER, false>(V, ph, sm, wf, cin_b, e1f, Eprev, e1b, Enext);
-                __syncthreads();
+                double e1f = 0.0, Eprev = 0.0, e1b = 0.0, Enext = 0.0, eend_b = 0.0;
+                const double carryF = R0 ? cin * ph.cF : 0.0;   // non-zero on the owner of row 0 in row-0-correction mode
+                if (ph.cls == 2) step_a<C, WARPS, AMER, true, R0>(V, L, ph, sm, k0, cin, 0.0, e1f, Eprev);
+                else if (ph.cls == 1) step_a<C, WARPS, AMER, false, R0>(V, L, ph, sm, -1, 0.0, carryF, e1f, Eprev);
+                FDM_CTA_STEP_SYNC();
+                if (ph.cls == 2) step_b<C, WARPS, AMER, true, R0>(V, ph, sm, wf, cin_b, e1f, Eprev, 0.0, e1b, Enext, eend_b);
+                else if (ph.cls == 1) step_b<C, WARPS, AMER, false, R0>(V, ph, sm, wf, cin_b, e1f, Eprev, carryF, e1b, Enext, eend_b);
+                FDM_CTA_STEP_SYNC();
                 if (ph.cls == 2) step_c<C, WARPS, AMER, true>(V, L, ph, sm, cin_b, e1b, Enext);
-                else if (ph.cls == 1) step_c<C, WARPS, AMER, false>(V, L, ph, sm, cin_b, e1b, Enext);
+                else if (!row0_corr) {
+                    if (ph.cls == 1) step_c<C, WARPS, AMER, false>(V, L, ph, sm, cin_b, e1b, Enext);
+                } else {
+                    // row-0 correction: the owner of row 0 knows xs at its slot 0 (= NCC^k0 xs_0: its padding slots pass
+                    // the value through) from the local pass and its carry, before the last pass starts
+                    double cs_b = 0.0;
+                    if (ph.cls == 1) {
+                        cs_b = bwd_carry<WARPS>(ph, sm, Enext);
+                        if (k0 >= 0) sm.smv[1] = fma(-sm.smv[2], carryF, fma(sm.cst[CST_AB], cs_b, eend_b));
+                    }
+                    if (ph.bar3) __syncthreads(); else __syncwarp();
+                    if (ph.cls == 1) {
+                        if (w == wf) step_cs<C, WARPS, AMER, true, true>(V, L, ph, sm, cs_b, cin_b, e1b);
+                        else if (ph.smc) step_cs<C, WARPS, AMER, true, false>(V, L, ph, sm, cs_b, cin_b, e1b);
+                        else step_cs<C, WARPS, AMER, false, false>(V, L, ph, sm, cs_b, cin_b, e1b);
+                    }
+                }
                 Vb = w_now;                                     // V[0] = V_min, V[-1] = V_max (:505-506)
                 ++gstep;
                 if (TRACE && trace) {

@@ -116,3 +116,35 @@ def test_cfg4_full_size_one_solve():
     assert err <= REL, err
     _v_close(res.V[0, :8193], o.V)
     assert (int(res.idx[0, 2]), int(res.idx[0, 3])) == (o.ex_lo, o.ex_hi)
+
+
+# Row-0 correction mode of the CTA kernel (fdm_cta.cuh, setup_phase): small time steps so that the correction's NM^i
+# tail dies inside the grid, every size class, row 0 at different slots of its owner thread (pad % 16).
+ROW0_SIZES = [600, 777, 1234, 2047, 2133, 2500, 3333, 4097, 6000, 8000, 8193]
+
+
+@pytest.mark.parametrize("n", ROW0_SIZES)
+def test_american_row0_mode_vs_oracle(n):
+    kw = dict(spot=100.0, strike=104.0, T=0.05, sigma=0.32, r=0.05, b=0.03, is_call=(n % 2 == 0), model=0, n_space=n,
+              n_time=160, rannacher=2, s_max_mult=4.5, divs_tau=[])
+    batch = hostlogic.build_american_batch([kw["spot"]], [kw["strike"]], [kw["T"]], [kw["sigma"]], [kw["r"]], [kw["b"]],
+                                           [kw["is_call"]], [n], [160], [2], [False], 4.5, div_taus=[[]])
+    res = solve_host(batch, dump=True, trace=True)
+    o = oracle.american_solve(**kw, trace=True)
+    assert res.status[0] == 0
+    _v_close(res.V[0, : n + 1], o.V)
+    assert abs(res.price[0] - o.price) <= REL * abs(o.price)
+    assert np.array_equal(res.ex_trace[0, : o.ex_trace.shape[0]], o.ex_trace)
+
+
+@pytest.mark.parametrize("n", ROW0_SIZES)
+def test_barrier_row0_mode_vs_oracle(n):
+    S0, K, T, sig, r, b = 100.0, 97.0, 0.25, 0.28, 0.04, 0.02
+    mon = [0.05, 0.1, 0.15, 0.2]
+    bt, lo, up = ("down-and-out", 88.0, None) if n % 2 else ("up-and-out", None, 125.0)
+    batch = hostlogic.build_barrier_batch([S0], [K], [T], [sig], [r], [b], [True], [bt], [lo], [up], [1.5], [mon], [n], [400])
+    res = solve_host(batch, dump=True)
+    o = oracle.barrier_solve(S0, K, T, sig, r, b, True, bt, lo, up, 1.5, mon, n, 400, True)
+    assert res.status[0] == 0
+    _v_close(res.V[0, : n + 1], o.V)
+    assert abs(res.price[0] - o.price) <= REL * abs(o.price)
