@@ -31,7 +31,8 @@ def norm_cdf(x: float) -> float:
     return 0.5 * (1.0 + math.erf(x / math.sqrt(2.0)))
 
 
-_KO_OF = {"down-and-in": "down-and-out", "up-and-in": "up-and-out"}
+_KO_OF = {"down-and-in": "down-and-out", "up-and-in": "up-and-out", "double-in": "double-out"}
+KO_TYPES = ("down-and-out", "up-and-out", "double-out")
 
 
 @dataclass
@@ -73,13 +74,16 @@ class DiscreteBarrierBase:
         return set(hostlogic.barrier_monitor_steps(self.T, self.N_time, self.monitor_times))
 
     # ---- solves -----------------------------------------------------------------------------------
-    def _descriptor(self, apply_KO: bool, sigma: float, barrier_type: Optional[str] = None) -> SolveBatch:
+    def _descriptor(self, apply_KO: bool, sigma: float, barrier_type: Optional[str] = None,
+                    N_time: Optional[int] = None) -> SolveBatch:
         bt = (self.barrier_type if barrier_type is None else barrier_type).lower()
-        ko = bt if (apply_KO and bt in ("down-and-out", "up-and-out")) else "none"
+        ko = bt if (apply_KO and bt in KO_TYPES) else "none"
         return hostlogic.build_barrier_batch(
             [self.S0], [self.K], [self.T], [sigma], [self.r_disc], [self.b_carry],
             [self.option_type.lower() == "call"], [ko], [self.lower_barrier], [self.upper_barrier], [self.rebate],
-            [self.monitor_times or []], [self.N_space], [self.N_time], S_min=[self._S_min], S_max=[self._S_max])
+            [self.monitor_times or []], [self.N_space], [self.N_time if N_time is None else N_time],
+            S_min=[self._S_min], S_max=[self._S_max], rannacher=int(getattr(self, "rannacher_steps", 0)),
+            rebate_discounted=bool(getattr(self, "rebate_discounted", False)))
 
     def _solve_many(self, specs: Sequence[Tuple[bool, float, Optional[str]]]):
         """One C-ABI call for several ``_solve_grid`` variants: specs = [(apply_KO, sigma, barrier_type)]."""
@@ -137,8 +141,55 @@ class DiscreteBarrierBase:
         vega = (self._interp_price_from_grid(V_up) - self._interp_price_from_grid(V_dn)) / (2.0 * dv_sigma)
         return {"price": price, "delta": delta, "gamma": gamma, "theta": theta, "vega": vega}
 
+    _TYPES = ("none", "down-and-out", "up-and-out", "down-and-in", "up-and-in")    # what the reference accepts (:502)
+
     def _check_type(self) -> str:
         bt = self.barrier_type.lower()
-        if bt not in ("none", "down-and-out", "up-and-out", "down-and-in", "up-and-in"):
+        if bt not in self._TYPES:
             raise ValueError(f"Unsupported barrier_type: {self.barrier_type}")
         return bt
+
+    # ---- engine options (not in the importable reference dataclass) --------------------------
+    def _pde_price_richardson(self, apply_KO: bool, barrier_type: Optional[str] = None,
+                              sigma: Optional[float] = None) -> float:
+        """Richardson extrapolation in time over N and N/2 steps, ``(4 p_N - p_{N/2}) / 3`` with
+        ``N/2 = max(1, N // 2)`` (fd_discrete_barrier_option.py:1979-2005); both solves in one C-ABI call."""
+        self.configure_grid()
+        self._build_log_grid()
+        sig = self.sigma if sigma is None else sigma
+        n_full = int(self.N_time)
+        if n_full < 2:
+            res = solve_host(self._descriptor(apply_KO, sig, barrier_type), dump=True)
+            return self._interp_price_from_grid(res.V[0, : self.N_space + 1].tolist())
+        res = solve_host(SolveBatch.concat([self._descriptor(apply_KO, sig, barrier_type),
+                                            self._descriptor(apply_KO, sig, barrier_type, N_time=max(1, n_full // 2))]),
+                         dump=True)
+        if int(res.status.max()) != 0:
+            raise FloatingPointError("non-finite value in the PDE solution")
+        p_n = self._interp_price_from_grid(res.V[0, : self.N_space + 1].tolist())
+        p_half = self._interp_price_from_grid(res.V[1, : self.N_space + 1].tolist())
+        return (4.0 * p_n - p_half) / 3.0
+
+    def price_richardson(self) -> float:
+        """PDE price with Richardson extrapolation in time; knock-in by parity of two PDE legs."""
+        bt = self._check_type()
+        if bt == "none":
+            return self._pde_price_richardson(apply_KO=False)
+        if bt in KO_TYPES:
+            return self._pde_price_richardson(apply_KO=True)
+        return (self._pde_price_richardson(apply_KO=False, barrier_type="none")
+                - self._pde_price_richardson(apply_KO=True, barrier_type=_KO_OF[bt]))
+
+    def greeks_one_sided(self, dv_sigma: float = 1e-3) -> Dict[str, float]:
+        """Knock-out (or vanilla PDE) greeks with the one-sided volatility bump ``(p(sigma + dv) - p(sigma)) / dv``
+        of fd_discrete_barrier_option.py:2076-2088: two solves instead of three."""
+        bt = self._check_type()
+        if bt not in KO_TYPES and bt != "none":
+            raise ValueError("greeks_one_sided: knock-out or vanilla barrier_type only")
+        sig = self.sigma
+        (V, V_up), _ = self._solve_many([(bt != "none", sig, None), (bt != "none", sig + dv_sigma, None)])
+        price = self._interp_price_from_grid(V)
+        delta, gamma = self._delta_gamma_from_grid(V)
+        vega = (self._interp_price_from_grid(V_up) - price) / dv_sigma
+        return {"price": price, "delta": delta, "gamma": gamma, "theta": self._pde_theta(price, delta, gamma),
+                "vega": vega}

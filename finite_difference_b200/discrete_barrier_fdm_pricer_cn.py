@@ -7,7 +7,7 @@ import math
 from dataclasses import dataclass
 from typing import Dict
 
-from .barrier import DiscreteBarrierBase, _KO_OF, norm_cdf, norm_pdf  # noqa: F401
+from .barrier import DiscreteBarrierBase, KO_TYPES, _KO_OF, norm_cdf, norm_pdf  # noqa: F401
 
 
 @dataclass
@@ -39,7 +39,7 @@ class DiscreteBarrierCrankNicolsonLog(DiscreteBarrierBase):
         bt = self._check_type()
         if bt == "none":
             return self._vanilla_bs_price_and_greeks()["price"]
-        if bt in ("down-and-out", "up-and-out"):
+        if bt in KO_TYPES:
             return self._pde_price_and_greeks(apply_KO=True, dv_sigma=1e-3)["price"]
         g_van = self._vanilla_bs_price_and_greeks()
         g_ko = self._pde_price_and_greeks(apply_KO=True, dv_sigma=1e-3, barrier_type=_KO_OF[bt])
@@ -49,7 +49,7 @@ class DiscreteBarrierCrankNicolsonLog(DiscreteBarrierBase):
         bt = self._check_type()
         if bt == "none":
             return self._vanilla_bs_price_and_greeks()
-        if bt in ("down-and-out", "up-and-out"):
+        if bt in KO_TYPES:
             return self._pde_price_and_greeks(apply_KO=True, dv_sigma=dv_sigma)
         g_van = self._vanilla_bs_price_and_greeks()
         g_ko = self._pde_price_and_greeks(apply_KO=True, dv_sigma=dv_sigma, barrier_type=_KO_OF[bt])

@@ -7,7 +7,7 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict
 
-from .barrier import DiscreteBarrierBase, _KO_OF
+from .barrier import DiscreteBarrierBase, KO_TYPES, _KO_OF
 
 
 @dataclass
@@ -16,7 +16,7 @@ class DiscreteBarrierCrankNicolsonLog(DiscreteBarrierBase):
         bt = self._check_type()
         if bt == "none":
             return self._interp_price_from_grid(self._solve_grid(apply_KO=False))
-        if bt in ("down-and-out", "up-and-out"):
+        if bt in KO_TYPES:
             return self._interp_price_from_grid(self._solve_grid(apply_KO=True))
         (V_van, V_ko), _ = self._solve_many([(False, self.sigma, "none"), (True, self.sigma, _KO_OF[bt])])
         return self._interp_price_from_grid(V_van) - self._interp_price_from_grid(V_ko)
@@ -28,7 +28,7 @@ class DiscreteBarrierCrankNicolsonLog(DiscreteBarrierBase):
 
     def greeks(self, dv_sigma: float = 1e-3) -> Dict[str, float]:
         bt = self._check_type()
-        if bt in ("none", "down-and-out", "up-and-out"):
+        if bt == "none" or bt in KO_TYPES:
             return self._direct_greeks(bt, dv_sigma)
         g_van = self._direct_greeks("none", dv_sigma)
         g_ko = self._direct_greeks(_KO_OF[bt], dv_sigma)

@@ -247,18 +247,24 @@ def barrier_monitor_steps_vec(T, N_time, monitor_times_2d, valid_mask):
     return mon_begin, k[keep].astype(np.int32)
 
 
-_KO_FLAG = {"none": 0, "down-and-out": FLAG_KO_DOWN, "up-and-out": FLAG_KO_UP}
+_KO_FLAG = {"none": 0, "down-and-out": FLAG_KO_DOWN, "up-and-out": FLAG_KO_UP, "double-out": FLAG_KO_DOWN | FLAG_KO_UP}
 
 
 def build_barrier_batch(S0, K, T, sigma, r_disc, b_carry, is_call, ko_type: Sequence[str], lower_barrier,
                         upper_barrier, rebate, monitor_times: Sequence, N_space, N_time,
-                        S_min=None, S_max=None) -> SolveBatch:
+                        S_min=None, S_max=None, rannacher=0, rebate_discounted=False) -> SolveBatch:
     """Descriptors for barrier-dataclass solves ``_solve_grid(apply_KO)`` (BAR:219-302).
 
     ``ko_type[i]`` in {"none", "down-and-out", "up-and-out"} is the projection actually applied
     (``apply_KO`` and ``barrier_type`` combined, BAR:199-213, :299).  ``monitor_times[i]`` is a list.
     ``N_space`` / ``N_time`` must be resolved (see :func:`barrier_configure`).
     ``lower_barrier`` / ``upper_barrier`` entries may be ``None`` / NaN.
+
+    Engine options beyond the importable dataclass (after the fragments of
+    ``fd_discrete_barrier_option.py:851-1007``; no runnable reference, checked against the extended oracle):
+    ``ko_type[i] == "double-out"`` (knocked out at or below the lower and at or above the upper level),
+    ``rannacher`` fully implicit start-up steps, ``rebate_discounted`` (a knocked-out node is worth
+    ``rebate * exp(-r_disc * tau)`` at time-to-expiry ``tau``: the rebate is paid at expiry).
     """
     n = len(S0)
     S0, K, T, sigma, r_disc, b_carry, rebate = (np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (n,)))
@@ -293,11 +299,14 @@ def build_barrier_batch(S0, K, T, sigma, r_disc, b_carry, is_call, ko_type: Sequ
 
     ko = np.array([_KO_FLAG[k] for k in ko_type], dtype=np.int64)
     flags = ko + np.where(np.asarray(is_call, dtype=bool), FLAG_CALL, 0)
-    level = np.where(ko == FLAG_KO_DOWN, low, np.where(ko == FLAG_KO_UP, up, 0.0))
+    both = ko == (FLAG_KO_DOWN | FLAG_KO_UP)
+    level = np.where(ko == FLAG_KO_UP, up, np.where(ko == 0, 0.0, low))
     # BAR:203 / :209: the projection is skipped when the matching barrier is None
-    missing = np.isnan(level)
+    missing = np.isnan(level) | (both & np.isnan(up))
     flags = np.where(missing, flags & ~(FLAG_KO_DOWN | FLAG_KO_UP), flags)
     level = np.where(missing, 0.0, level)
+    level_up = np.where(both & ~missing, up, 0.0) if np.any(both) else None
+    rannacher = np.ascontiguousarray(np.broadcast_to(np.asarray(rannacher, dtype=np.int32), (n,)))
 
     max_mon = max((len(m) if m is not None else 0) for m in monitor_times) if n else 0
     if max_mon:
@@ -310,13 +319,19 @@ def build_barrier_batch(S0, K, T, sigma, r_disc, b_carry, is_call, ko_type: Sequ
         mon_begin, mon_step = barrier_monitor_steps_vec(T, N_time, mt, valid)
     else:
         mon_begin, mon_step = np.zeros(n + 1, dtype=np.int32), np.zeros(0, dtype=np.int32)
+    mon_rebate = None
+    if rebate_discounted and len(mon_step):
+        owner = np.repeat(np.arange(n), np.diff(mon_begin))
+        tau_k = mon_step * (T / N_time)[owner]                    # tau_next = (m + 1) * dt at the projection
+        mon_rebate = rebate[owner] * np.exp(-r_disc[owner] * tau_k)
 
     return SolveBatch(
         x_min=x_min, dx=dx, sigma=sigma, r=r_disc, b=b_carry, spot=S0, strike=K,
-        n_space=N_space.astype(np.int32), flags=flags.astype(np.int32), rannacher=np.zeros(n, dtype=np.int32),
+        n_space=N_space.astype(np.int32), flags=flags.astype(np.int32), rannacher=rannacher,
         seg_begin=np.arange(n + 1, dtype=np.int32), seg_steps=N_time.astype(np.int32),
-        seg_dt=T / N_time, seg_tau0=np.zeros(n), seg_restart=np.zeros(n, dtype=np.int32),
-        seg_div=np.zeros(n), barrier=level, rebate=rebate, mon_begin=mon_begin, mon_step=mon_step)
+        seg_dt=T / N_time, seg_tau0=np.zeros(n), seg_restart=(rannacher > 0).astype(np.int32),
+        seg_div=np.zeros(n), barrier=level, rebate=rebate, mon_begin=mon_begin, mon_step=mon_step,
+        barrier_up=level_up, mon_rebate=mon_rebate)
 
 
 # --------------------------------------------------------------------------------------

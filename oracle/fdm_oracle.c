@@ -501,9 +501,30 @@ int fdo_barrier_configure(const FdoBarrier *p, int32_t N_space_in, int32_t N_tim
 }
 
 /* _solve_grid, BAR:219-302, then price/delta/gamma, BAR:308-353.  V_out: N_space+1. */
+/* Engine options beyond the importable dataclass, after the non-parsing fragments of
+ * fd_discrete_barrier_option.py: `rannacher` fully implicit start-up steps (theta = 1 for the first steps, :912-1007),
+ * `rebate_discounted` (value at a knocked-out node = rebate * exp(-r_disc * tau), the rebate being paid at expiry,
+ * :851-867) and ko_kind 3 = double-out (:887-893).  No runnable reference exists for them: PARITY UNPINNED; this
+ * restatement keeps the operation order of the pinned path and is what the CUDA kernel is checked against.
+ * With (0, 0) and ko_kind <= 2 the arithmetic is exactly the pinned fdo_barrier_solve. */
+static int barrier_solve_impl(const FdoBarrier *p, int rannacher, int rebate_discounted, double *V_out, double *s_out,
+                              int32_t *monitor_steps_out, FdoBarrierInfo *info);
+
 int fdo_barrier_solve(const FdoBarrier *p, double *V_out, double *s_out,
                       int32_t *monitor_steps_out /* optional, N_time flags */,
                       FdoBarrierInfo *info)
+{
+    return barrier_solve_impl(p, 0, 0, V_out, s_out, monitor_steps_out, info);
+}
+
+int fdo_barrier_solve_ext(const FdoBarrier *p, int32_t rannacher, int32_t rebate_discounted, double *V_out,
+                          double *s_out, int32_t *monitor_steps_out, FdoBarrierInfo *info)
+{
+    return barrier_solve_impl(p, rannacher, rebate_discounted, V_out, s_out, monitor_steps_out, info);
+}
+
+static int barrier_solve_impl(const FdoBarrier *p, int rannacher, int rebate_discounted, double *V_out, double *s_out,
+                              int32_t *monitor_steps_out, FdoBarrierInfo *info)
 {
     if (!p || !V_out || !info) return FDO_EINVAL;
     int N = p->N_space;
@@ -570,6 +591,15 @@ int fdo_barrier_solve(const FdoBarrier *p, double *V_out, double *s_out,
 
     int n_int = N - 1;
     for (int m = 0; m < M; ++m) {                                      /* BAR:278-300 */
+        if (rannacher > 0 && (m == 0 || m == rannacher)) {             /* extension: theta = 1 start-up steps */
+            const double theta = m < rannacher ? 1.0 : 0.5;
+            A_L = -theta * dt * a;
+            A_C = 1.0 - theta * dt * bcoef;
+            A_U = -theta * dt * c;
+            B_L = (1.0 - theta) * dt * a;
+            B_C = 1.0 + (1.0 - theta) * dt * bcoef;
+            B_U = (1.0 - theta) * dt * c;
+        }
         double tau_next = (m + 1) * dt;
         double V_min_next, V_max_next;
         if (p->is_call) {                                              /* BAR:153-171 */
@@ -592,12 +622,16 @@ int fdo_barrier_solve(const FdoBarrier *p, double *V_out, double *s_out,
         memcpy(V + 1, xi, (size_t)n_int * sizeof(double));
 
         if (p->apply_KO && is_mon[m + 1]) {                            /* BAR:299-300, 199-213 */
+            const double reb = rebate_discounted ? p->rebate * exp(-p->r_disc * tau_next) : p->rebate;
             if (p->ko_kind == 1 && !isnan(p->lower_barrier)) {
                 for (int i = 0; i < n_nodes; ++i)
-                    if (s[i] <= p->lower_barrier) V[i] = p->rebate;
+                    if (s[i] <= p->lower_barrier) V[i] = reb;
             } else if (p->ko_kind == 2 && !isnan(p->upper_barrier)) {
                 for (int i = 0; i < n_nodes; ++i)
-                    if (s[i] >= p->upper_barrier) V[i] = p->rebate;
+                    if (s[i] >= p->upper_barrier) V[i] = reb;
+            } else if (p->ko_kind == 3 && !isnan(p->lower_barrier) && !isnan(p->upper_barrier)) {
+                for (int i = 0; i < n_nodes; ++i)
+                    if (s[i] <= p->lower_barrier || s[i] >= p->upper_barrier) V[i] = reb;
             }
         }
     }

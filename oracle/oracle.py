@@ -89,6 +89,10 @@ def lib():
         L.fdo_barrier_solve.argtypes = [C.POINTER(_FdoBarrier), C.POINTER(C.c_double),
                                         C.POINTER(C.c_double), C.POINTER(C.c_int32),
                                         C.POINTER(_FdoBarrierInfo)]
+        L.fdo_barrier_solve_ext.restype = C.c_int
+        L.fdo_barrier_solve_ext.argtypes = [C.POINTER(_FdoBarrier), C.c_int32, C.c_int32, C.POINTER(C.c_double),
+                                            C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                            C.POINTER(_FdoBarrierInfo)]
         L.fdo_american_batch.restype = C.c_int
         L.fdo_american_batch.argtypes = [C.c_int64, C.POINTER(_FdoAmerican), C.POINTER(C.c_double),
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32]
@@ -260,7 +264,7 @@ class BarrierResult:
     N_time: int
 
 
-_KO = {"none": 0, "down-and-out": 1, "up-and-out": 2}
+_KO = {"none": 0, "down-and-out": 1, "up-and-out": 2, "double-out": 3}
 
 
 def _bar_struct(S0, K, T, sigma, r_disc, b_carry, is_call, barrier_type, lower_barrier,
@@ -298,8 +302,11 @@ def barrier_configure(S0, K, T, sigma, r_disc, b_carry, is_call, barrier_type,
 
 def barrier_solve(S0, K, T, sigma, r_disc, b_carry, is_call, barrier_type,
                   lower_barrier=None, upper_barrier=None, rebate=0.0, monitor_times=None,
-                  N_space=None, N_time=None, apply_KO=True) -> BarrierResult:
-    """One barrier ``_solve_grid(apply_KO)`` + price/delta/gamma from the grid."""
+                  N_space=None, N_time=None, apply_KO=True, rannacher=0, rebate_discounted=False) -> BarrierResult:
+    """One barrier ``_solve_grid(apply_KO)`` + price/delta/gamma from the grid.
+
+    ``rannacher`` / ``rebate_discounted`` / ``barrier_type="double-out"`` are the engine options of SURVEY.md 8f-2
+    (``fdo_barrier_solve_ext``; no runnable reference: parity unpinned)."""
     _, _, ns, nt = barrier_configure(S0, K, T, sigma, r_disc, b_carry, is_call, barrier_type,
                                      lower_barrier, upper_barrier, rebate, monitor_times,
                                      N_space, N_time)
@@ -310,8 +317,12 @@ def barrier_solve(S0, K, T, sigma, r_disc, b_carry, is_call, barrier_type,
     s = np.empty(ns + 1, dtype=np.float64)
     flags = np.zeros(nt + 1, dtype=np.int32)
     info = _FdoBarrierInfo()
-    rc = lib().fdo_barrier_solve(C.byref(p), _dptr(V), _dptr(s),
-                                 flags.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(info))
+    if rannacher or rebate_discounted or barrier_type == "double-out":
+        rc = lib().fdo_barrier_solve_ext(C.byref(p), C.c_int32(int(rannacher)), C.c_int32(int(bool(rebate_discounted))),
+                                         _dptr(V), _dptr(s), flags.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(info))
+    else:
+        rc = lib().fdo_barrier_solve(C.byref(p), _dptr(V), _dptr(s),
+                                     flags.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(info))
     if rc != 0:
         raise ValueError(f"fdo_barrier_solve failed rc={rc}")
     return BarrierResult(V=V, s_nodes=s, price=info.price, delta=info.delta, gamma=info.gamma,
