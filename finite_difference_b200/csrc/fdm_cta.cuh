@@ -18,6 +18,10 @@
 //   measured 8..10 % slower on 2048..8192-node grids: the warps stay in lock-step anyway and the polls cost issue slots.)
 //   * size classes: 4 / 5 / 8 / 16 warps of 16 slots per thread serve up to 2048 / 2560 / 4096 / 8192 rows; a solve
 //     runs in the smallest class that holds it (2133-node barrier grids: 5 warps, two CTAs per SM).
+//   Measured and dropped (round 1, tools/time_cta3.py): 8 slots per thread with twice the warps (8-12 % slower on
+//   2048..4096 rows: the per-warp scan and control overhead doubles); the scans' masked level weights precomputed in
+//   shared memory (30 instructions fewer per warp-step, no change in time); no block barriers at all (+5 % at most:
+//   the barriers are not what the step waits for).
 //
 // Included by fdm_b200.cu (single translation unit); uses its helpers.
 
@@ -37,7 +41,7 @@ constexpr double TRUNC_EPS = 1e-22;
 // its linear variant then spills inside the time loop and the table warps stay faster (8192-node barrier grids: 5.5e11
 // with tables, 4.1e11 with the correction), so that one variant keeps the tables.  Measured gains elsewhere: 8192-node
 // American +8 %, 2133-node barrier grids +33 %.
-template <int WARPS, bool AMER>
+template <int C, int WARPS, bool AMER>
 __host__ __device__ constexpr bool row0_mode()
 {
 #ifdef FDM_CTA_ROW0_ALL
@@ -45,7 +49,7 @@ __host__ __device__ constexpr bool row0_mode()
 #elif defined(FDM_CTA_NO_ROW0_CORR)
     return false;
 #else
-    return WARPS < 16 || AMER;
+    return C < 16 || WARPS < 16 || AMER;
 #endif
 }
 
@@ -162,7 +166,7 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
         // (rho^(n-i) term below 1e-24); otherwise the per-slot tables below stay in charge.
         double GF = 0.0;
         int wz = -1;
-        if (row0_mode<WARPS, AMER>() && converged) {
+        if (row0_mode<C, WARPS, AMER>() && converged) {
             const double rinf = pv_inv[P], nmc = pv_nm[P], nccc = pv_ncc[P];
             const double kappa = 1.0 / (1.0 - nmc * nccc);
             const double dl = A_L * A_U * rinf * rinf;                  // delta * r_inf
@@ -215,7 +219,7 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
     if (ph.cls == 2) ph.cls = 1;
 #endif
     ph.gz = 0.0; ph.cF = 0.0; ph.smc = 0; ph.bar3 = 0; ph.invw = sm.r2;
-    if (row0_mode<WARPS, AMER>()) {
+    if (row0_mode<C, WARPS, AMER>()) {
         const int wz = sm.ish[12];
         ph.smc = (wz >= 0 && w >= wf && w <= wz) ? 1 : 0;
         ph.bar3 = (wz > wf) ? 1 : 0;
@@ -605,11 +609,11 @@ template <int C, int WARPS>
 constexpr int smem_doubles() { return Layout<C, WARPS>::TOTAL; }
 
 // resident CTAs per SM the registers are sized for: 4 or 5 warps leave room for two CTAs (255 / 200 registers)
-template <int WARPS>
-constexpr int cta_min_blocks() { return WARPS <= 5 ? 2 : 1; }
+template <int C, int WARPS>
+constexpr int cta_min_blocks() { return 32 * WARPS * C <= 2560 ? 2 : 1; }
 
 template <int C, int WARPS, bool AMER, bool TRACE>
-__global__ void __launch_bounds__(32 * WARPS, cta_min_blocks<WARPS>())
+__global__ void __launch_bounds__(32 * WARPS, cta_min_blocks<C, WARPS>())
 fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int want_american, const int n_lo)
 {
     using LY = Layout<C, WARPS>;
@@ -732,7 +736,7 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
             Ph ph;
             setup_phase<C, WARPS, AMER>(implicit_phase ? 1.0 : 0.5, dt, ca, cc, bcoef, n_int, pad, sm, ph);
             const int wf = sm.ish[10];
-            constexpr bool R0 = row0_mode<WARPS, AMER>();
+            constexpr bool R0 = row0_mode<C, WARPS, AMER>();
             const bool row0_corr = R0 && sm.ish[12] >= 0;       // CTA-uniform
             const double top_mult = (t == NT - 1) ? sm.cst[CST_TOP] : 0.0;
             double w_next = fetch_boundary(m);
