@@ -197,9 +197,12 @@ __device__ __forceinline__ bool setup_phase(double theta, double dt, double a, d
     const double bscale = 1.0 / scale;
     ph.NM = NM;
     ph.NCC = NCC;
-    ph.INV = rinv * scale;
-    ph.cA = (lane == 0) ? A_L * bscale / NM : ((lane == 31) ? A_U * bscale / NCC : 0.0);
-    ph.cB = (lane == 0) ? B_L * bscale / NM : ((lane == 31) ? B_U * bscale / NCC : 0.0);
+    // American, theta = 1/2: the step solves for 2 R (see march_step), so the Dirichlet terms double and the pivot
+    // scaling halves -- powers of two, exact
+    const double dbl = (AMER && ph.half) ? 2.0 : 1.0;
+    ph.INV = rinv * scale / dbl;
+    ph.cA = (lane == 0) ? A_L * bscale / NM * dbl : ((lane == 31) ? A_U * bscale / NCC * dbl : 0.0);
+    ph.cB = (lane == 0) ? B_L * bscale / NM * dbl : ((lane == 31) ? B_U * bscale / NCC * dbl : 0.0);
 
     ph.P[0] = 1.0;
 #pragma unroll
@@ -320,7 +323,13 @@ struct CarryShf {
     }
 };
 
-// One theta-scheme step.  V: vc (American) / V (linear) on entry and exit; L: 3 dt lambda (American) / scratch.
+// One theta-scheme step.  V: vc (American) / V (linear) on entry and exit; L: 6 dt lambda (American) / scratch.
+// The American state keeps Lq = 6 dt lambda = 2 relu(3 phi - 3 vc) because that is ONE FP64 instruction, d + |d|
+// (exact: 2 d or +0), where relu itself costs three integer instructions per node on the sign mask; the kernel is
+// issue-limited, not FP64-pipe-limited.  The factor two is carried by exact power-of-two constants: with theta = 1/2
+// the right-hand side becomes 2 R = 4 vc + Lq (the system is linear: INV is halved, the Dirichlet terms doubled in
+// setup_phase) and G = vc + Lq / 3; with theta = 1, R = vc + Lq / 3 and G = Lq / 6.  Every intermediate is the old
+// one times a power of two, so the results are bit-identical to the (vc, 3 dt lambda) form.
 // The optional last slot is handled without branches: on lanes that do not hold it its multipliers are 1 / 0 and
 // its V, L stay 0, which makes it the identity in both sweeps.
 template <int C, bool AMER>
@@ -335,15 +344,15 @@ __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const
         if (ph.half) {
 #pragma unroll
             for (int k = 0; k < C; ++k) {
-                const double g = fma(2.0 / 3.0, L[k], V[k]);
-                V[k] = fma(2.0, V[k], L[k]);
+                const double g = fma(1.0 / 3.0, L[k], V[k]);
+                V[k] = fma(4.0, V[k], L[k]);
                 L[k] = g;
             }
         } else {
 #pragma unroll
             for (int k = 0; k < C; ++k) {
-                const double g = (1.0 / 3.0) * L[k];
-                V[k] = fma(2.0 / 3.0, L[k], V[k]);
+                const double g = (1.0 / 6.0) * L[k];
+                V[k] = fma(1.0 / 3.0, L[k], V[k]);
                 L[k] = g;
             }
         }
@@ -420,10 +429,10 @@ __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const
         const double vc = fma(ph.INV, xs, -L[k]);
         if (AMER) {
             if (i + PF < C) pf[i + PF] = T.phi3[slot_of(i + PF) * 32 + lane];
-            // exercise iff phi > vc (fd_american_option_pricer.py:496); Ls = 3 dt lambda_new = relu(3 phi - 3 vc)
+            // exercise iff phi > vc (fd_american_option_pricer.py:496); Lq = 6 dt lambda_new = 2 relu(3 phi - 3 vc)
             const double d = fma(-3.0, vc, pf[i]);
-            const int msk = keep ? ~(__double2hiint(d) >> 31) : 0;
-            L[k] = __hiloint2double(__double2hiint(d) & msk, __double2loint(d) & msk);
+            const double lq = d + fabs(d);
+            L[k] = keep ? lq : 0.0;
         }
         V[k] = keep ? vc : 0.0;
     }
