@@ -119,7 +119,7 @@ def run_reference(args):
     from oracle import oracle
     oracle.build()
     threads = host_threads()
-    n_sample = args.cpu_options or max(16, 16 * threads)
+    n_sample = args.cpu_options or max(48, 48 * threads)
     w = workload(n_sample)
     sel = np.arange(n_sample)
     for _ in range(args.warmup):
@@ -347,7 +347,7 @@ def run_b200(args):
         from oracle import oracle
         oracle.build()
         threads = host_threads()
-        n_sample = args.cpu_options or max(16, 16 * threads)
+        n_sample = args.cpu_options or max(48, 48 * threads)
         n_sample = min(n_sample, len(mine))
         sel = np.arange(n_sample)
         dt, ns_cpu, p_cpu, lo_cpu, hi_cpu = oracle_scenario(w, mine[sel], threads)
@@ -402,7 +402,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--options", type=int, default=100_000, help="options per GPU (8 solves each)")
-    ap.add_argument("--cpu-options", type=int, default=0, help="options in the CPU sample (default 16 x threads)")
+    ap.add_argument("--cpu-options", type=int, default=0, help="options in the CPU sample (default 48 x threads: about 20 core-seconds of CPU work)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     args = ap.parse_args()
     if args.impl == "reference":

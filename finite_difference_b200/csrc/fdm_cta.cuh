@@ -354,15 +354,11 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const double *nm = ph.slot;
     const double *lc = ph.slot + 3 * C * 32;
+    if (AMER) {
+        american_rhs<C, RELU_FP64>(V, L, ph.q, ph.pd);
+    } else {
 #pragma unroll
-    for (int k = 0; k < C; ++k) {
-        if (AMER) {
-            const double g = fma(ph.q, V[k], L[k]);
-            V[k] = fma(ph.pd, V[k], g);
-            L[k] = g;
-        } else {
-            L[k] = ph.q * V[k];
-        }
+        for (int k = 0; k < C; ++k) L[k] = ph.q * V[k];
     }
     if (TBL && k0 >= 0) {
 #pragma unroll
@@ -442,11 +438,7 @@ __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph 
             else           { c2 = fma(TBL ? ncc[k * 32 + lane] : ph.NCC, c2, V[k]); xs = c2; }
             const double vc = fma(TBL ? inv[k * 32 + lane] : ph.INV, xs, -L[k]);
             if (AMER) {
-                // exercise iff phi > vc (:496): dt*lambda_new = max(phi - vc, 0) on the sign mask, V = vc + dt*lambda_new
-                const double d = sm.r0[k * NT + t] - vc;
-                const int msk = ~(__double2hiint(d) >> 31);
-                L[k] = __hiloint2double(__double2hiint(d) & msk, __double2loint(d) & msk);
-                V[k] = vc + L[k];
+                american_project<RELU_FP64>(sm.r0[k * NT + t], vc, V[k], L[k]);
             } else {
                 V[k] = vc;
             }
@@ -488,10 +480,7 @@ __device__ __forceinline__ void step_cs(double (&V)[C], double (&L)[C], const Ph
             if (CORR) xs = fma(gzx, sm.nmp[k], xs);
             const double vc = fma(INVT ? ph.invw[k * 32 + lane] : ph.INV, xs, -L[k]);
             if (AMER) {
-                const double d = sm.r0[k * NT + t] - vc;
-                const int msk = ~(__double2hiint(d) >> 31);
-                L[k] = __hiloint2double(__double2hiint(d) & msk, __double2loint(d) & msk);
-                V[k] = vc + L[k];
+                american_project<RELU_FP64>(sm.r0[k * NT + t], vc, V[k], L[k]);
             } else {
                 V[k] = vc;
             }

@@ -69,6 +69,8 @@ __host__ __device__ constexpr int class_of(int n_int)
     return 0;
 }
 
+template <int N> struct IntC { static constexpr int value = N; };
+
 enum { LC_KAP = 0, LC_KAPL, LC_KAPU, LC_D, LC_ZC, LC_AB1, LC_AB2, LC_ABL, LC_CA, LC_CB, LC_N };
 constexpr int PW_MAX = 16;      // powers of NM kept in shared memory (warp-uniform, broadcast reads)
 
@@ -293,10 +295,10 @@ __device__ __forceinline__ bool setup_phase(double theta, double dt, double a, d
 // direct carry, split in two so that independent work can be issued between the shuffles and their use
 template <bool UP>
 struct CarryShf {
-    double t1, t2, t3, t4, t5, t6;       // scalars, always initialised: an array here ends up in local memory
+    double t1, t2, t3, t4, t5, t6;       // scalars (an array here ends up in local memory); combine() reads exactly
+                                         // the ones issue() wrote for the same `terms`, so none is pre-set
     __device__ __forceinline__ void issue(const double e_end, const int terms)
     {
-        t1 = t2 = t3 = t4 = t5 = t6 = 0.0;
         if (terms) {
             t1 = UP ? __shfl_up_sync(FULL, e_end, 1) : __shfl_down_sync(FULL, e_end, 1);
             t2 = UP ? __shfl_up_sync(FULL, e_end, 2) : __shfl_down_sync(FULL, e_end, 2);
@@ -332,11 +334,12 @@ struct CarryShf {
 // one times a power of two, so the results are bit-identical to the (vc, 3 dt lambda) form.
 // The optional last slot is handled without branches: on lanes that do not hold it its multipliers are 1 / 0 and
 // its V, L stay 0, which makes it the identity in both sweeps.
-template <int C, bool AMER>
+template <int C, bool AMER, int TERMS>
 __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const Ph<C> &ph, const double cin_f,
                                            const double cin_b, const bool last, const Tables<C> &T, const int lane)
 {
     constexpr int H = C / 2, PW = C - H;
+    constexpr int terms = TERMS;                        // the time loop is specialised per carry form (see the kernel)
     const double NM = ph.NM, NCC = ph.NCC;
     const double nmL = last ? NM : 1.0, nccL = last ? NCC : 1.0;
     // right-hand side R (into V) and subtrahend G (into L)
@@ -373,22 +376,22 @@ __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const
     const double af2 = last ? pw(PW) : pw(PW - 1);
     const double e_end = fma(af2, a, b);
     CarryShf<true> shf_f;
-    shf_f.issue(e_end, ph.terms);
+    shf_f.issue(e_end, terms);
     // ---- backward local pass on u_loc, while the forward carries are in flight ------------------------
     double e1 = cin_b, e2 = 0.0;
 #pragma unroll
     for (int k = C - 1; k >= H; --k) e1 = fma(k < C - 1 ? NCC : nccL, e1, V[k]);
 #pragma unroll
     for (int k = H - 1; k >= 0; --k) e2 = fma(NCC, e2, V[k]);
-    const double c_in = shf_f.combine(e_end, ph.terms, T.Wf, T.Af, lane);            // carry into slot 0
+    const double c_in = shf_f.combine(e_end, terms, T.Wf, T.Af, lane);            // carry into slot 0
     const double pH = pw(H);
     const double c_mid = fma(pH, c_in, a);                                           // carry into slot H (= u_{H-1})
     // true u = u_loc + NM^(k+1) carry  =>  backward local ends pick up kap * carry
     const double kapU = LCV(ph, T, lane, kapU, LC_KAPU);
     double e_end_b = fma(LCV(ph, T, lane, ab2, LC_AB2), fma(kapU, c_mid, e1), fma(LCV(ph, T, lane, kapL, LC_KAPL), c_in, e2));
     CarryShf<false> shf_b;
-    shf_b.issue(e_end_b, ph.terms);
-    double cb = shf_b.combine(e_end_b, ph.terms, T.Wb, T.Ab, lane);
+    shf_b.issue(e_end_b, terms);
+    double cb = shf_b.combine(e_end_b, terms, T.Wb, T.Ab, lane);
     // Sherman-Morrison: g = delta x_0 from lane 0's inclusive end value xs_0; R_0 -= g
     const double g = LCV(ph, T, lane, kap, LC_KAP) * __shfl_sync(FULL, fma(LCV(ph, T, lane, abl, LC_ABL), cb, e_end_b), 0);
     const double c_in2 = fma(-g, LCV(ph, T, lane, D, LC_D), c_in);
@@ -573,11 +576,16 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
             }
             double w_next = fetch_boundary(m);
             double cin = LCV(ph, T, lane, cB, LC_CB) * Vb - LCV(ph, T, lane, cA, LC_CA) * w_next;   // non-zero on lanes 0 and 31 only
+            // The time loop is compiled once per carry form (TT = 2 / 4 / 6 direct terms, 0 = scan), so the step has no
+            // branches on ph.terms: ~35 fewer instructions per warp-step (BRA / UISETP / PLOP3 and the shuffle
+            // temporaries' moves) and a tighter schedule.  Measured on B200: +5..14 % on every lean shape.
+            auto time_loop = [&](auto tt) {
+            constexpr int TT = decltype(tt)::value;
             for (; m < m_end; ++m) {
                 const double w_now = w_next;
                 w_next = fetch_boundary(m + 1);
                 double cin_n = LCV(ph, T, lane, cB, LC_CB) * w_now - LCV(ph, T, lane, cA, LC_CA) * w_next;
-                march_step<C, AMER>(V, L, ph, (lane == 0) ? cin : 0.0, (lane == 31) ? cin : 0.0, last, T, lane);
+                march_step<C, AMER, TT>(V, L, ph, (lane == 0) ? cin : 0.0, (lane == 31) ? cin : 0.0, last, T, lane);
                 Vb = w_now;                                     // V[0] = V_min, V[-1] = V_max, :505-506
                 ++gstep;
                 if (TRACE && trace) {
@@ -611,6 +619,13 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
                     cin_n = LCV(ph, T, lane, cB, LC_CB) * Vb - LCV(ph, T, lane, cA, LC_CA) * w_next;
                 }
                 cin = cin_n;
+            }
+            };
+            switch (ph.terms) {
+            case 2: time_loop(IntC<2>{}); break;
+            case 4: time_loop(IntC<4>{}); break;
+            case 6: time_loop(IntC<6>{}); break;
+            default: time_loop(IntC<0>{}); break;
             }
         }
         if (retry) break;
