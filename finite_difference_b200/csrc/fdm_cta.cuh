@@ -53,6 +53,18 @@ __host__ __device__ constexpr bool row0_mode()
 #endif
 }
 
+// One-term warp-to-warp sums compiled as straight-line code (K1 loops): +15..30 % in every class except the 16-warp
+// American one, which measured 28 % SLOWER with them (8192 nodes: 3.70 -> 5.18 ms) and keeps the general loops.
+template <int C, int WARPS, bool AMER>
+__host__ __device__ constexpr bool k1_mode()
+{
+#ifdef FDM_CTA_K1_NOT_16A
+    return !(WARPS == 16 && AMER);
+#else
+    return true;
+#endif
+}
+
 // nearest node to `level` with the reference's first-minimum tie-break
 // (fd_american_option_pricer.py:253; interior_only: discrete_barrier_fdm_pricer_cn.py:335).
 // |s_j - level| is V-shaped in j, so a window around the analytic position holds the argmin.
@@ -82,7 +94,7 @@ struct Layout {
     static constexpr int SLOTS = WARPS <= 4 ? WARPS : (WARPS <= 5 ? 4 : 6);   // 5 warps: two CTAs per SM must fit shared memory
     static constexpr int SLOT_DOUBLES = 3 * C * 32 + 8 * 32;         // nm, ncc, inv [k][lane] + 8 per-lane constants
     static constexpr int R2 = NP > SLOTS * SLOT_DOUBLES ? NP : SLOTS * SLOT_DOUBLES;
-    static constexpr int SMALL = 4 * WARPS + 16 + 64 + 32 + 8 + C + 8;   // part, cst, PAc, wb, ishare, nmp, smv
+    static constexpr int SMALL = 4 * WARPS + 16 + 64 + 32 + 8 + C + 8 + 320;   // part, cst, PAc, wb, ishare, nmp, smv, scw
     static constexpr int TOTAL = 2 * NP + R2 + SMALL;
 };
 
@@ -97,12 +109,16 @@ struct Sm {
     int *ish;       // [0] P [1] spot node [2] strike node [3,4] KO range [5] status [6,7] ex lo/hi [8] Kf [9] Kb
                     // [10] first table warp [11] last table warp [12] last warp the row-0 correction reaches (-1: table mode)
     double *nmp;    // [C] powers NM^k of the steady-state forward multiplier (row-0 correction)
+    double *scw;    // [2][5][32] masked level weights of the scalar warps' scans (forward, backward): a^(2^lv) or 0
     double *smv;    // [0] GF NCC^-k0, factor of the row-0 correction  [1] xs at slot 0 of the owner of row 0, current step
                     // [2] Kc: what the Dirichlet carry leaves in [1] through the k0 dead slots below row 0
 };
 
 enum { CST_NM = 0, CST_NCC, CST_INV, CST_AF, CST_AB, CST_HF1, CST_HF2, CST_HB1, CST_HB2, CST_TOP, CST_PD };
 enum { LC_AF = 0, LC_AB, LC_HF1, LC_HF2, LC_HB1, LC_HB2, LC_PAF, LC_PAB };
+
+// warp roles of the specialised time loops (kernel): fixed per warp for a phase
+enum { ROLE_ANY = -1, ROLE_PAD = 0, ROLE_TBL, ROLE_SCALAR, ROLE_SCALAR_R0, ROLE_OWNER, ROLE_SMC };
 
 struct Ph {
     double q, pd, NM, NCC, INV;
@@ -294,6 +310,14 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
             }
             sm.PAc[lane] = PAf;
             sm.PAc[32 + lane] = PAb;
+            double af = aF, ab = aB;                     // level weights by repeated squaring, as warp_scan forms them
+#pragma unroll
+            for (int lv = 0; lv < 5; ++lv) {
+                sm.scw[lv * 32 + lane] = (lane >= (1 << lv)) ? af : 0.0;
+                sm.scw[160 + lv * 32 + lane] = (lane + (1 << lv) < 32) ? ab : 0.0;
+                af *= af;
+                ab *= ab;
+            }
         }
     } else if (lane == 0) {
         sm.part[0 * WARPS + w] = 0.0; sm.part[1 * WARPS + w] = 0.0;
@@ -342,6 +366,25 @@ __device__ __forceinline__ double warp_scan(double e, double a, int lane)
     return E;
 }
 
+// the scalar warps' scan with the masked level weights read from shared memory (one LDS per level instead of a
+// compare, two selects and a multiply); same values as warp_scan<false, UP>
+#ifdef FDM_CTA_NO_SCAN_TABLE
+constexpr bool SCAN_TABLE = false;
+#else
+constexpr bool SCAN_TABLE = true;
+#endif
+template <bool UP>
+__device__ __forceinline__ double warp_scan_tab(double e, const double *__restrict__ wt, int lane)
+{
+    double E = e;
+#pragma unroll
+    for (int lv = 0; lv < 5; ++lv) {
+        const double tE = UP ? __shfl_up_sync(FULL, E, 1 << lv) : __shfl_down_sync(FULL, E, 1 << lv);
+        E = fma(wt[lv * 32 + lane], tE, E);
+    }
+    return E;
+}
+
 // ---- the three phases of one time step (barriers sit between them, outside any branch) -----------
 
 // RHS, forward local pass, intra-warp scan.  k0 >= 0 on the thread that owns row 0: its Dirichlet term
@@ -371,14 +414,15 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
     for (int k = H; k < C; ++k) e2 = fma(TBL ? nm[k * 32 + lane] : ph.NM, e2, V[k]);
     double e_end = fma(TBL ? lc[LC_HF2 * 32 + lane] : sm.cst[CST_HF2], e1, e2);
     if (!TBL && R0) e_end = fma(sm.cst[CST_AF], carryF, e_end);  // Dirichlet term of row 0 as a carry into its owner
-    const double E = warp_scan<TBL, true>(e_end, TBL ? lc[LC_AF * 32 + lane] : sm.cst[CST_AF], lane);
+    const double E = (!TBL && SCAN_TABLE) ? warp_scan_tab<true>(e_end, sm.scw, lane)
+                                          : warp_scan<TBL, true>(e_end, TBL ? lc[LC_AF * 32 + lane] : sm.cst[CST_AF], lane);
     if (lane == 31) sm.part[0 * WARPS + w] = E;           // pE_f
     const double up = __shfl_up_sync(FULL, E, 1);
     Eprev = (lane == 0) ? 0.0 : up;
     e1_keep = e1;
 }
 
-template <int C, int WARPS, bool AMER, bool TBL, bool R0>
+template <int C, int WARPS, bool AMER, bool TBL, bool R0, bool K1>
 __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &sm, const int wf, const double cin_b,
                                        const double e1_fwd, const double Eprev, const double carryF, double &e1_keep,
                                        double &Enext, double &eend_keep)
@@ -389,7 +433,11 @@ __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &s
     const double *lc = ph.slot + 3 * C * 32;
     // carry into this warp from the warps below (truncated Horner sum)
     double S = 0.0;
-    for (int v = max(wf, w - ph.Kf); v < w; ++v) S = fma(sm.part[1 * WARPS + v], S, sm.part[0 * WARPS + v]);
+    if (K1) { if (w > wf) S = sm.part[0 * WARPS + w - 1]; }       // one term: the total of the warp below
+    else {
+#pragma unroll 1
+        for (int v = max(wf, w - ph.Kf); v < w; ++v) S = fma(sm.part[1 * WARPS + v], S, sm.part[0 * WARPS + v]);
+    }
     const double cs = fma(TBL ? lc[LC_PAF * 32 + lane] : sm.PAc[lane], S, Eprev) + ((TBL || !R0) ? 0.0 : carryF);
     {
         double c1 = cs;
@@ -406,7 +454,8 @@ __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &s
 #pragma unroll
     for (int k = H - 1; k >= 0; --k) e2 = fma(TBL ? ncc[k * 32 + lane] : ph.NCC, e2, V[k]);
     const double e_end = fma(TBL ? lc[LC_HB2 * 32 + lane] : sm.cst[CST_HB2], e1, e2);
-    const double E = warp_scan<TBL, false>(e_end, TBL ? lc[LC_AB * 32 + lane] : sm.cst[CST_AB], lane);
+    const double E = (!TBL && SCAN_TABLE) ? warp_scan_tab<false>(e_end, sm.scw + 160, lane)
+                                          : warp_scan<TBL, false>(e_end, TBL ? lc[LC_AB * 32 + lane] : sm.cst[CST_AB], lane);
     if (lane == 0) sm.part[2 * WARPS + w] = E;            // pE_b
     const double dn = __shfl_down_sync(FULL, E, 1);
     Enext = (lane == 31) ? 0.0 : dn;
@@ -414,7 +463,7 @@ __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &s
     eend_keep = e_end;
 }
 
-template <int C, int WARPS, bool AMER, bool TBL>
+template <int C, int WARPS, bool AMER, bool TBL, bool K1>
 __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph &ph, const Sm &sm, const double cin_b,
                                        const double e1_bwd, const double Enext)
 {
@@ -424,7 +473,11 @@ __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph 
     const double *ncc = ph.slot + C * 32, *inv = ph.slot + 2 * C * 32;
     const double *lc = ph.slot + 3 * C * 32;
     double S = 0.0;
-    for (int v = min(WARPS - 1, w + ph.Kb); v > w; --v) S = fma(sm.part[3 * WARPS + v], S, sm.part[2 * WARPS + v]);
+    if (K1) { if (w < WARPS - 1) S = sm.part[2 * WARPS + w + 1]; }
+    else {
+#pragma unroll 1
+        for (int v = min(WARPS - 1, w + ph.Kb); v > w; --v) S = fma(sm.part[3 * WARPS + v], S, sm.part[2 * WARPS + v]);
+    }
     const double cs = fma(TBL ? lc[LC_PAB * 32 + lane] : sm.PAc[32 + lane], S, Enext);
     double c1 = cs + cin_b;
     double c2 = fma(TBL ? lc[LC_HB1 * 32 + lane] : sm.cst[CST_HB1], cs, e1_bwd);
@@ -449,12 +502,16 @@ __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph 
 // step_c of a scalar-coefficient warp with the backward carry `cs` already summed (bwd_carry).  CORR: the row-0
 // correction reaches this warp: xs'_k = xs_k - gz xs_0 NM^k (one extra FMA per slot, off the recurrence chain).
 // INVT: the warp of row 0 (pivot scaling by slot, zero on the dead slots).
-template <int WARPS>
+template <int WARPS, bool K1>
 __device__ __forceinline__ double bwd_carry(const Ph &ph, const Sm &sm, const double Enext)
 {
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     double S = 0.0;
-    for (int v = min(WARPS - 1, w + ph.Kb); v > w; --v) S = fma(sm.part[3 * WARPS + v], S, sm.part[2 * WARPS + v]);
+    if (K1) { if (w < WARPS - 1) S = sm.part[2 * WARPS + w + 1]; }
+    else {
+#pragma unroll 1
+        for (int v = min(WARPS - 1, w + ph.Kb); v > w; --v) S = fma(sm.part[3 * WARPS + v], S, sm.part[2 * WARPS + v]);
+    }
     return fma(sm.PAc[32 + lane], S, Enext);
 }
 
@@ -620,6 +677,7 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
     sm.ish = (int *)(sm.wb + 32);
     sm.nmp = sm.wb + 32 + 8;
     sm.smv = sm.nmp + C;
+    sm.scw = sm.smv + 8;
 
     const int64_t sid = first + blockIdx.x;
     if (sid >= B.n_solves) return;
@@ -711,10 +769,9 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
             if (step - fill_base >= 32 || step < fill_base) {
                 fill_base = step;
                 const double tau = fma((double)(step + lane + 1), dt, tau0);
-                double vmin, vmax;
-                boundary_values(is_call, b76, r, b_bdry, k_eff, sn_bdry, tau, vmin, vmax, put_smin, node_s(x_min, dx, 0));
+                const double wv = moving_boundary_value(is_call, b76, r, b_bdry, k_eff, sn_bdry, tau, put_smin, node_s(x_min, dx, 0));
                 __syncwarp();
-                sm.wb[lane] = is_call ? vmax : vmin;
+                sm.wb[lane] = wv;
                 __syncwarp();
             }
             return bdry_thread ? sm.wb[step - fill_base] : 0.0;
@@ -730,6 +787,13 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
             const double top_mult = (t == NT - 1) ? sm.cst[CST_TOP] : 0.0;
             double w_next = fetch_boundary(m);
             double cin = ph.cB * Vb - ph.cA * w_next;           // non-zero on the two boundary threads only
+            // The time loop is compiled once per warp role (warp-uniform, fixed for the phase), so a step has no
+            // branches on the role: between two block barriers each warp runs straight-line code.  Every role executes
+            // the same sequence of block barriers (different BAR.SYNC sites on barrier 0, as in any warp-specialised
+            // kernel).  Role-less form: FDM_CTA_ONE_LOOP.
+            auto time_loop = [&](auto role_tag, auto k1_tag) {
+            constexpr int ROLE = decltype(role_tag)::value;
+            constexpr bool K1 = decltype(k1_tag)::value != 0;   // warp-to-warp sums of one term (the usual case)
             for (; m < m_end; ++m) {
                 const double w_now = w_next;
                 w_next = fetch_boundary(m + 1);
@@ -737,27 +801,34 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                 const double cin_b = cin * top_mult;            // enters the top row through its ncc
                 double e1f = 0.0, Eprev = 0.0, e1b = 0.0, Enext = 0.0, eend_b = 0.0;
                 const double carryF = R0 ? cin * ph.cF : 0.0;   // non-zero on the owner of row 0 in row-0-correction mode
-                if (ph.cls == 2) step_a<C, WARPS, AMER, true, R0>(V, L, ph, sm, k0, cin, 0.0, e1f, Eprev);
-                else if (ph.cls == 1) step_a<C, WARPS, AMER, false, R0>(V, L, ph, sm, -1, 0.0, carryF, e1f, Eprev);
+                constexpr bool ANY = ROLE == ROLE_ANY;
+                const bool tbl = ANY ? ph.cls == 2 : ROLE == ROLE_TBL;
+                const bool scl = ANY ? ph.cls == 1 : (ROLE != ROLE_TBL && ROLE != ROLE_PAD);
+                if (tbl) step_a<C, WARPS, AMER, true, R0>(V, L, ph, sm, k0, cin, 0.0, e1f, Eprev);
+                else if (scl) step_a<C, WARPS, AMER, false, R0>(V, L, ph, sm, -1, 0.0, carryF, e1f, Eprev);
                 FDM_CTA_STEP_SYNC();
-                if (ph.cls == 2) step_b<C, WARPS, AMER, true, R0>(V, ph, sm, wf, cin_b, e1f, Eprev, 0.0, e1b, Enext, eend_b);
-                else if (ph.cls == 1) step_b<C, WARPS, AMER, false, R0>(V, ph, sm, wf, cin_b, e1f, Eprev, carryF, e1b, Enext, eend_b);
+                if (tbl) step_b<C, WARPS, AMER, true, R0, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, 0.0, e1b, Enext, eend_b);
+                else if (scl) step_b<C, WARPS, AMER, false, R0, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, carryF, e1b, Enext, eend_b);
                 FDM_CTA_STEP_SYNC();
-                if (ph.cls == 2) step_c<C, WARPS, AMER, true>(V, L, ph, sm, cin_b, e1b, Enext);
-                else if (!row0_corr) {
-                    if (ph.cls == 1) step_c<C, WARPS, AMER, false>(V, L, ph, sm, cin_b, e1b, Enext);
+                const bool r0c = ANY || ROLE == ROLE_PAD ? row0_corr : (ROLE == ROLE_SCALAR_R0 || ROLE == ROLE_OWNER || ROLE == ROLE_SMC);
+                if (tbl) step_c<C, WARPS, AMER, true, K1>(V, L, ph, sm, cin_b, e1b, Enext);
+                else if (!r0c) {
+                    if (scl) step_c<C, WARPS, AMER, false, K1>(V, L, ph, sm, cin_b, e1b, Enext);
                 } else {
                     // row-0 correction: the owner of row 0 knows xs at its slot 0 (= NCC^k0 xs_0: its padding slots pass
                     // the value through) from the local pass and its carry, before the last pass starts
                     double cs_b = 0.0;
-                    if (ph.cls == 1) {
-                        cs_b = bwd_carry<WARPS>(ph, sm, Enext);
-                        if (k0 >= 0) sm.smv[1] = fma(-sm.smv[2], carryF, fma(sm.cst[CST_AB], cs_b, eend_b));
+                    if (scl) {
+                        cs_b = bwd_carry<WARPS, K1>(ph, sm, Enext);
+                        if ((ANY || ROLE == ROLE_OWNER) && k0 >= 0)
+                            sm.smv[1] = fma(-sm.smv[2], carryF, fma(sm.cst[CST_AB], cs_b, eend_b));
                     }
                     if (ph.bar3) __syncthreads(); else __syncwarp();
-                    if (ph.cls == 1) {
-                        if (w == wf) step_cs<C, WARPS, AMER, true, true>(V, L, ph, sm, cs_b, cin_b, e1b);
-                        else if (ph.smc) step_cs<C, WARPS, AMER, true, false>(V, L, ph, sm, cs_b, cin_b, e1b);
+                    if (scl) {
+                        const bool own = ANY ? w == wf : ROLE == ROLE_OWNER;
+                        const bool smc = ANY ? ph.smc != 0 : ROLE == ROLE_SMC;
+                        if (own) step_cs<C, WARPS, AMER, true, true>(V, L, ph, sm, cs_b, cin_b, e1b);
+                        else if (smc) step_cs<C, WARPS, AMER, true, false>(V, L, ph, sm, cs_b, cin_b, e1b);
                         else step_cs<C, WARPS, AMER, false, false>(V, L, ph, sm, cs_b, cin_b, e1b);
                     }
                 }
@@ -795,6 +866,30 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                 }
                 cin = cin_n;
             }
+            };
+#ifdef FDM_CTA_ONE_LOOP
+            time_loop(IntC<ROLE_ANY>{}, IntC<0>{});
+#else
+            const int role = ph.cls == 0 ? ROLE_PAD : (ph.cls == 2 ? ROLE_TBL : (!row0_corr ? ROLE_SCALAR
+                             : (w == wf ? ROLE_OWNER : (ph.smc ? ROLE_SMC : ROLE_SCALAR_R0))));
+            auto by_role = [&](auto k1_tag) {
+                switch (role) {
+                case ROLE_PAD: time_loop(IntC<ROLE_PAD>{}, k1_tag); break;
+                case ROLE_TBL: time_loop(IntC<ROLE_TBL>{}, k1_tag); break;
+                case ROLE_SCALAR: time_loop(IntC<ROLE_SCALAR>{}, k1_tag); break;
+                case ROLE_OWNER: if constexpr (R0) time_loop(IntC<ROLE_OWNER>{}, k1_tag); break;
+                case ROLE_SMC: if constexpr (R0) time_loop(IntC<ROLE_SMC>{}, k1_tag); break;
+                default: if constexpr (R0) time_loop(IntC<ROLE_SCALAR_R0>{}, k1_tag); break;
+                }
+            };
+#ifdef FDM_CTA_NO_K1
+            by_role(IntC<0>{});
+#else
+            // (not with the third barrier of a far-reaching row-0 correction: that combination measured slower than the
+            // general loops -- 2048 nodes x 400 steps, sigma 0.25..0.30: 1.65 ms against 1.2..1.4)
+            if (k1_mode<C, WARPS, AMER>() && ph.Kf == 1 && ph.Kb == 1 && !ph.bar3) by_role(IntC<1>{}); else by_role(IntC<0>{});
+#endif
+#endif
         }
         if (cash != 0.0) {
             __syncthreads();

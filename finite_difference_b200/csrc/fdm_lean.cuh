@@ -69,7 +69,6 @@ __host__ __device__ constexpr int class_of(int n_int)
     return 0;
 }
 
-template <int N> struct IntC { static constexpr int value = N; };
 
 enum { LC_KAP = 0, LC_KAPL, LC_KAPU, LC_D, LC_ZC, LC_AB1, LC_AB2, LC_ABL, LC_CA, LC_CB, LC_N };
 constexpr int PW_MAX = 16;      // powers of NM kept in shared memory (warp-uniform, broadcast reads)
@@ -558,10 +557,8 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
                 const double r_ = *(volatile const double *)&B.r[sid];
                 const double b_ = B.b_bdry ? *(volatile const double *)&B.b_bdry[sid] : *(volatile const double *)&B.b[sid];
                 const double tau = fma((double)(step + lane + 1), dt_, tau0_);
-                double vmin, vmax;
-                boundary_values(is_call, b76, r_, b_, ((volatile double *)T.par)[0], ((volatile double *)T.par)[1], tau,
-                                vmin, vmax, put_smin, ((volatile double *)T.par)[2]);
-                my_w = is_call ? vmax : vmin;
+                my_w = moving_boundary_value(is_call, b76, r_, b_, ((volatile double *)T.par)[0],
+                                             ((volatile double *)T.par)[1], tau, put_smin, ((volatile double *)T.par)[2]);
             }
             const double w = __shfl_sync(FULL, my_w, step - fill_base);
             return bdry_lane ? w : 0.0;

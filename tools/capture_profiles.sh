@@ -15,6 +15,7 @@ for spec in "am500 fdm_lean_kernel 20000" "am500div fdm_warp_kernel 5000" "am400
       -o gpurun_out/${R}_prof_$1 -f python tools/ncu_shapes.py $1 $3 > gpurun_out/${R}_ncu_$1.log 2>&1
   # the reports are ~23 MB each and gpurun brings back 64 MiB at most: summarise here, keep the text
   python tools/ncu_summary.py gpurun_out/${R}_prof_$1.ncu-rep gpurun_out/${R}_$1_ncu_full_summary.txt $3 > /dev/null
+  python tools/ncu_opmix.py gpurun_out/${R}_prof_$1.ncu-rep > gpurun_out/${R}_$1_ncu_opmix.txt 2>/dev/null
   ncu -i gpurun_out/${R}_prof_$1.ncu-rep --page source --csv --print-source sass > gpurun_out/_src.csv 2>/dev/null
   python tools/ncu_hot.py gpurun_out/_src.csv 25 > gpurun_out/${R}_$1_ncu_hot_sass.txt
   rm -f gpurun_out/${R}_prof_$1.ncu-rep gpurun_out/_src.csv
