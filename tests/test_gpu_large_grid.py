@@ -148,3 +148,40 @@ def test_barrier_row0_mode_vs_oracle(n):
     assert res.status[0] == 0
     _v_close(res.V[0, : n + 1], o.V)
     assert abs(res.price[0] - o.price) <= REL * abs(o.price)
+
+
+# The CTA kernel compiles its time loop per warp role and per form of the warp-to-warp sums (fdm_cta.cuh): which loops
+# a solve runs depends on the stiffness theta*dt*alpha of its time step.  Volatility bands at the time steps of the
+# benchmark shapes (8192 nodes, dt = 1e-4; 2048 nodes, dt = 2.5e-3) walk through one-term sums without and with the
+# third barrier, and multi-term sums; calls and puts put the moving boundary in the last / the first warp.
+STIFF_CASES = [(n, m, T, sig, call) for (n, m, T) in ((8192, 200, 0.02), (2048, 100, 0.25), (4096, 120, 0.03))
+               for sig in (0.16, 0.28, 0.35, 0.45) for call in (False, True)]
+
+
+@pytest.mark.parametrize("n,m,T,sig,call", STIFF_CASES)
+def test_american_stiffness_bands_vs_oracle(n, m, T, sig, call):
+    kw = dict(spot=229.74, strike=235.0 if call else 225.0, T=T, sigma=sig, r=0.06, b=0.06, is_call=call, model=0,
+              n_space=n, n_time=m, rannacher=2, s_max_mult=4.5, divs_tau=[])
+    batch = hostlogic.build_american_batch([kw["spot"]], [kw["strike"]], [T], [sig], [kw["r"]], [kw["b"]], [call], [n], [m],
+                                           [2], [False], 4.5, div_taus=[[]])
+    res = solve_host(batch, dump=True, trace=True)
+    o = oracle.american_solve(**kw, trace=True)
+    assert res.status[0] == 0
+    _v_close(res.V[0, : n + 1], o.V)
+    assert abs(res.price[0] - o.price) <= REL * abs(o.price)
+    assert np.array_equal(res.ex_trace[0, : o.ex_trace.shape[0]], o.ex_trace)
+
+
+@pytest.mark.parametrize("sig", (0.12, 0.3, 0.5))
+def test_barrier_stiffness_bands_vs_oracle(sig):
+    # 16-warp linear class (table warps + scalar warps) and the 5-warp class of the barrier scenario runner
+    for n, m, T in ((8192, 200, 0.02), (2133, 125, 0.25)):
+        S0, K, r, b = 100.0, 97.0, 0.04, 0.02
+        mon = [T * 0.25, T * 0.5, T * 0.75]
+        batch = hostlogic.build_barrier_batch([S0], [K], [T], [sig], [r], [b], [True], ["down-and-out"], [88.0], [None],
+                                              [0.0], [mon], [n], [m])
+        res = solve_host(batch, dump=True)
+        o = oracle.barrier_solve(S0, K, T, sig, r, b, True, "down-and-out", 88.0, None, 0.0, mon, n, m, True)
+        assert res.status[0] == 0
+        _v_close(res.V[0, : n + 1], o.V)
+        assert abs(res.price[0] - o.price) <= REL * abs(o.price)
