@@ -37,24 +37,25 @@ namespace cta {
 
 constexpr double TRUNC_EPS = 1e-22;
 
-// Row-0 correction (see setup_phase) instead of per-slot table warps.  The 16-warp class runs at its 128-register cap:
-// its linear variant then spills inside the time loop and the table warps stay faster (8192-node barrier grids: 5.5e11
-// with tables, 4.1e11 with the correction), so that one variant keeps the tables.  Measured gains elsewhere: 8192-node
-// American +8 %, 2133-node barrier grids +33 %.
+// Row-0 correction (see setup_phase) instead of per-slot table warps, in every class.  (Before the time loop was
+// compiled per warp role the 16-warp linear variant kept the tables: at its 128-register cap the correction's extra
+// live values spilled inside the loop, 4.1 against 5.5e11 on 8192-node barrier grids.  With the per-role loops the
+// correction wins there too: 7.8e11 -> 1.09e12.)  FDM_CTA_NO_ROW0_CORR builds the table-only kernel.
 template <int C, int WARPS, bool AMER>
 __host__ __device__ constexpr bool row0_mode()
 {
-#ifdef FDM_CTA_ROW0_ALL
-    return true;
-#elif defined(FDM_CTA_NO_ROW0_CORR)
+#ifdef FDM_CTA_NO_ROW0_CORR
     return false;
 #else
-    return C < 16 || WARPS < 16 || AMER;
+    return true;
 #endif
 }
 
-// One-term warp-to-warp sums compiled as straight-line code (K1 loops): +15..30 % in every class except the 16-warp
-// American one, which measured 28 % SLOWER with them (8192 nodes: 3.70 -> 5.18 ms) and keeps the general loops.
+// One-term warp-to-warp sums compiled as straight-line code (K1 loops): +15..30 % in every class.  (A first version
+// ran a 16-warp American batch that mixed K1 and general solves 28 % SLOWER, 8192 nodes: 3.70 -> 5.18 ms, while every
+// solve alone was faster: the loops were ~1000 instructions each and several were live per SM.  Fixed by shrinking the
+// loops -- boundary exponentials out of line, general Horner loops not unrolled; FDM_CTA_K1_NOT_16A restores the
+// exception.)
 template <int C, int WARPS, bool AMER>
 __host__ __device__ constexpr bool k1_mode()
 {
