@@ -99,7 +99,10 @@ constexpr int smem_doubles() { return 32 * C + 2 * DIRECT_TERMS * 32 + 2 * SCAN_
 template <int C>
 struct Ph {
     static constexpr int H = C / 2, PW = C - C / 2;
-    static constexpr bool P_SMEM = C > 13;   // where the powers of NM live (measured: registers win up to 13 slots)
+#ifndef FDM_LEAN_PSMEM_MIN
+#define FDM_LEAN_PSMEM_MIN 14
+#endif
+    static constexpr bool P_SMEM = C >= FDM_LEAN_PSMEM_MIN;   // where the powers of NM live (measured: registers win up to 13 slots)
     double NM, NCC, INV;      // -A_L/den_inf, -A_U/den_inf, scale/den_inf
     double P[PW + 1];         // P[j] = NM^j, j = 0..PW (registers, C <= 13; else Tables::pw)
     double cA, cB;            // boundary coefficients of this lane, already divided by NM (lane 0) / NCC (lane 31)
