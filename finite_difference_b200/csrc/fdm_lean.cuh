@@ -102,7 +102,9 @@ struct Ph {
 #ifndef FDM_LEAN_PSMEM_MIN
 #define FDM_LEAN_PSMEM_MIN 14
 #endif
-    static constexpr bool P_SMEM = C >= FDM_LEAN_PSMEM_MIN;   // where the powers of NM live (measured: registers win up to 13 slots)
+    // where the powers of NM live: registers win up to 13 slots (re-measured with the per-form loops: 400x400
+    // American 8.49e11 with registers, 7.60e11 with shared memory), shared memory from 14
+    static constexpr bool P_SMEM = C >= FDM_LEAN_PSMEM_MIN;
     double NM, NCC, INV;      // -A_L/den_inf, -A_U/den_inf, scale/den_inf
     double P[PW + 1];         // P[j] = NM^j, j = 0..PW (registers, C <= 13; else Tables::pw)
     double cA, cB;            // boundary coefficients of this lane, already divided by NM (lane 0) / NCC (lane 31)
