@@ -13,6 +13,10 @@
 //     short Horner sum over the preceding warps' totals -> local pass.  The warp-to-warp multipliers decay like
 //     |c'|^(32 C) (1e-17 at C = 16), so the Horner sum is truncated after K terms with the neglected
 //     weight below 1e-22 (K is found per phase).
+//   * the time loop is compiled once per warp role (padding, table, scalar, scalar in row-0 mode, owner of row 0,
+//     correction-reach) and per form of the warp-to-warp sums (one term / general), picked by a switch outside the
+//     loop: between two block barriers every warp runs straight-line code (see the kernel; 512 -> ~350 instructions
+//     per warp-step, +50..75 % over the one-loop form on every class);
 //   Two block-wide barriers per time step.  (Tried and dropped: passing the warp totals through a shared-memory
 //   ring with per-warp progress counters instead of the barriers -- the warps need their nearest neighbours only --
 //   measured 8..10 % slower on 2048..8192-node grids: the warps stay in lock-step anyway and the polls cost issue slots.)
