@@ -1,0 +1,596 @@
+// fdm_api.cu -- the C ABI of libfdm_b200 (include/fdm_b200.h): validation, the host-buffer entry points with their
+// device workspace, the dispatch to the per-class kernel launchers (fdm_internal.h), the book fan-out / epilogue
+// kernels and the FP64 micro-benchmark.
+//
+// No CPU fallback exists: every entry point fails with FDM_ERR_NO_DEVICE / FDM_ERR_CUDA if the GPU path cannot run.
+
+#include <mutex>
+
+#include "fdm_common.cuh"
+#include "fdm_lean_classes.cuh"
+#include "fdm_book.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+}  // namespace
+
+int fdm_fail(int code, const char *fmt, const char *detail)
+{
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+namespace {
+
+inline int fail(int code, const char *fmt, const char *detail = "") { return fdm_fail(code, fmt, detail); }
+
+// Device workspace of the host-buffer entry points: grow-only, one per process, reused across calls
+// (cudaMalloc/cudaFree cost milliseconds and synchronise the device).  Guarded by g_arena_mu; the host
+// entries are synchronous, so holding the lock for the whole call serialises them.
+std::mutex g_arena_mu;
+char *g_arena = nullptr;
+size_t g_arena_bytes = 0;
+int g_arena_dev = -1;
+
+cudaError_t arena_get(size_t bytes, char **out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (g_arena && (dev != g_arena_dev || bytes > g_arena_bytes)) {
+        cudaFree(g_arena);
+        g_arena = nullptr;
+        g_arena_bytes = 0;
+    }
+    if (!g_arena) {
+        e = cudaMalloc((void **)&g_arena, bytes);
+        if (e != cudaSuccess) { g_arena = nullptr; return e; }
+        g_arena_bytes = bytes;
+        g_arena_dev = dev;
+    }
+    *out = g_arena;
+    return cudaSuccess;
+}
+
+}  // namespace
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// FP64 pipe micro-benchmark
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[blockIdx.x] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+
+// the register-lean kernels of the size classes present (fdm_lean.cuh); solves of other classes exit at once
+int launch_lean_classes(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool am, bool lin, bool dv, int class_mask,
+                        int32_t *n_launches)
+{
+    typedef int (*Fn)(const FdmBatch &, const FdmOut &, cudaStream_t, bool, bool, bool, int32_t *);
+    constexpr lean::ClassList cl = lean::class_list();
+    for (int i = 0; i < cl.n; ++i) {
+        if (!(class_mask & (1 << i))) continue;
+        Fn fn = nullptr;
+        switch (cl.c[i]) {
+#ifdef FDM_LEAN_ALL_CLASSES
+        case 4: fn = fdm_launch_lean_4; break;
+        case 7: fn = fdm_launch_lean_7; break;
+        case 8: fn = fdm_launch_lean_8; break;
+#endif
+        case 10: fn = fdm_launch_lean_10; break;
+        case 13: fn = fdm_launch_lean_13; break;
+        case 16: fn = fdm_launch_lean_16; break;
+        default: break;
+        }
+        if (!fn) continue;
+        const int rc = fn(b, o, st, am, lin, dv, n_launches);
+        if (rc != FDM_OK) return rc;
+    }
+    return FDM_OK;
+}
+
+// launch hints of the size classes present in a call (FdmBatch.reserved bits 20..29):
+// bit 20+i: class i of lean::class_list() is present; bit 28: a warp-sized grid outside every class is present;
+// bit 29: these hints are valid
+int lean_hint_bits(int n_space)
+{
+    if (n_space > FDM_WARP_MAX_N_SPACE) return 0;
+    constexpr lean::ClassList cl = lean::class_list();
+    const int c = lean::class_of(n_space - 1);
+    if (c == 0) return 1 << 28;
+    for (int i = 0; i < cl.n; ++i) if (cl.c[i] == c) return 1 << (20 + i);
+    return 1 << 28;
+}
+constexpr int LEAN_HINTS_VALID = 1 << 29;
+
+int validate(const FdmBatch *b, const FdmOut *o)
+{
+    if (!b || !o) return fail(FDM_ERR_INVALID, "batch / out is NULL%s");
+    if (b->n_solves < 0) return fail(FDM_ERR_INVALID, "n_solves < 0%s");
+    if (b->n_solves == 0) return FDM_OK;
+    if (!b->x_min || !b->dx || !b->sigma || !b->r || !b->b || !b->spot || !b->strike || !b->n_space ||
+        !b->flags || !b->rannacher || !b->seg_begin || !b->seg_steps || !b->seg_dt || !b->seg_tau0 ||
+        !b->seg_restart || !b->seg_div)
+        return fail(FDM_ERR_INVALID, "a required FdmBatch array is NULL%s");
+    if (!o->price) return fail(FDM_ERR_INVALID, "FdmOut.price is NULL%s");
+    if (b->n_space_max < 3) return fail(FDM_ERR_INVALID, "n_space_max < 3%s");
+    if (b->n_space_max > FDM_MAX_N_SPACE)
+        return fail(FDM_ERR_UNSUPPORTED, "n_space_max exceeds FDM_MAX_N_SPACE (8193)%s");
+    if (b->n_mon_total > 0 && (!b->mon_begin || !b->mon_step))
+        return fail(FDM_ERR_INVALID, "monitor tables missing%s");
+    return FDM_OK;
+}
+
+// flags of the whole call (FdmBatch.reserved): bit0 any american, bit1 any linear, bit2 any dividend,
+// bit3 any solve with n_space <= FDM_WARP_MAX_N_SPACE, bit4 any larger solve,
+// bits 8..19 the largest n_space of the small class (0 = unknown)
+int launch(const FdmBatch &b, const FdmOut &o, cudaStream_t st, int family_mask, int32_t *n_launches)
+{
+    const bool am = family_mask & 1, lin = family_mask & 2, dv = family_mask & 4;
+    bool small = family_mask & 8, large = family_mask & 16;
+    if (!small && !large) {
+        large = b.n_space_max > FDM_WARP_MAX_N_SPACE;
+        small = true;                                   // unknown mix: the warp kernel skips what it cannot hold
+    }
+    if (b.n_space_max <= FDM_WARP_MAX_N_SPACE) large = false;
+    int rc = FDM_OK;
+    if (small) {
+        int small_max = (family_mask >> 8) & 0xfff;
+        if (small_max == 0 || small_max > FDM_WARP_MAX_N_SPACE)
+            small_max = b.n_space_max < FDM_WARP_MAX_N_SPACE ? b.n_space_max : FDM_WARP_MAX_N_SPACE;
+        const int rows = small_max - 1;
+        // register-lean kernels first (one launch per size class present), then fdm_warp_kernel for the rest:
+        // sizes outside the classes and the solves the lean kernel handed back
+        static const bool no_lean = getenv("FDM_B200_NO_LEAN") != nullptr;
+        int only_rest = 0;
+        if (!no_lean) {
+            const bool hinted = family_mask & LEAN_HINTS_VALID;
+            const int class_mask = hinted ? (family_mask >> 20) & 0xff : 0xff;
+            rc = launch_lean_classes(b, o, st, am, lin, dv, class_mask, n_launches);
+            if (rc != FDM_OK) return rc;
+            only_rest = 1;
+        }
+        if (rows <= 32 * 4) rc = fdm_launch_warp_4(b, o, st, am, lin, dv, only_rest, n_launches);
+        else if (rows <= 32 * 8) rc = fdm_launch_warp_8(b, o, st, am, lin, dv, only_rest, n_launches);
+        else if (rows <= 32 * 13) rc = fdm_launch_warp_13(b, o, st, am, lin, dv, only_rest, n_launches);
+        else rc = fdm_launch_warp_16(b, o, st, am, lin, dv, only_rest, n_launches);
+        if (rc != FDM_OK) return rc;
+    }
+    if (large) {
+        // one launch per CTA size class that can be populated: 4 / 5 / 8 / 16 warps of 16 slots per thread serve
+        // up to 2048 / 2560 / 4096 / 8192 interior rows; a solve runs in the smallest class that holds it
+        // (n_lo = largest n_space of the class below), other classes' CTAs exit at once
+        const int rows_max = b.n_space_max - 1;
+        rc = fdm_launch_cta_4(b, o, st, am, lin, dv, FDM_WARP_MAX_N_SPACE, n_launches);
+        if (rc == FDM_OK && rows_max > 2048) rc = fdm_launch_cta_5(b, o, st, am, lin, dv, 2049, n_launches);
+        if (rc == FDM_OK && rows_max > 2560) rc = fdm_launch_cta_8(b, o, st, am, lin, dv, 2561, n_launches);
+        if (rc == FDM_OK && rows_max > 4096) rc = fdm_launch_cta_16(b, o, st, am, lin, dv, 4097, n_launches);
+    }
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fdm_version(void) { return FDM_ABI_VERSION; }
+
+int fdm_sizeof(int which)
+{
+    switch (which) {
+    case 0: return (int)sizeof(FdmBatch);
+    case 1: return (int)sizeof(FdmOut);
+    case 2: return (int)sizeof(FdmAmericanBook);
+    case 3: return (int)sizeof(FdmBookOut);
+    default: return -1;
+    }
+}
+
+const char *fdm_last_error(void) { return g_err; }
+
+int fdm_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(FDM_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+// Device-pointer entry.  The family mask cannot be derived without reading device memory, so
+// `reserved` carries it: bit0 any American solve, bit1 any linear (European / barrier) solve,
+// bit2 any dividend jump.  0 means "unknown": launch both families with dividend scratch.
+int fdm_solve_batch(const FdmBatch *batch, const FdmOut *out, void *stream, int32_t *n_launches)
+{
+    g_err[0] = 0;
+    if (n_launches) *n_launches = 0;
+    int rc = validate(batch, out);
+    if (rc != FDM_OK || batch->n_solves == 0) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(FDM_ERR_NO_DEVICE, "no CUDA device; libfdm_b200 has no CPU fallback%s");
+    int mask = batch->reserved;
+    if ((mask & 3) == 0) mask |= 7;
+    return launch(*batch, *out, (cudaStream_t)stream, mask, n_launches);
+}
+
+int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launches, float *kernel_ms)
+{
+    g_err[0] = 0;
+    if (n_launches) *n_launches = 0;
+    if (kernel_ms) *kernel_ms = 0.f;
+    int rc = validate(hb, ho);
+    if (rc != FDM_OK || hb->n_solves == 0) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(FDM_ERR_NO_DEVICE, "no CUDA device; libfdm_b200 has no CPU fallback%s");
+
+    const int64_t n = hb->n_solves;
+    const int64_t nseg = hb->seg_begin[n];
+    const int64_t nmon = (hb->mon_begin && hb->n_mon_total > 0) ? hb->mon_begin[n] : 0;
+    const bool has_ko = hb->barrier && hb->rebate;
+
+    const int mask = fdm_launch_hints(hb->n_space, hb->flags, n, hb->seg_div, nseg);
+
+    // one device arena for descriptors and results
+    auto up8 = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += up8(bytes); return o; };
+    const size_t o_d[9] = {take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8),
+                           take(n * 8), take(has_ko ? n * 8 : 0), take(has_ko ? n * 8 : 0)};
+    const size_t o_nspace = take(n * 4), o_flags = take(n * 4), o_ran = take(n * 4);
+    const size_t o_segb = take((n + 1) * 4), o_monb = take(nmon ? (n + 1) * 4 : 0);
+    const size_t o_ssteps = take(nseg * 4), o_sdt = take(nseg * 8), o_stau = take(nseg * 8);
+    const size_t o_srst = take(nseg * 4), o_sdiv = take(nseg * 8), o_mon = take(nmon * 4);
+    const size_t o_bb = take(hb->b_bdry ? n * 8 : 0), o_bup = take(hb->barrier_up ? n * 8 : 0);
+    const size_t o_mreb = take((hb->mon_rebate && nmon) ? nmon * 8 : 0);
+    const size_t in_bytes = off;
+    const size_t r_price = take(n * 8), r_delta = take(n * 8), r_gamma = take(n * 8);
+    const size_t r_sv = take(n * 32), r_ss = take(n * 32), r_idx = take(n * 16), r_status = take(n * 4);
+    const size_t r_dump = take(ho->v_dump ? (size_t)n * ho->v_dump_stride * 8 : 0);
+    const size_t r_trace = take(ho->ex_trace ? (size_t)n * ho->ex_trace_stride * 4 : 0);
+    (void)in_bytes;
+
+    std::lock_guard<std::mutex> arena_lock(g_arena_mu);
+    char *arena = nullptr;
+    FDM_CUDA(arena_get(off, &arena));
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    rc = FDM_OK;
+#define FDM_TRY(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess && rc == FDM_OK)                                             \
+            rc = fail(FDM_ERR_CUDA, #call ": %s", cudaGetErrorString(e_));                 \
+    } while (0)
+    FDM_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    FDM_TRY(cudaEventCreate(&e0));
+    FDM_TRY(cudaEventCreate(&e1));
+    auto h2d = [&](size_t o, const void *src, size_t bytes) {
+        if (bytes && src) FDM_TRY(cudaMemcpyAsync(arena + o, src, bytes, cudaMemcpyHostToDevice, st));
+    };
+    const double *hd[9] = {hb->x_min, hb->dx, hb->sigma, hb->r, hb->b, hb->spot, hb->strike,
+                           has_ko ? hb->barrier : nullptr, has_ko ? hb->rebate : nullptr};
+    for (int i = 0; i < 9; ++i) h2d(o_d[i], hd[i], n * 8);
+    h2d(o_nspace, hb->n_space, n * 4);
+    h2d(o_flags, hb->flags, n * 4);
+    h2d(o_ran, hb->rannacher, n * 4);
+    h2d(o_segb, hb->seg_begin, (n + 1) * 4);
+    if (nmon) h2d(o_monb, hb->mon_begin, (n + 1) * 4);
+    h2d(o_ssteps, hb->seg_steps, nseg * 4);
+    h2d(o_sdt, hb->seg_dt, nseg * 8);
+    h2d(o_stau, hb->seg_tau0, nseg * 8);
+    h2d(o_srst, hb->seg_restart, nseg * 4);
+    h2d(o_sdiv, hb->seg_div, nseg * 8);
+    if (nmon) h2d(o_mon, hb->mon_step, nmon * 4);
+    if (hb->b_bdry) h2d(o_bb, hb->b_bdry, n * 8);
+    if (hb->barrier_up) h2d(o_bup, hb->barrier_up, n * 8);
+    if (hb->mon_rebate && nmon) h2d(o_mreb, hb->mon_rebate, nmon * 8);
+
+    FdmBatch db = *hb;
+    db.x_min = (const double *)(arena + o_d[0]);
+    db.dx = (const double *)(arena + o_d[1]);
+    db.sigma = (const double *)(arena + o_d[2]);
+    db.r = (const double *)(arena + o_d[3]);
+    db.b = (const double *)(arena + o_d[4]);
+    db.spot = (const double *)(arena + o_d[5]);
+    db.strike = (const double *)(arena + o_d[6]);
+    db.barrier = has_ko ? (const double *)(arena + o_d[7]) : nullptr;
+    db.rebate = has_ko ? (const double *)(arena + o_d[8]) : nullptr;
+    db.n_space = (const int32_t *)(arena + o_nspace);
+    db.flags = (const int32_t *)(arena + o_flags);
+    db.rannacher = (const int32_t *)(arena + o_ran);
+    db.seg_begin = (const int32_t *)(arena + o_segb);
+    db.mon_begin = nmon ? (const int32_t *)(arena + o_monb) : nullptr;
+    db.seg_steps = (const int32_t *)(arena + o_ssteps);
+    db.seg_dt = (const double *)(arena + o_sdt);
+    db.seg_tau0 = (const double *)(arena + o_stau);
+    db.seg_restart = (const int32_t *)(arena + o_srst);
+    db.seg_div = (const double *)(arena + o_sdiv);
+    db.mon_step = nmon ? (const int32_t *)(arena + o_mon) : nullptr;
+    db.b_bdry = hb->b_bdry ? (const double *)(arena + o_bb) : nullptr;
+    db.barrier_up = hb->barrier_up ? (const double *)(arena + o_bup) : nullptr;
+    db.mon_rebate = (hb->mon_rebate && nmon) ? (const double *)(arena + o_mreb) : nullptr;
+
+    FdmOut dout = *ho;
+    dout.price = (double *)(arena + r_price);
+    dout.delta = (double *)(arena + r_delta);
+    dout.gamma = (double *)(arena + r_gamma);
+    dout.stencil_v = (double *)(arena + r_sv);
+    dout.stencil_s = (double *)(arena + r_ss);
+    dout.idx = (int32_t *)(arena + r_idx);
+    dout.status = (int32_t *)(arena + r_status);
+    dout.v_dump = ho->v_dump ? (double *)(arena + r_dump) : nullptr;
+    dout.ex_trace = ho->ex_trace ? (int32_t *)(arena + r_trace) : nullptr;
+    if (ho->ex_trace) FDM_TRY(cudaMemsetAsync(arena + r_trace, 0xff, (size_t)n * ho->ex_trace_stride * 4, st));
+    if (ho->v_dump) FDM_TRY(cudaMemsetAsync(arena + r_dump, 0, (size_t)n * ho->v_dump_stride * 8, st));
+
+    if (rc == FDM_OK) {
+        FDM_TRY(cudaEventRecord(e0, st));
+        int lrc = launch(db, dout, st, mask, n_launches);
+        if (lrc != FDM_OK) rc = lrc;
+        FDM_TRY(cudaEventRecord(e1, st));
+    }
+    auto d2h = [&](void *dst, size_t o, size_t bytes) {
+        if (dst && bytes) FDM_TRY(cudaMemcpyAsync(dst, arena + o, bytes, cudaMemcpyDeviceToHost, st));
+    };
+    if (rc == FDM_OK) {
+        d2h(ho->price, r_price, n * 8);
+        d2h(ho->delta, r_delta, n * 8);
+        d2h(ho->gamma, r_gamma, n * 8);
+        d2h(ho->stencil_v, r_sv, n * 32);
+        d2h(ho->stencil_s, r_ss, n * 32);
+        d2h(ho->idx, r_idx, n * 16);
+        d2h(ho->status, r_status, n * 4);
+        if (ho->v_dump) d2h(ho->v_dump, r_dump, (size_t)n * ho->v_dump_stride * 8);
+        if (ho->ex_trace) d2h(ho->ex_trace, r_trace, (size_t)n * ho->ex_trace_stride * 4);
+        FDM_TRY(cudaStreamSynchronize(st));
+        if (kernel_ms && rc == FDM_OK) FDM_TRY(cudaEventElapsedTime(kernel_ms, e0, e1));
+    }
+#undef FDM_TRY
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    return rc;
+}
+
+int fdm_book_solves_per_option(int32_t what, int32_t use_richardson)
+{
+    book::Role r[8];
+    if (what < 0 || what > FDM_BOOK_SCENARIO) return fail(FDM_ERR_INVALID, "unknown book fan-out%s");
+    return book::roles_of(what, use_richardson != 0, r);
+}
+
+int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int64_t *node_steps,
+                           int32_t *n_launches, float *kernel_ms)
+{
+    g_err[0] = 0;
+    if (n_launches) *n_launches = 0;
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (node_steps) *node_steps = 0;
+    if (!hb || !ho) return fail(FDM_ERR_INVALID, "book / out is NULL%s");
+    if (hb->n_options < 0) return fail(FDM_ERR_INVALID, "n_options < 0%s");
+    if (hb->what < 0 || hb->what > FDM_BOOK_SCENARIO) return fail(FDM_ERR_INVALID, "unknown book fan-out%s");
+    const int64_t n = hb->n_options;
+    if (n == 0) return FDM_OK;
+    if (!hb->spot || !hb->strike || !hb->T || !hb->sigma || !hb->r || !hb->b || !hb->flags || !hb->n_space ||
+        !hb->n_time || !hb->rannacher)
+        return fail(FDM_ERR_INVALID, "a required FdmAmericanBook array is NULL%s");
+    book::RoleTable roles;
+    roles.n = book::roles_of(hb->what, hb->use_richardson != 0, roles.r);
+    // host-side validation (the reference raises ValueError, fd_american_option_pricer.py:68-69, :123-124)
+    int n_space_max = 3, small_max = 0, mask = 1;
+    int64_t ns_total = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (!(hb->spot[i] > 0.0) || !(hb->strike[i] > 0.0) || !(hb->T[i] > 0.0))
+            return fail(FDM_ERR_INVALID, "spot, strike and time_to_expiry must be positive%s");
+        const int ns = hb->n_space[i] < 3 ? 3 : hb->n_space[i];
+        const int nt = hb->n_time[i] < 4 ? 4 : hb->n_time[i];
+        if (ns > FDM_MAX_N_SPACE) return fail(FDM_ERR_UNSUPPORTED, "n_space exceeds FDM_MAX_N_SPACE (8193)%s");
+        if (ns > n_space_max) n_space_max = ns;
+        if (ns <= FDM_WARP_MAX_N_SPACE) {
+            mask |= 8 | LEAN_HINTS_VALID | lean_hint_bits(ns);
+            if (ns > small_max) small_max = ns;
+        } else mask |= 16;
+        for (int k = 0; k < roles.n; ++k) {
+            const double sg = hb->sigma[i] + roles.r[k].bump * hb->dv_sigma;
+            if (!(sg > 0.0)) return fail(FDM_ERR_INVALID, "sigma (after bumps) must be positive%s");
+            int steps = nt;
+            if (roles.r[k].fine == 1) steps = (hb->flags[i] & FDM_FLAG_BLACK76) ? 2 * nt : 2 * ns;
+            if (roles.r[k].fine == 2) steps = 2 * nt;
+            ns_total += (int64_t)ns * steps;
+        }
+    }
+    mask |= small_max << 8;
+    if (node_steps) *node_steps = ns_total;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(FDM_ERR_NO_DEVICE, "no CUDA device; libfdm_b200 has no CPU fallback%s");
+
+    const int64_t m = n * roles.n;                   // solves
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += up(bytes); return o; };
+    // option inputs
+    const size_t i_d[6] = {take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8)};
+    const size_t i_fl = take(n * 4), i_ns = take(n * 4), i_nt = take(n * 4), i_rn = take(n * 4);
+    // expanded descriptors
+    const size_t s_d[7] = {take(m * 8), take(m * 8), take(m * 8), take(m * 8), take(m * 8), take(m * 8), take(m * 8)};
+    const size_t s_ns = take(m * 4), s_fl = take(m * 4), s_rn = take(m * 4), s_sb = take((m + 1) * 4);
+    const size_t s_st = take(m * 4), s_dt = take(m * 8), s_t0 = take(m * 8), s_rs = take(m * 4), s_dv = take(m * 8);
+    // per-solve results
+    const size_t r_p = take(m * 8), r_d = take(m * 8), r_g = take(m * 8), r_idx = take(m * 16), r_st = take(m * 4);
+    // per-option outputs
+    const size_t o_d[6] = {take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8)};
+    const size_t o_lo = take(n * 4), o_hi = take(n * 4), o_st = take(n * 4);
+
+    std::lock_guard<std::mutex> arena_lock(g_arena_mu);
+    char *arena = nullptr;
+    FDM_CUDA(arena_get(off, &arena));
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = FDM_OK;
+#define FDM_TRY(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess && rc == FDM_OK)                                             \
+            rc = fail(FDM_ERR_CUDA, #call ": %s", cudaGetErrorString(e_));                 \
+    } while (0)
+    FDM_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    FDM_TRY(cudaEventCreate(&e0));
+    FDM_TRY(cudaEventCreate(&e1));
+    const double *hd[6] = {hb->spot, hb->strike, hb->T, hb->sigma, hb->r, hb->b};
+    for (int i = 0; i < 6; ++i) FDM_TRY(cudaMemcpyAsync(arena + i_d[i], hd[i], n * 8, cudaMemcpyHostToDevice, st));
+    FDM_TRY(cudaMemcpyAsync(arena + i_fl, hb->flags, n * 4, cudaMemcpyHostToDevice, st));
+    FDM_TRY(cudaMemcpyAsync(arena + i_ns, hb->n_space, n * 4, cudaMemcpyHostToDevice, st));
+    FDM_TRY(cudaMemcpyAsync(arena + i_nt, hb->n_time, n * 4, cudaMemcpyHostToDevice, st));
+    FDM_TRY(cudaMemcpyAsync(arena + i_rn, hb->rannacher, n * 4, cudaMemcpyHostToDevice, st));
+
+    FdmAmericanBook db = *hb;
+    db.spot = (const double *)(arena + i_d[0]); db.strike = (const double *)(arena + i_d[1]);
+    db.T = (const double *)(arena + i_d[2]); db.sigma = (const double *)(arena + i_d[3]);
+    db.r = (const double *)(arena + i_d[4]); db.b = (const double *)(arena + i_d[5]);
+    db.flags = (const int32_t *)(arena + i_fl); db.n_space = (const int32_t *)(arena + i_ns);
+    db.n_time = (const int32_t *)(arena + i_nt); db.rannacher = (const int32_t *)(arena + i_rn);
+
+    FdmBatch sb;
+    memset(&sb, 0, sizeof(sb));
+    sb.n_solves = m; sb.n_space_max = n_space_max; sb.n_seg_total = (int32_t)m; sb.reserved = mask;
+    sb.x_min = (const double *)(arena + s_d[0]); sb.dx = (const double *)(arena + s_d[1]);
+    sb.sigma = (const double *)(arena + s_d[2]); sb.r = (const double *)(arena + s_d[3]);
+    sb.b = (const double *)(arena + s_d[4]); sb.spot = (const double *)(arena + s_d[5]);
+    sb.strike = (const double *)(arena + s_d[6]);
+    sb.n_space = (const int32_t *)(arena + s_ns); sb.flags = (const int32_t *)(arena + s_fl);
+    sb.rannacher = (const int32_t *)(arena + s_rn); sb.seg_begin = (const int32_t *)(arena + s_sb);
+    sb.seg_steps = (const int32_t *)(arena + s_st); sb.seg_dt = (const double *)(arena + s_dt);
+    sb.seg_tau0 = (const double *)(arena + s_t0); sb.seg_restart = (const int32_t *)(arena + s_rs);
+    sb.seg_div = (const double *)(arena + s_dv);
+
+    FdmOut so;
+    memset(&so, 0, sizeof(so));
+    so.price = (double *)(arena + r_p); so.delta = (double *)(arena + r_d); so.gamma = (double *)(arena + r_g);
+    so.idx = (int32_t *)(arena + r_idx); so.status = (int32_t *)(arena + r_st);
+
+    FdmBookOut dbo;
+    dbo.price_log2 = (double *)(arena + o_d[0]); dbo.price = (double *)(arena + o_d[1]);
+    dbo.delta = (double *)(arena + o_d[2]); dbo.gamma = (double *)(arena + o_d[3]);
+    dbo.vega = (double *)(arena + o_d[4]); dbo.theta = (double *)(arena + o_d[5]);
+    dbo.ex_lo = (int32_t *)(arena + o_lo); dbo.ex_hi = (int32_t *)(arena + o_hi); dbo.status = (int32_t *)(arena + o_st);
+
+    if (rc == FDM_OK) {
+        FDM_TRY(cudaMemsetAsync(arena + o_d[0], 0, o_st + up(n * 4) - o_d[0], st));
+        FDM_TRY(cudaEventRecord(e0, st));
+        const int threads = 256;
+        book::expand_kernel<<<(unsigned)((m + threads - 1) / threads), threads, 0, st>>>(db, sb, roles);
+        int lrc = launch(sb, so, st, mask, n_launches);
+        if (lrc != FDM_OK) rc = lrc;
+        book::combine_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(db, so, dbo, roles.n);
+        FDM_TRY(cudaGetLastError());
+        if (n_launches) *n_launches += 2;
+        FDM_TRY(cudaEventRecord(e1, st));
+    }
+    auto d2h = [&](void *dst, size_t o, size_t bytes) {
+        if (dst && bytes) FDM_TRY(cudaMemcpyAsync(dst, arena + o, bytes, cudaMemcpyDeviceToHost, st));
+    };
+    if (rc == FDM_OK) {
+        d2h(ho->price_log2, o_d[0], n * 8); d2h(ho->price, o_d[1], n * 8); d2h(ho->delta, o_d[2], n * 8);
+        d2h(ho->gamma, o_d[3], n * 8); d2h(ho->vega, o_d[4], n * 8); d2h(ho->theta, o_d[5], n * 8);
+        d2h(ho->ex_lo, o_lo, n * 4); d2h(ho->ex_hi, o_hi, n * 4); d2h(ho->status, o_st, n * 4);
+        FDM_TRY(cudaStreamSynchronize(st));
+        if (kernel_ms && rc == FDM_OK) FDM_TRY(cudaEventElapsedTime(kernel_ms, e0, e1));
+    }
+#undef FDM_TRY
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    return rc;
+}
+
+int fdm_launch_hints(const int32_t *n_space, const int32_t *flags, int64_t n_solves, const double *seg_div,
+                     int64_t n_seg)
+{
+    if (!n_space || !flags || n_solves < 0) return 0;
+    int mask = 0, small_max = 0;
+    for (int64_t i = 0; i < n_solves; ++i) {
+        mask |= (flags[i] & FDM_FLAG_AMERICAN) ? 1 : 2;
+        if (n_space[i] <= FDM_WARP_MAX_N_SPACE) {
+            mask |= 8 | LEAN_HINTS_VALID | lean_hint_bits(n_space[i]);
+            if (n_space[i] > small_max) small_max = n_space[i];
+        } else {
+            mask |= 16;
+        }
+    }
+    mask |= small_max << 8;
+    if (seg_div) {
+        for (int64_t i = 0; i < n_seg; ++i) if (seg_div[i] != 0.0) { mask |= 4; break; }
+    } else {
+        mask |= 4;
+    }
+    return mask;
+}
+
+int fdm_release_workspace(void)
+{
+    std::lock_guard<std::mutex> arena_lock(g_arena_mu);
+    if (g_arena) cudaFree(g_arena);
+    g_arena = nullptr;
+    g_arena_bytes = 0;
+    g_arena_dev = -1;
+    return FDM_OK;
+}
+
+int fdm_fp64_peak(double *tflops_out, float *ms_out)
+{
+    g_err[0] = 0;
+    if (!tflops_out) return fail(FDM_ERR_INVALID, "tflops_out is NULL%s");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(FDM_ERR_NO_DEVICE, "no CUDA device%s");
+    int dev = 0, sms = 0;
+    FDM_CUDA(cudaGetDevice(&dev));
+    FDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *sink = nullptr;
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    FDM_CUDA(cudaMalloc((void **)&sink, blocks * sizeof(double)));
+    cudaEvent_t e0, e1;
+    FDM_CUDA(cudaEventCreate(&e0));
+    FDM_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        FDM_CUDA(cudaEventRecord(e0));
+        fp64_peak_kernel<<<blocks, threads>>>(sink, iters, 1.0 + rep);
+        FDM_CUDA(cudaEventRecord(e1));
+        FDM_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        FDM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    const double flops = 2.0 * 64.0 * (double)iters * (double)threads * (double)blocks;
+    *tflops_out = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return FDM_OK;
+}
+
+}  // extern "C"

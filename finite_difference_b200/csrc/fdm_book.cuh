@@ -4,9 +4,11 @@
 // reference's operation order.  Host <-> device traffic is ~56 B in and ~60 B out per OPTION instead of
 // ~104 B + ~108 B per SOLVE.  Dividend-free books only (dividend segment tables are built on the host).
 //
-// Included by fdm_b200.cu.
+// Included by fdm_api.cu.
 
 #pragma once
+
+#include "fdm_common.cuh"
 
 namespace book {
 

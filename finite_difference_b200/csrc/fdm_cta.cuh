@@ -27,9 +27,11 @@
 //   shared memory (30 instructions fewer per warp-step, no change in time); no block barriers at all (+5 % at most:
 //   the barriers are not what the step waits for).
 //
-// Included by fdm_b200.cu (single translation unit); uses its helpers.
+// Included by fdm_cta_inst.cu (one translation unit per size class).
 
 #pragma once
+
+#include "fdm_common.cuh"
 
 namespace cta {
 

@@ -1,0 +1,41 @@
+// fdm_cta_inst.cu -- one size class of fdm_cta_kernel (compiled with -DFDM_INST_W=4|5|8|16 warps) and its launcher.
+#include "fdm_cta.cuh"
+
+#ifndef FDM_INST_W
+#error "compile with -DFDM_INST_W=<warps per CTA>"
+#endif
+#define FDM_CAT2(a, b) a##b
+#define FDM_CAT(a, b) FDM_CAT2(a, b)
+
+int FDM_CAT(fdm_launch_cta_, FDM_INST_W)(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american,
+                                         bool any_linear, bool any_div, int n_lo, int32_t *n_launches)
+{
+    constexpr int C = 16, WARPS = FDM_INST_W;
+    (void)any_div;
+    const bool trace = o.ex_trace != nullptr;
+    const size_t smem = (size_t)cta::smem_doubles<C, WARPS>() * sizeof(double);
+    auto k_am = cta::fdm_cta_kernel<C, WARPS, true, false>;
+    auto k_amt = cta::fdm_cta_kernel<C, WARPS, true, true>;
+    auto k_lin = cta::fdm_cta_kernel<C, WARPS, false, false>;
+    FDM_CUDA(cudaFuncSetAttribute(k_am, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FDM_CUDA(cudaFuncSetAttribute(k_amt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FDM_CUDA(cudaFuncSetAttribute(k_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t max_grid = 0x7fffffff;
+    int launches = 0;
+    for (int64_t first = 0; first < b.n_solves; first += max_grid) {
+        const int64_t count = (b.n_solves - first < max_grid) ? (b.n_solves - first) : max_grid;
+        const dim3 grid((unsigned)count), block(32 * WARPS);
+        if (any_american) {
+            if (trace) k_amt<<<grid, block, smem, st>>>(b, o, first, 1, n_lo);
+            else       k_am<<<grid, block, smem, st>>>(b, o, first, 1, n_lo);
+            ++launches;
+        }
+        if (any_linear) {
+            k_lin<<<grid, block, smem, st>>>(b, o, first, 0, n_lo);
+            ++launches;
+        }
+        FDM_CUDA(cudaGetLastError());
+    }
+    if (n_launches) *n_launches += launches;
+    return FDM_OK;
+}

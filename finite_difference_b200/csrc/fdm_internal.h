@@ -1,0 +1,30 @@
+// fdm_internal.h -- what the translation units of libfdm_b200 share on the HOST side: the error reporter and one launch
+// function per compiled kernel instance (fdm_warp_inst.cu / fdm_lean_inst.cu / fdm_cta_inst.cu are compiled once per
+// size class, in parallel; fdm_api.cu holds the C ABI and dispatches to them).  Not part of the public ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fdm_b200.h"
+
+// sets the thread-local message of fdm_last_error() and returns `code`
+int fdm_fail(int code, const char *fmt, const char *detail = "");
+
+// fdm_warp_kernel<C>: C slots per lane, up to 32 C interior rows.  only_rest: take only what the lean kernels left.
+#define FDM_DECL_WARP(C)                                                                                         \
+    int fdm_launch_warp_##C(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american, bool any_linear, \
+                            bool any_div, int only_rest, int32_t *n_launches);
+FDM_DECL_WARP(4) FDM_DECL_WARP(8) FDM_DECL_WARP(13) FDM_DECL_WARP(16)
+
+// fdm_lean_kernel<C>: 32 (C-1) <= interior rows <= 32 C
+#define FDM_DECL_LEAN(C)                                                                                         \
+    int fdm_launch_lean_##C(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american, bool any_linear, \
+                            bool any_div, int32_t *n_launches);
+FDM_DECL_LEAN(4) FDM_DECL_LEAN(7) FDM_DECL_LEAN(8) FDM_DECL_LEAN(10) FDM_DECL_LEAN(13) FDM_DECL_LEAN(16)
+
+// fdm_cta_kernel<16, W>: W warps of 16 slots per thread; n_lo = largest n_space of the class below
+#define FDM_DECL_CTA(W)                                                                                          \
+    int fdm_launch_cta_##W(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american, bool any_linear, \
+                           bool any_div, int n_lo, int32_t *n_launches);
+FDM_DECL_CTA(4) FDM_DECL_CTA(5) FDM_DECL_CTA(8) FDM_DECL_CTA(16)
