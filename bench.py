@@ -1,25 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- option-node-steps/s of the batched FD engine on BASELINE.json's headline workload.
+"""bench.py -- option-node-steps/s of the batched FD engine on BASELINE.json's workloads.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--options M]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--config cfg3|cfg4|cfg5|cfg2|am400|am500div|dbfp] [--scaling weak|strong] [--options M]
 
-Workload (BASELINE.json configs[2], SURVEY.md 8d "cfg3"): an American Black-76 scenario sweep in
-the shape of run_american_scenarios.py -- per option ``price_log2()`` + ``greeks_log2()`` = 8 PDE
-solves on a 500-node grid (5000 time steps, 2.5e6 node-steps per option), 100 000 options per
-GPU (weak scaling: every rank prices its own shard of an N x 100k-option book, no communication
-during the solve, one result all-gather per step).
+Default workload (BASELINE.json configs[2], SURVEY.md 8d "cfg3"): an American Black-76 scenario sweep in the shape of
+run_american_scenarios.py -- per option ``price_log2()`` + ``greeks_log2()`` = 8 PDE solves on a 500-node grid (5000
+time steps, 2.5e6 node-steps per option).  ``--scaling weak`` (default): 100 000 options PER GPU; ``--scaling
+strong``: the configuration's stated book (cfg3 100 000, cfg4 16 384, cfg5 1 000 000 options) sharded over the N
+GPUs.  No communication during the solve, one result collective per step.
 
-One "step" = one pass of the hot path over the rank's shard.
+One "step" = one pass of the hot path over the rank's shard.  Three timed legs, the same kernels in each:
 
-* ``value``: device-resident descriptors (already in HBM), CUDA events on the launching stream.
-* ``e2e``: the same sweep through the public host API (``AmericanBook.run_fused`` ->
-  ``fdm_american_book_host``): numpy option arrays in host memory -> H2D of the per-option
-  scalars -> fan-out, solves and Richardson / vega epilogue on the device -> D2H of the results.
-* ``roofline``: FP64 (DFMA pipe) -- algorithmic flops (22 per American node-step)
-  over the kernel's event time against the FP64 peak measured live by ``fdm_fp64_peak``.
-* ``cpu_baseline``: the C oracle (a port of the reference's Python arithmetic) on the host
-  cores over a bounded sample of the same workload; the same call is the parity gate.
-* ``--impl reference``: the CPU arm alone (oracle port, all host threads), same metric/config.
+* ``roofline``: fan-out + solves + epilogue alone (CUDA events on the launching stream around
+  ``DeviceBookRun.launch``) -- algorithmic flops (22 per American node-step, 13 per European / barrier node-step,
+  SURVEY.md 8d) against the FP64 peak measured live by ``fdm_fp64_peak``.
+* ``value``: per-option inputs resident in HBM; launch + the result collective (N > 1), CUDA events, max over ranks.
+* ``e2e``: the public API with HOST buffers -- at N = 1 ``AmericanBook.run_fused`` / ``BarrierBook.run_fused``
+  (``fdm_american_book_host``: H2D, kernels, D2H inside the call), at N > 1 ``shard.ShardedBookRun.step`` (H2D of
+  the shard's inputs from pinned memory, kernels, the same collective as ``value``, D2H of the whole book's results
+  on rank 0).
+
+Parity is gated on what is timed: the results left in HBM by the ``value`` leg and the host results of the ``e2e`` leg
+are both compared with the CPU oracle on a sample (prices <= 1e-10 relative, exercise intervals identical); at N > 1
+rank 0 checks the gathered rows of a sample that spans every rank's shard.
+
+``other_configs`` (N = 1): the remaining BASELINE configurations and kernel families, each with its own clocks,
+roofline and parity.  ``cpu_baseline``: the C oracle port on all host cores plus, when ``baseline/_ref`` is staged,
+the UNMODIFIED Python reference on a small sample (``python_reference``).
+``--impl reference``: the CPU arm alone, same metric / config.
 """
 from __future__ import annotations
 
@@ -38,61 +47,187 @@ if ROOT not in sys.path:
 
 METRIC = "option-node-steps/sec (FP64 CN, batched)"
 UNIT = "node-steps/s"
-FLOPS_PER_NODE_STEP_AMERICAN = 22.0
-SEED = 20251018 + 3
-N_SPACE = N_TIME = 500
-T_EXP = 31.0 / 365.0
+FLOPS_AMERICAN = 22.0        # American IT step
+FLOPS_LINEAR = 13.0          # European / barrier CN step
+SEED = 20251018
 F0 = 229.74
-SOLVES_PER_OPTION = 8
+T_RUNNER = 31.0 / 365.0
 
 
-def workload(n_options: int, seed: int = SEED):
-    """cfg3 draw order: K, sigma, NACA rate, call/put."""
+# --------------------------------------------------------------------------------------
+# workloads (synthetic inputs of SURVEY.md 8d; seed = 20251018 + config index)
+# --------------------------------------------------------------------------------------
+
+def _american_draws(n, seed):
+    """Draw order K, sigma, NACA rate, call/put, then dividend cash amounts."""
     rng = np.random.default_rng(seed)
-    K = rng.uniform(180.0, 280.0, n_options)
-    sigma = rng.uniform(0.15, 0.45, n_options)
-    naca = rng.uniform(0.03, 0.10, n_options)
-    is_call = rng.uniform(size=n_options) < 0.5
-    r = np.log1p(naca)          # flat NACA curve -> NACC forward rate, fd_american_black76.py:186-207
-    return dict(K=K, sigma=sigma, r=r, is_call=is_call)
+    K = rng.uniform(180.0, 280.0, n)
+    sigma = rng.uniform(0.15, 0.45, n)
+    naca = rng.uniform(0.03, 0.10, n)
+    is_call = rng.uniform(size=n) < 0.5
+    cash = rng.uniform(2.0, 9.0, (n, 2))
+    return dict(K=K, sigma=sigma, naca=naca, r=np.log1p(naca), is_call=is_call, cash=cash)
 
 
-def make_book(w, sel):
+def _barrier_draws(n, seed):
+    rng = np.random.default_rng(seed)
+    K = rng.uniform(80, 120, n)
+    sigma = rng.uniform(0.10, 0.50, n)
+    r = rng.uniform(0.01, 0.08, n)
+    q = rng.uniform(0.0, 0.03, n)
+    T = rng.choice([0.5, 1.0, 2.0], n)
+    B = 100.0 * rng.uniform(0.70, 0.95, n)
+    return dict(K=K, sigma=sigma, r=r, b=r - q, T=T, B=B)
+
+
+def workload(n_options: int, seed: int = SEED + 3):
+    """cfg3 draws (kept under this name: the round-1 records and the golden generator use it)."""
+    return _american_draws(n_options, seed)
+
+
+class Part:
+    """One book of a configuration: how to build it for a selection of options and how the oracle prices it."""
+
+    def __init__(self, kind, what, draws, build, oracle, flops, node_steps_per_option):
+        self.kind, self.what, self.draws, self.build, self.oracle, self.flops = kind, what, draws, build, oracle, flops
+        self.node_steps_per_option = node_steps_per_option
+
+
+def _am_book(d, sel, n_space, n_time, black76, T, divs):
     from finite_difference_b200.book import AmericanBook
-    return AmericanBook(np.full(len(sel), F0), w["K"][sel], T_EXP, w["sigma"][sel], w["r"][sel], w["r"][sel],
-                        w["is_call"][sel], N_SPACE, N_TIME, 2, black76=True)
+    n = len(sel)
+    div_taus = None
+    if divs:
+        # two cash dividends at valuation + 46 d and + 256 d (SURVEY.md 8d cfg4) -> tau = T - t, ascending in tau
+        begin = np.arange(0, 2 * n + 1, 2, dtype=np.int32)
+        tau = np.tile([T - 256.0 / 365.0, T - 46.0 / 365.0], n)
+        cash = d["cash"][sel][:, ::-1].reshape(-1)
+        div_taus = (begin, tau, np.ascontiguousarray(cash))
+    return AmericanBook(np.full(n, F0), d["K"][sel], T, d["sigma"][sel], d["r"][sel], d["r"][sel], d["is_call"][sel],
+                        n_space, n_time, 2, black76=black76, div_taus=div_taus)
 
 
-def config_dict(n_opt_per_gpu, world):
-    return {"workload": "cfg3: American Black-76 scenario sweep (run_american_scenarios shape: price_log2 + "
-                        "greeks_log2 = 8 solves/option, 500 nodes x 5000 steps/option, T=31/365)",
-            "options_per_gpu": int(n_opt_per_gpu), "solves_per_option": SOLVES_PER_OPTION,
-            "node_steps_per_option": 2_500_000,
-            "sharding": f"by option over {world} GPU(s), result all-gather per step" if world > 1 else "single GPU",
-            "l2": "flushed (256 MiB memset) between timed steps; descriptors are read once per solve"}
-
-
-# --------------------------------------------------------------------------------------
-# CPU arm (oracle port)
-# --------------------------------------------------------------------------------------
-
-def oracle_scenario(w, sel, n_threads=0):
-    """The 8 solves of each selected option through the C oracle.  Returns (seconds, node_steps,
-    base prices, ex_lo, ex_hi)."""
+def _am_oracle(d, sel, n_space, n_time, black76, T, divs, what, threads):
+    """The reference's fan-out through the C oracle (one OpenMP batch) and its epilogue, independent of book.py:
+    returns (seconds, node_steps, dict of per-option arrays)."""
     from oracle import oracle
     n = len(sel)
-    K, sig, r, call = w["K"][sel], w["sigma"][sel], w["r"][sel], w["is_call"][sel]
     h = 0.01
-    sig_all = np.concatenate([sig, sig, sig, sig, sig + h, sig - h, sig + 2 * h, sig - 2 * h])
-    nt_all = np.concatenate([np.full(n, N_TIME), np.full(n, 2 * N_TIME), np.full(n, N_TIME), np.full(n, 2 * N_TIME),
-                             np.full(4 * n, N_TIME)])
-    tile = lambda a: np.tile(a, SOLVES_PER_OPTION)
+    fine1 = 2 * n_time if black76 else 2 * n_space                 # price_log2's fine solve, AM:671 / B76:545
+    roles = {"price_log": [(n_time, 0.0)],
+             "greeks_log2": [(n_time, 0.0), (2 * n_time, 0.0), (n_time, h), (n_time, -h), (n_time, 2 * h), (n_time, -2 * h)],
+             "scenario": [(n_time, 0.0), (fine1, 0.0), (n_time, 0.0), (2 * n_time, 0.0), (n_time, h), (n_time, -h),
+                          (n_time, 2 * h), (n_time, -2 * h)]}[what]
+    params = []
+    for nt, bump in roles:
+        for i in sel:
+            dv = [(T - 256.0 / 365.0, float(d["cash"][i, 1])), (T - 46.0 / 365.0, float(d["cash"][i, 0]))] if divs else []
+            params.append(dict(spot=F0, strike=float(d["K"][i]), T=T, sigma=float(d["sigma"][i]) + bump, r=float(d["r"][i]),
+                               b=float(d["r"][i]), is_call=bool(d["is_call"][i]), model=1 if black76 else 0,
+                               n_space=n_space, n_time=nt, rannacher=2, divs_tau=dv))
     t0 = time.perf_counter()
-    price, lo, hi = oracle.american_batch_prices_arrays(F0, tile(K), T_EXP, sig_all, tile(r), tile(r), tile(call), 1,
-                                                        N_SPACE, nt_all, 2, 4.5, n_threads)
-    dt = time.perf_counter() - t0
-    return dt, int(np.sum(nt_all) * N_SPACE), price, lo, hi
+    price, lo, hi = oracle.american_batch_prices(params, threads)
+    secs = time.perf_counter() - t0
+    P = price.reshape(len(roles), n)
+    out = {"ex_lo": lo[:n], "ex_hi": hi[:n]}
+    if what == "price_log":
+        out["price_log2"] = P[0]
+    else:
+        k0 = 0
+        if what == "scenario":
+            out["price_log2"] = (4.0 * P[1] - P[0]) / 3.0
+            k0 = 2
+        out["price"] = (4.0 * P[k0 + 1] - P[k0]) / 3.0
+        D_h = (P[k0 + 2] - P[k0 + 3]) / (2.0 * h)
+        D_2h = (P[k0 + 4] - P[k0 + 5]) / (4.0 * h)
+        out["vega"] = (4.0 * D_h - D_2h) / 3.0 / 100.0
+    return secs, n_space * sum(nt for nt, _ in roles) * n, out
 
+
+def _bar_book(d, sel, what):
+    from finite_difference_b200.book import BarrierBook
+    n = len(sel)
+    mons = [[k / 12.0 for k in range(1, int(round(12 * t)) + 1)] for t in d["T"][sel]]
+    return BarrierBook(np.full(n, 100.0), d["K"][sel], d["T"][sel], d["sigma"][sel], d["r"][sel], d["b"][sel], "call",
+                       "down-and-out", list(d["B"][sel]), None, 0.0, mons, 400, 400)
+
+
+def _bar_oracle(d, sel, what, threads):
+    from oracle import oracle
+    n = len(sel)
+    dv = 1e-3
+    bumps = (0.0,) if what == "solve" else (0.0, dv, -dv)
+    params = []
+    for bump in bumps:
+        for i in sel:
+            T = float(d["T"][i])
+            params.append(dict(S0=100.0, K=float(d["K"][i]), T=T, sigma=float(d["sigma"][i]) + bump, r_disc=float(d["r"][i]),
+                               b_carry=float(d["b"][i]), is_call=True, barrier_type="down-and-out",
+                               lower_barrier=float(d["B"][i]), upper_barrier=None, rebate=0.0,
+                               monitor_times=[k / 12.0 for k in range(1, int(round(12 * T)) + 1)], N_space=400, N_time=400))
+    t0 = time.perf_counter()
+    price, delta, gamma = oracle.barrier_batch_prices(params, threads)
+    secs = time.perf_counter() - t0
+    out = {"price": price[:n], "delta": delta[:n], "gamma": gamma[:n]}
+    if what == "greeks":
+        out["vega"] = (price[n:2 * n] - price[2 * n:3 * n]) / (2.0 * dv)
+    return secs, 400 * 400 * len(bumps) * n, out
+
+
+def american_part(seed, n_space, n_time, black76, T, divs, what):
+    spo = {"price_log": n_time, "greeks_log2": 7 * n_time,
+           "scenario": 8 * n_time + (2 * n_time if black76 else 2 * n_space)}[what] * n_space
+    return Part("american", what, lambda n: _american_draws(n, seed),
+                lambda d, sel: _am_book(d, sel, n_space, n_time, black76, T, divs),
+                lambda d, sel, th: _am_oracle(d, sel, n_space, n_time, black76, T, divs, what, th), FLOPS_AMERICAN, spo)
+
+
+def barrier_part(seed, what):
+    return Part("barrier", what, lambda n: _barrier_draws(n, seed), lambda d, sel: _bar_book(d, sel, what),
+                lambda d, sel, th: _bar_oracle(d, sel, what, th), FLOPS_LINEAR, 400 * 400 * (3 if what == "greeks" else 1))
+
+
+class Config:
+    def __init__(self, name, desc, parts, weak_options, strong_options, cpu_sample, shares=None):
+        self.name, self.desc, self.parts = name, desc, parts
+        self.weak_options, self.strong_options, self.cpu_sample = weak_options, strong_options, cpu_sample
+        self.shares = shares or [1.0 / len(parts)] * len(parts)       # split of the option count over the parts
+
+
+def make_config(name: str, steps_cfg4: int = 10000) -> Config:
+    if name == "cfg3":
+        return Config("cfg3", "cfg3: American Black-76 scenario sweep (run_american_scenarios shape: price_log2 + greeks_log2 = "
+                      "8 solves/option, 500 nodes x 5000 steps/option, T=31/365)",
+                      [american_part(SEED + 3, 500, 500, True, T_RUNNER, False, "scenario")], 100_000, 100_000, 48)
+    if name == "cfg4":
+        return Config("cfg4", f"cfg4: high-resolution grids, American equity with two cash dividends, 8192 nodes x {steps_cfg4} "
+                      "steps, price_log (1 solve/option), T=1", [american_part(SEED + 4, 8192, steps_cfg4, False, 1.0, True, "price_log")],
+                      2048, 16384, 1)
+    if name == "cfg5":
+        return Config("cfg5", "cfg5: Greeks by bump-and-reprice on a mixed book, 50 % American equity (greeks_log2: 5 grids "
+                      "sigma, +-h, +-2h at N plus the 2N Richardson grid = 6 solves, 400 x 400, T=1) + 50 % discrete "
+                      "down-and-out barrier calls (greeks: 3 grids sigma, +-1e-3, 400 x 400, monthly monitoring)",
+                      [american_part(SEED + 5, 400, 400, False, 1.0, False, "greeks_log2"), barrier_part(SEED + 5, "greeks")],
+                      125_000, 1_000_000, 8)
+    if name == "cfg2":
+        return Config("cfg2", "cfg2: 10k discrete down-and-out barrier calls, CN with monthly monitoring, 400 x 400, greeks() = "
+                      "3 solves/option", [barrier_part(SEED + 2, "greeks")], 10_000, 10_000, 16)
+    if name == "cfg2price":
+        return Config("cfg2price", "cfg2: 10k discrete down-and-out barrier calls, CN with monthly monitoring, 400 x 400, one "
+                      "knock-out solve/option", [barrier_part(SEED + 2, "solve")], 10_000, 10_000, 16)
+    if name == "am400":
+        return Config("am400", "headline: 100k-option American CN batch, one solve each, 400 nodes x 400 steps (equity, no "
+                      "dividends, T=1)", [american_part(SEED + 1, 400, 400, False, 1.0, False, "price_log")], 100_000, 100_000, 64)
+    if name == "am500div":
+        return Config("am500div", "runner default with dividends: American equity, 500 x 500, two cash dividends, price_log2 + "
+                      "greeks_log2 = 8 solves/option, T=1", [american_part(SEED + 6, 500, 500, False, 1.0, True, "scenario")],
+                      12_500, 12_500, 8)
+    raise SystemExit(f"unknown --config {name}")
+
+
+# --------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------
 
 _REAL_STDOUT = None
 
@@ -111,40 +246,35 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if rank != 0:
-        return 0
-    from oracle import oracle
-    oracle.build()
-    threads = host_threads()
-    n_sample = args.cpu_options or max(48, 48 * threads)
-    w = workload(n_sample)
-    sel = np.arange(n_sample)
-    for _ in range(args.warmup):
-        oracle_scenario(w, sel[: max(threads, 8)], threads)
-    total_t, total_ns = 0.0, 0
-    for _ in range(args.steps):
-        dt, ns, *_ = oracle_scenario(w, sel, threads)
-        total_t += dt
-        total_ns += ns
-    value = total_ns / total_t
-    sample = f"{n_sample} options x 8 solves per step (of {args.options} per GPU), C oracle port of the reference, OpenMP"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args.options, world),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    emit(line)
-    return 0
+def split_counts(n, shares):
+    c = [int(round(n * s)) for s in shares]
+    c[-1] = n - sum(c[:-1])
+    return c
 
 
-# --------------------------------------------------------------------------------------
-# clocks
-# --------------------------------------------------------------------------------------
+def compare(ref: dict, got: dict) -> dict:
+    """Prices relative to max(|ref|, 1e-2) (absolute floor 1e-12 for tiny prices), exercise intervals
+    exact; sensitivities reported, bounded loosely (differences of prices divided by the bump)."""
+    out = {"n_options": int(len(next(iter(ref.values()))))}
+    ok = True
+    for k in ("price_log2", "price"):
+        if k in ref and k in got:
+            e = float(np.max(np.abs(got[k] - ref[k]) / np.maximum(np.abs(ref[k]), 1e-2)))
+            out["max_rel_err_" + k] = e
+            ok &= e <= 1e-10
+    for k, tol in (("delta", 1e-8), ("gamma", 1e-7), ("vega", 1e-6)):
+        if k in ref and k in got:
+            e = float(np.max(np.abs(got[k] - ref[k]) / np.maximum(np.abs(ref[k]), 1e-3)))
+            out["max_rel_err_" + k] = e
+            ok &= e <= tol
+    if "ex_lo" in ref and "ex_lo" in got:
+        same = bool(np.array_equal(got["ex_lo"], ref["ex_lo"]) and np.array_equal(got["ex_hi"], ref["ex_hi"]))
+        out["exercise_intervals_identical"] = same
+        ok &= same
+    out["tolerance"] = 1e-10
+    out["ok"] = bool(ok)
+    return out
+
 
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU every 100 ms (NVML) while running."""
@@ -194,199 +324,450 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------
+# CPU arm
+# --------------------------------------------------------------------------------------
+
+def cpu_arm(cfg: Config, n_sample: int, threads: int):
+    """The configuration's fan-out through the C oracle port on `threads` host cores, over the first `n_sample`
+    options of every part.  Returns (seconds, node_steps, [per-part reference dicts], [per-part selections])."""
+    secs = ns = 0.0
+    refs, sels = [], []
+    for part, share in zip(cfg.parts, cfg.shares):
+        k = max(1, int(round(n_sample * share)))
+        d = part.draws(k)
+        sel = np.arange(k)
+        s, n, ref = part.oracle(d, sel, threads)
+        secs += s
+        ns += n
+        refs.append(ref)
+        sels.append(sel)
+    return secs, ns, refs, sels
+
+
+def python_reference_leg(threads: int, n_sample: int = 16):
+    """cfg3 sample through the UNMODIFIED Python reference staged under baseline/_ref (None if not staged)."""
+    try:
+        from oracle import pyref
+        if not pyref.available():
+            return None, None
+        n = max(1, min(n_sample, 2 * threads))
+        w = workload(n)
+        out = pyref.time_cfg3(F0, w["K"], w["sigma"], w["naca"], w["is_call"], 500, 500, threads)
+        info = {"value": out["node_steps"] / out["seconds"], "unit": UNIT, "cores": int(out["procs"]),
+                "per_core": out["node_steps"] / out["cpu_seconds"],
+                "sample": f"first {n} options of cfg3 x 8 solves through the unmodified fd_american_black76.AmericanFwdFDMPricer "
+                          f"(price_log2 + greeks_log2) from baseline/_ref, one process per core ({out['seconds']:.1f} s wall)"}
+        return info, out
+    except Exception as exc:  # the reference arm must never take the bench down
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}, None
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return 0
+    from oracle import oracle
+    oracle.build()
+    cfg = make_config(args.config, args.cfg4_steps)
+    threads = host_threads()
+    n_sample = args.cpu_options or max(cfg.cpu_sample, cfg.cpu_sample * threads)
+    for _ in range(args.warmup):
+        cpu_arm(cfg, max(len(cfg.parts), min(n_sample, threads)), threads)
+    total_t = total_ns = 0.0
+    for _ in range(args.steps):
+        s, n, _, _ = cpu_arm(cfg, n_sample, threads)
+        total_t += s
+        total_ns += n
+    value = total_ns / total_t
+    n_opt = options_of(cfg, args, world)
+    sample = (f"sample: {n_sample} options per step (of {n_opt} in the configuration), the reference's fan-out through the C "
+              "oracle port of its Python arithmetic, OpenMP over solves")
+    pyinfo, _ = python_reference_leg(threads) if cfg.name == "cfg3" else (None, None)
+    cpu = {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    if pyinfo:
+        cpu["python_reference"] = pyinfo
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(cfg, args, world, n_opt, sample=n_sample),
+            "cpu_baseline": cpu,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    emit(line)
+    return 0
+
+
+def options_of(cfg, args, world):
+    if args.options:
+        return args.options * (world if args.scaling == "weak" else 1)
+    return cfg.weak_options * world if args.scaling == "weak" else cfg.strong_options
+
+
+def config_dict(cfg, args, world, n_total, collective="none", sample=None):
+    d = {"workload": cfg.desc, "options_total": int(n_total),
+         "options_per_gpu": int(-(-n_total // world)),
+         "node_steps_per_option": [int(p.node_steps_per_option) for p in cfg.parts],
+         "sharding": (f"by option over {world} GPUs, no communication during the solve; result collective per step: "
+                      f"{collective} of the packed per-option results (value and e2e legs alike)") if world > 1 else "single GPU",
+         "l2": "flushed (256 MiB memset) between timed steps; per-option inputs are read once per solve"}
+    if sample is not None:
+        d["cpu_sample_options_per_step"] = int(sample)
+    return d
+
+
+# --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
 
-def run_b200(args):
+class ShardRuns:
+    """This rank's books of one configuration, resident in HBM, with their result gathers."""
+
+    def __init__(self, cfg, n_total, rank, world, dev, dst=0):
+        from finite_difference_b200 import shard
+        self.cfg, self.n_total, self.world, self.rank = cfg, n_total, world, rank
+        counts = split_counts(n_total, cfg.shares)
+        self.parts = []
+        for part, cnt in zip(cfg.parts, counts):
+            d = part.draws(cnt)
+            mine = shard.partition(np.full(cnt, float(part.node_steps_per_option)), world)[rank]
+            book = part.build(d, mine)
+            sr = shard.ShardedBookRun(book, mine, cnt, part.what, dst=dst, device=dev)
+            self.parts.append(dict(part=part, draws=d, mine=mine, book=book, sr=sr, count=cnt))
+        self.node_steps = sum(p["sr"].run.node_steps for p in self.parts)
+        self.flops = sum(p["sr"].run.node_steps * p["part"].flops for p in self.parts)
+        self.n_solves = sum(p["sr"].run.n_solves for p in self.parts)
+        self.h2d = sum(p["sr"].run.h2d_bytes for p in self.parts)
+        self.collective = self.parts[0]["sr"].gather.collective
+
+    def launch(self):
+        return sum(p["sr"].run.launch() for p in self.parts)
+
+    def collect(self, d2h):
+        outs = []
+        for p in self.parts:
+            g = p["sr"].gather
+            if self.world > 1 or d2h:
+                outs.append(g(p["sr"].run.packed) if d2h else g.exchange(p["sr"].run.packed))
+            else:
+                outs.append(None)
+        return outs
+
+    def e2e_step(self):
+        return [p["sr"].step() for p in self.parts]
+
+
+def time_config(cfg, args, rank, world, local, n_total, steps, warmup, with_cpu, threads):
+    """All legs of one configuration.  Returns (line dict or None on ranks > 0, ok)."""
     import torch
     import torch.distributed as dist
-    from finite_difference_b200 import DeviceBatch, _lib, shard
+    from finite_difference_b200 import _lib
+    from finite_difference_b200.book import DeviceBookRun
 
-    rank, world, local = shard.init_distributed()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (finite_difference_b200 has no CPU fallback)")
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    _lib.load()
-
-    # ---- the book and this rank's shard --------------------------------------------------
-    n_total = args.options * world
-    w = workload(n_total)
-    cost = np.full(n_total, 2.5e6)
-    mine = shard.partition(cost, world)[rank]
-    book = make_book(w, mine)
-    batch, lay = book.fanout("scenario")
-    node_steps = batch.node_steps()
-    dbatch = DeviceBatch(batch, device=dev)
-    # per-solve outputs the epilogue needs: price, delta, gamma (+ exercise interval)
-    gather_in = gather_out = None
-    if world > 1:
-        gather_in = torch.empty((batch.n_solves, 3), dtype=torch.float64, device=dev)
-        gather_out = torch.empty((world * batch.n_solves, 3), dtype=torch.float64, device=dev)
+    runs = ShardRuns(cfg, n_total, rank, world, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
-
-    def step():
-        n = dbatch.solve(stream)
-        if world > 1:
-            torch.stack((dbatch.price, dbatch.delta, dbatch.gamma), dim=1, out=gather_in)
-            dist.all_gather_into_tensor(gather_out, gather_in)
-        return n
 
     def barrier():
         if world > 1:
             dist.barrier()
 
     peak_before, _ = _lib.fp64_peak_tflops()
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for _ in range(max(warmup, 3)):
+        runs.launch()
+        runs.collect(d2h=False)
     torch.cuda.synchronize(dev)
 
-    # ---- timed region: K steps, CUDA events on the launching stream -------------------------
-    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    # ---- value leg: K steps, CUDA events on the launching stream ------------------------------------------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(steps)] for _ in range(3)]
     launches = 0
     barrier()
     torch.cuda.synchronize(dev)
     with ClockSampler(local) as clocks:
         t_wall0 = time.perf_counter()
-        for i in range(args.steps):
+        for i in range(steps):
             flush.fill_(i & 0xff)                     # L2 flush, outside the per-step events
-            e0[i].record(stream)
-            launches += dbatch.solve(stream)
-            k0[i].record(stream)
-            if world > 1:
-                torch.stack((dbatch.price, dbatch.delta, dbatch.gamma), dim=1, out=gather_in)
-                dist.all_gather_into_tensor(gather_out, gather_in)
-            e1[i].record(stream)
+            ev[0][i].record(stream)
+            launches += runs.launch()
+            ev[1][i].record(stream)
+            runs.collect(d2h=False)
+            ev[2][i].record(stream)
         torch.cuda.synchronize(dev)
         t_wall = time.perf_counter() - t_wall0
     barrier()
-    step_ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
-    kern_ms = sum(a.elapsed_time(b) for a, b in zip(e0, k0))
+    step_ms = sum(a.elapsed_time(b) for a, b in zip(ev[0], ev[2]))
+    kern_ms = sum(a.elapsed_time(b) for a, b in zip(ev[0], ev[1]))
     peak_after, _ = _lib.fp64_peak_tflops()
+    dev_results = [{k: v.cpu().numpy() for k, v in p["sr"].run.cols.items()} for p in runs.parts]   # what the timed leg left in HBM
 
     t = torch.tensor([step_ms, kern_ms, t_wall * 1e3], dtype=torch.float64, device=dev)
-    ns = torch.tensor([float(node_steps)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(runs.node_steps), float(runs.n_solves)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ns, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     step_ms_max, kern_ms_max, wall_ms_max = (float(x) for x in t.tolist())
-    total_node_steps = float(ns.item())
-    value = total_node_steps * args.steps / (step_ms_max * 1e-3)
+    total_node_steps, total_solves = (float(x) for x in tot.tolist())
+    value = total_node_steps * steps / (step_ms_max * 1e-3)
 
-    # ---- end to end through the public host API ----------------------------------------------
-    res = book.run_fused("scenario")                 # warm-up (including the result gather: NCCL sets up its
-    if world > 1:                                    # point-to-point channels on first use)
-        shard.gather_results({k: res[k] for k in ("price_log2", "price", "delta", "gamma", "vega", "theta")},
-                             mine, n_total, device=dev, dst=0)
+    # ---- end to end through the public host API -------------------------------------------------------------
+    def e2e_once():
+        if world == 1:
+            return [p["book"].run_fused(p["part"].what) for p in runs.parts]
+        return runs.e2e_step()
+
+    e2e_out = e2e_once()                               # warm-up (NCCL sets up its channels on first use)
     barrier()
     torch.cuda.synchronize(dev)
-    e2e_steps = max(1, args.steps)
+    e2e_steps = max(1, steps)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        t_it = time.perf_counter()
-        out = book.run_fused("scenario")
-        if os.environ.get("FDM_BENCH_DEBUG"):
-            print(f"[debug] e2e iteration wall {1e3 * (time.perf_counter() - t_it):.1f} ms kernel {out['kernel_ms']:.1f} ms",
-                  file=sys.stderr, flush=True)
-        if world > 1:
-            # the sweep's one collective: per-option results to rank 0 (the other ranks keep their shards)
-            shard.gather_results({k: out[k] for k in ("price_log2", "price", "delta", "gamma", "vega", "theta")},
-                                 mine, n_total, device=dev, dst=0)
+        e2e_out = e2e_once()
     torch.cuda.synchronize(dev)
     e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = total_node_steps * e2e_steps / (float(e2e_ms.item()) * 1e-3)
-    h2d, d2h = out["h2d_bytes"], out["d2h_bytes"]                      # per-option scalars in, per-option results out
-    desc_bytes = sum(getattr(batch, f).nbytes for f in
-                     ("x_min", "dx", "sigma", "r", "b", "spot", "strike", "n_space", "flags", "rannacher", "seg_begin",
-                      "seg_steps", "seg_dt", "seg_tau0", "seg_restart", "seg_div"))
-    res_bytes = batch.n_solves * (3 * 8 + 2 * 32 + 16 + 4)
+    if world == 1:
+        h2d = sum(o["h2d_bytes"] for o in e2e_out)
+        d2h = sum(o["d2h_bytes"] for o in e2e_out)
+        e2e_path = ("AmericanBook / BarrierBook .run_fused -> fdm_american_book_host / fdm_barrier_book_host: per-option scalars "
+                    "H2D, fan-out + solves + Richardson / bump epilogue on the device, per-option results D2H")
+    else:
+        h2d = runs.h2d
+        d2h = sum(p["sr"].gather.d2h_bytes for p in runs.parts) if rank == 0 else 0
+        e2e_path = ("shard.ShardedBookRun.step: H2D of the shard's per-option inputs from pinned memory, fdm_american_book / "
+                    f"fdm_barrier_book on the device, {runs.collective} of the packed results, rows put in book order on the "
+                    "device, D2H of the whole book's results on rank 0")
 
+    # ---- parity of what was timed ---------------------------------------------------------------------------
+    parity, cpu, ok = None, None, True
+    if with_cpu and rank == 0:
+        from oracle import oracle
+        oracle.build()
+        parity = {"value_leg": [], "e2e_leg": []}
+        n_sample = args.cpu_options or max(cfg.cpu_sample, cfg.cpu_sample * threads)
+        secs = ns_cpu = 0.0
+        for p, dres, eres in zip(runs.parts, dev_results, e2e_out):
+            k = min(p["count"], max(1, int(round(n_sample * p["count"] / n_total))))
+            sel = np.arange(k)                                   # the first k options of the part: they span every rank
+            s, n, ref = p["part"].oracle(p["draws"], sel, threads)
+            secs += s
+            ns_cpu += n
+            # value leg: this rank's rows of the sample, as left in HBM by the timed steps
+            loc = np.nonzero(p["mine"] < k)[0]
+            gsel = p["mine"][loc]
+            parity["value_leg"].append(compare({a: b[gsel] for a, b in ref.items()}, {a: b[loc] for a, b in dres.items()}))
+            # e2e leg: rank 0 holds the whole book in book order (at N > 1 the gathered rows of every rank)
+            if rank == 0 and eres is not None:
+                parity["e2e_leg"].append(compare(ref, {a: np.asarray(b)[:k] for a, b in eres.items() if isinstance(b, np.ndarray)}))
+                if world == 1:                                   # same kernels, same inputs: the two legs agree bit for bit
+                    same = all(np.array_equal(eres[a], dres[a]) for a in dres if isinstance(eres.get(a), np.ndarray))
+                    parity["e2e_equals_value_leg_bitwise"] = bool(same and parity.get("e2e_equals_value_leg_bitwise", True))
+        ok = all(x["ok"] for x in parity["value_leg"] + parity["e2e_leg"])
+        parity["ok"] = ok
+        cpu = {"value": ns_cpu / secs, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"first {n_sample} options of the workload ({secs:.1f} s wall), every solve of their fan-out through the C "
+                         "oracle port of the reference's Python arithmetic, OpenMP over solves"}
+    flag = torch.tensor([0.0 if ok else 1.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    ok = float(flag.item()) == 0.0
     if rank != 0:
-        return 0
+        return None, ok
 
-    # ---- roofline (rank 0's kernel) --------------------------------------------------------------
+    # ---- roofline (rank 0's kernels) ---------------------------------------------------------------------------
     peak = max(peak_before, peak_after)
-    kern_s = kern_ms * 1e-3 / args.steps
-    achieved = node_steps * FLOPS_PER_NODE_STEP_AMERICAN / kern_s / 1e12
+    kern_s = kern_ms * 1e-3 / steps
+    achieved = runs.flops / kern_s / 1e12
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            tj = json.load(open(tpath))
-            traffic = tj["dram_bytes_per_solve"] * batch.n_solves
-        except Exception:
-            traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        if cfg.name in tj.get("configs", {}):
+            traffic = tj["configs"][cfg.name]["dram_bytes_per_solve"] * runs.n_solves
+        elif cfg.name == "cfg3":
+            traffic = tj["dram_bytes_per_solve"] * runs.n_solves
+    except Exception:
+        pass
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = runs.h2d + sum(p["sr"].run.d2h_bytes for p in runs.parts) + runs.n_solves * (104 + 52)
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "peak_source": "fdm_fp64_peak register-resident DFMA micro-benchmark, measured in this run "
-                               "(MEASURED_PEAKS.json has no FP64 entry)",
-                "flops_per_node_step": FLOPS_PER_NODE_STEP_AMERICAN, "kernel": "fdm_lean_kernel<16,true,false>",
-                "kernel_ms_per_launch": kern_ms / args.steps,
-                "launches_per_step": "fdm_lean_kernel<16,true,false> (all 800k solves) + fdm_warp_kernel<16,true,false> in "
-                                     "only_rest mode (takes what the lean kernel hands back: nothing here, exits at once)",
-                "hbm": {"algorithmic_bytes_per_launch": desc_bytes + res_bytes,
-                        "achieved_gbs": (desc_bytes + res_bytes) / kern_s / 1e9, "peak_gbs": hbm_peak,
-                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                        "frac": (desc_bytes + res_bytes) / kern_s / 1e9 / hbm_peak}}
-
-    # ---- CPU baseline + parity gate (rank 0, N = 1 only) ----------------------------------------
-    cpu = None
-    parity = None
-    if world == 1 and not args.no_cpu:
-        from oracle import oracle
-        oracle.build()
-        threads = host_threads()
-        n_sample = args.cpu_options or max(48, 48 * threads)
-        n_sample = min(n_sample, len(mine))
-        sel = np.arange(n_sample)
-        dt, ns_cpu, p_cpu, lo_cpu, hi_cpu = oracle_scenario(w, mine[sel], threads)
-        cpu = {"value": ns_cpu / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"first {n_sample} options x 8 solves of the workload ({dt:.1f} s wall), C oracle port of "
-                         "the reference's Python arithmetic, OpenMP"}
-        # parity: base-N solve prices and exercise intervals of the sampled options, GPU (host API) vs oracle
-        full = book.fanout("scenario")[0]
-        from finite_difference_b200 import solve_host
-        gres = solve_host(full.take(np.concatenate([k * len(mine) + sel for k in range(SOLVES_PER_OPTION)])))
-        rel = np.abs(gres.price - p_cpu) / np.maximum(np.abs(p_cpu), 1e-2)
-        same_ex = bool(np.array_equal(gres.idx[:, 2], lo_cpu) and np.array_equal(gres.idx[:, 3], hi_cpu))
-        parity = {"n_solves": int(len(p_cpu)), "max_rel_err_price": float(rel.max()), "tolerance": 1e-10,
-                  "exercise_intervals_identical": same_ex}
-        if not (rel.max() <= 1e-10 and same_ex):
-            emit({"error": "parity gate failed", "parity": parity})
-            return 1
-
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": step_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args.options, world),
+                               "(MEASURED_PEAKS.json has no FP64 entry; profiles/fp64_peak.json keeps a record with clocks)",
+                "flops_per_node_step": runs.flops / runs.node_steps,
+                "kernel_ms_per_step": kern_ms / steps,
+                "launches_per_step": launches / steps,
+                "what": "fan-out kernel + solve kernels + epilogue kernel of one step (the solve kernels are > 99.9 % of it)",
+                "hbm": {"algorithmic_bytes_per_step": int(alg_bytes), "achieved_gbs": alg_bytes / kern_s / 1e9,
+                        "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                        "frac": alg_bytes / kern_s / 1e9 / hbm_peak}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(warmup, 3), "ms_per_step": step_ms_max / steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(cfg, args, world, n_total, runs.collective),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "ms_per_step": float(e2e_ms.item()) / e2e_steps,
-                    "path": "AmericanBook.run_fused('scenario') -> fdm_american_book_host: per-option scalars H2D, "
-                            "fan-out + solves + Richardson/bump epilogue on the device, per-option results D2H"},
+                    "steps": e2e_steps, "ms_per_step": float(e2e_ms.item()) / e2e_steps, "path": e2e_path},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "wall_ms_timed_region": wall_ms_max,
-            "options_total": int(n_total), "solves_per_step": int(batch.n_solves * world),
-            "sanity": {"price_log2_mean": float(np.mean(res["price_log2"])), "status_max": int(res["status"].max())}}
+            "solves_per_step": int(total_solves),
+            "fp64_peak": {"tflops_before": peak_before, "tflops_after": peak_after}}
     if cpu is not None:
         line["cpu_baseline"] = cpu
         line["parity"] = parity
-    emit(line)
+    del runs, flush
+    torch.cuda.empty_cache()
+    return line, ok
+
+
+def dbfp_config(args, local, threads):
+    """The barrier scenario runner's own grid (run_config_scenarios shape): DiscreteBarrierFDMPricer rows, 2133 space
+    nodes x 500 steps, 2 solves per row (sigma, sigma + 1e-4): fdm_cta_kernel, 5-warp class."""
+    import datetime as dt
+    import pandas as pd
+    import torch
+    from finite_difference_b200 import DeviceBatch, _lib, hostlogic, run_config_scenarios as rcs
+    from oracle import oracle
+    n = 2048
+    rng = np.random.default_rng(SEED + 6)
+    val, mat = dt.date(2025, 7, 28), dt.date(2025, 8, 28)
+    mons = [d for d in (val + dt.timedelta(days=i) for i in range(32)) if d.weekday() < 5]
+    down = rng.uniform(size=n) < 0.5
+    frame = pd.DataFrame(dict(
+        scenario_name=[f"s{i}" for i in range(n)], S0=229.74, K=rng.uniform(180, 280, n), sigma=rng.uniform(0.15, 0.45, n),
+        rate=rng.choice(np.round(np.linspace(0.03, 0.10, 15), 4), n), barrier_type=np.where(down, "down-and-out", "up-and-out"),
+        upper_barrier=np.where(down, np.nan, rng.uniform(240, 330, n)), lower_barrier=np.where(down, rng.uniform(150, 220, n), np.nan),
+        FA_price=np.nan, FA_delta=np.nan, FA_gamma=np.nan, FA_vega=np.nan))
+    base = dict(valuation=val, maturity=mat, monitor_dates=mons, opt_type="put", num_time_steps=500)
+    cache = {}
+    pricers = [rcs._build_pricer(r["S0"], r["K"], r["sigma"], r["rate"], r["barrier_type"], rcs._opt(r["upper_barrier"]),
+                                 rcs._opt(r["lower_barrier"]), _curve_cache=cache, **base) for _, r in frame.iterrows()]
+    a_ = []
+    for p in pricers:
+        a_.append(p._solve_args(True))
+        a_.append(p._solve_args(True, sigma=p.sigma + 1e-4))
+    batch = hostlogic.build_dbfp_batch(**{k: [a[k] for a in a_] for k in a_[0]})
+    dev = DeviceBatch(batch)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        dev.solve()
+    torch.cuda.synchronize()
+    steps = 3
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(steps)] for _ in range(2)]
+    launches = 0
+    peak, _ = _lib.fp64_peak_tflops()
+    with ClockSampler(local) as clocks:
+        for i in range(steps):
+            flush.fill_(i)
+            ev[0][i].record()
+            launches += dev.solve()
+            ev[1][i].record()
+        torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in zip(*ev)) / steps
+    res = dev.results()
+    worst = 0.0
+    for i in range(0, 32, 2):
+        a = a_[i]
+        o = oracle.dbfp_solve(a["S_min"], a["S_max"], a["S0_eff"], a["S0_eff"], a["K"], a["T"], a["sigma"], a["r"], a["b"], a["q"],
+                              a["is_call"], a["ko_type"], a["lower_barrier"], a["upper_barrier"], a["rebate_amount"],
+                              a["rebate_at_hit"], a["monitor_times"], a["num_space_nodes"], a["num_time_steps"],
+                              a["rannacher_steps"])
+        worst = max(worst, abs(res.price[i] - o.price) / max(abs(o.price), 1e-2))
+    rcs.run_scenarios_frame(frame.iloc[:64], base)            # warm-up
+    t0 = time.perf_counter()
+    rcs.run_scenarios_frame(frame, base)
+    e2e_s = time.perf_counter() - t0
+    ns = batch.node_steps()
+    return {"workload": f"dbfp: barrier scenario sweep (run_config_scenarios shape, DiscreteBarrierFDMPricer): {n} rows x 2 solves, "
+                        "2133 space nodes x 500 steps, weekday monitoring, Rannacher 2",
+            "value": ns / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "steps": steps, "gpu_launches": launches,
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "fp64", "flops_per_node_step": FLOPS_LINEAR, "achieved": ns * FLOPS_LINEAR / ms / 1e9, "peak": peak,
+                         "unit": "TFLOP/s", "frac": ns * FLOPS_LINEAR / ms / 1e9 / peak},
+            "e2e": {"value": ns / e2e_s, "unit": UNIT, "seconds": e2e_s,
+                    "path": "run_config_scenarios.run_scenarios_frame -> BarrierScenarioBook (numpy over rows) -> "
+                            "fdm_solve_batch_host -> result frame"},
+            "parity": {"n_solves": 16, "max_rel_err_price": worst, "tolerance": 1e-10, "ok": bool(worst <= 1e-10)}}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from finite_difference_b200 import _lib, shard
+
+    rank, world, local = shard.init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (finite_difference_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    _lib.load()
+    threads = host_threads()
+    cfg = make_config(args.config, args.cfg4_steps)
+    n_total = options_of(cfg, args, world)
+    # at N > 1 the oracle runs on rank 0 only (the other ranks wait in the flag all-reduce)
+    line, ok = time_config(cfg, args, rank, world, local, n_total, args.steps, args.warmup,
+                           with_cpu=not args.no_cpu, threads=threads)
+    if rank == 0 and line is not None:
+        if not ok:
+            emit({"error": "parity gate failed", "parity": line.get("parity"), "config": line["config"]})
+            return 1
+        if world == 1 and not args.no_cpu and cfg.name == "cfg3":
+            pyinfo, pyout = python_reference_leg(threads)
+            if pyinfo:
+                line["cpu_baseline"]["python_reference"] = pyinfo
+            if pyout is not None:
+                # the same options through the GPU path, against the reference's own Python outputs
+                n = len(pyout["price"])
+                w = workload(n)
+                from finite_difference_b200.book import AmericanBook
+                bk = AmericanBook(np.full(n, F0), w["K"], pyout["T"], w["sigma"], pyout["r"], pyout["r"], w["is_call"], 500, 500, 2,
+                                  black76=True)
+                got = bk.run_fused("scenario")
+                pp = compare({k: pyout[k] for k in ("price_log2", "price", "delta", "gamma", "vega")}, got)
+                line["parity"]["vs_python_reference"] = pp
+                if not pp["ok"]:
+                    emit({"error": "parity gate failed (python reference)", "parity": pp})
+                    return 1
+        if world == 1 and not args.no_others and cfg.name == "cfg3":
+            others = {}
+            sub = argparse.Namespace(**vars(args))
+            sub.options, sub.scaling, sub.cpu_options = 0, "weak", 0
+            for name, opts, kw in (("cfg2", 10_000, {}), ("cfg2price", 10_000, {}), ("am400", 100_000, {}),
+                                   ("am500div", 12_500, {}), ("cfg4", 592, {"steps": 2500}), ("cfg5", 125_000, {})):
+                c2 = make_config(name, kw.get("steps", 1000))
+                sub.options = opts
+                try:
+                    l2, ok2 = time_config(c2, sub, 0, 1, local, opts, 3, 3, True, threads)
+                    keep = {k: l2[k] for k in ("value", "unit", "ms_per_step", "steps", "clocks", "e2e", "gpu_launches", "roofline",
+                                               "parity", "solves_per_step")}
+                    keep["workload"] = c2.desc
+                    keep["options"] = opts
+                    others[name] = keep
+                    ok &= ok2
+                except Exception as exc:
+                    others[name] = {"error": f"{type(exc).__name__}: {exc}"}
+                    ok = False
+            try:
+                others["dbfp"] = dbfp_config(args, local, threads)
+                ok &= others["dbfp"]["parity"]["ok"]
+            except Exception as exc:
+                others["dbfp"] = {"error": f"{type(exc).__name__}: {exc}"}
+                ok = False
+            line["other_configs"] = others
+            if not ok:
+                emit({"error": "parity gate failed in other_configs", "other_configs": others})
+                return 1
+        emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return 0 if ok else 1
 
 
 def main():
@@ -401,9 +782,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--options", type=int, default=100_000, help="options per GPU (8 solves each)")
-    ap.add_argument("--cpu-options", type=int, default=0, help="options in the CPU sample (default 48 x threads: about 20 core-seconds of CPU work)")
+    ap.add_argument("--config", default="cfg3", help="cfg3 (default) | cfg4 | cfg5 | cfg2 | cfg2price | am400 | am500div")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --options per GPU; strong: the configuration's stated book sharded over the GPUs")
+    ap.add_argument("--options", type=int, default=0, help="options per GPU (weak) or in total (strong); 0 = the configuration's")
+    ap.add_argument("--cfg4-steps", type=int, default=10000, help="time steps of --config cfg4 (10 000 in BASELINE.json)")
+    ap.add_argument("--cpu-options", type=int, default=0, help="options in the CPU sample (default: about 20 core-seconds of CPU work)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
+    ap.add_argument("--no-others", action="store_true", help="skip other_configs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

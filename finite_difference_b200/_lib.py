@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(_HERE, "libfdm_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 FLAG_CALL = 0x01
 FLAG_AMERICAN = 0x02
@@ -21,6 +21,9 @@ FLAG_KO_DOWN = 0x10
 FLAG_KO_UP = 0x20
 FLAG_BDRY_TOP_NEXT = 0x40
 FLAG_PUT_BDRY_SMIN = 0x80
+FLAG_INVALID = 0x100
+
+STATUS_OK, STATUS_NONFINITE, STATUS_STIFF, STATUS_NOT_SOLVED = 0, 1, 2, -1
 
 MAX_N_SPACE = 8193
 WARP_MAX_N_SPACE = 513
@@ -43,6 +46,7 @@ class FdmBatch(C.Structure):
         ("seg_steps", C.c_void_p), ("seg_dt", C.c_void_p), ("seg_tau0", C.c_void_p),
         ("seg_restart", C.c_void_p), ("seg_div", C.c_void_p), ("mon_step", C.c_void_p),
         ("b_bdry", C.c_void_p), ("barrier_up", C.c_void_p), ("mon_rebate", C.c_void_p),
+        ("mon_end", C.c_void_p),
     ]
 
 
@@ -62,6 +66,8 @@ class FdmAmericanBook(C.Structure):
         ("r", C.c_void_p), ("b", C.c_void_p), ("flags", C.c_void_p), ("n_space", C.c_void_p),
         ("n_time", C.c_void_p), ("rannacher", C.c_void_p),
         ("s_max_mult", C.c_double), ("dv_sigma", C.c_double), ("what", C.c_int32), ("use_richardson", C.c_int32),
+        ("div_begin", C.c_void_p), ("div_tau", C.c_void_p), ("div_cash", C.c_void_p), ("n_div_total", C.c_int64),
+        ("n_space_max", C.c_int32), ("hints", C.c_int32),
     ]
 
 
@@ -70,10 +76,26 @@ class FdmBookOut(C.Structure):
                                           "ex_lo", "ex_hi", "status")]
 
 
+class FdmBarrierBook(C.Structure):
+    _fields_ = [
+        ("n_options", C.c_int64),
+        ("S0", C.c_void_p), ("K", C.c_void_p), ("T", C.c_void_p), ("sigma", C.c_void_p), ("r_disc", C.c_void_p),
+        ("b_carry", C.c_void_p), ("x_min", C.c_void_p), ("dx", C.c_void_p), ("barrier", C.c_void_p),
+        ("barrier_up", C.c_void_p), ("rebate", C.c_void_p), ("flags", C.c_void_p), ("n_space", C.c_void_p),
+        ("n_time", C.c_void_p), ("mon_begin", C.c_void_p), ("mon_step", C.c_void_p), ("n_mon_total", C.c_int64),
+        ("dv_sigma", C.c_double), ("what", C.c_int32), ("n_space_max", C.c_int32), ("hints", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 BOOK_PRICE_LOG, BOOK_PRICE_LOG2, BOOK_GREEKS_LOG2, BOOK_SCENARIO = 0, 1, 2, 3
+BARRIER_BOOK_SOLVE, BARRIER_BOOK_GREEKS = 0, 1
 
 EXPORTS = ("fdm_version", "fdm_sizeof", "fdm_last_error", "fdm_device_count", "fdm_solve_batch",
-           "fdm_solve_batch_host", "fdm_launch_hints", "fdm_book_solves_per_option", "fdm_american_book_host", "fdm_release_workspace", "fdm_fp64_peak")
+           "fdm_solve_batch_host", "fdm_launch_hints", "fdm_book_solves_per_option", "fdm_american_book_host",
+           "fdm_american_book_workspace", "fdm_american_book", "fdm_barrier_book_solves_per_option",
+           "fdm_barrier_book_workspace", "fdm_barrier_book", "fdm_barrier_book_host", "fdm_release_workspace",
+           "fdm_fp64_peak")
 
 
 class FdmError(RuntimeError):
@@ -116,6 +138,21 @@ def load(path: str | None = None):
     L.fdm_american_book_host.restype = C.c_int
     L.fdm_american_book_host.argtypes = [C.POINTER(FdmAmericanBook), C.POINTER(FdmBookOut), C.POINTER(C.c_int64),
                                          _pi, C.POINTER(C.c_float)]
+    L.fdm_american_book_workspace.restype = C.c_size_t
+    L.fdm_american_book_workspace.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int32]
+    L.fdm_american_book.restype = C.c_int
+    L.fdm_american_book.argtypes = [C.POINTER(FdmAmericanBook), C.POINTER(FdmBookOut), C.c_void_p, C.c_size_t,
+                                    C.c_void_p, _pi]
+    L.fdm_barrier_book_solves_per_option.restype = C.c_int
+    L.fdm_barrier_book_solves_per_option.argtypes = [C.c_int32]
+    L.fdm_barrier_book_workspace.restype = C.c_size_t
+    L.fdm_barrier_book_workspace.argtypes = [C.c_int64, C.c_int32]
+    L.fdm_barrier_book.restype = C.c_int
+    L.fdm_barrier_book.argtypes = [C.POINTER(FdmBarrierBook), C.POINTER(FdmBookOut), C.c_void_p, C.c_size_t,
+                                   C.c_void_p, _pi]
+    L.fdm_barrier_book_host.restype = C.c_int
+    L.fdm_barrier_book_host.argtypes = [C.POINTER(FdmBarrierBook), C.POINTER(FdmBookOut), C.POINTER(C.c_int64),
+                                        _pi, C.POINTER(C.c_float)]
     L.fdm_fp64_peak.restype = C.c_int
     L.fdm_fp64_peak.argtypes = [_pd, C.POINTER(C.c_float)]
     if L.fdm_version() != ABI_VERSION:

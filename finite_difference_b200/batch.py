@@ -235,6 +235,7 @@ class SolveBatch:
                                    "seg_div", "mon_begin", "mon_step", "b_bdry", "barrier_up", "mon_rebate"):
             arr = getattr(self, name)
             setattr(s, name, None if arr is None else ptr(name, arr))
+        s.mon_end = None                      # ABI 3: shared monitor tables are used by the device-side book fan-out only
         return s
 
 

@@ -26,7 +26,7 @@ import numpy as np
 from . import hostlogic
 from .batch import DeviceBatch, SolveBatch, SolveResults, solve_host
 
-__all__ = ["AmericanBook", "BarrierBook", "norm_cdf", "lapack_delta_gamma"]
+__all__ = ["AmericanBook", "BarrierBook", "DeviceBookRun", "unpack_columns", "norm_cdf", "lapack_delta_gamma"]
 
 
 def _f64(v, n=None):
@@ -92,12 +92,44 @@ class AmericanBook:
         self.black76 = np.ascontiguousarray(np.broadcast_to(np.asarray(black76, dtype=bool), (n,)))
         self.s_max_mult = float(s_max_mult)
         self.div_taus = div_taus
+        self._div_csr = None
+
+    def div_csr(self):
+        """Dividends as CSR arrays ``(begin[n+1] int32, tau float64, cash float64)`` for the fused entries, or
+        ``None`` for a dividend-free book.  ``div_taus`` may already be such a triple (vectorised books)."""
+        if self._div_csr is None:
+            d = self.div_taus
+            if d is None:
+                return None
+            if isinstance(d, tuple) and len(d) == 3 and isinstance(d[0], np.ndarray):
+                begin, tau, cash = d
+            else:
+                counts = np.fromiter((len(x) if (x is not None and not self.black76[i]) else 0 for i, x in enumerate(d)),
+                                     dtype=np.int64, count=self.n_opt)
+                begin = np.concatenate([[0], np.cumsum(counts)])
+                flat = [tc for i, x in enumerate(d) if (x is not None and not self.black76[i]) for tc in x]
+                arr = np.asarray(flat, dtype=np.float64).reshape(-1, 2)
+                tau, cash = arr[:, 0], arr[:, 1]
+            if int(begin[-1]) == 0:
+                return None
+            self._div_csr = (np.ascontiguousarray(begin, dtype=np.int32), np.ascontiguousarray(tau, dtype=np.float64),
+                             np.ascontiguousarray(cash, dtype=np.float64))
+        return self._div_csr
+
+    def _div_lists(self):
+        """Per-option ``[(tau, cash)]`` lists for the host-side descriptor builder."""
+        d = self.div_taus
+        if isinstance(d, tuple) and len(d) == 3 and isinstance(d[0], np.ndarray):
+            begin, tau, cash = d
+            return [list(zip(tau[begin[i]:begin[i + 1]].tolist(), cash[begin[i]:begin[i + 1]].tolist()))
+                    for i in range(self.n_opt)]
+        return d
 
     # ---- fan-out -----------------------------------------------------------------------
     def _solves(self, n_time, sigma) -> SolveBatch:
         return hostlogic.build_american_batch(
             self.spot, self.strike, self.T, sigma, self.r, self.b, self.is_call, self.n_space, n_time,
-            self.rannacher, self.black76, self.s_max_mult, div_taus=self.div_taus)
+            self.rannacher, self.black76, self.s_max_mult, div_taus=self._div_lists())
 
     def _fine_steps_price_log2(self):
         return np.where(self.black76, 2 * self.n_time, 2 * self.n_space)
@@ -178,31 +210,61 @@ class AmericanBook:
     # ---- public ----------------------------------------------------------------------------
     _WHAT = {"price_log": 0, "price_log2": 1, "greeks_log2": 2, "scenario": 3}
 
-    def run_fused(self, what: str = "scenario", dv_sigma: float = 0.01, use_richardson: bool = True) -> Dict[str, np.ndarray]:
-        """One ``fdm_american_book_host`` call: per-option scalars go to the device (~56 B each), the
-        fan-out into solves, the solves and the Richardson / bump epilogue all run there, and only the
-        per-option results come back.  Dividend-free books only.  The grid bounds are evaluated with the
-        device's exp/log (<= 1 ulp from libm), so prices agree with :meth:`run` to ~1e-14 relative."""
-        import ctypes as C
+    def _book_struct(self, what, dv_sigma, use_richardson, ptr):
+        """``FdmAmericanBook`` with pointers produced by ``ptr(name, numpy array)`` (host or device)."""
         from . import _lib
-        if self.div_taus is not None and any(self.div_taus):
-            raise ValueError("run_fused handles dividend-free books; use run()")
-        L = _lib.load()
         n = self.n_opt
-        f64 = {k: np.ascontiguousarray(getattr(self, k), dtype=np.float64) for k in ("spot", "strike", "T", "sigma", "r", "b")}
-        flags = np.ascontiguousarray(np.where(self.is_call, _lib.FLAG_CALL, 0) + np.where(self.black76, _lib.FLAG_BLACK76, 0),
-                                     dtype=np.int32)
-        i32 = {"n_space": self.n_space, "n_time": self.n_time, "rannacher": self.rannacher}
-        i32 = {k: np.ascontiguousarray(v, dtype=np.int32) for k, v in i32.items()}
         bk = _lib.FdmAmericanBook()
         bk.n_options = n
-        for k, v in f64.items():
-            setattr(bk, k, v.ctypes.data)
-        bk.flags = flags.ctypes.data
-        for k, v in i32.items():
-            setattr(bk, k, v.ctypes.data)
+        for k in ("spot", "strike", "T", "sigma", "r", "b"):
+            setattr(bk, k, ptr(k, np.ascontiguousarray(getattr(self, k), dtype=np.float64)))
+        flags = np.ascontiguousarray(np.where(self.is_call, _lib.FLAG_CALL, 0) + np.where(self.black76, _lib.FLAG_BLACK76, 0),
+                                     dtype=np.int32)
+        bk.flags = ptr("flags", flags)
+        for k in ("n_space", "n_time", "rannacher"):
+            setattr(bk, k, ptr(k, np.ascontiguousarray(getattr(self, k), dtype=np.int32)))
         bk.s_max_mult, bk.dv_sigma = self.s_max_mult, float(dv_sigma)
         bk.what, bk.use_richardson = self._WHAT[what], int(bool(use_richardson))
+        csr = self.div_csr()
+        if csr is not None:
+            bk.div_begin, bk.div_tau, bk.div_cash = (ptr(k, v) for k, v in zip(("div_begin", "div_tau", "div_cash"), csr))
+            bk.n_div_total = int(csr[0][-1])
+        bk.n_space_max = int(self.n_space.max()) if n else 3
+        ns = np.ascontiguousarray(self.n_space, dtype=np.int32)
+        fl = np.full(n, _lib.FLAG_AMERICAN, dtype=np.int32)
+        bk.hints = int(_lib.load().fdm_launch_hints(ns.ctypes.data_as(_lib._pi), fl.ctypes.data_as(_lib._pi), n, None, 0)) & ~4
+        return bk
+
+    def solve_steps(self, what: str = "scenario", use_richardson: bool = True) -> int:
+        """Metric unit of one pass: sum over the executed solves of num_space_nodes x time steps."""
+        ns, nt = self.n_space.astype(np.int64), self.n_time.astype(np.int64)
+        fine1 = np.where(self.black76, 2 * nt, 2 * ns)
+        total = 0
+        if what == "price_log":
+            total += nt
+        if what in ("price_log2", "scenario"):
+            total = total + nt + (fine1 if use_richardson else 0)
+        if what in ("greeks_log2", "scenario"):
+            total = total + nt + ((2 * nt + 4 * nt) if use_richardson else 2 * nt)
+        return int(np.sum(ns * total))
+
+    def run_fused(self, what: str = "scenario", dv_sigma: float = 0.01, use_richardson: bool = True) -> Dict[str, np.ndarray]:
+        """One ``fdm_american_book_host`` call: per-option scalars (and the dividend tables) go to the device
+        (~56 B per option + 16 B per dividend), the fan-out into solves -- time segments between dividends
+        included -- the solves and the Richardson / bump epilogue all run there, and only the per-option results
+        come back.  The grid bounds are evaluated with the device's exp/log (<= 1 ulp from libm), so prices agree
+        with :meth:`run` to ~1e-14 relative."""
+        import ctypes as C
+        from . import _lib
+        L = _lib.load()
+        n = self.n_opt
+        keep = []
+
+        def host_ptr(_name, arr):
+            keep.append(arr)
+            return arr.ctypes.data
+
+        bk = self._book_struct(what, dv_sigma, use_richardson, host_ptr)
         res = {k: np.empty(n) for k in ("price_log2", "price", "delta", "gamma", "vega", "theta")}
         res.update({k: np.empty(n, dtype=np.int32) for k in ("ex_lo", "ex_hi", "status")})
         out = _lib.FdmBookOut()
@@ -215,10 +277,17 @@ class AmericanBook:
                 res.pop(k)
         if what == "greeks_log2":
             res.pop("price_log2")
+        n_div = int(bk.n_div_total)
         res.update(node_steps=int(ns.value), n_solves=n * int(L.fdm_book_solves_per_option(bk.what, bk.use_richardson)),
                    kernel_ms=float(ms.value), n_launches=int(nl.value),
-                   h2d_bytes=n * (6 * 8 + 4 * 4), d2h_bytes=n * (6 * 8 + 3 * 4))
+                   h2d_bytes=n * (6 * 8 + 4 * 4) + (n_div * 16 + (n + 1) * 4 if n_div else 0),
+                   d2h_bytes=n * (6 * 8 + 3 * 4))
         return res
+
+    def device_run(self, what: str = "scenario", dv_sigma: float = 0.01, use_richardson: bool = True, device=None,
+                   width: Optional[int] = None) -> "DeviceBookRun":
+        """The book resident in HBM: :class:`DeviceBookRun` (``fdm_american_book``, no host copies in ``launch``)."""
+        return DeviceBookRun(self, "american", what, dict(dv_sigma=dv_sigma, use_richardson=use_richardson), device, width)
 
     def run(self, what: str = "scenario", dv_sigma: float = 0.01, use_richardson: bool = True,
             dedupe: bool = False, lapack_greeks: bool = False) -> Dict[str, np.ndarray]:
@@ -375,6 +444,48 @@ class BarrierBook:
             theta = -(0.5 * self.sigma * self.sigma * self.S0 * self.S0 * g
                       + self.b_carry * self.S0 * d - self.r_disc * p)                            # :460-464
             out.update(vega=vega, theta=theta)
+        return self._parity_legs(out)
+
+    # ---- fused paths: fan-out (sigma bumps), solves and vega / theta epilogue on the device ------------------
+    _WHAT = {"solve": 0, "greeks": 1}
+
+    def _table(self) -> SolveBatch:
+        """Per-option descriptors at the base volatility (grid, knock-out flags and levels, monitor steps): none of
+        them depends on the volatility bump, so the three solves of ``greeks`` share them."""
+        if getattr(self, "_tab", None) is None:
+            self._tab = self._solves(self.sigma)
+        return self._tab
+
+    def _book_struct(self, what, dv_sigma, ptr):
+        from . import _lib
+        t = self._table()
+        n = self.n_opt
+        bk = _lib.FdmBarrierBook()
+        bk.n_options = n
+        for name, arr in (("S0", t.spot), ("K", t.strike), ("T", self.T), ("sigma", t.sigma), ("r_disc", t.r),
+                          ("b_carry", t.b), ("x_min", t.x_min), ("dx", t.dx), ("barrier", t.barrier), ("rebate", t.rebate)):
+            setattr(bk, name, ptr(name, np.ascontiguousarray(arr, dtype=np.float64)))
+        if t.barrier_up is not None:
+            bk.barrier_up = ptr("barrier_up", t.barrier_up)
+        bk.flags = ptr("flags", t.flags)
+        bk.n_space = ptr("n_space", t.n_space)
+        bk.n_time = ptr("n_time", np.ascontiguousarray(self.N_time, dtype=np.int32))
+        if t.mon_step is not None and len(t.mon_step):
+            bk.mon_begin = ptr("mon_begin", t.mon_begin)
+            bk.mon_step = ptr("mon_step", t.mon_step)
+            bk.n_mon_total = len(t.mon_step)
+        bk.dv_sigma, bk.what = float(dv_sigma), self._WHAT[what]
+        bk.n_space_max = int(t.n_space.max()) if n else 3
+        bk.hints = int(_lib.load().fdm_launch_hints(t.n_space.ctypes.data_as(_lib._pi), t.flags.ctypes.data_as(_lib._pi),
+                                                    n, None, 0)) & ~4
+        return bk
+
+    def solve_steps(self, what: str = "greeks") -> int:
+        k = 3 if what == "greeks" else 1
+        return int(np.sum(self.N_space.astype(np.int64) * self.N_time.astype(np.int64))) * k
+
+    def _parity_legs(self, out):
+        """``none`` -> closed-form BS, knock-in -> BS minus knock-out (discrete_barrier_fdm_pricer_cn.py:489-500, :522-535)."""
         kinds = np.array(self.barrier_type)
         needs_bs = np.isin(kinds, ("none", "down-and-in", "up-and-in"))
         if needs_bs.any():
@@ -383,8 +494,43 @@ class BarrierBook:
             ki = needs_bs & ~none
             for k in ("price", "delta", "gamma", "vega", "theta"):
                 if k in out:
-                    out[k] = np.where(none, bs[k], np.where(ki, bs[k] - out[k], out[k]))         # :489-500, :522-535
+                    out[k] = np.where(none, bs[k], np.where(ki, bs[k] - out[k], out[k]))
         return out
+
+    def run_fused(self, what: str = "greeks", dv_sigma: float = 1e-3) -> Dict[str, np.ndarray]:
+        """One ``fdm_barrier_book_host`` call: ~100 B per option (+ 4 B per monitor date) to the device; the base
+        and bumped solves are expanded there and share the grid and the monitor table; price, delta, gamma, vega
+        and theta per option come back.  Same values as :meth:`run` (same descriptors, same kernels, the epilogue
+        in the reference's operation order)."""
+        import ctypes as C
+        from . import _lib
+        L = _lib.load()
+        n = self.n_opt
+        keep = []
+
+        def host_ptr(_name, arr):
+            keep.append(arr)
+            return arr.ctypes.data
+
+        bk = self._book_struct(what, dv_sigma, host_ptr)
+        res = {k: np.empty(n) for k in ("price", "delta", "gamma", "vega", "theta")}
+        res["status"] = np.empty(n, dtype=np.int32)
+        out = _lib.FdmBookOut()
+        for k, v in res.items():
+            setattr(out, k, v.ctypes.data)
+        ns, nl, ms = C.c_int64(0), C.c_int32(0), C.c_float(0.0)
+        _lib.check(L.fdm_barrier_book_host(C.byref(bk), C.byref(out), C.byref(ns), C.byref(nl), C.byref(ms)))
+        if what == "solve":
+            res.pop("vega")
+        res = self._parity_legs(res)
+        res.update(node_steps=int(ns.value), n_solves=n * (3 if what == "greeks" else 1), kernel_ms=float(ms.value),
+                   n_launches=int(nl.value), h2d_bytes=n * (10 * 8 + 3 * 4) + int(bk.n_mon_total) * 4 + (n + 1) * 4,
+                   d2h_bytes=n * (5 * 8 + 4))
+        return res
+
+    def device_run(self, what: str = "greeks", dv_sigma: float = 1e-3, device=None, width: Optional[int] = None):
+        """The book resident in HBM: :class:`DeviceBookRun` (``fdm_barrier_book``); knock-out legs only."""
+        return DeviceBookRun(self, "barrier", what, dict(dv_sigma=dv_sigma), device, width)
 
     def price(self):
         return self.run("greeks")["price"]          # the reference's price() runs all three solves, :486-487
@@ -392,3 +538,109 @@ class BarrierBook:
     def greeks(self, dv_sigma: float = 1e-3):
         o = self.run("greeks", dv_sigma)
         return {k: o[k] for k in ("price", "delta", "gamma", "vega", "theta")}
+
+
+# --------------------------------------------------------------------------------------
+# Books resident in HBM
+# --------------------------------------------------------------------------------------
+
+class DeviceBookRun:
+    """A book whose per-option inputs, workspace and results live in HBM (torch tensors); ``launch`` queues fan-out,
+    solves and epilogue on a stream through the device-pointer entries ``fdm_american_book`` / ``fdm_barrier_book``
+    with no host copy and no synchronisation.
+
+    The results are views of ONE byte buffer ``packed`` (``width`` rows per column, ``width >= n``): six float64
+    columns ``price_log2, price, delta, gamma, vega, theta`` followed by three int32 columns ``ex_lo, ex_hi,
+    status`` -- the unit of the multi-GPU result gather (:func:`finite_difference_b200.shard.gather_packed`).
+    ``upload()`` refreshes the inputs from pinned host staging buffers (the H2D leg of an end-to-end step).
+    """
+
+    F64_COLS = ("price_log2", "price", "delta", "gamma", "vega", "theta")
+    I32_COLS = ("ex_lo", "ex_hi", "status")
+
+    def __init__(self, book, kind: str, what: str, opts: dict, device=None, width: Optional[int] = None):
+        import torch
+        from . import _lib
+        if not torch.cuda.is_available():
+            raise _lib.FdmError(-4, "no CUDA device; finite_difference_b200 has no CPU fallback")
+        self.torch, self.kind, self.book, self.what = torch, kind, book, what
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.n = n = book.n_opt
+        self.width = width = int(width) if width is not None else n
+        if width < n:
+            raise ValueError("width must be >= the number of options")
+        self._host, self._dev = {}, {}
+
+        def dev_ptr(name, arr):
+            h = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+            d = h.to(self.device, non_blocking=False)
+            self._host[name], self._dev[name] = h, d
+            return d.data_ptr()
+
+        L = _lib.load()
+        if kind == "american":
+            self._struct = book._book_struct(what, opts["dv_sigma"], opts["use_richardson"], dev_ptr)
+            need = L.fdm_american_book_workspace(n, int(self._struct.n_div_total), self._struct.what, self._struct.use_richardson)
+            self._entry = L.fdm_american_book
+            self.node_steps = book.solve_steps(what, opts["use_richardson"])
+            self.n_solves = n * int(L.fdm_book_solves_per_option(self._struct.what, self._struct.use_richardson))
+        else:
+            self._struct = book._book_struct(what, opts["dv_sigma"], dev_ptr)
+            need = L.fdm_barrier_book_workspace(n, self._struct.what)
+            self._entry = L.fdm_barrier_book
+            self.node_steps = book.solve_steps(what)
+            self.n_solves = n * int(L.fdm_barrier_book_solves_per_option(self._struct.what))
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self._host.values())
+        self.workspace = torch.empty(max(int(need), 256), dtype=torch.uint8, device=self.device)
+        self.row_bytes = 8 * len(self.F64_COLS) + 4 * len(self.I32_COLS)
+        self.packed = torch.zeros(width * self.row_bytes, dtype=torch.uint8, device=self.device)
+        self.cols = {}
+        self._out = _lib.FdmBookOut()
+        for j, name in enumerate(self.F64_COLS):
+            v = self.packed[j * width * 8:(j + 1) * width * 8].view(torch.float64)
+            self.cols[name] = v[:n]
+            setattr(self._out, name, v.data_ptr())
+        base = 8 * len(self.F64_COLS) * width
+        for j, name in enumerate(self.I32_COLS):
+            v = self.packed[base + j * width * 4: base + (j + 1) * width * 4].view(torch.int32)
+            self.cols[name] = v[:n]
+            setattr(self._out, name, v.data_ptr())
+        self.d2h_bytes = n * self.row_bytes
+        self.n_launches = 0
+
+    def upload(self, stream=None):
+        """H2D of every per-option input array from its pinned staging buffer (asynchronous on ``stream``)."""
+        torch = self.torch
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(st):
+            for name, h in self._host.items():
+                self._dev[name].copy_(h, non_blocking=True)
+
+    def launch(self, stream=None) -> int:
+        import ctypes as C
+        from . import _lib
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            st = stream if stream is not None else torch.cuda.current_stream(self.device)
+            nl = C.c_int32(0)
+            _lib.check(self._entry(C.byref(self._struct), C.byref(self._out), C.c_void_p(self.workspace.data_ptr()),
+                                   C.c_size_t(self.workspace.numel()), C.c_void_p(st.cuda_stream), C.byref(nl)))
+        self.n_launches = int(nl.value)
+        return self.n_launches
+
+    def results(self) -> Dict[str, np.ndarray]:
+        """Synchronise and copy the result columns to the host."""
+        self.torch.cuda.synchronize(self.device)
+        return {k: v.cpu().numpy() for k, v in self.cols.items()}
+
+
+def unpack_columns(buf: np.ndarray, width: int, n: int) -> Dict[str, np.ndarray]:
+    """Columns of one ``DeviceBookRun.packed`` byte buffer (host copy)."""
+    out = {}
+    nf = len(DeviceBookRun.F64_COLS)
+    for j, name in enumerate(DeviceBookRun.F64_COLS):
+        out[name] = buf[j * width * 8:(j + 1) * width * 8].view(np.float64)[:n]
+    base = 8 * nf * width
+    for j, name in enumerate(DeviceBookRun.I32_COLS):
+        out[name] = buf[base + j * width * 4: base + (j + 1) * width * 4].view(np.int32)[:n]
+    return out

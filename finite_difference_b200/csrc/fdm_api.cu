@@ -22,41 +22,54 @@ int fdm_fail(int code, const char *fmt, const char *detail)
     return code;
 }
 
+
 namespace {
 
 inline int fail(int code, const char *fmt, const char *detail = "") { return fdm_fail(code, fmt, detail); }
 
-// Device workspace of the host-buffer entry points: grow-only, one per process, reused across calls
-// (cudaMalloc/cudaFree cost milliseconds and synchronise the device).  Guarded by g_arena_mu; the host
-// entries are synchronous, so holding the lock for the whole call serialises them.
-std::mutex g_arena_mu;
-char *g_arena = nullptr;
-size_t g_arena_bytes = 0;
-int g_arena_dev = -1;
+// Device workspaces of the host-buffer entry points: grow-only, ONE PER DEVICE, reused across calls (cudaMalloc /
+// cudaFree cost milliseconds and synchronise the device).  Each has its own lock, held for the whole (synchronous)
+// call: host threads driving different devices run concurrently, threads sharing a device serialise.
+constexpr int MAX_DEVICES = 64;
+struct Arena {
+    std::mutex mu;
+    char *p = nullptr;
+    size_t bytes = 0;
+};
+Arena g_arenas[MAX_DEVICES];
 
-cudaError_t arena_get(size_t bytes, char **out)
+// caller holds a.mu and has `dev` current
+cudaError_t arena_get(Arena &a, size_t bytes, char **out)
 {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (g_arena && (dev != g_arena_dev || bytes > g_arena_bytes)) {
-        cudaFree(g_arena);
-        g_arena = nullptr;
-        g_arena_bytes = 0;
+    if (a.p && bytes > a.bytes) {
+        cudaFree(a.p);
+        a.p = nullptr;
+        a.bytes = 0;
     }
-    if (!g_arena) {
-        e = cudaMalloc((void **)&g_arena, bytes);
-        if (e != cudaSuccess) { g_arena = nullptr; return e; }
-        g_arena_bytes = bytes;
-        g_arena_dev = dev;
+    if (!a.p) {
+        const cudaError_t e = cudaMalloc((void **)&a.p, bytes);
+        if (e != cudaSuccess) { a.p = nullptr; return e; }
+        a.bytes = bytes;
     }
-    *out = g_arena;
+    *out = a.p;
     return cudaSuccess;
 }
 
-}  // namespace
+inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-namespace {
+// stream + two events of one host-entry call; on every exit path the stream is drained before it is destroyed, so
+// nothing queued on it can still touch the arena when the arena's lock is released
+struct CallCtx {
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~CallCtx()
+    {
+        if (st) cudaStreamSynchronize(st);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (st) cudaStreamDestroy(st);
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // FP64 pipe micro-benchmark
@@ -123,6 +136,7 @@ int lean_hint_bits(int n_space)
 }
 constexpr int LEAN_HINTS_VALID = 1 << 29;
 
+
 int validate(const FdmBatch *b, const FdmOut *o)
 {
     if (!b || !o) return fail(FDM_ERR_INVALID, "batch / out is NULL%s");
@@ -140,6 +154,27 @@ int validate(const FdmBatch *b, const FdmOut *o)
         return fail(FDM_ERR_INVALID, "monitor tables missing%s");
     return FDM_OK;
 }
+
+// what only a host copy of the arrays can tell (fdm_solve_batch_host): every kernel skips a solve outside the size
+// classes it was launched for, so a bad n_space would otherwise come back as an untouched result
+int validate_host_arrays(const FdmBatch *b)
+{
+    const int64_t n = b->n_solves;
+    for (int64_t i = 0; i < n; ++i) {
+        if (b->n_space[i] < 3 || b->n_space[i] > b->n_space_max)
+            return fail(FDM_ERR_INVALID, "n_space[i] outside [3, n_space_max]%s");
+        if (b->seg_begin[i + 1] <= b->seg_begin[i]) return fail(FDM_ERR_INVALID, "a solve has no time segment%s");
+    }
+    if (b->seg_begin[0] != 0 || b->seg_begin[n] > b->n_seg_total)
+        return fail(FDM_ERR_INVALID, "seg_begin does not match n_seg_total%s");
+    const int64_t nseg = b->seg_begin[n];
+    for (int64_t j = 0; j < nseg; ++j) {
+        if (b->seg_steps[j] < 1) return fail(FDM_ERR_INVALID, "seg_steps < 1%s");
+        if (!(b->seg_dt[j] > 0.0)) return fail(FDM_ERR_INVALID, "seg_dt must be positive%s");
+    }
+    return FDM_OK;
+}
+
 
 // flags of the whole call (FdmBatch.reserved): bit0 any american, bit1 any linear, bit2 any dividend,
 // bit3 any solve with n_space <= FDM_WARP_MAX_N_SPACE, bit4 any larger solve,
@@ -190,6 +225,127 @@ int launch(const FdmBatch &b, const FdmOut &o, cudaStream_t st, int family_mask,
 }
 
 }  // namespace
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// books: workspace layouts and the queued fan-out -> solves -> epilogue sequence
+// ---------------------------------------------------------------------------------------------
+
+struct SolveWs {                 // expanded descriptors and per-solve results of a book, offsets into the workspace
+    size_t d[7], ns, fl, rn, sb, st, dt, t0, rs, dv;          // FdmBatch arrays (x_min dx sigma r b spot strike ...)
+    size_t bar, reb, bup, mb, me;                             // barrier books only
+    size_t p, dl, g, idx, status;                             // FdmOut arrays
+    size_t total;
+};
+
+SolveWs solve_ws(int64_t m, int64_t nseg, bool barrier)
+{
+    SolveWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += up256(bytes); return o; };
+    for (int i = 0; i < 7; ++i) w.d[i] = take(m * 8);
+    w.ns = take(m * 4); w.fl = take(m * 4); w.rn = take(m * 4); w.sb = take((m + 1) * 4);
+    w.st = take(nseg * 4); w.dt = take(nseg * 8); w.t0 = take(nseg * 8); w.rs = take(nseg * 4); w.dv = take(nseg * 8);
+    w.bar = take(barrier ? m * 8 : 0); w.reb = take(barrier ? m * 8 : 0); w.bup = take(barrier ? m * 8 : 0);
+    w.mb = take(barrier ? m * 4 : 0); w.me = take(barrier ? m * 4 : 0);
+    w.p = take(m * 8); w.dl = take(m * 8); w.g = take(m * 8); w.idx = take(m * 16); w.status = take(m * 4);
+    w.total = off;
+    return w;
+}
+
+void bind_solve_ws(const SolveWs &w, char *ws, int64_t m, int64_t nseg, FdmBatch &sb, FdmOut &so)
+{
+    memset(&sb, 0, sizeof(sb));
+    memset(&so, 0, sizeof(so));
+    sb.n_solves = m; sb.n_seg_total = (int32_t)nseg;
+    sb.x_min = (const double *)(ws + w.d[0]); sb.dx = (const double *)(ws + w.d[1]);
+    sb.sigma = (const double *)(ws + w.d[2]); sb.r = (const double *)(ws + w.d[3]);
+    sb.b = (const double *)(ws + w.d[4]); sb.spot = (const double *)(ws + w.d[5]);
+    sb.strike = (const double *)(ws + w.d[6]);
+    sb.n_space = (const int32_t *)(ws + w.ns); sb.flags = (const int32_t *)(ws + w.fl);
+    sb.rannacher = (const int32_t *)(ws + w.rn); sb.seg_begin = (const int32_t *)(ws + w.sb);
+    sb.seg_steps = (const int32_t *)(ws + w.st); sb.seg_dt = (const double *)(ws + w.dt);
+    sb.seg_tau0 = (const double *)(ws + w.t0); sb.seg_restart = (const int32_t *)(ws + w.rs);
+    sb.seg_div = (const double *)(ws + w.dv);
+    so.price = (double *)(ws + w.p); so.delta = (double *)(ws + w.dl); so.gamma = (double *)(ws + w.g);
+    so.idx = (int32_t *)(ws + w.idx); so.status = (int32_t *)(ws + w.status);
+}
+
+// queue fan-out, solves and epilogue of an American book on `st`; db / dbo hold device pointers
+int american_book_queue(const FdmAmericanBook &db, const FdmBookOut &dbo, char *ws, cudaStream_t st, int mask,
+                        int n_space_max, const book::RoleTable &roles, int32_t *n_launches)
+{
+    const int64_t n = db.n_options, m = n * roles.n;
+    const int64_t ndiv = db.div_begin ? db.n_div_total : 0;
+    const int64_t nseg = (n + ndiv) * roles.n;
+    if (m + 1 > 0x7fffffff || nseg > 0x7fffffff) return fail(FDM_ERR_UNSUPPORTED, "book too large for 32-bit CSR tables%s");
+    const SolveWs w = solve_ws(m, nseg, false);
+    FdmBatch sb;
+    FdmOut so;
+    bind_solve_ws(w, ws, m, nseg, sb, so);
+    sb.n_space_max = n_space_max;
+    sb.reserved = mask;
+    FDM_CUDA(cudaMemsetAsync(ws + w.status, 0xff, m * 4, st));            // FDM_STATUS_NOT_SOLVED until a kernel takes it
+    const int threads = 256;
+    book::expand_kernel<<<(unsigned)((m + threads - 1) / threads), threads, 0, st>>>(db, sb, roles);
+    const int rc = launch(sb, so, st, mask, n_launches);
+    if (rc != FDM_OK) return rc;
+    book::combine_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(db, so, dbo, roles.n);
+    FDM_CUDA(cudaGetLastError());
+    if (n_launches) *n_launches += 2;
+    return FDM_OK;
+}
+
+int barrier_roles(int what) { return what == FDM_BARRIER_BOOK_GREEKS ? 3 : 1; }
+
+int barrier_book_queue(const FdmBarrierBook &db, const FdmBookOut &dbo, char *ws, cudaStream_t st, int mask,
+                       int n_space_max, int32_t *n_launches)
+{
+    const int n_roles = barrier_roles(db.what);
+    const int64_t n = db.n_options, m = n * n_roles;
+    if (m + 1 > 0x7fffffff) return fail(FDM_ERR_UNSUPPORTED, "book too large for 32-bit CSR tables%s");
+    const SolveWs w = solve_ws(m, m, true);
+    FdmBatch sb;
+    FdmOut so;
+    bind_solve_ws(w, ws, m, m, sb, so);
+    sb.n_space_max = n_space_max;
+    sb.reserved = mask;
+    sb.barrier = (const double *)(ws + w.bar);
+    sb.rebate = (const double *)(ws + w.reb);
+    sb.barrier_up = db.barrier_up ? (const double *)(ws + w.bup) : nullptr;
+    if (db.mon_begin && db.mon_step && db.n_mon_total > 0) {
+        sb.n_mon_total = (int32_t)db.n_mon_total;
+        sb.mon_begin = (const int32_t *)(ws + w.mb);
+        sb.mon_end = (const int32_t *)(ws + w.me);
+        sb.mon_step = db.mon_step;                                         // shared by the option's solves
+    }
+    FDM_CUDA(cudaMemsetAsync(ws + w.status, 0xff, m * 4, st));
+    const int threads = 256;
+    book::barrier_expand_kernel<<<(unsigned)((m + threads - 1) / threads), threads, 0, st>>>(db, sb, n_roles);
+    const int rc = launch(sb, so, st, mask, n_launches);
+    if (rc != FDM_OK) return rc;
+    book::barrier_combine_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(db, so, dbo, n_roles);
+    FDM_CUDA(cudaGetLastError());
+    if (n_launches) *n_launches += 2;
+    return FDM_OK;
+}
+
+int no_device()
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(FDM_ERR_NO_DEVICE, "no CUDA device; libfdm_b200 has no CPU fallback%s");
+    return FDM_OK;
+}
+
+#define FDM_TRY(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess && rc == FDM_OK)                                             \
+            rc = fail(FDM_ERR_CUDA, #call ": %s", cudaGetErrorString(e_));                 \
+    } while (0)
+
+}  // namespace
 
 extern "C" {
 
@@ -202,6 +358,7 @@ int fdm_sizeof(int which)
     case 1: return (int)sizeof(FdmOut);
     case 2: return (int)sizeof(FdmAmericanBook);
     case 3: return (int)sizeof(FdmBookOut);
+    case 4: return (int)sizeof(FdmBarrierBook);
     default: return -1;
     }
 }
@@ -225,11 +382,11 @@ int fdm_solve_batch(const FdmBatch *batch, const FdmOut *out, void *stream, int3
     if (n_launches) *n_launches = 0;
     int rc = validate(batch, out);
     if (rc != FDM_OK || batch->n_solves == 0) return rc;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-        return fail(FDM_ERR_NO_DEVICE, "no CUDA device; libfdm_b200 has no CPU fallback%s");
+    if ((rc = no_device()) != FDM_OK) return rc;
     int mask = batch->reserved;
     if ((mask & 3) == 0) mask |= 7;
+    // a solve that no launched kernel takes (n_space beyond n_space_max, hints that miss its class) stays visible
+    if (out->status) FDM_CUDA(cudaMemsetAsync(out->status, 0xff, batch->n_solves * 4, (cudaStream_t)stream));
     return launch(*batch, *out, (cudaStream_t)stream, mask, n_launches);
 }
 
@@ -240,9 +397,8 @@ int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launch
     if (kernel_ms) *kernel_ms = 0.f;
     int rc = validate(hb, ho);
     if (rc != FDM_OK || hb->n_solves == 0) return rc;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-        return fail(FDM_ERR_NO_DEVICE, "no CUDA device; libfdm_b200 has no CPU fallback%s");
+    if ((rc = validate_host_arrays(hb)) != FDM_OK) return rc;
+    if ((rc = no_device()) != FDM_OK) return rc;
 
     const int64_t n = hb->n_solves;
     const int64_t nseg = hb->seg_begin[n];
@@ -252,39 +408,36 @@ int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launch
     const int mask = fdm_launch_hints(hb->n_space, hb->flags, n, hb->seg_div, nseg);
 
     // one device arena for descriptors and results
-    auto up8 = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off += up8(bytes); return o; };
+    auto take = [&](size_t bytes) { size_t o = off; off += up256(bytes); return o; };
     const size_t o_d[9] = {take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8),
                            take(n * 8), take(has_ko ? n * 8 : 0), take(has_ko ? n * 8 : 0)};
     const size_t o_nspace = take(n * 4), o_flags = take(n * 4), o_ran = take(n * 4);
     const size_t o_segb = take((n + 1) * 4), o_monb = take(nmon ? (n + 1) * 4 : 0);
+    const size_t o_mone = take((nmon && hb->mon_end) ? n * 4 : 0);
     const size_t o_ssteps = take(nseg * 4), o_sdt = take(nseg * 8), o_stau = take(nseg * 8);
     const size_t o_srst = take(nseg * 4), o_sdiv = take(nseg * 8), o_mon = take(nmon * 4);
     const size_t o_bb = take(hb->b_bdry ? n * 8 : 0), o_bup = take(hb->barrier_up ? n * 8 : 0);
     const size_t o_mreb = take((hb->mon_rebate && nmon) ? nmon * 8 : 0);
-    const size_t in_bytes = off;
     const size_t r_price = take(n * 8), r_delta = take(n * 8), r_gamma = take(n * 8);
     const size_t r_sv = take(n * 32), r_ss = take(n * 32), r_idx = take(n * 16), r_status = take(n * 4);
     const size_t r_dump = take(ho->v_dump ? (size_t)n * ho->v_dump_stride * 8 : 0);
     const size_t r_trace = take(ho->ex_trace ? (size_t)n * ho->ex_trace_stride * 4 : 0);
-    (void)in_bytes;
 
-    std::lock_guard<std::mutex> arena_lock(g_arena_mu);
+    int dev = 0;
+    FDM_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) return fail(FDM_ERR_UNSUPPORTED, "device index beyond the workspace table%s");
+    Arena &ar = g_arenas[dev];
+    std::lock_guard<std::mutex> arena_lock(ar.mu);
     char *arena = nullptr;
-    FDM_CUDA(arena_get(off, &arena));
-    cudaStream_t st = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    FDM_CUDA(arena_get(ar, off, &arena));
+    CallCtx cx;                                      // destroyed (stream drained) before the lock is released
     rc = FDM_OK;
-#define FDM_TRY(call)                                                                      \
-    do {                                                                                   \
-        cudaError_t e_ = (call);                                                           \
-        if (e_ != cudaSuccess && rc == FDM_OK)                                             \
-            rc = fail(FDM_ERR_CUDA, #call ": %s", cudaGetErrorString(e_));                 \
-    } while (0)
-    FDM_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    FDM_TRY(cudaEventCreate(&e0));
-    FDM_TRY(cudaEventCreate(&e1));
+    FDM_TRY(cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking));
+    FDM_TRY(cudaEventCreate(&cx.e0));
+    FDM_TRY(cudaEventCreate(&cx.e1));
+    if (rc != FDM_OK) return rc;
+    cudaStream_t st = cx.st;
     auto h2d = [&](size_t o, const void *src, size_t bytes) {
         if (bytes && src) FDM_TRY(cudaMemcpyAsync(arena + o, src, bytes, cudaMemcpyHostToDevice, st));
     };
@@ -296,6 +449,7 @@ int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launch
     h2d(o_ran, hb->rannacher, n * 4);
     h2d(o_segb, hb->seg_begin, (n + 1) * 4);
     if (nmon) h2d(o_monb, hb->mon_begin, (n + 1) * 4);
+    if (nmon && hb->mon_end) h2d(o_mone, hb->mon_end, n * 4);
     h2d(o_ssteps, hb->seg_steps, nseg * 4);
     h2d(o_sdt, hb->seg_dt, nseg * 8);
     h2d(o_stau, hb->seg_tau0, nseg * 8);
@@ -321,6 +475,7 @@ int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launch
     db.rannacher = (const int32_t *)(arena + o_ran);
     db.seg_begin = (const int32_t *)(arena + o_segb);
     db.mon_begin = nmon ? (const int32_t *)(arena + o_monb) : nullptr;
+    db.mon_end = (nmon && hb->mon_end) ? (const int32_t *)(arena + o_mone) : nullptr;
     db.seg_steps = (const int32_t *)(arena + o_ssteps);
     db.seg_dt = (const double *)(arena + o_sdt);
     db.seg_tau0 = (const double *)(arena + o_stau);
@@ -343,12 +498,13 @@ int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launch
     dout.ex_trace = ho->ex_trace ? (int32_t *)(arena + r_trace) : nullptr;
     if (ho->ex_trace) FDM_TRY(cudaMemsetAsync(arena + r_trace, 0xff, (size_t)n * ho->ex_trace_stride * 4, st));
     if (ho->v_dump) FDM_TRY(cudaMemsetAsync(arena + r_dump, 0, (size_t)n * ho->v_dump_stride * 8, st));
+    FDM_TRY(cudaMemsetAsync(arena + r_status, 0xff, n * 4, st));          // FDM_STATUS_NOT_SOLVED
 
     if (rc == FDM_OK) {
-        FDM_TRY(cudaEventRecord(e0, st));
+        FDM_TRY(cudaEventRecord(cx.e0, st));
         int lrc = launch(db, dout, st, mask, n_launches);
         if (lrc != FDM_OK) rc = lrc;
-        FDM_TRY(cudaEventRecord(e1, st));
+        FDM_TRY(cudaEventRecord(cx.e1, st));
     }
     auto d2h = [&](void *dst, size_t o, size_t bytes) {
         if (dst && bytes) FDM_TRY(cudaMemcpyAsync(dst, arena + o, bytes, cudaMemcpyDeviceToHost, st));
@@ -364,12 +520,8 @@ int fdm_solve_batch_host(const FdmBatch *hb, const FdmOut *ho, int32_t *n_launch
         if (ho->v_dump) d2h(ho->v_dump, r_dump, (size_t)n * ho->v_dump_stride * 8);
         if (ho->ex_trace) d2h(ho->ex_trace, r_trace, (size_t)n * ho->ex_trace_stride * 4);
         FDM_TRY(cudaStreamSynchronize(st));
-        if (kernel_ms && rc == FDM_OK) FDM_TRY(cudaEventElapsedTime(kernel_ms, e0, e1));
+        if (kernel_ms && rc == FDM_OK) FDM_TRY(cudaEventElapsedTime(kernel_ms, cx.e0, cx.e1));
     }
-#undef FDM_TRY
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
-    if (st) cudaStreamDestroy(st);
     return rc;
 }
 
@@ -378,6 +530,44 @@ int fdm_book_solves_per_option(int32_t what, int32_t use_richardson)
     book::Role r[8];
     if (what < 0 || what > FDM_BOOK_SCENARIO) return fail(FDM_ERR_INVALID, "unknown book fan-out%s");
     return book::roles_of(what, use_richardson != 0, r);
+}
+
+size_t fdm_american_book_workspace(int64_t n_options, int64_t n_div_total, int32_t what, int32_t use_richardson)
+{
+    book::Role r[8];
+    if (n_options <= 0 || what < 0 || what > FDM_BOOK_SCENARIO) return 0;
+    const int nr = book::roles_of(what, use_richardson != 0, r);
+    if (n_div_total < 0) n_div_total = 0;
+    return solve_ws(n_options * nr, (n_options + n_div_total) * nr, false).total;
+}
+
+int fdm_american_book(const FdmAmericanBook *book_, const FdmBookOut *out, void *workspace, size_t workspace_bytes,
+                      void *stream, int32_t *n_launches)
+{
+    g_err[0] = 0;
+    if (n_launches) *n_launches = 0;
+    if (!book_ || !out) return fail(FDM_ERR_INVALID, "book / out is NULL%s");
+    const FdmAmericanBook &bk = *book_;
+    if (bk.n_options < 0) return fail(FDM_ERR_INVALID, "n_options < 0%s");
+    if (bk.what < 0 || bk.what > FDM_BOOK_SCENARIO) return fail(FDM_ERR_INVALID, "unknown book fan-out%s");
+    if (bk.n_options == 0) return FDM_OK;
+    if (!bk.spot || !bk.strike || !bk.T || !bk.sigma || !bk.r || !bk.b || !bk.flags || !bk.n_space || !bk.n_time ||
+        !bk.rannacher)
+        return fail(FDM_ERR_INVALID, "a required FdmAmericanBook array is NULL%s");
+    if (bk.div_begin && bk.n_div_total > 0 && (!bk.div_tau || !bk.div_cash))
+        return fail(FDM_ERR_INVALID, "dividend tables missing%s");
+    if (bk.n_space_max < 3) return fail(FDM_ERR_INVALID, "n_space_max must be set (>= 3) for the device entry%s");
+    if (bk.n_space_max > FDM_MAX_N_SPACE) return fail(FDM_ERR_UNSUPPORTED, "n_space exceeds FDM_MAX_N_SPACE (8193)%s");
+    const size_t need = fdm_american_book_workspace(bk.n_options, bk.div_begin ? bk.n_div_total : 0, bk.what, bk.use_richardson);
+    if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255))
+        return fail(FDM_ERR_INVALID, "workspace missing, misaligned or smaller than fdm_american_book_workspace()%s");
+    int rc = no_device();
+    if (rc != FDM_OK) return rc;
+    book::RoleTable roles;
+    roles.n = book::roles_of(bk.what, bk.use_richardson != 0, roles.r);
+    int mask = (bk.hints & ~6) | 1;                                  // American solves only
+    if (bk.div_begin && bk.n_div_total > 0) mask |= 4;
+    return american_book_queue(bk, *out, (char *)workspace, (cudaStream_t)stream, mask, bk.n_space_max, roles, n_launches);
 }
 
 int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int64_t *node_steps,
@@ -395,6 +585,8 @@ int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int6
     if (!hb->spot || !hb->strike || !hb->T || !hb->sigma || !hb->r || !hb->b || !hb->flags || !hb->n_space ||
         !hb->n_time || !hb->rannacher)
         return fail(FDM_ERR_INVALID, "a required FdmAmericanBook array is NULL%s");
+    const int64_t ndiv = hb->div_begin ? hb->div_begin[n] : 0;
+    if (ndiv > 0 && (!hb->div_tau || !hb->div_cash)) return fail(FDM_ERR_INVALID, "dividend tables missing%s");
     book::RoleTable roles;
     roles.n = book::roles_of(hb->what, hb->use_richardson != 0, roles.r);
     // host-side validation (the reference raises ValueError, fd_american_option_pricer.py:68-69, :123-124)
@@ -411,6 +603,20 @@ int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int6
             mask |= 8 | LEAN_HINTS_VALID | lean_hint_bits(ns);
             if (ns > small_max) small_max = ns;
         } else mask |= 16;
+        if (ndiv > 0) {
+            // dividends strictly inside (0, T), ascending, no two on the same tau: the reference's segment lengths
+            // must be positive (fd_american_option_pricer.py:498 divides by dt)
+            const int d0 = hb->div_begin[i], d1 = hb->div_begin[i + 1];
+            if (d1 < d0) return fail(FDM_ERR_INVALID, "div_begin must be ascending%s");
+            if (d1 > d0 && (hb->flags[i] & FDM_FLAG_BLACK76))
+                return fail(FDM_ERR_INVALID, "Black-76 options take no dividends (fd_american_black76.py:89)%s");
+            double prev = 0.0;
+            for (int d = d0; d < d1; ++d) {
+                if (!(hb->div_tau[d] > prev) || !(hb->div_tau[d] < hb->T[i]))
+                    return fail(FDM_ERR_INVALID, "zero-length time segment (dividend taus must be strictly ascending inside (0, T))%s");
+                prev = hb->div_tau[d];
+            }
+        }
         for (int k = 0; k < roles.n; ++k) {
             const double sg = hb->sigma[i] + roles.r[k].bump * hb->dv_sigma;
             if (!(sg > 0.0)) return fail(FDM_ERR_INVALID, "sigma (after bumps) must be positive%s");
@@ -421,49 +627,47 @@ int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int6
         }
     }
     mask |= small_max << 8;
+    if (ndiv > 0) mask |= 4;
     if (node_steps) *node_steps = ns_total;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-        return fail(FDM_ERR_NO_DEVICE, "no CUDA device; libfdm_b200 has no CPU fallback%s");
+    int rc = no_device();
+    if (rc != FDM_OK) return rc;
 
-    const int64_t m = n * roles.n;                   // solves
-    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off += up(bytes); return o; };
+    auto take = [&](size_t bytes) { size_t o = off; off += up256(bytes); return o; };
     // option inputs
     const size_t i_d[6] = {take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8)};
     const size_t i_fl = take(n * 4), i_ns = take(n * 4), i_nt = take(n * 4), i_rn = take(n * 4);
-    // expanded descriptors
-    const size_t s_d[7] = {take(m * 8), take(m * 8), take(m * 8), take(m * 8), take(m * 8), take(m * 8), take(m * 8)};
-    const size_t s_ns = take(m * 4), s_fl = take(m * 4), s_rn = take(m * 4), s_sb = take((m + 1) * 4);
-    const size_t s_st = take(m * 4), s_dt = take(m * 8), s_t0 = take(m * 8), s_rs = take(m * 4), s_dv = take(m * 8);
-    // per-solve results
-    const size_t r_p = take(m * 8), r_d = take(m * 8), r_g = take(m * 8), r_idx = take(m * 16), r_st = take(m * 4);
+    const size_t i_db = take(ndiv ? (n + 1) * 4 : 0), i_dt = take(ndiv * 8), i_dc = take(ndiv * 8);
     // per-option outputs
     const size_t o_d[6] = {take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8)};
     const size_t o_lo = take(n * 4), o_hi = take(n * 4), o_st = take(n * 4);
+    // expanded descriptors and per-solve results
+    const size_t o_ws = take(fdm_american_book_workspace(n, ndiv, hb->what, hb->use_richardson));
 
-    std::lock_guard<std::mutex> arena_lock(g_arena_mu);
+    int dev = 0;
+    FDM_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) return fail(FDM_ERR_UNSUPPORTED, "device index beyond the workspace table%s");
+    Arena &ar = g_arenas[dev];
+    std::lock_guard<std::mutex> arena_lock(ar.mu);
     char *arena = nullptr;
-    FDM_CUDA(arena_get(off, &arena));
-    cudaStream_t st = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    int rc = FDM_OK;
-#define FDM_TRY(call)                                                                      \
-    do {                                                                                   \
-        cudaError_t e_ = (call);                                                           \
-        if (e_ != cudaSuccess && rc == FDM_OK)                                             \
-            rc = fail(FDM_ERR_CUDA, #call ": %s", cudaGetErrorString(e_));                 \
-    } while (0)
-    FDM_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    FDM_TRY(cudaEventCreate(&e0));
-    FDM_TRY(cudaEventCreate(&e1));
+    FDM_CUDA(arena_get(ar, off, &arena));
+    CallCtx cx;
+    FDM_TRY(cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking));
+    FDM_TRY(cudaEventCreate(&cx.e0));
+    FDM_TRY(cudaEventCreate(&cx.e1));
+    if (rc != FDM_OK) return rc;
+    cudaStream_t st = cx.st;
     const double *hd[6] = {hb->spot, hb->strike, hb->T, hb->sigma, hb->r, hb->b};
     for (int i = 0; i < 6; ++i) FDM_TRY(cudaMemcpyAsync(arena + i_d[i], hd[i], n * 8, cudaMemcpyHostToDevice, st));
     FDM_TRY(cudaMemcpyAsync(arena + i_fl, hb->flags, n * 4, cudaMemcpyHostToDevice, st));
     FDM_TRY(cudaMemcpyAsync(arena + i_ns, hb->n_space, n * 4, cudaMemcpyHostToDevice, st));
     FDM_TRY(cudaMemcpyAsync(arena + i_nt, hb->n_time, n * 4, cudaMemcpyHostToDevice, st));
     FDM_TRY(cudaMemcpyAsync(arena + i_rn, hb->rannacher, n * 4, cudaMemcpyHostToDevice, st));
+    if (ndiv) {
+        FDM_TRY(cudaMemcpyAsync(arena + i_db, hb->div_begin, (n + 1) * 4, cudaMemcpyHostToDevice, st));
+        FDM_TRY(cudaMemcpyAsync(arena + i_dt, hb->div_tau, ndiv * 8, cudaMemcpyHostToDevice, st));
+        FDM_TRY(cudaMemcpyAsync(arena + i_dc, hb->div_cash, ndiv * 8, cudaMemcpyHostToDevice, st));
+    }
 
     FdmAmericanBook db = *hb;
     db.spot = (const double *)(arena + i_d[0]); db.strike = (const double *)(arena + i_d[1]);
@@ -471,24 +675,10 @@ int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int6
     db.r = (const double *)(arena + i_d[4]); db.b = (const double *)(arena + i_d[5]);
     db.flags = (const int32_t *)(arena + i_fl); db.n_space = (const int32_t *)(arena + i_ns);
     db.n_time = (const int32_t *)(arena + i_nt); db.rannacher = (const int32_t *)(arena + i_rn);
-
-    FdmBatch sb;
-    memset(&sb, 0, sizeof(sb));
-    sb.n_solves = m; sb.n_space_max = n_space_max; sb.n_seg_total = (int32_t)m; sb.reserved = mask;
-    sb.x_min = (const double *)(arena + s_d[0]); sb.dx = (const double *)(arena + s_d[1]);
-    sb.sigma = (const double *)(arena + s_d[2]); sb.r = (const double *)(arena + s_d[3]);
-    sb.b = (const double *)(arena + s_d[4]); sb.spot = (const double *)(arena + s_d[5]);
-    sb.strike = (const double *)(arena + s_d[6]);
-    sb.n_space = (const int32_t *)(arena + s_ns); sb.flags = (const int32_t *)(arena + s_fl);
-    sb.rannacher = (const int32_t *)(arena + s_rn); sb.seg_begin = (const int32_t *)(arena + s_sb);
-    sb.seg_steps = (const int32_t *)(arena + s_st); sb.seg_dt = (const double *)(arena + s_dt);
-    sb.seg_tau0 = (const double *)(arena + s_t0); sb.seg_restart = (const int32_t *)(arena + s_rs);
-    sb.seg_div = (const double *)(arena + s_dv);
-
-    FdmOut so;
-    memset(&so, 0, sizeof(so));
-    so.price = (double *)(arena + r_p); so.delta = (double *)(arena + r_d); so.gamma = (double *)(arena + r_g);
-    so.idx = (int32_t *)(arena + r_idx); so.status = (int32_t *)(arena + r_st);
+    db.div_begin = ndiv ? (const int32_t *)(arena + i_db) : nullptr;
+    db.div_tau = ndiv ? (const double *)(arena + i_dt) : nullptr;
+    db.div_cash = ndiv ? (const double *)(arena + i_dc) : nullptr;
+    db.n_div_total = ndiv;
 
     FdmBookOut dbo;
     dbo.price_log2 = (double *)(arena + o_d[0]); dbo.price = (double *)(arena + o_d[1]);
@@ -497,16 +687,11 @@ int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int6
     dbo.ex_lo = (int32_t *)(arena + o_lo); dbo.ex_hi = (int32_t *)(arena + o_hi); dbo.status = (int32_t *)(arena + o_st);
 
     if (rc == FDM_OK) {
-        FDM_TRY(cudaMemsetAsync(arena + o_d[0], 0, o_st + up(n * 4) - o_d[0], st));
-        FDM_TRY(cudaEventRecord(e0, st));
-        const int threads = 256;
-        book::expand_kernel<<<(unsigned)((m + threads - 1) / threads), threads, 0, st>>>(db, sb, roles);
-        int lrc = launch(sb, so, st, mask, n_launches);
+        FDM_TRY(cudaMemsetAsync(arena + o_d[0], 0, o_st + up256(n * 4) - o_d[0], st));
+        FDM_TRY(cudaEventRecord(cx.e0, st));
+        const int lrc = american_book_queue(db, dbo, arena + o_ws, st, mask, n_space_max, roles, n_launches);
         if (lrc != FDM_OK) rc = lrc;
-        book::combine_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(db, so, dbo, roles.n);
-        FDM_TRY(cudaGetLastError());
-        if (n_launches) *n_launches += 2;
-        FDM_TRY(cudaEventRecord(e1, st));
+        FDM_TRY(cudaEventRecord(cx.e1, st));
     }
     auto d2h = [&](void *dst, size_t o, size_t bytes) {
         if (dst && bytes) FDM_TRY(cudaMemcpyAsync(dst, arena + o, bytes, cudaMemcpyDeviceToHost, st));
@@ -516,12 +701,156 @@ int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int6
         d2h(ho->gamma, o_d[3], n * 8); d2h(ho->vega, o_d[4], n * 8); d2h(ho->theta, o_d[5], n * 8);
         d2h(ho->ex_lo, o_lo, n * 4); d2h(ho->ex_hi, o_hi, n * 4); d2h(ho->status, o_st, n * 4);
         FDM_TRY(cudaStreamSynchronize(st));
-        if (kernel_ms && rc == FDM_OK) FDM_TRY(cudaEventElapsedTime(kernel_ms, e0, e1));
+        if (kernel_ms && rc == FDM_OK) FDM_TRY(cudaEventElapsedTime(kernel_ms, cx.e0, cx.e1));
     }
-#undef FDM_TRY
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
-    if (st) cudaStreamDestroy(st);
+    return rc;
+}
+
+int fdm_barrier_book_solves_per_option(int32_t what)
+{
+    if (what != FDM_BARRIER_BOOK_SOLVE && what != FDM_BARRIER_BOOK_GREEKS) return fail(FDM_ERR_INVALID, "unknown barrier book fan-out%s");
+    return barrier_roles(what);
+}
+
+size_t fdm_barrier_book_workspace(int64_t n_options, int32_t what)
+{
+    if (n_options <= 0 || (what != FDM_BARRIER_BOOK_SOLVE && what != FDM_BARRIER_BOOK_GREEKS)) return 0;
+    const int64_t m = n_options * barrier_roles(what);
+    return solve_ws(m, m, true).total;
+}
+
+static int barrier_book_check(const FdmBarrierBook &bk)
+{
+    if (bk.n_options < 0) return fail(FDM_ERR_INVALID, "n_options < 0%s");
+    if (bk.what != FDM_BARRIER_BOOK_SOLVE && bk.what != FDM_BARRIER_BOOK_GREEKS)
+        return fail(FDM_ERR_INVALID, "unknown barrier book fan-out%s");
+    if (bk.n_options == 0) return FDM_OK;
+    if (!bk.S0 || !bk.K || !bk.T || !bk.sigma || !bk.r_disc || !bk.b_carry || !bk.x_min || !bk.dx || !bk.barrier ||
+        !bk.rebate || !bk.flags || !bk.n_space || !bk.n_time)
+        return fail(FDM_ERR_INVALID, "a required FdmBarrierBook array is NULL%s");
+    if (bk.n_mon_total > 0 && (!bk.mon_begin || !bk.mon_step)) return fail(FDM_ERR_INVALID, "monitor tables missing%s");
+    return FDM_OK;
+}
+
+int fdm_barrier_book(const FdmBarrierBook *book_, const FdmBookOut *out, void *workspace, size_t workspace_bytes,
+                     void *stream, int32_t *n_launches)
+{
+    g_err[0] = 0;
+    if (n_launches) *n_launches = 0;
+    if (!book_ || !out) return fail(FDM_ERR_INVALID, "book / out is NULL%s");
+    const FdmBarrierBook &bk = *book_;
+    int rc = barrier_book_check(bk);
+    if (rc != FDM_OK || bk.n_options == 0) return rc;
+    if (bk.n_space_max < 3) return fail(FDM_ERR_INVALID, "n_space_max must be set (>= 3) for the device entry%s");
+    if (bk.n_space_max > FDM_MAX_N_SPACE) return fail(FDM_ERR_UNSUPPORTED, "n_space exceeds FDM_MAX_N_SPACE (8193)%s");
+    const size_t need = fdm_barrier_book_workspace(bk.n_options, bk.what);
+    if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255))
+        return fail(FDM_ERR_INVALID, "workspace missing, misaligned or smaller than fdm_barrier_book_workspace()%s");
+    if ((rc = no_device()) != FDM_OK) return rc;
+    const int mask = (bk.hints & ~7) | 2;                            // linear solves, no dividends
+    return barrier_book_queue(bk, *out, (char *)workspace, (cudaStream_t)stream, mask, bk.n_space_max, n_launches);
+}
+
+int fdm_barrier_book_host(const FdmBarrierBook *hb, const FdmBookOut *ho, int64_t *node_steps, int32_t *n_launches,
+                          float *kernel_ms)
+{
+    g_err[0] = 0;
+    if (n_launches) *n_launches = 0;
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (node_steps) *node_steps = 0;
+    if (!hb || !ho) return fail(FDM_ERR_INVALID, "book / out is NULL%s");
+    int rc = barrier_book_check(*hb);
+    const int64_t n = hb->n_options;
+    if (rc != FDM_OK || n == 0) return rc;
+    const int n_roles = barrier_roles(hb->what);
+    int n_space_max = 3, small_max = 0, mask = 2;
+    int64_t ns_total = 0;
+    const int64_t nmon = (hb->mon_begin && hb->n_mon_total > 0) ? hb->mon_begin[n] : 0;
+    for (int64_t i = 0; i < n; ++i) {
+        // discrete_barrier_fdm_pricer_cn.py:61-66
+        if (!(hb->T[i] > 0.0)) return fail(FDM_ERR_INVALID, "T must be positive%s");
+        if (!(hb->sigma[i] - hb->dv_sigma * (n_roles > 1 ? 1.0 : 0.0) > 0.0)) return fail(FDM_ERR_INVALID, "sigma must be positive%s");
+        if (!(hb->S0[i] > 0.0)) return fail(FDM_ERR_INVALID, "S0 must be positive%s");
+        const int ns = hb->n_space[i];
+        if (ns < 3 || hb->n_time[i] < 1) return fail(FDM_ERR_INVALID, "N_space must be >= 3 and N_time >= 1%s");
+        if (ns > FDM_MAX_N_SPACE) return fail(FDM_ERR_UNSUPPORTED, "n_space exceeds FDM_MAX_N_SPACE (8193)%s");
+        if (ns > n_space_max) n_space_max = ns;
+        if (ns <= FDM_WARP_MAX_N_SPACE) {
+            mask |= 8 | LEAN_HINTS_VALID | lean_hint_bits(ns);
+            if (ns > small_max) small_max = ns;
+        } else mask |= 16;
+        if (nmon && hb->mon_begin[i + 1] < hb->mon_begin[i]) return fail(FDM_ERR_INVALID, "mon_begin must be ascending%s");
+        ns_total += (int64_t)ns * hb->n_time[i] * n_roles;
+    }
+    mask |= small_max << 8;
+    if (node_steps) *node_steps = ns_total;
+    if ((rc = no_device()) != FDM_OK) return rc;
+
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += up256(bytes); return o; };
+    const int ND = 11;
+    const double *hd[ND] = {hb->S0, hb->K, hb->T, hb->sigma, hb->r_disc, hb->b_carry, hb->x_min, hb->dx, hb->barrier,
+                            hb->rebate, hb->barrier_up};
+    size_t i_d[ND];
+    for (int i = 0; i < ND; ++i) i_d[i] = take(hd[i] ? n * 8 : 0);
+    const size_t i_fl = take(n * 4), i_ns = take(n * 4), i_nt = take(n * 4);
+    const size_t i_mb = take(nmon ? (n + 1) * 4 : 0), i_ms = take(nmon * 4);
+    const size_t o_d[5] = {take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8)};
+    const size_t o_st = take(n * 4);
+    const size_t o_ws = take(fdm_barrier_book_workspace(n, hb->what));
+
+    int dev = 0;
+    FDM_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) return fail(FDM_ERR_UNSUPPORTED, "device index beyond the workspace table%s");
+    Arena &ar = g_arenas[dev];
+    std::lock_guard<std::mutex> arena_lock(ar.mu);
+    char *arena = nullptr;
+    FDM_CUDA(arena_get(ar, off, &arena));
+    CallCtx cx;
+    FDM_TRY(cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking));
+    FDM_TRY(cudaEventCreate(&cx.e0));
+    FDM_TRY(cudaEventCreate(&cx.e1));
+    if (rc != FDM_OK) return rc;
+    cudaStream_t st = cx.st;
+    for (int i = 0; i < ND; ++i)
+        if (hd[i]) FDM_TRY(cudaMemcpyAsync(arena + i_d[i], hd[i], n * 8, cudaMemcpyHostToDevice, st));
+    FDM_TRY(cudaMemcpyAsync(arena + i_fl, hb->flags, n * 4, cudaMemcpyHostToDevice, st));
+    FDM_TRY(cudaMemcpyAsync(arena + i_ns, hb->n_space, n * 4, cudaMemcpyHostToDevice, st));
+    FDM_TRY(cudaMemcpyAsync(arena + i_nt, hb->n_time, n * 4, cudaMemcpyHostToDevice, st));
+    if (nmon) {
+        FDM_TRY(cudaMemcpyAsync(arena + i_mb, hb->mon_begin, (n + 1) * 4, cudaMemcpyHostToDevice, st));
+        FDM_TRY(cudaMemcpyAsync(arena + i_ms, hb->mon_step, nmon * 4, cudaMemcpyHostToDevice, st));
+    }
+    FdmBarrierBook db = *hb;
+    const double **dp[ND] = {&db.S0, &db.K, &db.T, &db.sigma, &db.r_disc, &db.b_carry, &db.x_min, &db.dx, &db.barrier,
+                             &db.rebate, &db.barrier_up};
+    for (int i = 0; i < ND; ++i) *dp[i] = hd[i] ? (const double *)(arena + i_d[i]) : nullptr;
+    db.flags = (const int32_t *)(arena + i_fl); db.n_space = (const int32_t *)(arena + i_ns);
+    db.n_time = (const int32_t *)(arena + i_nt);
+    db.mon_begin = nmon ? (const int32_t *)(arena + i_mb) : nullptr;
+    db.mon_step = nmon ? (const int32_t *)(arena + i_ms) : nullptr;
+    db.n_mon_total = nmon;
+
+    FdmBookOut dbo;
+    memset(&dbo, 0, sizeof(dbo));
+    dbo.price = (double *)(arena + o_d[0]); dbo.delta = (double *)(arena + o_d[1]); dbo.gamma = (double *)(arena + o_d[2]);
+    dbo.vega = (double *)(arena + o_d[3]); dbo.theta = (double *)(arena + o_d[4]); dbo.status = (int32_t *)(arena + o_st);
+
+    if (rc == FDM_OK) {
+        FDM_TRY(cudaEventRecord(cx.e0, st));
+        const int lrc = barrier_book_queue(db, dbo, arena + o_ws, st, mask, n_space_max, n_launches);
+        if (lrc != FDM_OK) rc = lrc;
+        FDM_TRY(cudaEventRecord(cx.e1, st));
+    }
+    auto d2h = [&](void *dst, size_t o, size_t bytes) {
+        if (dst && bytes) FDM_TRY(cudaMemcpyAsync(dst, arena + o, bytes, cudaMemcpyDeviceToHost, st));
+    };
+    if (rc == FDM_OK) {
+        d2h(ho->price, o_d[0], n * 8); d2h(ho->delta, o_d[1], n * 8); d2h(ho->gamma, o_d[2], n * 8);
+        d2h(ho->vega, o_d[3], n * 8); d2h(ho->theta, o_d[4], n * 8); d2h(ho->status, o_st, n * 4);
+        FDM_TRY(cudaStreamSynchronize(st));
+        if (kernel_ms && rc == FDM_OK) FDM_TRY(cudaEventElapsedTime(kernel_ms, cx.e0, cx.e1));
+    }
     return rc;
 }
 
@@ -550,11 +879,19 @@ int fdm_launch_hints(const int32_t *n_space, const int32_t *flags, int64_t n_sol
 
 int fdm_release_workspace(void)
 {
-    std::lock_guard<std::mutex> arena_lock(g_arena_mu);
-    if (g_arena) cudaFree(g_arena);
-    g_arena = nullptr;
-    g_arena_bytes = 0;
-    g_arena_dev = -1;
+    int cur = 0;
+    const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
+    for (int d = 0; d < MAX_DEVICES; ++d) {
+        Arena &a = g_arenas[d];
+        std::lock_guard<std::mutex> arena_lock(a.mu);
+        if (a.p) {
+            cudaSetDevice(d);
+            cudaFree(a.p);
+        }
+        a.p = nullptr;
+        a.bytes = 0;
+    }
+    if (have_cur) cudaSetDevice(cur);
     return FDM_OK;
 }
 

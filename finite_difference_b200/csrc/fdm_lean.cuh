@@ -434,6 +434,7 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
     if (sid >= B.n_solves) return;
     const int flags = B.flags[sid];
     if (((flags & FDM_FLAG_AMERICAN) != 0) != (want_american != 0)) return;
+    if (flags & FDM_FLAG_INVALID) return;                       // rejected by the book fan-out: status stays -1
     const int lane = threadIdx.x;
     const int n = B.n_space[sid];
     const int n_int = n - 1;
@@ -506,7 +507,7 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
 
     const int seg_b = B.seg_begin[sid], seg_e = B.seg_begin[sid + 1];
     int mon_i = 0, mon_e = 0;
-    if (ko && B.mon_begin) { mon_i = B.mon_begin[sid]; mon_e = B.mon_begin[sid + 1]; }
+    if (ko && B.mon_begin) { mon_i = B.mon_begin[sid]; mon_e = B.mon_end ? B.mon_end[sid] : B.mon_begin[sid + 1]; }
     int next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
     int gstep = 0;
     int32_t *trace = (TRACE && O.ex_trace) ? O.ex_trace + sid * O.ex_trace_stride : nullptr;

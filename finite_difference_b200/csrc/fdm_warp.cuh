@@ -282,6 +282,7 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
     const int flags = B.flags[sid];
     // each launch handles one family (American / linear); the other family's solves are skipped
     if (((flags & FDM_FLAG_AMERICAN) != 0) != (want_american != 0)) return;
+    if (flags & FDM_FLAG_INVALID) return;                       // rejected by the book fan-out: status stays -1
 
     const int lane = threadIdx.x;
     const int n = B.n_space[sid];
@@ -352,7 +353,7 @@ fdm_warp_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
     // ---- time march ---------------------------------------------------------------------------
     const int seg_b = B.seg_begin[sid], seg_e = B.seg_begin[sid + 1];
     int mon_i = 0, mon_e = 0;
-    if (ko && B.mon_begin) { mon_i = B.mon_begin[sid]; mon_e = B.mon_begin[sid + 1]; }
+    if (ko && B.mon_begin) { mon_i = B.mon_begin[sid]; mon_e = B.mon_end ? B.mon_end[sid] : B.mon_begin[sid + 1]; }
     int next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
     int gstep = 0;                                              // steps marched so far (all segments)
 #ifdef FDM_PROFILE_CYCLES

@@ -17,7 +17,8 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-__all__ = ["rank_world", "partition", "my_options", "gather_results", "init_distributed"]
+__all__ = ["rank_world", "partition", "my_options", "gather_results", "init_distributed", "PackedGather",
+           "ShardedBookRun"]
 
 
 def rank_world() -> tuple:
@@ -145,3 +146,124 @@ def gather_results(local: Dict[str, "np.ndarray"], owned: np.ndarray, n_total: i
                 out[k] = full_group[:, off: off + w].reshape((n_total,) + v.shape[1:])
             off += w
     return out
+
+
+class PackedGather:
+    """The final result gather of a sharded sweep, on the device.
+
+    Every rank holds its shard's results as one byte buffer of ``width`` rows per column (``n_f64`` float64 columns
+    followed by ``n_i32`` int32 columns: ``book.DeviceBookRun.packed``).  One collective (``dist.gather`` onto
+    ``dst``, or ``all_gather_into_tensor`` with ``dst=None``) moves the buffers; the receiving rank puts the rows into
+    book order with one ``index_select`` per dtype ON THE DEVICE and copies the two blocks to pinned host memory
+    (two D2H copies).  No host-side packing, no per-row scatter.
+
+    ``owned``: this rank's ascending global option indices (``shard.partition``); the owners are exchanged once here.
+    """
+
+    def __init__(self, owned: np.ndarray, n_total: int, width: int, n_f64: int = 6, n_i32: int = 3, device=None,
+                 dst: Optional[int] = 0):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.dst, self.n_total, self.width, self.n_f64, self.n_i32 = dst, int(n_total), int(width), n_f64, n_i32
+        if device is None:
+            device = (torch.device("cuda", torch.cuda.current_device())
+                      if (dist.is_initialized() and dist.get_backend() == "nccl") else torch.device("cpu"))
+        self.device = torch.device(device)
+        self.row_bytes = 8 * n_f64 + 4 * n_i32
+        owned = np.asarray(owned, dtype=np.int64)
+        if len(owned) > width:
+            raise ValueError("width must hold the largest shard")
+        if width % 2:
+            raise ValueError("width must be even (the int32 columns follow the float64 columns in one buffer)")
+        idx = torch.full((width,), -1, dtype=torch.int64, device=self.device)
+        idx[: len(owned)] = torch.from_numpy(owned).to(self.device)
+        if self.world > 1:
+            all_idx = torch.empty((self.world * width,), dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(all_idx, idx)
+        else:
+            all_idx = idx
+        self.receives = dst is None or self.rank == dst
+        self.collective = "none" if self.world == 1 else ("all_gather_into_tensor" if dst is None else f"gather(dst={dst})")
+        if self.receives:
+            all_idx_h = all_idx.cpu().numpy()
+            pos = np.nonzero(all_idx_h >= 0)[0]
+            perm = np.empty(self.n_total, dtype=np.int64)
+            perm[all_idx_h[pos]] = pos                     # book index -> row of the gathered layout
+            self.perm = torch.from_numpy(perm).to(self.device)
+            self.buf = torch.empty((self.world, width * self.row_bytes), dtype=torch.uint8, device=self.device)
+            pin = self.device.type == "cuda"
+            self.host_f64 = torch.empty((n_f64, self.n_total), dtype=torch.float64, pin_memory=pin)
+            self.host_i32 = torch.empty((n_i32, self.n_total), dtype=torch.int32, pin_memory=pin)
+            self.d2h_bytes = self.host_f64.numel() * 8 + self.host_i32.numel() * 4
+
+    def exchange(self, packed):
+        """The collective and the reordering alone: returns ``(f64 [n_f64, n_total], i32 [n_i32, n_total])`` DEVICE
+        tensors in book order on the receiving rank(s), ``None`` elsewhere.  Asynchronous on the current stream."""
+        torch, dist = self.torch, self.dist
+        w = self.width
+        if self.world > 1:
+            if self.dst is None:
+                dist.all_gather_into_tensor(self.buf.view(-1), packed)
+            else:
+                dist.gather(packed, list(self.buf.unbind(0)) if self.receives else None, dst=self.dst)
+        elif self.receives:
+            self.buf[0].copy_(packed)
+        if not self.receives:
+            return None
+        nf, ni = self.n_f64, self.n_i32
+        f = self.buf[:, : 8 * nf * w].view(torch.float64).view(self.world, nf, w).permute(1, 0, 2).reshape(nf, self.world * w)
+        i = self.buf[:, 8 * nf * w:].view(torch.int32).view(self.world, ni, w).permute(1, 0, 2).reshape(ni, self.world * w)
+        return torch.index_select(f, 1, self.perm), torch.index_select(i, 1, self.perm)
+
+    def __call__(self, packed, sync: bool = True):
+        """``packed``: uint8 tensor of ``width * row_bytes`` bytes on ``self.device``.  Returns ``(f64 [n_f64, n_total],
+        i32 [n_i32, n_total])`` numpy views of the pinned host blocks on the receiving rank(s), ``None`` elsewhere."""
+        got = self.exchange(packed)
+        if got is None:
+            return None
+        self.host_f64.copy_(got[0], non_blocking=True)
+        self.host_i32.copy_(got[1], non_blocking=True)
+        if sync and self.device.type == "cuda":
+            self.torch.cuda.current_stream(self.device).synchronize()
+        return self.host_f64.numpy(), self.host_i32.numpy()
+
+
+class ShardedBookRun:
+    """One rank's part of a sweep sharded by option over the GPUs of one box -- the multi-GPU form of
+    ``AmericanBook.run_fused`` / ``BarrierBook.run_fused``.  ``step()`` = H2D of this shard's per-option inputs from
+    pinned host memory, fan-out + solves + epilogue on the device (``DeviceBookRun``), one result collective, and on
+    the receiving rank the D2H of the whole book's results in book order.  No communication during the solve
+    (the reference is the serial loop at run_american_scenarios.py:239).
+    """
+
+    def __init__(self, book_shard, owned: np.ndarray, n_total: int, what: str = "scenario", dst: Optional[int] = 0,
+                 device=None, **opts):
+        from .book import DeviceBookRun
+        world = rank_world()[1]
+        width = self.shard_width(n_total, world)
+        self.run = book_shard.device_run(what, device=device, width=width, **opts)
+        self.gather = PackedGather(owned, n_total, width, len(DeviceBookRun.F64_COLS), len(DeviceBookRun.I32_COLS),
+                                   device=self.run.device, dst=dst)
+        self.n_total = int(n_total)
+
+    @staticmethod
+    def shard_width(n_total: int, world: int) -> int:
+        """Rows per column of every rank's packed result buffer: the largest shard, rounded up to an even count."""
+        w = -(-int(n_total) // max(world, 1))
+        return w + (w & 1)
+
+    def step(self, upload: bool = True):
+        from .book import DeviceBookRun
+        if upload:
+            self.run.upload()
+        self.run.launch()
+        got = self.gather(self.run.packed)
+        if got is None:
+            return None
+        f64, i32 = got
+        out = {k: f64[j] for j, k in enumerate(DeviceBookRun.F64_COLS)}
+        out.update({k: i32[j] for j, k in enumerate(DeviceBookRun.I32_COLS)})
+        return out

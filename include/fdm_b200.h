@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FDM_ABI_VERSION 2
+#define FDM_ABI_VERSION 3
 
 /* error codes */
 #define FDM_OK                0
@@ -59,6 +59,18 @@ extern "C" {
    s_nodes[-1], one node ABOVE the kernel grid. */
 #define FDM_FLAG_BDRY_TOP_NEXT 0x40  /* top Dirichlet value uses S = exp(x_min + (n_space+1) dx), :378 with :540 */
 #define FDM_FLAG_PUT_BDRY_SMIN 0x80  /* put: V_min = K e^{-r tau} * S_min * e^{(b-r) tau}, discrete_barrier_fdm_pricer.py:391 */
+#define FDM_FLAG_INVALID 0x100       /* set by the book fan-out on a solve whose inputs the reference rejects (a zero-length
+                                        dividend segment divides by zero at fd_american_option_pricer.py:498; non-positive
+                                        spot / strike / sigma / T raise at :68-69, :123-124): no kernel touches it, its status
+                                        stays FDM_STATUS_NOT_SOLVED */
+
+/* per-solve status (FdmOut.status, FdmBookOut.status) */
+#define FDM_STATUS_OK           0
+#define FDM_STATUS_NONFINITE    1   /* price is not finite */
+#define FDM_STATUS_STIFF        2   /* CTA kernel: pivots not converged inside its table (best effort result) */
+#define FDM_STATUS_NOT_SOLVED  -1   /* no kernel took the solve: n_space outside [3, n_space_max], launch hints that miss
+                                       its size class, or FDM_FLAG_INVALID.  status[] is filled with this value before
+                                       the launches, so a skipped solve is always visible */
 
 /* largest num_space_nodes any compiled kernel variant handles (one CTA per solve above
    FDM_WARP_MAX_N_SPACE, one warp per solve up to it) */
@@ -110,6 +122,9 @@ typedef struct FdmBatch {
     const double *barrier_up;  /* upper KO level of a double-out solve (KO_DOWN | KO_UP) */
     const double *mon_rebate;  /* [n_mon_total] value written at knocked-out nodes at each monitor step, e.g.
                                   rebate * exp(-b tau) (discrete_barrier_fdm_pricer.py:421-424); NULL: rebate[] */
+    /* ABI 3 (optional) */
+    const int32_t *mon_end;    /* [n_solves] end of each solve's monitor range; NULL: mon_begin[i+1].  Lets several solves
+                                  (the sigma bumps of one option) share one monitor table */
 } FdmBatch;
 
 /*
@@ -125,7 +140,7 @@ typedef struct FdmOut {
     int32_t *idx;       /* [4*n_solves]: {spot node (SNAP) or lower bracket node, strike node (SNAP) or
                            stencil centre node, ex_lo, ex_hi}.  ex_lo/ex_hi: first/last interior index k
                            (node k+1) in the exercise set after the last step, -1 if empty / not American */
-    int32_t *status;    /* 0 ok, 1 non-finite price */
+    int32_t *status;    /* FDM_STATUS_* */
     double *v_dump;     /* optional: full value vector, v_dump_stride doubles per solve */
     int64_t v_dump_stride;
     int32_t *ex_trace;  /* optional: (lo,hi) per marched step, ex_trace_stride int32 per solve */
@@ -135,8 +150,8 @@ typedef struct FdmOut {
 /* ABI version of the loaded library (== FDM_ABI_VERSION of the header it was built from). */
 int fdm_version(void);
 
-/* sizeof() of the ABI structs as this library was compiled: 0 FdmBatch, 1 FdmOut, 2 FdmAmericanBook, 3 FdmBookOut
-   (-1: unknown).  Lets a binding verify its own struct declarations at load time. */
+/* sizeof() of the ABI structs as this library was compiled: 0 FdmBatch, 1 FdmOut, 2 FdmAmericanBook, 3 FdmBookOut,
+   4 FdmBarrierBook (-1: unknown).  Lets a binding verify its own struct declarations at load time. */
 int fdm_sizeof(int which);
 
 /* Message of the last failure on the calling thread ("" if none). */
@@ -149,7 +164,11 @@ int fdm_device_count(void);
  * Launch all solves of `batch` on the current CUDA device, asynchronously on `stream`
  * (a cudaStream_t passed as void*; NULL = default stream).  Device pointers in, device
  * pointers out; no allocation, no synchronisation.  `n_launches`, if not NULL, receives the
- * number of kernels launched.
+ * number of kernels launched.  `status[]` (if given) is set to FDM_STATUS_NOT_SOLVED on the stream
+ * first: the arrays cannot be validated on the host here, and every kernel skips a solve outside
+ * its size class.
+ * Threading: re-entrant; any number of host threads and devices (each call runs on the caller's
+ * current device and stream and owns no state).
  */
 int fdm_solve_batch(const FdmBatch *batch, const FdmOut *out, void *stream, int32_t *n_launches);
 
@@ -165,6 +184,9 @@ int fdm_launch_hints(const int32_t *n_space, const int32_t *flags, int64_t n_sol
  * Host-buffer entry point: copies the descriptors to the device, solves, copies the results
  * back and synchronises.  `batch` and `out` hold HOST pointers.  `kernel_ms`, if not NULL,
  * receives the device time of the solve kernels alone (CUDA events).
+ * n_space[i] outside [3, n_space_max], seg_steps < 1 or seg_dt <= 0 are rejected with FDM_ERR_INVALID.
+ * Threading: one grow-only workspace and one lock PER DEVICE; host threads driving different devices
+ * run concurrently, threads sharing a device serialise (the call is synchronous anyway).
  */
 int fdm_solve_batch_host(const FdmBatch *batch, const FdmOut *out, int32_t *n_launches, float *kernel_ms);
 
@@ -172,7 +194,7 @@ int fdm_solve_batch_host(const FdmBatch *batch, const FdmOut *out, int32_t *n_la
  * Books: the fan-out behind the pricer classes' public methods, expanded and combined on the device.
  * Replaces N x { price_log2(); greeks_log2() } (run_american_scenarios.py:144-172) -- or any one of
  * price_log / price_log2 / greeks_log2 (fd_american_option_pricer.py:659-751; Black-76:
- * fd_american_black76.py:533-625) -- for N dividend-free options.  Per-option inputs are the scalars
+ * fd_american_black76.py:533-625) -- for N options, with or without discrete cash dividends.  Per-option inputs are the scalars
  * the reference constructor derives (:117-149): T = time_to_expiry, r = discount_rate_nacc,
  * b = carry_rate_nacc.
  */
@@ -190,6 +212,15 @@ typedef struct FdmAmericanBook {
     double dv_sigma;             /* volatility bump h of greeks_log2 (0.01) */
     int32_t what;                /* FDM_BOOK_* */
     int32_t use_richardson;
+    /* ABI 3: discrete cash dividends (fd_american_option_pricer.py:304-315, :554-602).  CSR per option, entries
+       ascending in tau = time to maturity at the ex-date, as _div_times_tau returns them; ignored for
+       FDM_FLAG_BLACK76 options (fd_american_black76.py:89).  NULL div_begin = no dividends. */
+    const int32_t *div_begin;    /* [n_options + 1] */
+    const double *div_tau, *div_cash;
+    int64_t n_div_total;         /* div_begin[n_options] (the device entry cannot read it) */
+    /* device entry only (the host entry derives them) */
+    int32_t n_space_max;         /* upper bound of max(n_space[i], 3) */
+    int32_t hints;               /* fdm_launch_hints() of (max(n_space,3), FDM_FLAG_AMERICAN); 0 = unknown */
 } FdmAmericanBook;
 
 typedef struct FdmBookOut {      /* n_options entries each; any pointer may be NULL */
@@ -203,16 +234,65 @@ typedef struct FdmBookOut {      /* n_options entries each; any pointer may be N
 int fdm_book_solves_per_option(int32_t what, int32_t use_richardson);
 
 /*
- * HOST pointers in `book` and `out`.  Copies ~56 B per option to the device, expands, solves, combines,
- * copies the results back and synchronises.  `node_steps` (optional) receives the metric unit
+ * HOST pointers in `book` and `out`.  Copies ~56 B per option (+ 16 B per dividend) to the device, expands, solves,
+ * combines, copies the results back and synchronises.  Raises FDM_ERR_INVALID where the reference raises
+ * (non-positive spot / strike / T / bumped sigma; a zero-length dividend segment).  `node_steps` (optional) receives the metric unit
  * sum(num_space_nodes x time steps) over all executed solves.
  */
 int fdm_american_book_host(const FdmAmericanBook *book, const FdmBookOut *out, int64_t *node_steps,
                            int32_t *n_launches, float *kernel_ms);
 
 /*
- * The host-buffer entry points keep one grow-only device workspace per process (no cudaMalloc per call).
- * This releases it.
+ * Device-pointer book entry: `book` and `out` hold DEVICE pointers (per-option arrays already in HBM), `workspace`
+ * is a device buffer of at least fdm_american_book_workspace() bytes, 256-byte aligned.  Fan-out, solves and
+ * epilogue are queued on `stream`; no allocation, no synchronisation, no host copies.  book->n_space_max must be
+ * set; book->hints may be 0.  Inputs the reference would reject cannot raise here: the option's solves are flagged
+ * FDM_FLAG_INVALID and its status is FDM_STATUS_NOT_SOLVED, its outputs NaN.  Re-entrant.
+ */
+size_t fdm_american_book_workspace(int64_t n_options, int64_t n_div_total, int32_t what, int32_t use_richardson);
+int fdm_american_book(const FdmAmericanBook *book, const FdmBookOut *out, void *workspace, size_t workspace_bytes,
+                      void *stream, int32_t *n_launches);
+
+/* ------------------------------------------------------------------------------------------------
+ * Barrier books: the fan-out behind DiscreteBarrierCrankNicolsonLog.price() / greeks()
+ * (discrete_barrier_fdm_pricer_cn.py:429-466: base solve, sigma + dv, sigma - dv on the grid frozen at the base
+ * volatility, :59-118) for N options, expanded and combined on the device.  Knock-in parity and the closed-form
+ * `none` leg (:489-500) stay with the caller.
+ */
+#define FDM_BARRIER_BOOK_SOLVE  0   /* 1 knock-out solve: price, delta, gamma */
+#define FDM_BARRIER_BOOK_GREEKS 1   /* 3 solves: + vega = (p(sigma+dv) - p(sigma-dv)) / (2 dv), theta (:457-464) */
+
+typedef struct FdmBarrierBook {
+    int64_t n_options;
+    const double *S0, *K, *T, *sigma, *r_disc, *b_carry;
+    const double *x_min, *dx;        /* log grid of configure_grid() (:59-131) at the base volatility */
+    const double *barrier;           /* knock-out level (lower level of a double-out) */
+    const double *barrier_up;        /* upper level of a double-out; may be NULL */
+    const double *rebate;
+    const int32_t *flags;            /* FDM_FLAG_CALL | FDM_FLAG_KO_DOWN | FDM_FLAG_KO_UP */
+    const int32_t *n_space, *n_time; /* N_space, N_time (resolved) */
+    const int32_t *mon_begin;        /* CSR [n_options + 1] into mon_step; shared by the option's solves */
+    const int32_t *mon_step;         /* 1-based monitor steps, ascending (:177-193) */
+    int64_t n_mon_total;
+    double dv_sigma;                 /* 1e-3 in the reference */
+    int32_t what;                    /* FDM_BARRIER_BOOK_* */
+    int32_t n_space_max;             /* device entry: upper bound of n_space[] */
+    int32_t hints;                   /* device entry: fdm_launch_hints() bits or 0 */
+    int32_t reserved;
+} FdmBarrierBook;
+
+int fdm_barrier_book_solves_per_option(int32_t what);
+size_t fdm_barrier_book_workspace(int64_t n_options, int32_t what);
+/* DEVICE pointers; FdmBookOut: price, delta, gamma, vega, theta, status are written (others ignored). */
+int fdm_barrier_book(const FdmBarrierBook *book, const FdmBookOut *out, void *workspace, size_t workspace_bytes,
+                     void *stream, int32_t *n_launches);
+/* HOST pointers; copies in, solves, copies out, synchronises. */
+int fdm_barrier_book_host(const FdmBarrierBook *book, const FdmBookOut *out, int64_t *node_steps,
+                          int32_t *n_launches, float *kernel_ms);
+
+/*
+ * The host-buffer entry points keep one grow-only device workspace per device (no cudaMalloc per call).
+ * This releases the workspaces of every device.
  */
 int fdm_release_workspace(void);
 

@@ -48,6 +48,30 @@ def _worker(rank, world, port, n_total, tmp):
         assert np.array_equal(only0["price"], np.arange(n_total) * 1.5) and np.array_equal(only0["idx"][:, 0], np.arange(n_total))
     else:
         assert only0 is None
+    # the device-side result gather (book.DeviceBookRun.packed layout), CPU tensors over gloo
+    import torch
+    width = shard.ShardedBookRun.shard_width(n_total, world)
+    assert width % 2 == 0 and width >= len(mine)
+    nf, ni = 6, 3
+    packed = torch.zeros(width * (8 * nf + 4 * ni), dtype=torch.uint8)
+    f = packed[: 8 * nf * width].view(torch.float64).view(nf, width)
+    i = packed[8 * nf * width:].view(torch.int32).view(ni, width)
+    for j in range(nf):
+        f[j, : len(mine)] = torch.from_numpy(mine * 10.0 + j)
+    for j in range(ni):
+        i[j, : len(mine)] = torch.from_numpy((mine * 10 + j).astype(np.int32))
+    for dst in (0, None):
+        g = shard.PackedGather(mine, n_total, width, nf, ni, dst=dst)
+        got = g(packed)
+        if dst is None or rank == dst:
+            F, I = got
+            assert F.shape == (nf, n_total) and I.shape == (ni, n_total)
+            for j in range(nf):
+                assert np.array_equal(F[j], np.arange(n_total) * 10.0 + j)
+            for j in range(ni):
+                assert np.array_equal(I[j], np.arange(n_total) * 10 + j)
+        else:
+            assert got is None
     np.save(os.path.join(tmp, f"r{rank}.npy"), mine)
     dist.barrier()
     dist.destroy_process_group()
