@@ -27,8 +27,8 @@
 //     exercised, V = phi exactly (fd_american_option_pricer.py:497), rebuilt as phi3 / 3 at read-out.
 //     The growth-factor matching of fdm_b200.cu (pd) is folded into inv, as the linear march always did.
 //
-// Solves this kernel does not take (dividend jumps, pivots not converged within MAX_PIVOT_ITERS rows, a zero
-// off-diagonal) are
+// Dividend jumps run here too: the spline's scratch overlays the tables between two segments (dividend_jump below).
+// Solves this kernel does not take (a degenerate operator: zero off-diagonal, non-finite pivot) are
 // marked by a NaN payload in price[] and solved by fdm_warp_kernel in a following launch.
 //
 // Included by fdm_lean_inst.cu (one translation unit per size class).
@@ -66,7 +66,7 @@ struct Tables {
     __device__ double pw(int j) const { return ((const volatile double *)(lc + LC_N * 32))[j]; }
 };
 template <int C>
-constexpr int smem_doubles() { return 32 * C + 2 * DIRECT_TERMS * 32 + 2 * SCAN_LEVELS * 32 + 4 + LC_N * 32 + PW_MAX; }
+__host__ __device__ constexpr int smem_doubles() { return 32 * C + 2 * DIRECT_TERMS * 32 + 2 * SCAN_LEVELS * 32 + 4 + LC_N * 32 + PW_MAX; }
 
 template <int C>
 struct Ph {
@@ -96,54 +96,37 @@ __device__ __forceinline__ double ipow(double a, int n)
     return r;
 }
 
-// Sweeps of the constant-coefficient factors on a register vector with exact Kogge-Stone carries: on return V
-// holds xs (den_inf * A_inf^-1 V).  Used once per phase for z; not on the per-step path.
-// nmL / nccL: multipliers of the optional last slot (NM / NCC where the lane holds it, else 1 with V[C-1] = 0).
-template <int C>
-__device__ __forceinline__ void const_sweeps(double (&V)[C], const bool last, const int cnt, const double NM,
-                                             const double NCC, const int lane)
+// a^n by repeated squaring (n up to ~500: per-lane constants of the row-0 correction; ~2 log2 n multiplications
+// instead of a dependent chain of n)
+__device__ __forceinline__ double ipow_sq(double a, int n)
 {
-    const double nmL = last ? NM : 1.0, nccL = last ? NCC : 1.0;
-    double e = 0.0;
-#pragma unroll
-    for (int k = 0; k < C; ++k) e = fma(k < C - 1 ? NM : nmL, e, V[k]);
-    double E = e, A = ipow(NM, cnt);
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double tE = __shfl_up_sync(FULL, E, d), tA = __shfl_up_sync(FULL, A, d);
-        const bool has = lane >= d;
-        E = fma(has ? A : 0.0, tE, E);
-        A *= has ? tA : 1.0;
+    double r = 1.0;
+#pragma unroll 1
+    while (n > 0) {
+        if (n & 1) r *= a;
+        a *= a;
+        n >>= 1;
     }
-    double c = __shfl_up_sync(FULL, E, 1);
-    c = (lane == 0) ? 0.0 : c;
-#pragma unroll
-    for (int k = 0; k < C; ++k) { c = fma(k < C - 1 ? NM : nmL, c, V[k]); V[k] = (k < C - 1 || last) ? c : 0.0; }
-    e = 0.0;
-#pragma unroll
-    for (int k = C - 1; k >= 0; --k) e = fma(k < C - 1 ? NCC : nccL, e, V[k]);
-    E = e;
-    A = ipow(NCC, cnt);
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double tE = __shfl_down_sync(FULL, E, d), tA = __shfl_down_sync(FULL, A, d);
-        const bool has = lane + d < 32;
-        E = fma(has ? A : 0.0, tE, E);
-        A *= has ? tA : 1.0;
-    }
-    c = __shfl_down_sync(FULL, E, 1);
-    c = (lane == 31) ? 0.0 : c;
-#pragma unroll
-    for (int k = C - 1; k >= 0; --k) { c = fma(k < C - 1 ? NCC : nccL, c, V[k]); V[k] = (k < C - 1 || last) ? c : 0.0; }
+    return r;
 }
 
 // Phase constants and carry tables.  Returns false if this solve has to go to fdm_warp_kernel.
+//
+// Everything here is closed form -- no iteration to the pivots' bit-wise fixed point, no sweeps of e0.  (The first
+// version iterated the pivot recurrence and the reference's (den, c') recurrence to their fixed points, 15..200
+// dependent divisions each, swept e0 through the factors with Kogge-Stone carries and built NM^row with a chain of up
+// to 500 multiplications: 37 000..51 000 cycles per phase, 5 % of a 500-step solve with its two phases and 17 % of a
+// two-dividend solve with its five or six.)
+//   * den_inf is the larger root of den^2 - A_C den + A_L A_U = 0 (the stable fixed point of den = A_C - A_L A_U / den),
+//     from the quadratic formula and one Newton step with the residual formed by FMAs: correct to an ulp.
+//   * the factors built from it reproduce A except for entry (0,0): delta = A_C - den_inf (exact subtraction).
+//   * sweeping e0 through the constant factors gives xs_i = NM^i kappa (1 - rho^(n-i)), rho = NM NCC, kappa = 1/(1-rho):
+//     xs_0 and the per-lane constants of the row-0 correction follow from powers by repeated squaring.
 template <int C, bool AMER>
 __device__ __forceinline__ bool setup_phase(double theta, double dt, double a, double c, double bcoef, int n_int,
                                             int lane, const RowLayout &ly, const Tables<C> &T, Ph<C> &ph)
 {
     constexpr int H = C / 2, PW = C - H;
-    const bool last = ly.cnt == C;
     const int cntU = ly.cnt - H;
     const double A_L = __dmul_rn(__dmul_rn(-theta, dt), a);
     const double A_C = __dsub_rn(1.0, __dmul_rn(__dmul_rn(theta, dt), bcoef));
@@ -155,22 +138,25 @@ __device__ __forceinline__ bool setup_phase(double theta, double dt, double a, d
     ph.q = (1.0 - theta) / theta;
     ph.half = theta == 0.5;
 
-    // pivots of the reference's recurrence (fd_american_option_pricer.py:443-451) to their bit-wise fixed point
-    double den = A_C, rinv = __drcp_rn(den);
-    bool conv = false;
-    for (int i = 1; i < MAX_PIVOT_ITERS; ++i) {
-        const double den_i = __dsub_rn(A_C, __dmul_rn(A_L, __dmul_rn(A_U, rinv)));
-        if (den_i == den) { conv = true; break; }
-        den = den_i;
-        rinv = __drcp_rn(den);
+    // steady-state pivot of the reference's recurrence den_i = A_C - A_L A_U / den_{i-1} (fd_american_option_pricer.py:443-451)
+    const double PLU = __dmul_rn(A_L, A_U), PLU_lo = __fma_rn(A_L, A_U, -PLU);
+    const double disc = __fma_rn(A_C, A_C, -4.0 * PLU);
+    double den = 0.5 * (A_C + sqrt(disc));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {                               // Newton on the quadratic, residual in extra precision
+        const double res = __fma_rn(__dsub_rn(den, A_C), den, PLU) + PLU_lo;
+        den -= res / (2.0 * den - A_C);
     }
+    const double rinv = 1.0 / den;
     const double NM = -(A_L * rinv), NCC = -(A_U * rinv);
-    // the verdict is taken by a warp vote at the end, so that the compiler sees uniform control flow around it
-    const bool bad = !conv || !(fabs(NM) > 0.0) || !(fabs(NCC) > 0.0) || !isfinite(rinv);
-    const double delta_sm = __dmul_rn(A_L, __dmul_rn(A_U, rinv));       // A_C - den_inf, as the recurrence forms it
+    const double rho = NM * NCC, kappa = 1.0 / (1.0 - rho);
+    // the verdict is taken by a warp vote at the end, so that control flow stays uniform
+    const bool bad = !(disc > 0.0) || !(fabs(NM) > 0.0) || !(fabs(NCC) > 0.0) || !isfinite(rinv) || !(fabs(rho) < 1.0) ||
+                     !isfinite(kappa);
+    const double delta_sm = __dsub_rn(A_C, den);                   // A = A_inf + delta e0 e0^T
 
-    // growth-factor matching (fdm_b200.cu): the V coefficient carries 1 + delta; folded into inv
-    const double pd = growth_matched_pd(A_L, A_C, A_U, B_L, B_C, B_U, ph.q, rinv, n_int);
+    // growth factor of smooth components matched to the exact row sums (growth_exact_pd); folded into inv
+    const double pd = growth_exact_pd(A_L, A_C, A_U, B_L, B_C, B_U, ph.q, rinv);
     const double scale = AMER ? 1.0 + (pd - 1.0) / (1.0 + ph.q) : p + (pd - 1.0);
     const double bscale = 1.0 / scale;
     ph.NM = NM;
@@ -198,9 +184,9 @@ __device__ __forceinline__ bool setup_phase(double theta, double dt, double a, d
     // backward local end of  NM^(k+1) carry : sum_k NCC^k NM^(k+1) over the slots of a half
     {
         double sL = 0.0, sU = 0.0, t = NM;
-        for (int k = 0; k < H; ++k) { sL += t; t *= NCC * NM; }
+        for (int k = 0; k < H; ++k) { sL += t; t *= rho; }
         t = NM;
-        for (int k = 0; k < cntU; ++k) { sU += t; t *= NCC * NM; }
+        for (int k = 0; k < cntU; ++k) { sU += t; t *= rho; }
         ph.kapL = sL;
         ph.kapU = sU;
     }
@@ -232,18 +218,14 @@ __device__ __forceinline__ bool setup_phase(double theta, double dt, double a, d
     ph.terms = terms;
     __syncwarp();
 
-    // Sherman-Morrison constants.  xsz = sweeps of e0 (den_inf * A_inf^-1 e0), exact carries.
-    double xsz[C];
-#pragma unroll
-    for (int k = 0; k < C; ++k) xsz[k] = (lane == 0 && k == 0) ? 1.0 : 0.0;
-    const_sweeps<C>(xsz, last, ly.cnt, NM, NCC, lane);
-    const double xs00 = __shfl_sync(FULL, xsz[0], 0);
+    // Sherman-Morrison constants.  xs = sweeps of e0 through the constant factors: xs_i = NM^i kappa (1 - rho^(n-i)).
+    const double xs00 = kappa * (1.0 - ipow_sq(rho, n_int));
     ph.kap = delta_sm * rinv / (1.0 + delta_sm * (rinv * xs00));       // g = delta x_0 = kap * xs_0(uncorrected)
     // forward: rows of lane l change by -g NM^(row0 + k) = NM^(k+1) * (-g NM^(row0 - 1))
-    double Dl = (lane == 0) ? 1.0 / NM : ipow(NM, ly.row0 - 1);
-    // backward: the carry into lane l is xs of the first row of lane l+1, which changes by -g xsz there
-    double Zl = __shfl_down_sync(FULL, xsz[0], 1);
-    if (lane == 31) Zl = 0.0;
+    double Dl = (lane == 0) ? 1.0 / NM : ipow_sq(NM, ly.row0 - 1);
+    // backward: the carry into lane l is xs of the first row of lane l+1, which changes by -g xs there
+    const int r_next = ly.row0 + ly.cnt;
+    double Zl = (lane == 31) ? 0.0 : ipow_sq(NM, r_next) * kappa * (1.0 - ipow_sq(rho, n_int - r_next));
     // Contributions below 1e-30 of the leading one are dropped: the direct carries neglect terms below 1e-20 as
     // well, and where they leave an exact zero (far out-of-the-money rows in the first steps) the correction must
     // not turn it negative -- the reference's exercise test phi > vc (:496) is strict.
@@ -417,8 +399,173 @@ __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const
     }
 }
 
+
+// ---- dividend jump (fd_american_option_pricer.py:321-386, :517-548) for the packed row layout --------------------
+// Natural cubic spline through (s_j, V_j) and V(S) <- spline(S - D).  Three shared-memory arrays of n + 2 doubles
+// OVERLAY the kernel's tables (a new phase rebuilds them anyway): A = knots s_j, Bv = values V_j on entry and the
+// jumped values on exit, Z = the spline's c coefficients (scratch before that).  Not inlined and no register arrays
+// in the signature, so the time loop's register allocation does not see it.  Returns this lane's new boundary node
+// value (lanes 0 and 31).
+//
+// The reference solves the spline's tridiagonal system serially (:338-359).  Here every lane eliminates only its own
+// rows (a first version swept 40 warm-up rows per lane and cost as much as 200 time steps per jump):
+//   * mu_i = h_i / (2 (x_{i+1} - x_{i-1}) - h_{i-1} mu_{i-1}) is the pivot recurrence; an error in mu_{i-1} shrinks by
+//     mu^2 ~ 0.07 per row, so GM = 14 warm-up rows of the mu recurrence alone (one division each) reproduce the serial
+//     values to 0.07^14 ~ 1e-16;
+//   * z_i = (alpha_i - h_{i-1} z_{i-1}) / l_i and c_j = z_j - mu_j c_{j+1} are LINEAR first-order recurrences with
+//     multipliers ~ -0.27: local pass with zero carry-in, the running product of the multipliers parked in Z, then
+//     true = local + product * carry, the carry being the neighbour's end value with its own two predecessors folded
+//     in (a lane's product is below 0.27^9 ~ 1e-5: three terms leave 1e-16).
+//   * one reciprocal of l_i serves mu_i and z_i, and 3 / h_i is carried to the next row.
+//   * every division is a reciprocal and a multiplication (an IEEE division costs ~40 instructions; the first
+//     compact version spent 40 % of its instructions there).
+// The spline agrees with the reference's serial sweep to a few ulps (not bit for bit).  The bracket of S_j - D is found once per lane from the logarithm and then
+// walked upwards (it is monotone in j) instead of one binary search per node.
+template <int C>
+__device__ __noinline__ double dividend_jump(const double Vb, const double cash, const bool is_call, const double k_eff,
+                                             const int n, const int lane, const int row0, const int cnt, const double x_min,
+                                             const double dx, double *A, double *Bv, double *Z)
+{
+    static_assert(3 * (32 * C + 3) <= smem_doubles<C>(), "the spline scratch must fit in the warp's tables");
+    // CODE SIZE matters more than instruction count here: 16 warps share a 32 KB instruction cache with the time loop
+    // they spend their life in, and a straight-line (unrolled) version of this function was 8000 instructions -- every
+    // jump of any warp flushed the loop out of the cache (ncu: no_instruction became the top stall, 8 warps per issue
+    // cycle).  So: runtime loops, the per-row values in small dynamically indexed local arrays.
+    constexpr int GM = 14;
+    const int j_first = row0 + 1;                              // this lane's interior knots j_first .. j_first + cnt - 1
+    double mur[C], zr[C];
+    if (lane == 0) { Bv[0] = Vb; A[0] = node_s(x_min, dx, 0); }
+    if (lane == 31) { Bv[n] = Vb; A[n] = node_s(x_min, dx, n); }
+    // Knots of the own rows: one exponential for the first, then s_{j+1} = s_j e^dx (16 multiplications instead of 16
+    // exponentials; the knots drift by at most cnt ulps from the reference's, which moves the spline by ~1e-15
+    // relative).  Where the caller marked a node as exercised (Z[j] > 0: its 6 dt lambda) the value is the payoff
+    // (fd_american_option_pricer.py:497) -- the state carries vc there.  The payoff TABLE of the time loop is not
+    // rebuilt from these knots: the caller keeps it in registers across the call.
+    {
+        const double qx = exp(dx);
+        double sj = node_s(x_min, dx, j_first);
+#pragma unroll 1
+        for (int k = 0; k < cnt; ++k) {
+            const int j = j_first + k;
+            A[j] = sj;
+            if (Z[j] > 0.0) Bv[j] = payoff(sj, k_eff, is_call);
+            sj = __dmul_rn(sj, qx);
+        }
+    }
+    __syncwarp();
+    // ---- forward: warm-up of the pivot recurrence, then the lane's own rows ----------------------------------
+    double mu_prev = 0.0, z_prev = 0.0, prod = 1.0;
+    {
+        const int i0 = max(1, j_first - GM);
+        double x_im1 = A[i0 - 1], x_i = A[i0];
+#pragma unroll 1
+        for (int i = i0; i < j_first; ++i) {
+            const double x_ip1 = A[i + 1];
+            const double l = __dsub_rn(__dmul_rn(2.0, __dsub_rn(x_ip1, x_im1)), __dmul_rn(__dsub_rn(x_i, x_im1), mu_prev));
+            mu_prev = __dmul_rn(__dsub_rn(x_ip1, x_i), __drcp_rn(l));
+            x_im1 = x_i;
+            x_i = x_ip1;
+        }
+        double y_im1 = Bv[j_first - 1], y_i = Bv[j_first];
+        double t_im1 = 3.0 * __drcp_rn(__dsub_rn(x_i, x_im1));
+#pragma unroll 1
+        for (int k = 0; k < cnt; ++k) {
+            const int i = j_first + k;
+            const double x_ip1 = A[i + 1], y_ip1 = Bv[i + 1];
+            const double h_i = __dsub_rn(x_ip1, x_i), h_im1 = __dsub_rn(x_i, x_im1);
+            const double t_i = 3.0 * __drcp_rn(h_i);
+            const double alpha = __dsub_rn(__dmul_rn(t_i, __dsub_rn(y_ip1, y_i)), __dmul_rn(t_im1, __dsub_rn(y_i, y_im1)));
+            const double rl = __drcp_rn(__dsub_rn(__dmul_rn(2.0, __dsub_rn(x_ip1, x_im1)), __dmul_rn(h_im1, mu_prev)));
+            mu_prev = __dmul_rn(h_i, rl);
+            z_prev = __dmul_rn(__dsub_rn(alpha, __dmul_rn(h_im1, z_prev)), rl);
+            prod = __dmul_rn(prod, -__dmul_rn(h_im1, rl));
+            mur[k] = mu_prev;
+            zr[k] = z_prev;
+            Z[i] = prod;                                       // z_i(true) = z_i(local) + prod_i * carry
+            x_im1 = x_i; x_i = x_ip1; y_im1 = y_i; y_i = y_ip1; t_im1 = t_i;
+        }
+    }
+    {
+        // carry into this lane = true z at the last row of the lane below
+        const double e1 = __shfl_up_sync(FULL, z_prev, 1), e2 = __shfl_up_sync(FULL, z_prev, 2), e3 = __shfl_up_sync(FULL, z_prev, 3);
+        const double p1 = __shfl_up_sync(FULL, prod, 1), p2 = __shfl_up_sync(FULL, prod, 2);
+        double carry = (lane >= 3) ? e3 : 0.0;
+        carry = (lane >= 2) ? fma(p2, carry, e2) : 0.0;
+        carry = (lane >= 1) ? fma(p1, carry, e1) : 0.0;        // z_0 = 0, :346
+        // ---- backward: c_j = z_j - mu_j c_{j+1}, :358-359; c_n = 0 -----------------------------------------------
+        double c_next = 0.0;
+        prod = 1.0;
+#pragma unroll 1
+        for (int k = cnt - 1; k >= 0; --k) {
+            const double z_true = fma(Z[j_first + k], carry, zr[k]);
+            c_next = __dsub_rn(z_true, __dmul_rn(mur[k], c_next));
+            prod = __dmul_rn(prod, -mur[k]);
+            zr[k] = c_next;
+            Z[j_first + k] = prod;
+        }
+        const double f1 = __shfl_down_sync(FULL, c_next, 1), f2 = __shfl_down_sync(FULL, c_next, 2), f3 = __shfl_down_sync(FULL, c_next, 3);
+        const double q1 = __shfl_down_sync(FULL, prod, 1), q2 = __shfl_down_sync(FULL, prod, 2);
+        carry = (lane <= 28) ? f3 : 0.0;
+        carry = (lane <= 29) ? fma(q2, carry, f2) : 0.0;
+        carry = (lane <= 30) ? fma(q1, carry, f1) : 0.0;
+#pragma unroll 1
+        for (int k = 0; k < cnt; ++k) Z[j_first + k] = fma(Z[j_first + k], carry, zr[k]);
+    }
+    if (lane == 0) Z[0] = 0.0;
+    if (lane == 31) Z[n] = 0.0;
+    __syncwarp();
+    // ---- evaluation at S_j - D, :517-548: nodes q = -1 (node 0, lane 0), 0 .. cnt-1 (own), cnt (node n, lane 31) -------
+    const double s_lo = A[0], s_hi = A[n];
+    int jj = -1;                                               // bracket of the previous node (monotone in j)
+    double nb = Vb;
+#pragma unroll 1
+    for (int q = (lane == 0 ? -1 : 0); q < cnt + (lane == 31 ? 1 : 0); ++q) {
+        const int jn = q < 0 ? 0 : (q == cnt ? n : j_first + q);
+        const double Sj = A[jn];
+        const double Sq = __dsub_rn(Sj, cash);
+        double cont;
+        if (Sq <= s_lo) cont = Bv[0];                          // :535-538
+        else if (Sq >= s_hi) cont = Bv[n];
+        else {
+            if (jj < 0) jj = min(max((int)floor((log(Sq) - x_min) / dx), 0), n - 1);
+            while (jj + 1 <= n - 1 && A[jj + 1] <= Sq) ++jj;   // the reference's binary search (:375-382) ends on the
+            while (jj > 0 && A[jj] > Sq) --jj;                 // knot interval with x_j <= Sq < x_{j+1}
+            const int j = jj;
+            const double xj = A[j], h = __dsub_rn(A[j + 1], xj);
+            const double cj = Z[j], cj1 = Z[j + 1];
+            const double yj = Bv[j];
+            const double rh = __drcp_rn(h), third = 1.0 / 3.0;  // one reciprocal for the three divisions of :360-364
+            const double bj = __dsub_rn(__dmul_rn(__dsub_rn(Bv[j + 1], yj), rh),
+                                        __dmul_rn(__dmul_rn(h, __dadd_rn(cj1, __dmul_rn(2.0, cj))), third));
+            const double dj = __dmul_rn(__dmul_rn(__dsub_rn(cj1, cj), rh), third);
+            const double dq = __dsub_rn(Sq, xj);
+            double acc = __dadd_rn(yj, __dmul_rn(bj, dq));                                          // :384, left to right
+            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(cj, dq), dq));
+            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(__dmul_rn(dj, dq), dq), dq));
+            cont = acc;
+        }
+        if (is_call) {
+            const double pv = payoff(Sj, k_eff, true);
+            cont = cont > pv ? cont : pv;                      // :542-544
+        }
+        if (q < 0 || q == cnt) nb = cont; else zr[q] = cont;
+    }
+    __syncwarp();                                              // every lane has read the old values
+#pragma unroll 1
+    for (int k = 0; k < cnt; ++k) Bv[j_first + k] = zr[k];
+    __syncwarp();
+    return nb;
+}
+
 #ifndef FDM_LEAN_MINB
 #define FDM_LEAN_MINB 0
+#endif
+
+// -DFDM_LEAN_PROFILE: per-region cycle counts of one warp (dev tool; printf from block 1000)
+#ifdef FDM_LEAN_PROFILE
+#define LEAN_TICK(slot) do { const long long t_ = clock64(); prof_acc[slot] += t_ - prof_t; prof_t = t_; } while (0)
+#else
+#define LEAN_TICK(slot)
 #endif
 template <int C>
 constexpr int min_blocks() { return FDM_LEAN_MINB ? FDM_LEAN_MINB : (C <= 4 ? 24 : C <= 8 ? 20 : 16); }
@@ -511,9 +658,11 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
     int next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
     int gstep = 0;
     int32_t *trace = (TRACE && O.ex_trace) ? O.ex_trace + sid * O.ex_trace_stride : nullptr;
-    // solves with a dividend jump go to fdm_warp_kernel (its spline scratch would cut this kernel's occupancy)
     bool retry = false;
-    for (int seg = seg_b; seg < seg_e; ++seg) retry |= B.seg_div[seg] != 0.0;
+#ifdef FDM_LEAN_PROFILE
+    long long prof_acc[5] = {0, 0, 0, 0, 0};
+    long long prof_t = clock64();
+#endif
 
     for (int seg = seg_b; seg < seg_e && !retry; ++seg) {
         const int n_steps = B.seg_steps[seg];
@@ -545,7 +694,10 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
             const bool implicit_phase = m < base_ran;
             const int m_end = implicit_phase ? min(base_ran, n_steps) : n_steps;
             Ph<C> ph;
-            if (!setup_phase<C, AMER>(implicit_phase ? 1.0 : 0.5, dt, ca, cc, bcoef, n_int, lane, ly, T, ph)) {
+            LEAN_TICK(0);
+            const bool phase_ok = setup_phase<C, AMER>(implicit_phase ? 1.0 : 0.5, dt, ca, cc, bcoef, n_int, lane, ly, T, ph);
+            LEAN_TICK(1);
+            if (!phase_ok) {
                 retry = true;
                 break;
             }
@@ -604,6 +756,40 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
             }
         }
         if (retry) break;
+        const double cash = B.seg_div[seg];
+        if (cash != 0.0) {
+            // ex-dividend jump.  The spline's scratch overlays this warp's tables: the next phase rebuilds the carry
+            // tables, and the payoff table and the boundary inputs are refilled here.
+            LEAN_TICK(2);
+            double *A = smem, *Bv = A + (n + 2), *Zs = Bv + (n + 2);
+            __syncwarp();
+            // Zs lies beyond the payoff table: park the exercise marks (6 dt lambda > 0) there first, then take the exact
+            // payoff table into the registers of L, and only then let the values overwrite its place
+#pragma unroll
+            for (int k = 0; k < C; ++k) if (k < ly.cnt) Zs[ly.row0 + k + 1] = AMER ? L[k] : 0.0;
+#pragma unroll
+            for (int k = 0; k < C; ++k) L[k] = T.phi3[k * 32 + lane];
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < C; ++k) if (k < ly.cnt) Bv[ly.row0 + k + 1] = V[k];
+            LEAN_TICK(3);
+            Vb = dividend_jump<C>(Vb, cash, is_call, k_eff, n, lane, ly.row0, ly.cnt, x_min, dx, A, Bv, Zs);
+            LEAN_TICK(4);
+#pragma unroll
+            for (int k = 0; k < C; ++k) V[k] = (k < ly.cnt) ? Bv[ly.row0 + k + 1] : 0.0;
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                T.phi3[k * 32 + lane] = L[k];
+                L[k] = 0.0;
+            }
+            if (lane == 0) {
+                T.par[0] = k_eff;
+                T.par[1] = (flags & FDM_FLAG_BDRY_TOP_NEXT) ? node_s(x_min, dx, n + 1) : sn;
+                T.par[2] = s0;
+            }
+            __syncwarp();
+        }
     }
     if (retry) {
         if (lane == 0) O.price[sid] = __longlong_as_double((long long)RETRY_BITS);
@@ -611,6 +797,12 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
     }
 
     // ---- read-out (as fdm_warp_kernel) ------------------------------------------------------------
+    LEAN_TICK(2);
+#ifdef FDM_LEAN_PROFILE
+    if (blockIdx.x == 1000 && lane == 0)
+        printf("lean<%d> steps=%d cycles: prologue+loops %lld | setup_phase %lld | time loops %lld | materialise %lld | jump %lld\n",
+               C, gstep, prof_acc[0], prof_acc[1], prof_acc[2], prof_acc[3], prof_acc[4]);
+#endif
     const double V0 = __shfl_sync(FULL, Vb, 0), VN = __shfl_sync(FULL, Vb, 31);
     int ex_lo = -1, ex_hi = -1;
     if (AMER) {

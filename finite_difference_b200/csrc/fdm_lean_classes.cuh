@@ -5,7 +5,6 @@
 namespace lean {
 
 constexpr unsigned long long RETRY_BITS = 0x7ff8b200dead0001ull;   // quiet NaN: "solve me with fdm_warp_kernel"
-constexpr int MAX_PIVOT_ITERS = 4096;
 
 // Compiled size classes: a kernel with C slots per lane serves 32 (C-1) <= n_int <= 32 C interior rows
 // (500 nodes -> 16, 400 -> 13, 300 -> 10).  Other sizes: fdm_warp_kernel.

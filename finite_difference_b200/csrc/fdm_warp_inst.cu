@@ -17,8 +17,10 @@ int FDM_CAT(fdm_launch_warp_, FDM_INST_C)(const FdmBatch &b, const FdmOut &o, cu
     const size_t smem = (size_t)(base + div_doubles) * sizeof(double);
     const int64_t max_grid = 0x7fffffff;
     int launches = 0;
-    for (int64_t first = 0; first < b.n_solves; first += max_grid) {
-        const int64_t count = (b.n_solves - first < max_grid) ? (b.n_solves - first) : max_grid;
+    const int per_cta = only_rest ? 32 : 1;                  // only_rest: one warp screens 32 solves (fdm_warp.cuh)
+    for (int64_t first = 0; first < b.n_solves; first += max_grid * per_cta) {
+        const int64_t left = b.n_solves - first;
+        const int64_t count = (left < max_grid * per_cta) ? (left + per_cta - 1) / per_cta : max_grid;
         const dim3 grid((unsigned)count), block(32);
         if (any_american) {
             if (trace) fdm_warp_kernel<C, true, true><<<grid, block, smem, st>>>(b, o, first, 1, any_div, only_rest);

@@ -221,3 +221,34 @@ def test_two_host_threads_on_one_device():
     [t.start() for t in th]
     [t.join() for t in th]
     assert np.array_equal(got[0], ref) and np.array_equal(got[1], ref)
+
+
+@pytest.mark.parametrize("n_space", [289, 300, 321, 385, 400, 417, 481, 500, 513])
+def test_lean_kernel_dividend_solves_vs_oracle(n_space):
+    """Dividend solves in the lean kernel's size classes (the spline jump runs inside fdm_lean_kernel, its scratch
+    overlaying the warp's tables): every node of the value vector and the exercise interval at EVERY step against
+    the oracle, for 1-3 dividends, calls (Rannacher restart after each jump) and puts."""
+    from finite_difference_b200 import solve_host
+    rng = np.random.default_rng(n_space)
+    cases = []
+    for i in range(6):
+        nd = 1 + i % 3
+        taus = np.sort(rng.uniform(0.08, 0.92, nd))
+        divs = [(float(t), float(rng.uniform(0.5, 6.0))) for t in taus]
+        cases.append(dict(spot=100.0, strike=float(rng.uniform(85, 115)), T=1.0, sigma=float(rng.uniform(0.15, 0.5)),
+                          r=float(rng.uniform(0.01, 0.09)), is_call=bool(i % 2), divs=divs, n_time=int(rng.integers(60, 140))))
+    parts = [hostlogic.build_american_batch([c["spot"]], [c["strike"]], [c["T"]], [c["sigma"]], [c["r"]], [c["r"]],
+                                            [c["is_call"]], [n_space], [c["n_time"]], [2], [False], 4.5, div_taus=[c["divs"]])
+             for c in cases]
+    batch = SolveBatch.concat(parts)
+    res = solve_host(batch, dump=True, trace=True)
+    assert np.all(res.status == 0)
+    for i, c in enumerate(cases):
+        o = oracle.american_solve(c["spot"], c["strike"], c["T"], c["sigma"], c["r"], c["r"], c["is_call"], 0, n_space,
+                                  c["n_time"], 2, 4.5, c["divs"], trace=True)
+        V = res.V[i, : n_space + 1]
+        tol = 1e-10 * np.abs(o.V) + 1e-12 * np.max(np.abs(o.V))
+        assert np.all(np.abs(V - o.V) <= tol), (i, float(np.max(np.abs(V - o.V))))
+        assert abs(res.price[i] - o.price) <= 1e-10 * max(abs(o.price), 1e-2)
+        steps = o.ex_trace.shape[0]
+        assert np.array_equal(res.ex_trace[i, :steps], o.ex_trace), i
