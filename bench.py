@@ -499,7 +499,7 @@ def time_config(cfg, args, rank, world, local, n_total, steps, warmup, with_cpu,
     step_ms = sum(a.elapsed_time(b) for a, b in zip(ev[0], ev[2]))
     kern_ms = sum(a.elapsed_time(b) for a, b in zip(ev[0], ev[1]))
     peak_after, _ = _lib.fp64_peak_tflops()
-    dev_results = [{k: v.cpu().numpy() for k, v in p["sr"].run.cols.items()} for p in runs.parts]   # what the timed leg left in HBM
+    dev_results = [p["sr"].run.results() for p in runs.parts]      # what the timed leg left in HBM (caller's option order)
 
     t = torch.tensor([step_ms, kern_ms, t_wall * 1e3], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(runs.node_steps), float(runs.n_solves)], dtype=torch.float64, device=dev)

@@ -73,7 +73,7 @@ class FdmAmericanBook(C.Structure):
 
 class FdmBookOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("price_log2", "price", "delta", "gamma", "vega", "theta",
-                                          "ex_lo", "ex_hi", "status")]
+                                          "ex_lo", "ex_hi", "status", "out_index")]
 
 
 class FdmBarrierBook(C.Structure):

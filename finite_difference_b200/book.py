@@ -210,30 +210,70 @@ class AmericanBook:
     # ---- public ----------------------------------------------------------------------------
     _WHAT = {"price_log": 0, "price_log2": 1, "greeks_log2": 2, "scenario": 3}
 
+    def launch_order(self) -> Optional[np.ndarray]:
+        """Order in which the fused entries lay the options out on the device: ascending stiffness ``alpha dt`` of
+        the base solve.  The kernels compile their time loop once per carry form (how far a row's influence reaches,
+        a function of ``alpha dt``), CTAs start in index order, and an SM's instruction cache holds about one such
+        loop -- a book sorted this way keeps neighbouring solves on the same loop (mixed-volatility books: +10..20 %).
+        Results are returned in the caller's order.  ``None``: nothing to gain (small or uniform book)."""
+        if self.n_opt < 64:
+            return None
+        S_min, S_max = hostlogic.american_domain_vec(self.spot, self.strike, self.T, self.sigma, self.s_max_mult)
+        dx = (np.log(S_max) - np.log(S_min)) / self.n_space
+        key = self.sigma * self.sigma / (dx * dx) * (self.T / self.n_time)
+        if float(key.max()) <= 1.0001 * float(key.min()):
+            return None
+        return np.argsort(key, kind="stable")
+
+    def _launch_inputs(self):
+        """Per-option input arrays in launch order, built once per book (``launch_order`` and the gathers by it cost
+        more than the H2D copies of a 100 000-option book)."""
+        if getattr(self, "_launch", None) is None:
+            from . import _lib
+            order = self.launch_order()
+
+            def take(a):
+                return np.ascontiguousarray(a if order is None else a[order])
+
+            arrs = {k: take(np.asarray(getattr(self, k), dtype=np.float64)) for k in ("spot", "strike", "T", "sigma", "r", "b")}
+            arrs["flags"] = take((np.where(self.is_call, _lib.FLAG_CALL, 0)
+                                  + np.where(self.black76, _lib.FLAG_BLACK76, 0)).astype(np.int32))
+            for k in ("n_space", "n_time", "rannacher"):
+                arrs[k] = take(np.asarray(getattr(self, k)).astype(np.int32))
+            csr = self.div_csr()
+            if csr is not None and order is not None:
+                begin, tau, cash = csr
+                lens = (begin[1:] - begin[:-1])[order].astype(np.int64)
+                nb = np.concatenate([[0], np.cumsum(lens)])
+                pos = np.repeat(begin[:-1][order].astype(np.int64) - nb[:-1], lens) + np.arange(int(nb[-1]))
+                csr = (nb.astype(np.int32), np.ascontiguousarray(tau[pos]), np.ascontiguousarray(cash[pos]))
+            ns = arrs["n_space"]
+            fl = np.full(self.n_opt, _lib.FLAG_AMERICAN, dtype=np.int32)
+            hints = int(_lib.load().fdm_launch_hints(ns.ctypes.data_as(_lib._pi), fl.ctypes.data_as(_lib._pi), self.n_opt,
+                                                     None, 0)) & ~4
+            self._launch = dict(order=None if order is None else np.ascontiguousarray(order, dtype=np.int32), arrs=arrs,
+                                csr=csr, hints=hints)
+        return self._launch
+
     def _book_struct(self, what, dv_sigma, use_richardson, ptr):
-        """``FdmAmericanBook`` with pointers produced by ``ptr(name, numpy array)`` (host or device)."""
+        """``(FdmAmericanBook, out_index)`` with pointers produced by ``ptr(name, numpy array)`` (host or device).  The
+        options are laid out in launch order (:meth:`launch_order`); ``out_index`` (int32 array or ``None``) goes into
+        ``FdmBookOut.out_index`` so that the results come back in the caller's order."""
         from . import _lib
+        li = self._launch_inputs()
         n = self.n_opt
         bk = _lib.FdmAmericanBook()
         bk.n_options = n
-        for k in ("spot", "strike", "T", "sigma", "r", "b"):
-            setattr(bk, k, ptr(k, np.ascontiguousarray(getattr(self, k), dtype=np.float64)))
-        flags = np.ascontiguousarray(np.where(self.is_call, _lib.FLAG_CALL, 0) + np.where(self.black76, _lib.FLAG_BLACK76, 0),
-                                     dtype=np.int32)
-        bk.flags = ptr("flags", flags)
-        for k in ("n_space", "n_time", "rannacher"):
-            setattr(bk, k, ptr(k, np.ascontiguousarray(getattr(self, k), dtype=np.int32)))
+        for k, v in li["arrs"].items():
+            setattr(bk, k, ptr(k, v))
         bk.s_max_mult, bk.dv_sigma = self.s_max_mult, float(dv_sigma)
         bk.what, bk.use_richardson = self._WHAT[what], int(bool(use_richardson))
-        csr = self.div_csr()
-        if csr is not None:
-            bk.div_begin, bk.div_tau, bk.div_cash = (ptr(k, v) for k, v in zip(("div_begin", "div_tau", "div_cash"), csr))
-            bk.n_div_total = int(csr[0][-1])
+        if li["csr"] is not None:
+            bk.div_begin, bk.div_tau, bk.div_cash = (ptr(k, v) for k, v in zip(("div_begin", "div_tau", "div_cash"), li["csr"]))
+            bk.n_div_total = int(li["csr"][0][-1])
         bk.n_space_max = int(self.n_space.max()) if n else 3
-        ns = np.ascontiguousarray(self.n_space, dtype=np.int32)
-        fl = np.full(n, _lib.FLAG_AMERICAN, dtype=np.int32)
-        bk.hints = int(_lib.load().fdm_launch_hints(ns.ctypes.data_as(_lib._pi), fl.ctypes.data_as(_lib._pi), n, None, 0)) & ~4
-        return bk
+        bk.hints = li["hints"]
+        return bk, li["order"]
 
     def solve_steps(self, what: str = "scenario", use_richardson: bool = True) -> int:
         """Metric unit of one pass: sum over the executed solves of num_space_nodes x time steps."""
@@ -264,12 +304,14 @@ class AmericanBook:
             keep.append(arr)
             return arr.ctypes.data
 
-        bk = self._book_struct(what, dv_sigma, use_richardson, host_ptr)
+        bk, out_index = self._book_struct(what, dv_sigma, use_richardson, host_ptr)
         res = {k: np.empty(n) for k in ("price_log2", "price", "delta", "gamma", "vega", "theta")}
         res.update({k: np.empty(n, dtype=np.int32) for k in ("ex_lo", "ex_hi", "status")})
         out = _lib.FdmBookOut()
         for k, v in res.items():
             setattr(out, k, v.ctypes.data)
+        if out_index is not None:
+            out.out_index = out_index.ctypes.data
         ns, nl, ms = C.c_int64(0), C.c_int32(0), C.c_float(0.0)
         _lib.check(L.fdm_american_book_host(C.byref(bk), C.byref(out), C.byref(ns), C.byref(nl), C.byref(ms)))
         if what in ("price_log", "price_log2"):
@@ -280,7 +322,7 @@ class AmericanBook:
         n_div = int(bk.n_div_total)
         res.update(node_steps=int(ns.value), n_solves=n * int(L.fdm_book_solves_per_option(bk.what, bk.use_richardson)),
                    kernel_ms=float(ms.value), n_launches=int(nl.value),
-                   h2d_bytes=n * (6 * 8 + 4 * 4) + (n_div * 16 + (n + 1) * 4 if n_div else 0),
+                   h2d_bytes=n * (6 * 8 + 4 * 4) + (n_div * 16 + (n + 1) * 4 if n_div else 0) + (n * 4 if out_index is not None else 0),
                    d2h_bytes=n * (6 * 8 + 3 * 4))
         return res
 
@@ -456,29 +498,67 @@ class BarrierBook:
             self._tab = self._solves(self.sigma)
         return self._tab
 
-    def _book_struct(self, what, dv_sigma, ptr):
-        from . import _lib
+    def launch_order(self) -> Optional[np.ndarray]:
+        """Ascending stiffness ``alpha dt``, as :meth:`AmericanBook.launch_order`."""
+        if self.n_opt < 64:
+            return None
         t = self._table()
+        key = t.sigma * t.sigma / (t.dx * t.dx) * (self.T / self.N_time)
+        if float(key.max()) <= 1.0001 * float(key.min()):
+            return None
+        return np.argsort(key, kind="stable")
+
+    def _launch_inputs(self):
+        """Per-option input arrays in launch order, built once per book."""
+        if getattr(self, "_launch", None) is None:
+            from . import _lib
+            t = self._table()
+            order = self.launch_order()
+
+            def take(a):
+                return np.ascontiguousarray(a if order is None else a[order])
+
+            arrs = {name: take(np.asarray(arr, dtype=np.float64)) for name, arr in
+                    (("S0", t.spot), ("K", t.strike), ("T", self.T), ("sigma", t.sigma), ("r_disc", t.r), ("b_carry", t.b),
+                     ("x_min", t.x_min), ("dx", t.dx), ("barrier", t.barrier), ("rebate", t.rebate))}
+            if t.barrier_up is not None:
+                arrs["barrier_up"] = take(t.barrier_up)
+            arrs["flags"] = take(t.flags)
+            arrs["n_space"] = take(t.n_space)
+            arrs["n_time"] = take(np.asarray(self.N_time).astype(np.int32))
+            mon = None
+            if t.mon_step is not None and len(t.mon_step):
+                if order is None:
+                    mon = (t.mon_begin, t.mon_step)
+                else:                                          # CSR rebuilt in launch order
+                    mb, me = t.mon_begin[:-1], t.mon_begin[1:]
+                    lens = (me - mb)[order].astype(np.int64)
+                    nb = np.concatenate([[0], np.cumsum(lens)])
+                    pos = np.repeat(mb[order].astype(np.int64) - nb[:-1], lens) + np.arange(int(nb[-1]))
+                    mon = (nb.astype(np.int32), np.ascontiguousarray(t.mon_step[pos]))
+            hints = int(_lib.load().fdm_launch_hints(arrs["n_space"].ctypes.data_as(_lib._pi),
+                                                     arrs["flags"].ctypes.data_as(_lib._pi), self.n_opt, None, 0)) & ~4
+            self._launch = dict(order=None if order is None else np.ascontiguousarray(order, dtype=np.int32), arrs=arrs,
+                                mon=mon, hints=hints)
+        return self._launch
+
+    def _book_struct(self, what, dv_sigma, ptr):
+        """``(FdmBarrierBook, out_index)``; see :meth:`AmericanBook._book_struct`."""
+        from . import _lib
+        li = self._launch_inputs()
         n = self.n_opt
         bk = _lib.FdmBarrierBook()
         bk.n_options = n
-        for name, arr in (("S0", t.spot), ("K", t.strike), ("T", self.T), ("sigma", t.sigma), ("r_disc", t.r),
-                          ("b_carry", t.b), ("x_min", t.x_min), ("dx", t.dx), ("barrier", t.barrier), ("rebate", t.rebate)):
-            setattr(bk, name, ptr(name, np.ascontiguousarray(arr, dtype=np.float64)))
-        if t.barrier_up is not None:
-            bk.barrier_up = ptr("barrier_up", t.barrier_up)
-        bk.flags = ptr("flags", t.flags)
-        bk.n_space = ptr("n_space", t.n_space)
-        bk.n_time = ptr("n_time", np.ascontiguousarray(self.N_time, dtype=np.int32))
-        if t.mon_step is not None and len(t.mon_step):
-            bk.mon_begin = ptr("mon_begin", t.mon_begin)
-            bk.mon_step = ptr("mon_step", t.mon_step)
-            bk.n_mon_total = len(t.mon_step)
+        for k, v in li["arrs"].items():
+            setattr(bk, k, ptr(k, v))
+        if li["mon"] is not None:
+            bk.mon_begin = ptr("mon_begin", li["mon"][0])
+            bk.mon_step = ptr("mon_step", li["mon"][1])
+            bk.n_mon_total = len(li["mon"][1])
         bk.dv_sigma, bk.what = float(dv_sigma), self._WHAT[what]
-        bk.n_space_max = int(t.n_space.max()) if n else 3
-        bk.hints = int(_lib.load().fdm_launch_hints(t.n_space.ctypes.data_as(_lib._pi), t.flags.ctypes.data_as(_lib._pi),
-                                                    n, None, 0)) & ~4
-        return bk
+        bk.n_space_max = int(self.N_space.max()) if n else 3
+        bk.hints = li["hints"]
+        return bk, li["order"]
 
     def solve_steps(self, what: str = "greeks") -> int:
         k = 3 if what == "greeks" else 1
@@ -512,12 +592,14 @@ class BarrierBook:
             keep.append(arr)
             return arr.ctypes.data
 
-        bk = self._book_struct(what, dv_sigma, host_ptr)
+        bk, out_index = self._book_struct(what, dv_sigma, host_ptr)
         res = {k: np.empty(n) for k in ("price", "delta", "gamma", "vega", "theta")}
         res["status"] = np.empty(n, dtype=np.int32)
         out = _lib.FdmBookOut()
         for k, v in res.items():
             setattr(out, k, v.ctypes.data)
+        if out_index is not None:
+            out.out_index = out_index.ctypes.data
         ns, nl, ms = C.c_int64(0), C.c_int32(0), C.c_float(0.0)
         _lib.check(L.fdm_barrier_book_host(C.byref(bk), C.byref(out), C.byref(ns), C.byref(nl), C.byref(ms)))
         if what == "solve":
@@ -549,6 +631,8 @@ class DeviceBookRun:
     solves and epilogue on a stream through the device-pointer entries ``fdm_american_book`` / ``fdm_barrier_book``
     with no host copy and no synchronisation.
 
+    The fan-out lays the options out in the book's ``launch_order()`` (ascending stiffness) and the epilogue scatters
+    every result back to its caller's row (``FdmBookOut.out_index``), so ``cols`` are in the caller's order.
     The results are views of ONE byte buffer ``packed`` (``width`` rows per column, ``width >= n``): six float64
     columns ``price_log2, price, delta, gamma, vega, theta`` followed by three int32 columns ``ex_lo, ex_hi,
     status`` -- the unit of the multi-GPU result gather (:func:`finite_difference_b200.shard.gather_packed`).
@@ -579,17 +663,19 @@ class DeviceBookRun:
 
         L = _lib.load()
         if kind == "american":
-            self._struct = book._book_struct(what, opts["dv_sigma"], opts["use_richardson"], dev_ptr)
+            self._struct, out_index = book._book_struct(what, opts["dv_sigma"], opts["use_richardson"], dev_ptr)
             need = L.fdm_american_book_workspace(n, int(self._struct.n_div_total), self._struct.what, self._struct.use_richardson)
             self._entry = L.fdm_american_book
             self.node_steps = book.solve_steps(what, opts["use_richardson"])
             self.n_solves = n * int(L.fdm_book_solves_per_option(self._struct.what, self._struct.use_richardson))
         else:
-            self._struct = book._book_struct(what, opts["dv_sigma"], dev_ptr)
+            self._struct, out_index = book._book_struct(what, opts["dv_sigma"], dev_ptr)
             need = L.fdm_barrier_book_workspace(n, self._struct.what)
             self._entry = L.fdm_barrier_book
             self.node_steps = book.solve_steps(what)
             self.n_solves = n * int(L.fdm_barrier_book_solves_per_option(self._struct.what))
+        # the fan-out lays the options out in launch order; out_index sends every result back to its caller's row
+        self._out_index = None if out_index is None else dev_ptr("out_index", out_index)
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self._host.values())
         self.workspace = torch.empty(max(int(need), 256), dtype=torch.uint8, device=self.device)
         self.row_bytes = 8 * len(self.F64_COLS) + 4 * len(self.I32_COLS)
@@ -605,6 +691,8 @@ class DeviceBookRun:
             v = self.packed[base + j * width * 4: base + (j + 1) * width * 4].view(torch.int32)
             self.cols[name] = v[:n]
             setattr(self._out, name, v.data_ptr())
+        if self._out_index is not None:
+            self._out.out_index = self._out_index
         self.d2h_bytes = n * self.row_bytes
         self.n_launches = 0
 
@@ -629,7 +717,7 @@ class DeviceBookRun:
         return self.n_launches
 
     def results(self) -> Dict[str, np.ndarray]:
-        """Synchronise and copy the result columns to the host."""
+        """Synchronise and copy the result columns to the host (the caller's option order)."""
         self.torch.cuda.synchronize(self.device)
         return {k: v.cpu().numpy() for k, v in self.cols.items()}
 

@@ -641,6 +641,7 @@ int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int6
     // per-option outputs
     const size_t o_d[6] = {take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8)};
     const size_t o_lo = take(n * 4), o_hi = take(n * 4), o_st = take(n * 4);
+    const size_t i_oi = take(ho->out_index ? n * 4 : 0);
     // expanded descriptors and per-solve results
     const size_t o_ws = take(fdm_american_book_workspace(n, ndiv, hb->what, hb->use_richardson));
 
@@ -685,6 +686,11 @@ int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int6
     dbo.delta = (double *)(arena + o_d[2]); dbo.gamma = (double *)(arena + o_d[3]);
     dbo.vega = (double *)(arena + o_d[4]); dbo.theta = (double *)(arena + o_d[5]);
     dbo.ex_lo = (int32_t *)(arena + o_lo); dbo.ex_hi = (int32_t *)(arena + o_hi); dbo.status = (int32_t *)(arena + o_st);
+    dbo.out_index = nullptr;
+    if (ho->out_index) {
+        FDM_TRY(cudaMemcpyAsync(arena + i_oi, ho->out_index, n * 4, cudaMemcpyHostToDevice, st));
+        dbo.out_index = (const int32_t *)(arena + i_oi);
+    }
 
     if (rc == FDM_OK) {
         FDM_TRY(cudaMemsetAsync(arena + o_d[0], 0, o_st + up256(n * 4) - o_d[0], st));
@@ -797,6 +803,7 @@ int fdm_barrier_book_host(const FdmBarrierBook *hb, const FdmBookOut *ho, int64_
     const size_t i_mb = take(nmon ? (n + 1) * 4 : 0), i_ms = take(nmon * 4);
     const size_t o_d[5] = {take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8)};
     const size_t o_st = take(n * 4);
+    const size_t i_oi = take(ho->out_index ? n * 4 : 0);
     const size_t o_ws = take(fdm_barrier_book_workspace(n, hb->what));
 
     int dev = 0;
@@ -835,6 +842,10 @@ int fdm_barrier_book_host(const FdmBarrierBook *hb, const FdmBookOut *ho, int64_
     memset(&dbo, 0, sizeof(dbo));
     dbo.price = (double *)(arena + o_d[0]); dbo.delta = (double *)(arena + o_d[1]); dbo.gamma = (double *)(arena + o_d[2]);
     dbo.vega = (double *)(arena + o_d[3]); dbo.theta = (double *)(arena + o_d[4]); dbo.status = (int32_t *)(arena + o_st);
+    if (ho->out_index) {
+        FDM_TRY(cudaMemcpyAsync(arena + i_oi, ho->out_index, n * 4, cudaMemcpyHostToDevice, st));
+        dbo.out_index = (const int32_t *)(arena + i_oi);
+    }
 
     if (rc == FDM_OK) {
         FDM_TRY(cudaEventRecord(cx.e0, st));

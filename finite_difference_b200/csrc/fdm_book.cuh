@@ -134,6 +134,7 @@ __global__ void combine_kernel(const FdmAmericanBook bk, const FdmOut res, const
     const bool rich = bk.use_richardson != 0;
     const int what = bk.what;
     const double h = bk.dv_sigma;
+    const int64_t oi = o.out_index ? o.out_index[i] : i;               // where this option's results go
     auto P = [&](int k) { return res.price[(int64_t)k * n + i]; };
     auto D = [&](int k) { return res.delta[(int64_t)k * n + i]; };
     auto G = [&](int k) { return res.gamma[(int64_t)k * n + i]; };
@@ -146,33 +147,33 @@ __global__ void combine_kernel(const FdmAmericanBook bk, const FdmOut res, const
     }
     if (unsolved) {                                                     // a solve no kernel took: nothing to combine
         const double nan = __longlong_as_double(0x7ff8000000000000ll);
-        if (o.status) o.status[i] = FDM_STATUS_NOT_SOLVED;
-        if (o.ex_lo) o.ex_lo[i] = -1;
-        if (o.ex_hi) o.ex_hi[i] = -1;
-        if (o.price_log2) o.price_log2[i] = nan;
-        if (o.price) o.price[i] = nan;
-        if (o.delta) o.delta[i] = nan;
-        if (o.gamma) o.gamma[i] = nan;
-        if (o.vega) o.vega[i] = nan;
-        if (o.theta) o.theta[i] = nan;
+        if (o.status) o.status[oi] = FDM_STATUS_NOT_SOLVED;
+        if (o.ex_lo) o.ex_lo[oi] = -1;
+        if (o.ex_hi) o.ex_hi[oi] = -1;
+        if (o.price_log2) o.price_log2[oi] = nan;
+        if (o.price) o.price[oi] = nan;
+        if (o.delta) o.delta[oi] = nan;
+        if (o.gamma) o.gamma[oi] = nan;
+        if (o.vega) o.vega[oi] = nan;
+        if (o.theta) o.theta[oi] = nan;
         return;
     }
-    if (o.status) o.status[i] = st;
-    if (o.ex_lo) o.ex_lo[i] = res.idx[4 * i + 2];                       // exercise interval of the first (base) solve
-    if (o.ex_hi) o.ex_hi[i] = res.idx[4 * i + 3];
+    if (o.status) o.status[oi] = st;
+    if (o.ex_lo) o.ex_lo[oi] = res.idx[4 * i + 2];                       // exercise interval of the first (base) solve
+    if (o.ex_hi) o.ex_hi[oi] = res.idx[4 * i + 3];
     int k0 = 0;
     if (what == FDM_BOOK_PRICE_LOG) {
-        if (o.price_log2) o.price_log2[i] = P(0);
-        if (o.price) o.price[i] = P(0);
-        if (o.delta) o.delta[i] = D(0);
-        if (o.gamma) o.gamma[i] = G(0);
+        if (o.price_log2) o.price_log2[oi] = P(0);
+        if (o.price) o.price[oi] = P(0);
+        if (o.delta) o.delta[oi] = D(0);
+        if (o.gamma) o.gamma[oi] = G(0);
         return;
     }
     if (what == FDM_BOOK_PRICE_LOG2 || what == FDM_BOOK_SCENARIO) {
         const double pN = P(0);
         double v = pN;
         if (rich) v = __dsub_rn(__dmul_rn(4.0, P(1)), pN) / 3.0;         // (4 p2N - pN) / 3, :672
-        if (o.price_log2) o.price_log2[i] = v;
+        if (o.price_log2) o.price_log2[oi] = v;
         k0 = rich ? 2 : 1;
         if (what == FDM_BOOK_PRICE_LOG2) return;
     }
@@ -196,11 +197,11 @@ __global__ void combine_kernel(const FdmAmericanBook bk, const FdmOut res, const
         theta = -__dsub_rn(diff, __dmul_rn(r, price));
     else
         theta = -__dsub_rn(__dadd_rn(diff, __dmul_rn(__dmul_rn(__dsub_rn(b, 0.0), S0), delta)), __dmul_rn(r, price));
-    if (o.price) o.price[i] = price;
-    if (o.delta) o.delta[i] = delta;
-    if (o.gamma) o.gamma[i] = gamma;
-    if (o.vega) o.vega[i] = dV / 100.0;                                  // :733
-    if (o.theta) o.theta[i] = theta;
+    if (o.price) o.price[oi] = price;
+    if (o.delta) o.delta[oi] = delta;
+    if (o.gamma) o.gamma[oi] = gamma;
+    if (o.vega) o.vega[oi] = dV / 100.0;                                  // :733
+    if (o.theta) o.theta[oi] = theta;
 }
 
 // ---- barrier books (DiscreteBarrierCrankNicolsonLog.price / greeks, discrete_barrier_fdm_pricer_cn.py:429-466) ----
@@ -259,6 +260,7 @@ __global__ void barrier_combine_kernel(const FdmBarrierBook bk, const FdmOut res
         unsolved |= sk < 0;
         st = max(st, sk);
     }
+    const int64_t oi = o.out_index ? o.out_index[i] : i;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     double price = nan, delta = nan, gamma = nan, vega = nan, theta = nan;
     if (!unsolved) {
@@ -269,12 +271,12 @@ __global__ void barrier_combine_kernel(const FdmBarrierBook bk, const FdmOut res
                            __dmul_rn(r, price));                                       // :440-444
         if (n_roles == 3) vega = __dsub_rn(res.price[n + i], res.price[2 * n + i]) / __dmul_rn(2.0, bk.dv_sigma);   // :457
     }
-    if (o.status) o.status[i] = unsolved ? FDM_STATUS_NOT_SOLVED : st;
-    if (o.price) o.price[i] = price;
-    if (o.delta) o.delta[i] = delta;
-    if (o.gamma) o.gamma[i] = gamma;
-    if (o.vega) o.vega[i] = vega;
-    if (o.theta) o.theta[i] = theta;
+    if (o.status) o.status[oi] = unsolved ? FDM_STATUS_NOT_SOLVED : st;
+    if (o.price) o.price[oi] = price;
+    if (o.delta) o.delta[oi] = delta;
+    if (o.gamma) o.gamma[oi] = gamma;
+    if (o.vega) o.vega[oi] = vega;
+    if (o.theta) o.theta[oi] = theta;
 }
 
 }  // namespace book

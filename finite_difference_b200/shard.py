@@ -157,7 +157,8 @@ class PackedGather:
     book order with one ``index_select`` per dtype ON THE DEVICE and copies the two blocks to pinned host memory
     (two D2H copies).  No host-side packing, no per-row scatter.
 
-    ``owned``: this rank's ascending global option indices (``shard.partition``); the owners are exchanged once here.
+    ``owned``: the global option index of every row of this rank's buffer (``shard.partition``, in the order the
+    rows are laid out); the owners are exchanged once here.
     """
 
     def __init__(self, owned: np.ndarray, n_total: int, width: int, n_f64: int = 6, n_i32: int = 3, device=None,

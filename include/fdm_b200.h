@@ -228,6 +228,11 @@ typedef struct FdmBookOut {      /* n_options entries each; any pointer may be N
     double *price, *delta, *gamma, *vega, *theta;   /* greeks_log2() (what = 2, 3; what = 0: price/delta/gamma) */
     int32_t *ex_lo, *ex_hi;      /* exercise interval of the base solve after its last step */
     int32_t *status;             /* max over the option's solves */
+    /* ABI 3 (optional): option i of the book writes its results to entry out_index[i] of every array above instead
+       of entry i.  A caller that lays a book out in a launch order of its own choosing (e.g. ascending stiffness, so
+       that neighbouring CTAs run the same specialised time loop) gets the results back in its original order with
+       no pass of its own.  NULL = identity.  Host pointer for the *_host entries, device pointer otherwise. */
+    const int32_t *out_index;
 } FdmBookOut;
 
 /* solves per option for (what, use_richardson) */
