@@ -179,14 +179,16 @@ __device__ __forceinline__ dd dd_div(dd a, dd b)
     return dd_add(dd_two_sum(q1, q2), dd{q3, 0.0});
 }
 
-// rinv_inf: this engine's converged pivot reciprocal.  Returns pd.
-__device__ __noinline__ double growth_matched_pd(double A_L, double A_C, double A_U, double B_L, double B_C,
-                                                 double B_U, double q, double rinv_inf, int max_rows)
+// The reference's factors at their bit-wise fixed point: c'_0 = A_U/A_C, den_i = A_C - A_L c'_{i-1}, c'_i = A_U/den_i
+// (fd_american_option_pricer.py:443-451).  The floating-point map den -> fl(A_C - fl(A_L fl(A_U / den))) is monotone
+// non-decreasing and the reference's pivots fall from den_0 = A_C, so they stop at the LARGEST fixed point below
+// A_C -- and so does the iteration from any start between that fixed point and A_C.  `den_start` lets a caller that
+// knows the root of the quadratic start a hair above it (cta::setup_phase: 3x fewer iterations); A_C reproduces the
+// reference's own sequence.  Returns false if no fixed point is reached within max_rows iterations.
+__device__ __noinline__ bool reference_steady_state(double A_L, double A_C, double A_U, double den_start, int max_rows,
+                                                    double &den_out, double &cp_out)
 {
-    // the reference's factors at their fixed point: c'_0 = A_U/A_C, den_i = A_C - A_L c'_{i-1}, c'_i = A_U/den_i
-    // Grids too short for either recurrence to reach its fixed point have no steady rows to match
-    // (and alpha dt is small there): pd = 1.
-    double den = A_C, cp = A_U / A_C;
+    double den = den_start, cp = A_U / den_start;
     bool fixed = false;
     for (int i = 1; i < max_rows && !fixed; ++i) {
         const double den_i = __dsub_rn(A_C, __dmul_rn(A_L, cp));
@@ -195,7 +197,15 @@ __device__ __noinline__ double growth_matched_pd(double A_L, double A_C, double 
         den = den_i;
         cp = cp_i;
     }
-    if (!fixed) return 1.0;
+    den_out = den;
+    cp_out = cp;
+    return fixed;
+}
+
+// pd from the reference's steady-state factors (den, cp) and this engine's converged pivot reciprocal rinv_inf
+__device__ __noinline__ double growth_pd_from_ref(double A_L, double den, double cp, double A_U, double B_L, double B_C,
+                                                  double B_U, double q, double rinv_inf)
+{
     const double nm = -__dmul_rn(A_L, rinv_inf), ncc = -__dmul_rn(A_U, rinv_inf);
     const dd S_ref = dd_mul(dd_two_sum(A_L, den), dd_two_sum(1.0, cp));
     const dd S_our = dd_div(dd_mul(dd_two_sum(1.0, -nm), dd_two_sum(1.0, -ncc)), dd{rinv_inf, 0.0});
@@ -203,6 +213,17 @@ __device__ __noinline__ double growth_matched_pd(double A_L, double A_C, double 
     const dd g = dd_add(dd{q, 0.0}, dd_div(S_B, S_ref));
     const dd pd = dd_add(dd_mul(S_our, g), dd{-q, 0.0});
     return pd.hi + pd.lo;
+}
+
+// rinv_inf: this engine's converged pivot reciprocal.  Returns pd.
+// Grids too short for the reference's recurrence to reach its fixed point have no steady rows to match (and alpha dt
+// is small there): pd = 1.
+__device__ __forceinline__ double growth_matched_pd(double A_L, double A_C, double A_U, double B_L, double B_C,
+                                                    double B_U, double q, double rinv_inf, int max_rows)
+{
+    double den, cp;
+    if (!reference_steady_state(A_L, A_C, A_U, A_C, max_rows, den, cp)) return 1.0;
+    return growth_pd_from_ref(A_L, den, cp, A_U, B_L, B_C, B_U, q, rinv_inf);
 }
 
 // The same fold against the EXACT row sums of A and B instead of the reference's rounded steady-state factors: the

@@ -163,7 +163,42 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
         // entry i < P is row i, entry P the steady state
         double r_prev = 0.0, r_cur = __drcp_rn(A_C);
         int P = -1;
-        for (int i = 0; i < cap; ++i) {
+        // Fast path (the usual case): with the row-0 correction only the STEADY state of the pivots is used, so the
+        // table below is not needed -- and the steady state need not be walked to from row 0.  The root of
+        // den^2 - A_C den + A_L A_U = 0 says where it is; the reference's own recurrence, started a hair above the root,
+        // settles on the same bit-wise fixed point as the reference's sweep from A_C (reference_steady_state) in a third
+        // of the iterations.  (Thread 0 walked both recurrences over 100..500 rows before: 11 % of a 2500-step solve
+        // at 8192 nodes with its five phases, 6 % of the 2133 x 500 barrier-runner solves.)
+        bool fast = false;
+        double den_ref = 0.0, cp_ref = 0.0;
+        if (row0_mode<C, WARPS, AMER>()) {
+            const double PLU = __dmul_rn(A_L, A_U), PLU_lo = __fma_rn(A_L, A_U, -PLU);
+            const double disc = __fma_rn(A_C, A_C, -4.0 * PLU);
+            if (disc > 0.0) {
+                double ds = 0.5 * (A_C + sqrt(disc));
+                for (int it = 0; it < 2; ++it) {
+                    const double res = __fma_rn(__dsub_rn(ds, A_C), ds, PLU) + PLU_lo;
+                    ds -= res / (2.0 * ds - A_C);
+                }
+                const double rs = 1.0 / ds, nmc = -(A_L * rs), nccc = -(A_U * rs), rho = nmc * nccc;
+                if (rho > 1e-20 && rho < 0.999 && fabs(nmc) < 1.0 && fabs(nmc) > 1e-10 && fabs(nccc) > 1e-10) {
+                    const double rows_conv = 37.0 / -log(rho);              // rows until the reference's sweep settles
+                    const double kappa = 1.0 / (1.0 - rho), dl = A_L * A_U * rs * rs;
+                    const double gf = dl * kappa / (1.0 + dl * kappa);
+                    const double rows_z = (log(1e-24) - log(fmax(fabs(gf), 1e-300))) / log(fabs(nmc));
+                    if (isfinite(gf) && rows_conv < 0.5 * n_int && rows_conv < 0.5 * cap && rows_z + 2.0 < 0.9 * n_int) {
+                        const double start = fmin(ds * (1.0 + 0x1p-42), A_C);
+                        fast = reference_steady_state(A_L, A_C, A_U, start, 4096, den_ref, cp_ref);
+                    }
+                }
+            }
+        }
+        if (fast) {
+            P = 0;
+            r_cur = __drcp_rn(den_ref);
+            pv_inv[0] = r_cur; pv_nm[0] = -(A_L * r_cur); pv_ncc[0] = -(A_U * r_cur);
+        }
+        for (int i = 0; i < cap && !fast; ++i) {
             const double den_next = __dsub_rn(A_C, __dmul_rn(A_L, __dmul_rn(A_U, r_cur)));
             const double r_next = __drcp_rn(den_next);
             pv_inv[i] = r_cur;
@@ -216,7 +251,8 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
         }
         sm.ish[12] = wz;
         // growth-factor matching (fdm_b200.cu, growth_matched_pd); the linear march folds p + delta into inv
-        const double pd = (P < cap && P < n_int) ? growth_matched_pd(A_L, A_C, A_U, B_L, B_C, B_U, ph.q, pv_inv[P], n_int) : 1.0;
+        const double pd = fast ? growth_pd_from_ref(A_L, den_ref, cp_ref, A_U, B_L, B_C, B_U, ph.q, pv_inv[P])
+                          : ((P < cap && P < n_int) ? growth_matched_pd(A_L, A_C, A_U, B_L, B_C, B_U, ph.q, pv_inv[P], n_int) : 1.0);
         if (!AMER) {
             const double scale = p + (pd - 1.0);
             for (int i = 0; i <= P; ++i) pv_inv[i] *= scale;
@@ -751,6 +787,14 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
     const double cc = __dadd_rn(alpha, beta);
     const double bcoef = __dsub_rn(__dmul_rn(-2.0, alpha), r);
 
+    // -DFDM_CTA_PROFILE: per-region cycle counts of one warp (dev tool; printf from block 40)
+#ifdef FDM_CTA_PROFILE
+    long long prof_acc[3] = {0, 0, 0};
+    long long prof_t = clock64();
+#define CTA_TICK(slot) do { const long long t_ = clock64(); prof_acc[slot] += t_ - prof_t; prof_t = t_; } while (0)
+#else
+#define CTA_TICK(slot)
+#endif
     const int seg_b = B.seg_begin[sid], seg_e = B.seg_begin[sid + 1];
     int mon_i = 0, mon_e = 0;
     if (ko && B.mon_begin) { mon_i = B.mon_begin[sid]; mon_e = B.mon_end ? B.mon_end[sid] : B.mon_begin[sid + 1]; }
@@ -788,7 +832,9 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
             const bool implicit_phase = m < base_ran;
             const int m_end = implicit_phase ? min(base_ran, n_steps) : n_steps;
             Ph ph;
+            CTA_TICK(0);
             setup_phase<C, WARPS, AMER>(implicit_phase ? 1.0 : 0.5, dt, ca, cc, bcoef, n_int, pad, sm, ph);
+            CTA_TICK(1);
             const int wf = sm.ish[10];
             constexpr bool R0 = row0_mode<C, WARPS, AMER>();
             const bool row0_corr = R0 && sm.ish[12] >= 0;       // CTA-uniform
@@ -900,6 +946,7 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
 #endif
         }
         if (cash != 0.0) {
+            CTA_TICK(0);
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < C; ++k) {
@@ -914,10 +961,17 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
             }
             __syncthreads();
             fill_payoff(false);                                 // r0 held cz during the jump
+            CTA_TICK(2);
         }
     }
 
     // ---- read-out: stage the value vector by node in shared memory, thread 0 finishes -------------
+    CTA_TICK(0);
+#ifdef FDM_CTA_PROFILE
+    if (blockIdx.x == 40 && threadIdx.x == 32 * (WARPS - 1))
+        printf("cta<%d warps> n=%d steps=%d cycles: prologue+loops %lld | setup_phase %lld | dividend jumps %lld\n", WARPS, n, gstep,
+               prof_acc[0], prof_acc[1], prof_acc[2]);
+#endif
     __syncthreads();
     double *Vs = sm.r1;
 #pragma unroll
