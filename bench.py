@@ -697,6 +697,55 @@ def dbfp_config(args, local, threads):
             "parity": {"n_solves": 16, "max_rel_err_price": worst, "tolerance": 1e-10, "ok": bool(worst <= 1e-10)}}
 
 
+def p2_config(args, local, threads):
+    """the row-varying S-space march of DiscreteBarrierFDMPricer2 (fdm_rowvar_kernel), 601 nodes x 600
+    steps, every step implicit (the regime in which the reference prices), down-and-out calls with monthly monitoring."""
+    import dataclasses
+    from datetime import date, timedelta
+    import torch
+    from finite_difference_b200 import _lib, rowvar
+    from oracle import oracle
+    rng = np.random.default_rng(SEED + 7)
+    val, mat = date(2025, 7, 28), date(2026, 7, 28)
+    mons = [val + timedelta(days=30 * k) for k in range(1, 13)]
+    contracts, marches = [], []
+    for i in range(32):
+        kw = dict(spot=100.0, strike=float(rng.uniform(85, 115)), valuation_date=val, maturity_date=mat, volatility=0.25,
+                  option_type="call", barrier_type="down-and-out", lower_barrier=float(rng.uniform(70, 92)), monitoring_dates=mons,
+                  flat_rate_nacc=float(rng.uniform(0.01, 0.08)), num_space_nodes=600, num_time_steps=600, rannacher_steps=600)
+        contracts.append(kw)
+        base = rowvar.march_inputs(**kw)
+        marches += [dataclasses.replace(base, sigma=float(sg)) for sg in np.linspace(0.12, 0.45, 64)]
+    batch = rowvar.RowVarBatch(marches)
+    peak, _ = _lib.fp64_peak_tflops()
+    rowvar.solve_rowvar_host(batch)
+    with ClockSampler(local) as clocks:
+        runs = [rowvar.solve_rowvar_host(batch) for _ in range(3)]
+    ms = min(r.kernel_ms for r in runs)
+    t0 = time.perf_counter()
+    res = rowvar.solve_rowvar_host(batch)
+    e2e_s = time.perf_counter() - t0
+    worst = 0.0
+    for i in range(0, 32, 4):                                   # volatility 0.12 + the construction volatility's own grid
+        kw = dict(contracts[i])
+        prep = oracle.pricer2_prepare(**kw)
+        prep["sigma"] = float(np.linspace(0.12, 0.45, 64)[0])
+        V = oracle.pricer2_march(prep, True)
+        ref = oracle.p2_interp_linear(prep["S_eff"], [float(x) for x in prep["s_nodes"]], [float(x) for x in V])
+        worst = max(worst, abs(res.price[i * 64] - ref) / max(abs(ref), 1e-2))
+    ns = batch.node_steps()
+    return {"workload": "p2: row-varying S-space march (DiscreteBarrierFDMPricer2._solve_pde_backward), 2048 down-and-out calls, "
+                        "601 nodes x 600 implicit steps, monthly monitoring",
+            "value": ns / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "steps": 3, "gpu_launches": res.n_launches,
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "fp64", "flops_per_node_step": FLOPS_LINEAR, "achieved": ns * FLOPS_LINEAR / ms / 1e9, "peak": peak,
+                         "unit": "TFLOP/s", "frac": ns * FLOPS_LINEAR / ms / 1e9 / peak,
+                         "note": "13 flops per node-step: right-hand side 5 + Thomas 8; the reference also rebuilds the matrix every step"},
+            "e2e": {"value": ns / e2e_s, "unit": UNIT, "seconds": e2e_s,
+                    "path": "rowvar.solve_rowvar_host -> fdm_rowvar_solve_host (grids and payoffs H2D, march, prices D2H)"},
+            "parity": {"n_solves": 8, "max_rel_err_price": worst, "tolerance": 1e-10, "ok": bool(worst <= 1e-10)}}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -758,6 +807,12 @@ def run_b200(args):
                 ok &= others["dbfp"]["parity"]["ok"]
             except Exception as exc:
                 others["dbfp"] = {"error": f"{type(exc).__name__}: {exc}"}
+                ok = False
+            try:
+                others["p2"] = p2_config(args, local, threads)
+                ok &= others["p2"]["parity"]["ok"]
+            except Exception as exc:
+                others["p2"] = {"error": f"{type(exc).__name__}: {exc}"}
                 ok = False
             line["other_configs"] = others
             if not ok:

@@ -23,7 +23,8 @@ FLAG_BDRY_TOP_NEXT = 0x40
 FLAG_PUT_BDRY_SMIN = 0x80
 FLAG_INVALID = 0x100
 
-STATUS_OK, STATUS_NONFINITE, STATUS_STIFF, STATUS_NOT_SOLVED = 0, 1, 2, -1
+STATUS_OK, STATUS_NONFINITE, STATUS_STIFF, STATUS_SINGULAR, STATUS_NOT_SOLVED = 0, 1, 2, 3, -1
+ROWVAR_MAX_NODES = 1024
 
 MAX_N_SPACE = 8193
 WARP_MAX_N_SPACE = 513
@@ -88,13 +89,25 @@ class FdmBarrierBook(C.Structure):
     ]
 
 
+class FdmRowVarBatch(C.Structure):
+    _fields_ = [("n_solves", C.c_int64), ("n_nodes_max", C.c_int32), ("n_mon_total", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("node_begin", "s_nodes", "v_terminal", "sigma", "r", "strike", "tenor", "dt", "lo_bar",
+                                  "up_bar", "h_minus", "h_plus", "s_eff", "n_steps", "rannacher", "flags", "bar_j",
+                                  "mon_begin", "mon_step")]
+
+
+class FdmRowVarOut(C.Structure):
+    _fields_ = [("price", C.c_void_p), ("status", C.c_void_p), ("v_dump", C.c_void_p), ("v_dump_stride", C.c_int64)]
+
+
 BOOK_PRICE_LOG, BOOK_PRICE_LOG2, BOOK_GREEKS_LOG2, BOOK_SCENARIO = 0, 1, 2, 3
 BARRIER_BOOK_SOLVE, BARRIER_BOOK_GREEKS = 0, 1
 
 EXPORTS = ("fdm_version", "fdm_sizeof", "fdm_last_error", "fdm_device_count", "fdm_solve_batch",
            "fdm_solve_batch_host", "fdm_launch_hints", "fdm_book_solves_per_option", "fdm_american_book_host",
            "fdm_american_book_workspace", "fdm_american_book", "fdm_barrier_book_solves_per_option",
-           "fdm_barrier_book_workspace", "fdm_barrier_book", "fdm_barrier_book_host", "fdm_release_workspace",
+           "fdm_barrier_book_workspace", "fdm_barrier_book", "fdm_barrier_book_host", "fdm_rowvar_solve",
+           "fdm_rowvar_solve_host", "fdm_release_workspace",
            "fdm_fp64_peak")
 
 
@@ -153,6 +166,10 @@ def load(path: str | None = None):
     L.fdm_barrier_book_host.restype = C.c_int
     L.fdm_barrier_book_host.argtypes = [C.POINTER(FdmBarrierBook), C.POINTER(FdmBookOut), C.POINTER(C.c_int64),
                                         _pi, C.POINTER(C.c_float)]
+    L.fdm_rowvar_solve.restype = C.c_int
+    L.fdm_rowvar_solve.argtypes = [C.POINTER(FdmRowVarBatch), C.POINTER(FdmRowVarOut), C.c_void_p, _pi]
+    L.fdm_rowvar_solve_host.restype = C.c_int
+    L.fdm_rowvar_solve_host.argtypes = [C.POINTER(FdmRowVarBatch), C.POINTER(FdmRowVarOut), _pi, C.POINTER(C.c_float)]
     L.fdm_fp64_peak.restype = C.c_int
     L.fdm_fp64_peak.argtypes = [_pd, C.POINTER(C.c_float)]
     if L.fdm_version() != ABI_VERSION:

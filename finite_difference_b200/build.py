@@ -30,6 +30,7 @@ def units(lean_classes=LEAN_CLASSES):
     u += [(f"warp_{c}", "fdm_warp_inst.cu", [f"-DFDM_INST_C={c}"]) for c in (4, 8, 13, 16)]
     u += [(f"lean_{c}", "fdm_lean_inst.cu", [f"-DFDM_INST_C={c}"]) for c in lean_classes]
     u += [(f"cta_{w}", "fdm_cta_inst.cu", [f"-DFDM_INST_W={w}"]) for w in (4, 5, 8, 16)]
+    u += [(f"rowvar_{c}", "fdm_rowvar_inst.cu", [f"-DFDM_INST_C={c}"]) for c in (7, 10, 13, 19, 26, 32)]
     # the large instances first: the longest compile bounds the build
     order = {"cta_16": 0, "cta_8": 1, "cta_5": 2, "cta_4": 3}
     return sorted(u, key=lambda x: order.get(x[0], 10))

@@ -359,6 +359,8 @@ int fdm_sizeof(int which)
     case 2: return (int)sizeof(FdmAmericanBook);
     case 3: return (int)sizeof(FdmBookOut);
     case 4: return (int)sizeof(FdmBarrierBook);
+    case 5: return (int)sizeof(FdmRowVarBatch);
+    case 6: return (int)sizeof(FdmRowVarOut);
     default: return -1;
     }
 }
@@ -859,6 +861,136 @@ int fdm_barrier_book_host(const FdmBarrierBook *hb, const FdmBookOut *ho, int64_
     if (rc == FDM_OK) {
         d2h(ho->price, o_d[0], n * 8); d2h(ho->delta, o_d[1], n * 8); d2h(ho->gamma, o_d[2], n * 8);
         d2h(ho->vega, o_d[3], n * 8); d2h(ho->theta, o_d[4], n * 8); d2h(ho->status, o_st, n * 4);
+        FDM_TRY(cudaStreamSynchronize(st));
+        if (kernel_ms && rc == FDM_OK) FDM_TRY(cudaEventElapsedTime(kernel_ms, cx.e0, cx.e1));
+    }
+    return rc;
+}
+
+// ---- row-varying solves ---------------------------------------------------------------------------------------------
+
+static int rowvar_check(const FdmRowVarBatch *b, const FdmRowVarOut *o)
+{
+    if (!b || !o) return fail(FDM_ERR_INVALID, "batch / out is NULL%s");
+    if (b->n_solves < 0) return fail(FDM_ERR_INVALID, "n_solves < 0%s");
+    if (b->n_solves == 0) return FDM_OK;
+    if (!b->node_begin || !b->s_nodes || !b->v_terminal || !b->sigma || !b->r || !b->strike || !b->tenor || !b->dt ||
+        !b->lo_bar || !b->up_bar || !b->h_minus || !b->h_plus || !b->s_eff || !b->n_steps || !b->rannacher || !b->flags ||
+        !b->bar_j)
+        return fail(FDM_ERR_INVALID, "a required FdmRowVarBatch array is NULL%s");
+    if (!o->price) return fail(FDM_ERR_INVALID, "FdmRowVarOut.price is NULL%s");
+    if (b->n_nodes_max < 3) return fail(FDM_ERR_INVALID, "n_nodes_max < 3%s");
+    if (b->n_nodes_max > FDM_ROWVAR_MAX_NODES) return fail(FDM_ERR_UNSUPPORTED, "grid larger than FDM_ROWVAR_MAX_NODES (1024)%s");
+    if (b->n_mon_total > 0 && (!b->mon_begin || !b->mon_step)) return fail(FDM_ERR_INVALID, "monitor tables missing%s");
+    return FDM_OK;
+}
+
+static int rowvar_launch(const FdmRowVarBatch &b, const FdmRowVarOut &o, cudaStream_t st, int32_t *n_launches)
+{
+    if (o.status) FDM_CUDA(cudaMemsetAsync(o.status, 0xff, b.n_solves * 4, st));      // FDM_STATUS_NOT_SOLVED
+    // one launch per size class that can be populated; a solve runs in the smallest class that holds it
+    typedef int (*Fn)(const FdmRowVarBatch &, const FdmRowVarOut &, cudaStream_t, int, int32_t *);
+    static const struct { int c; Fn fn; } cls[] = {{7, fdm_launch_rowvar_7},   {10, fdm_launch_rowvar_10}, {13, fdm_launch_rowvar_13},
+                                                   {19, fdm_launch_rowvar_19}, {26, fdm_launch_rowvar_26}, {32, fdm_launch_rowvar_32}};
+    int n_lo = 0;
+    for (const auto &k : cls) {
+        const int rc = k.fn(b, o, st, n_lo, n_launches);
+        if (rc != FDM_OK) return rc;
+        n_lo = 32 * k.c;
+        if (b.n_nodes_max <= n_lo) break;
+    }
+    return FDM_OK;
+}
+
+int fdm_rowvar_solve(const FdmRowVarBatch *batch, const FdmRowVarOut *out, void *stream, int32_t *n_launches)
+{
+    g_err[0] = 0;
+    if (n_launches) *n_launches = 0;
+    int rc = rowvar_check(batch, out);
+    if (rc != FDM_OK || batch->n_solves == 0) return rc;
+    if ((rc = no_device()) != FDM_OK) return rc;
+    return rowvar_launch(*batch, *out, (cudaStream_t)stream, n_launches);
+}
+
+int fdm_rowvar_solve_host(const FdmRowVarBatch *hb, const FdmRowVarOut *ho, int32_t *n_launches, float *kernel_ms)
+{
+    g_err[0] = 0;
+    if (n_launches) *n_launches = 0;
+    if (kernel_ms) *kernel_ms = 0.f;
+    int rc = rowvar_check(hb, ho);
+    if (rc != FDM_OK || hb->n_solves == 0) return rc;
+    const int64_t n = hb->n_solves;
+    if (hb->node_begin[0] != 0) return fail(FDM_ERR_INVALID, "node_begin[0] must be 0%s");
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t k = hb->node_begin[i + 1] - hb->node_begin[i];
+        if (k < 3 || k > hb->n_nodes_max) return fail(FDM_ERR_INVALID, "node count outside [3, n_nodes_max]%s");
+        if (hb->n_steps[i] < 1) return fail(FDM_ERR_INVALID, "n_steps < 1%s");
+    }
+    if ((rc = no_device()) != FDM_OK) return rc;
+    const int64_t nn = hb->node_begin[n];
+    const int64_t nmon = (hb->mon_begin && hb->n_mon_total > 0) ? hb->mon_begin[n] : 0;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += up256(bytes); return o; };
+    const size_t o_nb = take((n + 1) * 8), o_s = take(nn * 8), o_v = take(nn * 8);
+    const int ND = 10;
+    const double *hd[ND] = {hb->sigma, hb->r, hb->strike, hb->tenor, hb->dt, hb->lo_bar, hb->up_bar, hb->h_minus, hb->h_plus, hb->s_eff};
+    size_t o_d[ND];
+    for (int i = 0; i < ND; ++i) o_d[i] = take(n * 8);
+    const int NI = 4;
+    const int32_t *hi[NI] = {hb->n_steps, hb->rannacher, hb->flags, hb->bar_j};
+    size_t o_i[NI];
+    for (int i = 0; i < NI; ++i) o_i[i] = take(n * 4);
+    const size_t o_mb = take(nmon ? (n + 1) * 4 : 0), o_ms = take(nmon * 4);
+    const size_t r_p = take(n * 8), r_st = take(n * 4);
+    const size_t r_dump = take(ho->v_dump ? (size_t)n * ho->v_dump_stride * 8 : 0);
+
+    int dev = 0;
+    FDM_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) return fail(FDM_ERR_UNSUPPORTED, "device index beyond the workspace table%s");
+    Arena &ar = g_arenas[dev];
+    std::lock_guard<std::mutex> arena_lock(ar.mu);
+    char *arena = nullptr;
+    FDM_CUDA(arena_get(ar, off, &arena));
+    CallCtx cx;
+    FDM_TRY(cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking));
+    FDM_TRY(cudaEventCreate(&cx.e0));
+    FDM_TRY(cudaEventCreate(&cx.e1));
+    if (rc != FDM_OK) return rc;
+    cudaStream_t st = cx.st;
+    auto h2d = [&](size_t o, const void *src, size_t bytes) {
+        if (bytes && src) FDM_TRY(cudaMemcpyAsync(arena + o, src, bytes, cudaMemcpyHostToDevice, st));
+    };
+    h2d(o_nb, hb->node_begin, (n + 1) * 8);
+    h2d(o_s, hb->s_nodes, nn * 8);
+    h2d(o_v, hb->v_terminal, nn * 8);
+    for (int i = 0; i < ND; ++i) h2d(o_d[i], hd[i], n * 8);
+    for (int i = 0; i < NI; ++i) h2d(o_i[i], hi[i], n * 4);
+    if (nmon) { h2d(o_mb, hb->mon_begin, (n + 1) * 4); h2d(o_ms, hb->mon_step, nmon * 4); }
+    FdmRowVarBatch db = *hb;
+    db.node_begin = (const int64_t *)(arena + o_nb);
+    db.s_nodes = (const double *)(arena + o_s);
+    db.v_terminal = (const double *)(arena + o_v);
+    const double **dp[ND] = {&db.sigma, &db.r, &db.strike, &db.tenor, &db.dt, &db.lo_bar, &db.up_bar, &db.h_minus, &db.h_plus, &db.s_eff};
+    for (int i = 0; i < ND; ++i) *dp[i] = (const double *)(arena + o_d[i]);
+    const int32_t **ip[NI] = {&db.n_steps, &db.rannacher, &db.flags, &db.bar_j};
+    for (int i = 0; i < NI; ++i) *ip[i] = (const int32_t *)(arena + o_i[i]);
+    db.mon_begin = nmon ? (const int32_t *)(arena + o_mb) : nullptr;
+    db.mon_step = nmon ? (const int32_t *)(arena + o_ms) : nullptr;
+    FdmRowVarOut dout = *ho;
+    dout.price = (double *)(arena + r_p);
+    dout.status = (int32_t *)(arena + r_st);
+    dout.v_dump = ho->v_dump ? (double *)(arena + r_dump) : nullptr;
+    if (ho->v_dump) FDM_TRY(cudaMemsetAsync(arena + r_dump, 0, (size_t)n * ho->v_dump_stride * 8, st));
+    if (rc == FDM_OK) {
+        FDM_TRY(cudaEventRecord(cx.e0, st));
+        const int lrc = rowvar_launch(db, dout, st, n_launches);
+        if (lrc != FDM_OK) rc = lrc;
+        FDM_TRY(cudaEventRecord(cx.e1, st));
+    }
+    if (rc == FDM_OK) {
+        FDM_TRY(cudaMemcpyAsync(ho->price, arena + r_p, n * 8, cudaMemcpyDeviceToHost, st));
+        if (ho->status) FDM_TRY(cudaMemcpyAsync(ho->status, arena + r_st, n * 4, cudaMemcpyDeviceToHost, st));
+        if (ho->v_dump) FDM_TRY(cudaMemcpyAsync(ho->v_dump, arena + r_dump, (size_t)n * ho->v_dump_stride * 8, cudaMemcpyDeviceToHost, st));
         FDM_TRY(cudaStreamSynchronize(st));
         if (kernel_ms && rc == FDM_OK) FDM_TRY(cudaEventElapsedTime(kernel_ms, cx.e0, cx.e1));
     }

@@ -28,3 +28,8 @@ FDM_DECL_LEAN(4) FDM_DECL_LEAN(7) FDM_DECL_LEAN(8) FDM_DECL_LEAN(10) FDM_DECL_LE
     int fdm_launch_cta_##W(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american, bool any_linear, \
                            bool any_div, int n_lo, int32_t *n_launches);
 FDM_DECL_CTA(4) FDM_DECL_CTA(5) FDM_DECL_CTA(8) FDM_DECL_CTA(16)
+
+// fdm_rowvar_kernel<C>: C rows per lane, up to 32 C nodes; n_lo = largest node count of the class below
+#define FDM_DECL_ROWVAR(C)                                                                                       \
+    int fdm_launch_rowvar_##C(const FdmRowVarBatch &b, const FdmRowVarOut &o, cudaStream_t st, int n_lo, int32_t *n_launches);
+FDM_DECL_ROWVAR(7) FDM_DECL_ROWVAR(10) FDM_DECL_ROWVAR(13) FDM_DECL_ROWVAR(19) FDM_DECL_ROWVAR(26) FDM_DECL_ROWVAR(32)

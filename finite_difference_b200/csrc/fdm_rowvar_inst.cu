@@ -1,0 +1,27 @@
+// fdm_rowvar_inst.cu -- one size class of fdm_rowvar_kernel (compiled with -DFDM_INST_C=<rows per lane>) and its launcher.
+#include "fdm_rowvar.cuh"
+
+#ifndef FDM_INST_C
+#error "compile with -DFDM_INST_C=<rows per lane>"
+#endif
+#define FDM_CAT2(a, b) a##b
+#define FDM_CAT(a, b) FDM_CAT2(a, b)
+
+int FDM_CAT(fdm_launch_rowvar_, FDM_INST_C)(const FdmRowVarBatch &b, const FdmRowVarOut &o, cudaStream_t st, int n_lo,
+                                            int32_t *n_launches)
+{
+    constexpr int C = FDM_INST_C;
+    const size_t smem = (size_t)rowvar::smem_doubles<C>() * sizeof(double);
+    auto kern = rowvar::fdm_rowvar_kernel<C>;
+    if (smem > 48 * 1024) FDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t max_grid = 0x7fffffff;
+    int launches = 0;
+    for (int64_t first = 0; first < b.n_solves; first += max_grid) {
+        const int64_t count = (b.n_solves - first < max_grid) ? (b.n_solves - first) : max_grid;
+        kern<<<dim3((unsigned)count), dim3(32), smem, st>>>(b, o, first, n_lo);
+        ++launches;
+        FDM_CUDA(cudaGetLastError());
+    }
+    if (n_launches) *n_launches += launches;
+    return FDM_OK;
+}

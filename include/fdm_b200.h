@@ -68,6 +68,8 @@ extern "C" {
 #define FDM_STATUS_OK           0
 #define FDM_STATUS_NONFINITE    1   /* price is not finite */
 #define FDM_STATUS_STIFF        2   /* CTA kernel: pivots not converged inside its table (best effort result) */
+#define FDM_STATUS_SINGULAR     3   /* row-varying solves: a pivot of the Thomas factorisation vanished (the reference raises
+                                       ZeroDivisionError, discrete_barrier_fdm_pricer_2.py:271-279); price is NaN */
 #define FDM_STATUS_NOT_SOLVED  -1   /* no kernel took the solve: n_space outside [3, n_space_max], launch hints that miss
                                        its size class, or FDM_FLAG_INVALID.  status[] is filled with this value before
                                        the launches, so a skipped solve is always visible */
@@ -151,7 +153,7 @@ typedef struct FdmOut {
 int fdm_version(void);
 
 /* sizeof() of the ABI structs as this library was compiled: 0 FdmBatch, 1 FdmOut, 2 FdmAmericanBook, 3 FdmBookOut,
-   4 FdmBarrierBook (-1: unknown).  Lets a binding verify its own struct declarations at load time. */
+   4 FdmBarrierBook, 5 FdmRowVarBatch, 6 FdmRowVarOut (-1: unknown).  Lets a binding verify its own struct declarations at load time. */
 int fdm_sizeof(int which);
 
 /* Message of the last failure on the calling thread ("" if none). */
@@ -294,6 +296,48 @@ int fdm_barrier_book(const FdmBarrierBook *book, const FdmBookOut *out, void *wo
 /* HOST pointers; copies in, solves, copies out, synchronises. */
 int fdm_barrier_book_host(const FdmBarrierBook *book, const FdmBookOut *out, int64_t *node_steps,
                           int32_t *n_launches, float *kernel_ms);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-varying solves: DiscreteBarrierFDMPricer2._solve_pde_backward (discrete_barrier_fdm_pricer_2.py:336-428) --
+ * Black-Scholes in S on a grid with snapped nodes, so every row of the tridiagonal system has its own coefficients;
+ * non-symmetric stencil on the two rows next to the barrier (:383-409); Dirichlet rows 0 and N inside the system;
+ * knock-out projection after the steps of the monitoring map (:423-425).  One call = a batch of such marches plus
+ * the linear read-out at the effective spot (:433-449).  The caller supplies what the class derives outside the
+ * march: the (escrow-shifted) grid, the terminal payoff, the effective barrier levels and the barrier interval.
+ */
+#define FDM_ROWVAR_MAX_NODES 1024
+
+typedef struct FdmRowVarBatch {
+    int64_t n_solves;
+    int32_t n_nodes_max;          /* upper bound of the per-solve node counts N + 1 (<= FDM_ROWVAR_MAX_NODES) */
+    int32_t n_mon_total;
+    const int64_t *node_begin;    /* CSR [n_solves + 1] into s_nodes / v_terminal */
+    const double *s_nodes;        /* grid S_0 .. S_N per solve (:468), ascending */
+    const double *v_terminal;     /* terminal payoff per node (:231-249) */
+    const double *sigma, *r, *strike, *tenor, *dt;
+    const double *lo_bar, *up_bar;   /* effective knock-out levels (:291-294); read only where the flag is set */
+    const double *h_minus, *h_plus;  /* non-symmetric stencil of rows bar_j and bar_j + 1 (:297-321) */
+    const double *s_eff;          /* read-out point: spot minus escrowed dividends (:470) */
+    const int32_t *n_steps;       /* num_time_steps M */
+    const int32_t *rannacher;     /* fully implicit steps at the start of the march (:351) */
+    const int32_t *flags;         /* FDM_FLAG_CALL | FDM_FLAG_KO_DOWN | FDM_FLAG_KO_UP */
+    const int32_t *bar_j;         /* left index of the interval holding the active barrier, -1 = none */
+    const int32_t *mon_begin;     /* CSR [n_solves + 1] into mon_step; NULL if n_mon_total == 0 */
+    const int32_t *mon_step;      /* 1-based count of completed steps after which the projection runs, ascending:
+                                     M - k for every key k < M of the reference's monitoring map (:455-466) */
+} FdmRowVarBatch;
+
+typedef struct FdmRowVarOut {
+    double *price;                /* linear interpolation at s_eff */
+    int32_t *status;              /* FDM_STATUS_*; may be NULL */
+    double *v_dump;               /* optional: value vector, v_dump_stride doubles per solve */
+    int64_t v_dump_stride;
+} FdmRowVarOut;
+
+/* DEVICE pointers, asynchronous on `stream`, no allocation. */
+int fdm_rowvar_solve(const FdmRowVarBatch *batch, const FdmRowVarOut *out, void *stream, int32_t *n_launches);
+/* HOST pointers: H2D, kernels, D2H, synchronises. */
+int fdm_rowvar_solve_host(const FdmRowVarBatch *batch, const FdmRowVarOut *out, int32_t *n_launches, float *kernel_ms);
 
 /*
  * The host-buffer entry points keep one grow-only device workspace per device (no cudaMalloc per call).

@@ -913,6 +913,121 @@ int fdo_barrier_batch(int64_t n_solves, const FdoBarrier *params, double *price_
     return failures ? FDO_EINVAL : FDO_OK;
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* DiscreteBarrierFDMPricer2 (P2 = discrete_barrier_fdm_pricer_2.py): S-space theta scheme with a ROW-VARYING        */
+/* tridiagonal matrix, a non-symmetric stencil on the two rows next to the barrier and knock-out projection.         */
+/* Restates _solve_pde_backward (P2:336-428), _solve_tridiagonal (P2:262-288) and _apply_knockout_projection         */
+/* (P2:241-257) operation for operation.  The explicit half of the standard rows carries the reference's sign        */
+/* (P2:373-375: a_expl, c_expl negative), which makes theta = 1/2 steps unstable; the march is well behaved when     */
+/* every step is implicit (rannacher_steps >= num_time_steps).  pow(x, 2.0) is what CPython's `x ** 2` calls.        */
+
+typedef struct {
+    double sigma, r, strike, tenor, dt;
+    double lo_bar, up_bar;          /* effective knock-out levels (NaN = None) */
+    double h_minus, h_plus;         /* non-symmetric stencil of rows bar_j, bar_j + 1 */
+    int32_t n_nodes;                /* N + 1 */
+    int32_t n_steps, rannacher, is_call;
+    int32_t ko_kind;                /* 0 none, 1 down-and-out, 2 up-and-out, 3 double-out (P2:246-253) */
+    int32_t bar_j;                  /* left index of the interval holding the active barrier, -1: none (P2:297-321) */
+    const double *s_nodes;          /* [n_nodes] shifted grid (P2:468) */
+    const double *v_terminal;       /* [n_nodes] terminal payoff, smoothed (P2:218-235) */
+    const uint8_t *project_after;   /* [n_steps + 1]: project_after[k] != 0 <=> step index k is in the monitoring map (P2:423-425) */
+} FdoPricer2;
+
+/* CPython evaluates `x ** 2` with libm's pow(); gcc would fold pow(x, 2.0) into x * x, which is not always the same
+ * double (glibc's pow is faithfully, not correctly, rounded).  The volatile pointer keeps the library call. */
+static double (*volatile p2_pow)(double, double) = pow;
+
+static int p2_tridiag(const double *sub, const double *diag, const double *sup, const double *rhs, double *x,
+                      double *c_star, double *d_star, int n)
+{
+    double beta = diag[0];
+    if (fabs(beta) < 1e-14) return FDO_EINVAL;                         /* P2:271-272 */
+    c_star[0] = sup[0] / beta;
+    d_star[0] = rhs[0] / beta;
+    for (int i = 1; i < n; ++i) {
+        beta = diag[i] - sub[i] * c_star[i - 1];
+        if (fabs(beta) < 1e-14) return FDO_EINVAL;
+        c_star[i] = (i < n - 1) ? (sup[i] / beta) : 0.0;
+        d_star[i] = (rhs[i] - sub[i] * d_star[i - 1]) / beta;
+    }
+    x[n - 1] = d_star[n - 1];
+    for (int i = n - 2; i >= 0; --i) x[i] = d_star[i] - c_star[i] * x[i + 1];
+    return FDO_OK;
+}
+
+int fdo_pricer2_solve(const FdoPricer2 *p, double *V_out)
+{
+    if (!p || !V_out || p->n_nodes < 3 || p->n_steps < 1) return FDO_EINVAL;
+    const int n = p->n_nodes, N = n - 1, M = p->n_steps;
+    const double *s = p->s_nodes;
+    double *buf = (double *)malloc((size_t)n * 7 * sizeof(double));
+    if (!buf) return FDO_ENOMEM;
+    double *sub = buf, *mainv = buf + n, *sup = buf + 2 * n, *rhs = buf + 3 * n, *V = buf + 4 * n, *cs = buf + 5 * n, *ds = buf + 6 * n;
+    const double dt = p->dt, r = p->r, sig = p->sigma;
+    const double dS = s[1] - s[0];                                     /* P2:345 */
+    memcpy(V, p->v_terminal, (size_t)n * sizeof(double));
+    int rc = FDO_OK;
+    if (dS == 0.0 || p2_pow(dS, 2.0) == 0.0) rc = FDO_EINVAL;         /* CPython raises ZeroDivisionError at P2:379 */
+    for (int m = M; m >= 1 && rc == FDO_OK; --m) {
+        const double theta = ((M - m) < p->rannacher) ? 1.0 : 0.5;     /* P2:351 */
+        for (int i = 0; i < n; ++i) { sub[i] = 0.0; mainv[i] = 0.0; sup[i] = 0.0; rhs[i] = 0.0; }
+        const double tau_left = p->tenor - (m - 1) * dt;               /* P2:359 */
+        if (p->is_call) { rhs[0] = 0.0; rhs[N] = s[N] - p->strike * exp(-r * tau_left); }
+        else            { rhs[0] = p->strike * exp(-r * tau_left); rhs[N] = 0.0; }
+        mainv[0] = 1.0;
+        mainv[N] = 1.0;
+        for (int i = 1; i < N; ++i) {
+            const double S = s[i];
+            const double sig2S2 = p2_pow(sig * S, 2.0);
+            double a_impl, b_impl, c_impl, a_expl, b_expl, c_expl;
+            if (p->bar_j < 0 || (i != p->bar_j && i != p->bar_j + 1)) {
+                const double dS2 = p2_pow(dS, 2.0);                    /* P2:373-380 */
+                a_impl = 0.5 * dt * theta * (sig2S2 / dS2 - r * S / dS);
+                b_impl = 1.0 + dt * theta * (sig2S2 / dS2 + r);
+                c_impl = 0.5 * dt * theta * (sig2S2 / dS2 + r * S / dS);
+                a_expl = -0.5 * dt * (1 - theta) * (sig2S2 / dS2 - r * S / dS);
+                b_expl = 1.0 - dt * (1 - theta) * (sig2S2 / dS2 + r);
+                c_expl = -0.5 * dt * (1 - theta) * (sig2S2 / dS2 + r * S / dS);
+            } else {
+                const double hm = p->h_minus, hp = p->h_plus;          /* P2:383-409 */
+                const double a1 = hp / (hm * (hm + hp));
+                const double b1 = (hp - hm) / (hm * hp);
+                const double c1 = -hm / (hp * (hm + hp));
+                const double d2 = 2.0 / (hm * (hm + hp));
+                const double e2 = -2.0 / (hm * hp);
+                const double f2 = 2.0 / (hp * (hm + hp));
+                const double L_left = 0.5 * sig2S2 * f2 + r * S * c1;
+                const double L_center = 0.5 * sig2S2 * e2 + r * S * b1 - r;
+                const double L_right = 0.5 * sig2S2 * d2 + r * S * a1;
+                a_impl = -theta * dt * L_left;
+                b_impl = 1.0 - theta * dt * L_center;
+                c_impl = -theta * dt * L_right;
+                a_expl = (1 - theta) * dt * L_left;
+                b_expl = 1.0 + (1 - theta) * dt * L_center;
+                c_expl = (1 - theta) * dt * L_right;
+            }
+            sub[i] = -a_impl;
+            mainv[i] = b_impl;
+            sup[i] = -c_impl;
+            rhs[i] = a_expl * V[i - 1] + b_expl * V[i] + c_expl * V[i + 1];
+        }
+        rc = p2_tridiag(sub, mainv, sup, rhs, V, cs, ds, n);
+        if (rc == FDO_OK && p->project_after && p->project_after[m - 1]) {   /* P2:423-425, P2:241-257 */
+            for (int i = 0; i < n; ++i) {
+                int ko = 0;
+                if (p->ko_kind == 1 && !isnan(p->lo_bar) && s[i] <= p->lo_bar) ko = 1;
+                else if (p->ko_kind == 2 && !isnan(p->up_bar) && s[i] >= p->up_bar) ko = 1;
+                else if (p->ko_kind == 3 && ((!isnan(p->lo_bar) && s[i] <= p->lo_bar) || (!isnan(p->up_bar) && s[i] >= p->up_bar))) ko = 1;
+                if (ko) V[i] = 0.0;
+            }
+        }
+    }
+    memcpy(V_out, V, (size_t)n * sizeof(double));
+    free(buf);
+    return rc;
+}
+
 int fdo_max_threads(void)
 {
 #ifdef _OPENMP

@@ -419,3 +419,180 @@ def max_threads() -> int:
 def norm_cdf(x: float) -> float:
     """discrete_barrier_fdm_pricer_cn.py:16-18"""
     return 0.5 * (1.0 + math.erf(x / math.sqrt(2.0)))
+
+
+# --------------------------------------------------------------------------------------
+# DiscreteBarrierFDMPricer2 (P2 = discrete_barrier_fdm_pricer_2.py): row-varying S-space solver
+# --------------------------------------------------------------------------------------
+
+class _FdoPricer2(C.Structure):
+    _fields_ = [("sigma", C.c_double), ("r", C.c_double), ("strike", C.c_double), ("tenor", C.c_double), ("dt", C.c_double),
+                ("lo_bar", C.c_double), ("up_bar", C.c_double), ("h_minus", C.c_double), ("h_plus", C.c_double),
+                ("n_nodes", C.c_int32), ("n_steps", C.c_int32), ("rannacher", C.c_int32), ("is_call", C.c_int32),
+                ("ko_kind", C.c_int32), ("bar_j", C.c_int32),
+                ("s_nodes", C.POINTER(C.c_double)), ("v_terminal", C.POINTER(C.c_double)),
+                ("project_after", C.POINTER(C.c_uint8))]
+
+
+P2_KO = {"none": 0, "down-and-out": 1, "up-and-out": 2, "double-out": 3, "down-and-in": 0, "up-and-in": 0, "double-in": 0}
+
+
+def p2_year_fraction(day_count: str, d0, d1) -> float:
+    """P2:120-130."""
+    dc = day_count.upper()
+    if dc in ("ACT/365", "ACT/365F", "ACT/365 FIXED"):
+        return max(0, (d1 - d0).days) / 365.0
+    if dc in ("ACT/360",):
+        return max(0, (d1 - d0).days) / 360.0
+    if dc in ("30/360", "30E/360"):
+        y0, m0, dd0 = d0.year, d0.month, min(d0.day, 30)
+        y1, m1, dd1 = d1.year, d1.month, min(d1.day, 30)
+        return ((y1 - y0) * 360 + (m1 - m0) * 30 + (dd1 - dd0)) / 360.0
+    return max(0, (d1 - d0).days) / 365.0
+
+
+def pricer2_prepare(spot, strike, valuation_date, maturity_date, volatility, option_type, barrier_type="none",
+                    lower_barrier=None, upper_barrier=None, monitoring_dates=None, flat_rate_nacc=0.0, dividends=None,
+                    num_space_nodes=600, num_time_steps=600, rannacher_steps=2, day_count="ACT/365",
+                    smooth_payoff_around_strike=True, payoff_smoothing_half_width_nodes=2) -> dict:
+    """Everything ``DiscreteBarrierFDMPricer2`` does outside ``_solve_pde_backward``, in the reference's own operation
+    order (constructor P2:51-116, grid P2:146-168, n_lim / BGK decision P2:173-226, payoff P2:231-249, monitoring map
+    P2:455-466, escrow shift P2:468-476, barrier interval P2:297-321).  Returns the inputs of ``fdo_pricer2_solve``."""
+    yf = lambda a, b: p2_year_fraction(day_count, a, b)
+    mons = sorted(monitoring_dates or [])
+    tenor = yf(valuation_date, maturity_date)
+    M = int(num_time_steps)
+    dt = tenor / max(1, M)
+    # grid
+    anchors = [float(spot), float(strike)]
+    if lower_barrier:
+        anchors.append(lower_barrier)
+    if upper_barrier:
+        anchors.append(upper_barrier)
+    s_max = 4.0 * max(anchors) * math.exp(float(volatility) * math.sqrt(max(tenor, 1e-12)))
+    N = max(200, int(num_space_nodes))
+    dS = (s_max - 0.0) / N
+    nodes = [0.0 + i * dS for i in range(N + 1)]
+    for x in (float(strike), lower_barrier, upper_barrier):
+        if x is None:
+            continue
+        j = min(range(len(nodes)), key=lambda i: abs(nodes[i] - x))
+        nodes[j] = float(x)
+    # decision + BGK
+    use_bgk, lo_adj, up_adj, k0, k1 = False, lower_barrier, upper_barrier, None, None
+    if not (barrier_type == "none" or len(mons) == 0):
+        first_mon, last_mon = min(mons), max(mons)
+        inside = [d for d in mons if valuation_date < d <= maturity_date]
+        if last_mon > first_mon and len(inside) > 0:
+            dt_uniform = tenor / max(1, M)
+            intervals = [yf(inside[i - 1], inside[i]) for i in range(1, len(inside))]
+            N_hat = sum(max(1, int(round(ti / dt_uniform))) for ti in intervals)
+            use_bgk = N_hat > 5 * M
+            a_b = yf(first_mon, last_mon) / max(1, len(inside))
+            adj = math.exp(0.5826 * float(volatility) * a_b)
+            if lower_barrier is not None:
+                lo_adj = lower_barrier / adj
+            if upper_barrier is not None:
+                up_adj = upper_barrier * adj
+            k0 = max(0, min(M, int(round(yf(valuation_date, first_mon) / dt))))
+            k1 = max(0, min(M, int(round(yf(valuation_date, last_mon) / dt))))
+            k0, k1 = min(k0, k1), max(k0, k1)
+    lo_eff, up_eff = (lo_adj, up_adj) if use_bgk else (lower_barrier, upper_barrier)
+    # monitoring map
+    project = np.zeros(M + 1, dtype=np.uint8)
+    if use_bgk:
+        project[k0:k1 + 1] = 1
+    else:
+        for d in mons:
+            if valuation_date < d <= maturity_date:
+                k = int(round(yf(valuation_date, d) / dt))
+                if 0 <= k <= M:
+                    project[k] = 1
+    # escrow shift
+    pv = 0.0
+    for pay_date, amount in (dividends or []):
+        tau = yf(valuation_date, pay_date)
+        if tau > 0:
+            pv += float(amount) * math.exp(-float(flat_rate_nacc) * tau)
+    s = [max(x - pv, 0.0) for x in nodes]
+    # terminal payoff
+    K = float(strike)
+    V = [max(x - K, 0.0) if option_type == "call" else max(K - x, 0.0) for x in s]
+    if smooth_payoff_around_strike and payoff_smoothing_half_width_nodes > 0:
+        m = int(payoff_smoothing_half_width_nodes)
+        k_star = min(range(len(s)), key=lambda i: abs(s[i] - K))
+        i0, i1 = max(0, k_star - m), min(len(s) - 1, k_star + m)
+        S0, V0, S1, V1 = s[i0], V[i0], s[i1], V[i1]
+        a = (V1 - V0) / ((S1 - S0) ** 2) if S1 != S0 else 0.0
+        for i in range(i0, i1 + 1):
+            V[i] = a * (s[i] - S0) ** 2 + V0
+    # barrier interval (only knock-OUT types have one, P2:304, :312)
+    bar_j, hm, hp = -1, 0.0, 0.0
+    H = None
+    if barrier_type in ("down-and-out", "double-out") and lo_eff is not None:
+        H = lo_eff
+    elif barrier_type in ("up-and-out", "double-out") and up_eff is not None:
+        H = up_eff
+    if H is not None:
+        if H <= s[0]:
+            bar_j, hm, hp = 0, 1e-12, s[1] - s[0]
+        elif H >= s[-1]:
+            bar_j, hm, hp = N - 1, s[N - 1] - s[N - 2], 1e-12
+        else:
+            j = max(0, min(N - 1, next(k for k in range(N) if s[k] <= H <= s[k + 1])))
+            bar_j, hm, hp = j, max(1e-12, H - s[j]), max(1e-12, s[j + 1] - H)
+    return dict(sigma=float(volatility), r=float(flat_rate_nacc), strike=K, tenor=tenor, dt=dt, lo_bar=lo_eff, up_bar=up_eff,
+                h_minus=hm, h_plus=hp, n_steps=M, rannacher=int(rannacher_steps), is_call=option_type == "call",
+                barrier_type=barrier_type, bar_j=bar_j, s_nodes=np.array(s), v_terminal=np.array(V), project_after=project,
+                S_eff=float(spot) - pv, use_bgk=use_bgk, k_first=k0, k_last=k1, pv_divs=pv)
+
+
+def pricer2_march(prep: dict, knock_out: bool = True) -> np.ndarray:
+    """``_solve_pde_backward`` (P2:336-428) on prepared inputs.  ``knock_out=False``: the vanilla leg of a knock-in
+    (``_solve_pde_backward(None, None, {}, S_shifted)``, P2:473-475)."""
+    L = lib()
+    s = np.ascontiguousarray(prep["s_nodes"], dtype=np.float64)
+    v = np.ascontiguousarray(prep["v_terminal"], dtype=np.float64)
+    proj = np.ascontiguousarray(prep["project_after"] if knock_out else np.zeros_like(prep["project_after"]), dtype=np.uint8)
+    nan = float("nan")
+    ko = P2_KO[prep["barrier_type"]] if knock_out else 0
+    p = _FdoPricer2(prep["sigma"], prep["r"], prep["strike"], prep["tenor"], prep["dt"],
+                    nan if (prep["lo_bar"] is None or not knock_out) else float(prep["lo_bar"]),
+                    nan if (prep["up_bar"] is None or not knock_out) else float(prep["up_bar"]),
+                    prep["h_minus"], prep["h_plus"], len(s), prep["n_steps"], prep["rannacher"], int(prep["is_call"]), ko,
+                    prep["bar_j"] if knock_out else -1, _dptr(s), _dptr(v), proj.ctypes.data_as(C.POINTER(C.c_uint8)))
+    V = np.empty(len(s))
+    L.fdo_pricer2_solve.restype = C.c_int
+    rc = L.fdo_pricer2_solve(C.byref(p), _dptr(V))
+    if rc != 0:
+        raise ZeroDivisionError("Tridiagonal pivot ~ 0") if rc == -1 else RuntimeError(f"fdo_pricer2_solve failed: {rc}")
+    return V
+
+
+def p2_interp_linear(x: float, xs, ys) -> float:
+    """P2:433-449."""
+    if x <= xs[0]:
+        return float(ys[0])
+    if x >= xs[-1]:
+        return float(ys[-1])
+    lo, hi = 0, len(xs) - 1
+    while hi - lo > 1:
+        mid = (lo + hi) // 2
+        if x < xs[mid]:
+            hi = mid
+        else:
+            lo = mid
+    x0, x1, y0, y1 = xs[lo], xs[hi], ys[lo], ys[hi]
+    w = (x - x0) / (x1 - x0)
+    return float((1 - w) * y0 + w * y1)
+
+
+def pricer2_price(**kw) -> Tuple[float, np.ndarray, dict]:
+    """``DiscreteBarrierFDMPricer2.price()`` (P2:468-482): (price, value vector, prepared inputs)."""
+    prep = pricer2_prepare(**kw)
+    V = pricer2_march(prep, True)
+    if prep["barrier_type"] in ("down-and-in", "up-and-in", "double-in"):
+        Vv = pricer2_march(prep, False)
+        V = np.array([Vv[i] - V[i] for i in range(len(V))])
+    s = prep["s_nodes"]
+    return p2_interp_linear(prep["S_eff"], [float(x) for x in s], [float(x) for x in V]), V, prep

@@ -38,7 +38,8 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.FdmOut) == 7 * 8 + 4 * 8
     # and the compiled library agrees with the ctypes declarations
     L = _lib.load()
-    for which, st in enumerate((_lib.FdmBatch, _lib.FdmOut, _lib.FdmAmericanBook, _lib.FdmBookOut, _lib.FdmBarrierBook)):
+    for which, st in enumerate((_lib.FdmBatch, _lib.FdmOut, _lib.FdmAmericanBook, _lib.FdmBookOut, _lib.FdmBarrierBook, _lib.FdmRowVarBatch,
+                                _lib.FdmRowVarOut)):
         assert L.fdm_sizeof(which) == C.sizeof(st), st.__name__
 
 
