@@ -424,12 +424,41 @@ class BarrierBook:
         nt = np.empty(n, dtype=np.int64)
         Nsp = np.broadcast_to(np.asarray(-1 if N_space is None else N_space, dtype=np.int64), (n,))
         Nti = np.broadcast_to(np.asarray(-1 if N_time is None else N_time, dtype=np.int64), (n,))
+        if n > 4096:
+            return self._configure_vec(Nsp, Nti)
         for i in range(n):
             _, _, ns[i], nt[i] = hostlogic.barrier_configure(
                 float(self.S0[i]), float(self.K[i]), float(self.T[i]), float(self.sigma[i]), self.lower[i],
                 self.upper[i], self.monitor_times[i], None if Nsp[i] < 0 else int(Nsp[i]),
                 None if Nti[i] < 0 else int(Nti[i]))
         return ns, nt
+
+    def _configure_vec(self, Nsp, Nti):
+        """``configure_grid`` (discrete_barrier_fdm_pricer_cn.py:59-118) over all options at once (large books: numpy's
+        log / sqrt can differ from ``math`` by an ulp, which matters only where a ceil() sits exactly on an integer)."""
+        n = self.n_opt
+        low = np.array([np.nan if v is None else v for v in self.lower], dtype=np.float64)
+        up = np.array([np.nan if v is None else v for v in self.upper], dtype=np.float64)
+        if np.any(~(self.T > 0)):
+            raise ValueError("T must be positive")
+        if np.any(~(self.sigma > 0)):
+            raise ValueError("sigma must be positive")
+        if np.any(~(self.S0 > 0)):
+            raise ValueError("S0 must be positive")
+        s_low = np.fmin(np.fmin(self.S0, self.K), np.fmin(np.where(low > 0, low, np.nan), np.where(up > 0, up, np.nan)))
+        s_high = np.fmax(np.fmax(self.S0, self.K), np.fmax(np.where(low > 0, low, np.nan), np.where(up > 0, up, np.nan)))
+        S_min, S_max = np.maximum(1e-8, s_low / 4.0), s_high * 4.0
+        bad = S_min >= S_max
+        S_min, S_max = np.where(bad, self.S0 / 5.0, S_min), np.where(bad, self.S0 * 5.0, S_max)
+        x_range = np.log(S_max) - np.log(S_min)
+        dx_target = self.sigma * np.sqrt(self.T) / 12
+        dx_target = np.where(dx_target <= 0.0, x_range / 300.0, dx_target)
+        ns = np.where(Nsp < 0, np.maximum(np.ceil(x_range / dx_target).astype(np.int64), 300), Nsp)
+        dx = x_range / ns
+        nt_opt = np.ceil(0.5 * self.sigma * self.sigma * self.T / (0.4 * dx * dx)).astype(np.int64)
+        n_valid = np.array([sum(1 for t in (m or []) if 0.0 < t < T) for m, T in zip(self.monitor_times, self.T)], dtype=np.int64)
+        nt = np.where(Nti < 0, np.maximum(np.maximum(nt_opt, ns), 10 * (n_valid + 1)), Nti)
+        return ns.astype(np.int64), nt.astype(np.int64)
 
     def _solves(self, sigma, apply_ko: bool = True) -> SolveBatch:
         ko = [_OUT_OF.get(bt, bt) if apply_ko else "none" for bt in self.barrier_type]

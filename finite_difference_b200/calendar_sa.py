@@ -38,9 +38,12 @@ class SouthAfrica:
         easter = _easter_sunday(year)
         days.add(easter - _dt.timedelta(days=2))     # Good Friday
         days.add(easter + _dt.timedelta(days=1))     # Family Day
-        for h in list(days):
-            if h.weekday() == 6:                     # a holiday on a Sunday moves to the Monday
-                days.add(h + _dt.timedelta(days=1))
+        for h in sorted(days):
+            if h.weekday() == 6:                     # a holiday on a Sunday is observed on the next day that is not
+                sub = h + _dt.timedelta(days=1)      # itself a holiday: 25 Dec on a Sunday (2016, 2022) -> 27 Dec, because
+                while sub in days:                   # the Monday is the Day of Goodwill
+                    sub += _dt.timedelta(days=1)
+                days.add(sub)
         return days
 
     def is_working_day(self, day: _dt.date) -> bool:

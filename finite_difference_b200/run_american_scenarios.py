@@ -6,10 +6,11 @@ Same function names, arguments, CSV schema and result keys (run_american_scenari
 * the reference runner cannot run: it parses the forward-curve dates with ``format="%Y/%m/%m"``
   (:140-142), which raises ``re.error`` on any pandas.  The curves here are built with ISO dates
   directly, which is what the line intends.
-* ``run_all_american_scenarios`` prices the whole CSV as ONE batch on the GPU (8 PDE solves per
-  row: ``price_log2()`` + ``greeks_log2()``, :144-172) instead of a serial Python loop, and can
-  shard the rows over the GPUs of a box (``torchrun``; see ``shard.py``).  ``run_american_scenario``
-  keeps the one-row path through the drop-in pricer class.
+* ``run_all_american_scenarios`` prices the whole CSV -- with or without cash dividends -- as ONE fused call on
+  the GPU (8 PDE solves per row: ``price_log2()`` + ``greeks_log2()``, :144-172) instead of a serial Python loop,
+  builds the result frame column-wise, and can shard the rows over the GPUs of a box (``torchrun``; see
+  ``shard.py``).  ``run_american_scenario`` keeps the one-row path through the drop-in pricer class.
+* books with per-row dates or a real (non-flat) daily curve: ``ingest.american_book_from_dates``.
 """
 from __future__ import annotations
 
@@ -93,24 +94,36 @@ def scenario_book(S0: Sequence[float], K: Sequence[float], sigma: Sequence[float
 
     def fwd_rate(start, end):
         t_far, t_near, tau = yf(valuation, end), yf(valuation, start), yf(start, end)
+        if len(rate) > 2048:                                    # numpy power / log: within an ulp of the scalar path
+            return -np.log((1.0 + rate) ** (-t_far) / (1.0 + rate) ** (-t_near)) / max(1e-12, tau)
         return np.array([-math.log((1.0 + x) ** (-t_far) / (1.0 + x) ** (-t_near)) / max(1e-12, tau) for x in rate])
 
     r = fwd_rate(probe.discount_start_date, probe.discount_end_date)
     b = fwd_rate(probe.carry_start_date, probe.carry_end_date)      # forward_curve is always given by the runner
     div_taus = probe._div_times_tau()
     n = len(rate)
+    csr = None
+    if div_taus:                                                # the same schedule for every row, as CSR arrays
+        k = len(div_taus)
+        csr = (np.arange(0, (n + 1) * k, k, dtype=np.int32), np.tile([t for t, _ in div_taus], n),
+               np.tile([c for _, c in div_taus], n))
     return AmericanBook(S0, K, probe.time_to_expiry, sigma, r, b, opt_type.lower() == "call", num_space_nodes,
-                        num_time_steps, rannacher_steps, black76=False,
-                        div_taus=[div_taus] * n if div_taus else None)
+                        num_time_steps, rannacher_steps, black76=False, div_taus=csr)
 
 
 def run_all_american_scenarios(config_csv_path: str, output_csv_path: str, base_params: Dict[str, Any],
-                               distributed: bool = False) -> pd.DataFrame:
+                               distributed: bool = False, lapack_greeks: bool = False,
+                               verbose: Optional[bool] = None) -> pd.DataFrame:
     """Read the configuration CSV, price every row in one GPU batch, write the results CSV
     (run_american_scenarios.py:209-277; columns scenario_name,S0,K,sigma,rate,FA_price,FA_delta,FA_gamma,FA_vega).
 
-    ``distributed=True`` under ``torchrun``: rows are sharded over the ranks, results all-gathered, and
-    rank 0 writes the CSV.
+    The whole file -- dividends in ``base_params["divs"]`` included -- is ONE fused call (``AmericanBook.run_fused``:
+    fan-out of the 8 solves per row, time segments between dividends, Richardson / bump epilogue on the device).
+    ``lapack_greeks=True`` takes the host-buffer path instead and recomputes delta / gamma with the reference's LAPACK
+    solve of the four-point cubic (fd_american_option_pricer.py:642-653; the in-kernel divided differences agree
+    with it to ~1e-9 relative).  ``distributed=True`` under ``torchrun``: rows are sharded over the ranks, results
+    gathered, rank 0 writes the CSV.  ``verbose``: one line per scenario like the reference (default: files up to
+    1000 rows).
     """
     config_df = pd.read_csv(config_csv_path)
     n = len(config_df)
@@ -120,28 +133,31 @@ def run_all_american_scenarios(config_csv_path: str, output_csv_path: str, base_
         rank, world, _ = shard.init_distributed()
         mine = shard.partition(np.ones(n), world)[rank]
     sub = config_df.iloc[mine]
-    cols = {}
     if len(sub):
         book = scenario_book(sub["S0"].to_numpy(float), sub["K"].to_numpy(float), sub["sigma"].to_numpy(float),
                              sub["rate"].to_numpy(float), **base_params)
-        out = book.run("scenario", lapack_greeks=True)
+        out = book.run("scenario", lapack_greeks=True) if lapack_greeks else book.run_fused("scenario")
         cols = {"price": out["price_log2"], "delta": out["delta"], "gamma": out["gamma"], "vega": out["vega"]}
     else:
         cols = {k: np.zeros(0) for k in _FA}
     if distributed and world > 1:
         cols = shard.gather_results(cols, mine, n)
-    all_results: List[Dict[str, Any]] = []
+    results_df = pd.DataFrame()
     if rank == 0:
-        for i, (_, row) in enumerate(config_df.iterrows()):
-            fa = {k: (row[f"FA_{k}"] if pd.notna(row[f"FA_{k}"]) else None) for k in _FA}
-            model = {k: float(cols[k][i]) for k in _FA}
-            result = _result_row(row["scenario_name"], row["S0"], row["K"], row["sigma"], row["rate"], model, fa)
-            all_results.append(result)
-            print(f"{row['scenario_name']}:  Price %Diff: {result['price_pct_diff']:.4f}%, "
-                  f"Delta %Diff: {result['delta_pct_diff']:.4f}%, Gamma %Diff: {result['gamma_pct_diff']:.4f}%, "
-                  f"Vega %Diff: {result['vega_pct_diff']:.4f}%")
-    results_df = pd.DataFrame(all_results)
-    if rank == 0:
+        # the reference's result dictionary (:174-204), one column at a time
+        data: Dict[str, Any] = {k: config_df[k].to_numpy() for k in ("scenario_name", "S0", "K", "sigma", "rate")}
+        for name in _FA:
+            m = np.asarray(cols[name], dtype=np.float64)
+            f = config_df[f"FA_{name}"].to_numpy(dtype=np.float64)
+            diff = np.abs(m - f)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                pct = np.where(np.isnan(f) | (f == 0.0), np.nan, diff / np.abs(f) * 100.0)
+            data[f"model_{name}"], data[f"FA_{name}"], data[f"{name}_diff"], data[f"{name}_pct_diff"] = m, f, diff, pct
+        results_df = pd.DataFrame(data)
+        if verbose if verbose is not None else n <= 1000:
+            for row in results_df.itertuples(index=False):
+                print(f"{row.scenario_name}:  Price %Diff: {row.price_pct_diff:.4f}%, Delta %Diff: {row.delta_pct_diff:.4f}%, "
+                      f"Gamma %Diff: {row.gamma_pct_diff:.4f}%, Vega %Diff: {row.vega_pct_diff:.4f}%")
         results_df.to_csv(output_csv_path, index=False)
         print(f"\nAmerican option results saved to {output_csv_path}")
     return results_df
