@@ -1,14 +1,15 @@
 #!/bin/bash
 # Round evidence: run on the GPU box through gpurun; everything lands in gpurun_out/ (copy the summaries to profiles/).
+#   gpurun --timeout 1700 -- 'bash tools/capture_profiles.sh r02'
 set -x
-R=${1:-r01}
+R=${1:-r02}
+python tools/fp64_peak.py > gpurun_out/${R}_fp64_peak.json 2> /dev/null
 python bench.py > gpurun_out/${R}_bench_n1.json 2> gpurun_out/${R}_bench_n1.err
 python bench.py --impl reference > gpurun_out/${R}_bench_reference_n1.json 2>/dev/null
-python tools/bench_configs.py > gpurun_out/${R}_other_configs_n1.jsonl 2> gpurun_out/${R}_other_configs_n1.err
-python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${R}_plain_launches.log 2>&1 && \
+python bench.py --steps 2 --warmup 3 --no-cpu --no-others > gpurun_out/${R}_plain_launches.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_cfg3_ncu_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${R}_ncu_launches.log 2>&1
-for spec in "am500 fdm_lean_kernel 20000" "am500div fdm_warp_kernel 5000" "am400 fdm_lean_kernel 20000" "bar400 fdm_lean_kernel 20000" "cfg4 fdm_cta_kernel<\(int\)16,.\(int\)16 148" "dbfp fdm_cta_kernel<\(int\)16,.\(int\)5 1184"; do
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-others > gpurun_out/${R}_ncu_launches.log 2>&1
+for spec in "am500 fdm_lean_kernel 20000" "am500div fdm_lean_kernel 5000" "am400 fdm_lean_kernel 20000" "bar400 fdm_lean_kernel 20000" "cfg4 fdm_cta_kernel<\(int\)16,.\(int\)16 148" "dbfp fdm_cta_kernel<\(int\)16,.\(int\)5 1184" "p2 fdm_rowvar_kernel 2048"; do
   set -- $spec
   python tools/ncu_shapes.py $1 $3 > gpurun_out/${R}_plain_$1.log 2>&1 && \
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s 1 -c 1 \

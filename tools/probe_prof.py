@@ -2,8 +2,7 @@
 import os, sys, copy
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from tools.time_variants import american, american_div, barrier
-from tools.time_cta import cfg4
+from tools.time_variants import american, american_div, barrier, cfg4
 from finite_difference_b200 import DeviceBatch
 which = sys.argv[1:] or ["lean"]
 cases = []

@@ -40,6 +40,34 @@ def american_div(n_opt, n, m, seed=5):
     return hostlogic.build_american_batch(np.full(n_opt, 229.74), K, 1.0, sig, r, r, call, n, m, 2, False, div_taus=dts)
 
 
+def cfg4(n_opt, n, m, divs=True, seed=4):
+    """cfg4-shaped batch: American equity, T = 1, two cash dividends."""
+    rng = np.random.default_rng(20251018 + seed)
+    K = rng.uniform(180, 280, n_opt); sig = rng.uniform(0.15, 0.45, n_opt)
+    r = np.log1p(rng.uniform(0.03, 0.10, n_opt)); call = rng.uniform(size=n_opt) < 0.5
+    cash = rng.uniform(2, 9, (n_opt, 2))
+    dts = [[(109.0 / 365.0, float(cash[i, 1])), (319.0 / 365.0, float(cash[i, 0]))] for i in range(n_opt)] if divs else None
+    return hostlogic.build_american_batch(np.full(n_opt, 229.74), K, 1.0, sig, r, r, call, n, m, 2, False, div_taus=dts)
+
+
+def american_T(n_opt, n, m, T, seed=4):
+    """American equity batch with a chosen maturity (so that dt matches a real configuration)."""
+    rng = np.random.default_rng(20251018 + seed)
+    K = rng.uniform(180, 280, n_opt); sig = rng.uniform(0.15, 0.45, n_opt)
+    r = np.log1p(rng.uniform(0.03, 0.10, n_opt)); call = rng.uniform(size=n_opt) < 0.5
+    return hostlogic.build_american_batch(np.full(n_opt, 229.74), K, T, sig, r, r, call, n, m, 2, False)
+
+
+def barrier_T(n_opt, n, m, T, seed=2):
+    rng = np.random.default_rng(20251018 + seed)
+    K = rng.uniform(80, 120, n_opt); sig = rng.uniform(0.10, 0.50, n_opt); r = rng.uniform(0.01, 0.08, n_opt)
+    b = r - rng.uniform(0, 0.03, n_opt); B = 100.0 * rng.uniform(0.70, 0.95, n_opt)
+    mons = [[k / 12.0 for k in range(1, int(12 * T) + 1)]] * n_opt
+    return hostlogic.build_barrier_batch(np.full(n_opt, 100.0), K, np.full(n_opt, T), sig, r, b, np.ones(n_opt, bool),
+                                         ["down-and-out"] * n_opt, list(B), [None] * n_opt, np.zeros(n_opt), mons,
+                                         np.full(n_opt, n), np.full(n_opt, m))
+
+
 if __name__ == "__main__":
     print("lib", _lib.lib_path())
     tf, ms = _lib.fp64_peak_tflops()
