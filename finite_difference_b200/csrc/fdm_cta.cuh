@@ -98,7 +98,13 @@ struct Layout {
     static constexpr int NP = NT * C + 2;
     // warps that may carry per-slot coefficients: 6 x 512 slots hold the padding plus a head of up to ~3000
     // rows (alpha*dt up to ~4e4 at 8193 nodes); stiffer solves are flagged with status 2
-    static constexpr int SLOTS = WARPS <= 4 ? WARPS : (WARPS <= 5 ? 4 : 6);   // 5 warps: two CTAs per SM must fit shared memory
+    // Per-slot coefficient tables serve the rare table mode only (pivots not converged / far-reaching row-0 tail); two
+    // staged table warps (1024 head rows) keep shared memory small enough for 4 / 3 / 2 resident CTAs of 4 / 5 / 8 warps
+    // (more staged slots would cost a CTA per SM); the 16-warp class has the SM to itself and stages six.
+#ifndef FDM_CTA_SLOTS_SMALL
+#define FDM_CTA_SLOTS_SMALL 2
+#endif
+    static constexpr int SLOTS = WARPS <= 8 ? (WARPS < FDM_CTA_SLOTS_SMALL ? WARPS : FDM_CTA_SLOTS_SMALL) : 6;
     static constexpr int SLOT_DOUBLES = 3 * C * 32 + 8 * 32;         // nm, ncc, inv [k][lane] + 8 per-lane constants
     static constexpr int R2 = NP > SLOTS * SLOT_DOUBLES ? NP : SLOTS * SLOT_DOUBLES;
     static constexpr int SMALL = 4 * WARPS + 16 + 64 + 32 + 8 + C + 8 + 320;   // part, cst, PAc, wb, ishare, nmp, smv, scw
@@ -697,9 +703,20 @@ __device__ __noinline__ double dividend_jump(double Vb, double cash, bool is_cal
 template <int C, int WARPS>
 constexpr int smem_doubles() { return Layout<C, WARPS>::TOTAL; }
 
-// resident CTAs per SM the registers are sized for: 4 or 5 warps leave room for two CTAs (255 / 200 registers)
+// resident CTAs per SM the registers are sized for.  More, smaller-budget CTAs beat fewer fat ones: every CTA is
+// latency-bound between its two block barriers, and independent CTAs fill each other's gaps (2133-node barrier
+// grids, 5 warps: 2 CTAs x 168 registers 6.4e11 -> 3 CTAs x 128 registers 7.2e11 node-steps/s).
+#ifndef FDM_CTA4_BLOCKS
+#define FDM_CTA4_BLOCKS 4
+#endif
+#ifndef FDM_CTA5_BLOCKS
+#define FDM_CTA5_BLOCKS 3
+#endif
+#ifndef FDM_CTA8_BLOCKS
+#define FDM_CTA8_BLOCKS 2
+#endif
 template <int C, int WARPS>
-constexpr int cta_min_blocks() { return 32 * WARPS * C <= 2560 ? 2 : 1; }
+constexpr int cta_min_blocks() { return WARPS == 4 ? FDM_CTA4_BLOCKS : (WARPS == 5 ? FDM_CTA5_BLOCKS : (WARPS == 8 ? FDM_CTA8_BLOCKS : 1)); }
 
 template <int C, int WARPS, bool AMER, bool TRACE>
 __global__ void __launch_bounds__(32 * WARPS, cta_min_blocks<C, WARPS>())
