@@ -220,6 +220,8 @@ int launch(const FdmBatch &b, const FdmOut &o, cudaStream_t st, int family_mask,
         if (rc == FDM_OK && rows_max > 2048) rc = fdm_launch_cta_5(b, o, st, am, lin, dv, 2049, n_launches);
         if (rc == FDM_OK && rows_max > 2560) rc = fdm_launch_cta_8(b, o, st, am, lin, dv, 2561, n_launches);
         if (rc == FDM_OK && rows_max > 4096) rc = fdm_launch_cta_16(b, o, st, am, lin, dv, 4097, n_launches);
+        // what the CTA kernels flagged FDM_STATUS_STIFF is solved again by fdm_exact_kernel (one CTA screens 256 solves)
+        if (rc == FDM_OK) rc = fdm_launch_cta_exact(b, o, st, n_launches);
     }
     return rc;
 }

@@ -698,6 +698,70 @@ __device__ __noinline__ double dividend_jump(double Vb, double cash, bool is_cal
     return nb;
 }
 
+// Read-out by ONE thread from the value vector staged by node (fd_american_option_pricer.py:613-653 with snapping;
+// discrete_barrier_fdm_pricer_cn.py:308-353 without): price, stencil, delta, gamma, indices, status.
+static __device__ __noinline__ void read_out(const FdmOut &O, const int64_t sid, const double *Vs, const int n, const bool snap,
+                                      const double x_min, const double dx, const double spot, const int spot_idx,
+                                      const int strike_idx, const int ex_lo, const int ex_hi, const int flagged)
+{
+    const double sn = node_s(x_min, dx, n);
+    double price, delta, gamma, sv[4], ss[4];
+    int idx_a, idx_b;
+    if (snap) {
+        const int i_near = min(max(spot_idx, 1), n - 2);
+        const double Sx = node_s(x_min, dx, spot_idx);
+        for (int q = 0; q < 4; ++q) { sv[q] = Vs[i_near - 1 + q]; ss[q] = node_s(x_min, dx, i_near - 1 + q); }
+        price = Vs[spot_idx];
+        const double z0 = ss[0] - Sx, z1 = ss[1] - Sx, z2 = ss[2] - Sx, z3 = ss[3] - Sx;
+        const double f01 = (sv[1] - sv[0]) / (z1 - z0);
+        const double f12 = (sv[2] - sv[1]) / (z2 - z1);
+        const double f23 = (sv[3] - sv[2]) / (z3 - z2);
+        const double f012 = (f12 - f01) / (z2 - z0);
+        const double f123 = (f23 - f12) / (z3 - z1);
+        const double f0123 = (f123 - f012) / (z3 - z0);
+        delta = f01 + f012 * (-(z0 + z1)) + f0123 * (z0 * z1 + z0 * z2 + z1 * z2);
+        gamma = 2.0 * f012 - 2.0 * f0123 * (z0 + z1 + z2);
+        idx_a = spot_idx;
+        idx_b = strike_idx;
+    } else {
+        const double s0 = node_s(x_min, dx, 0);
+        int lo = 0;
+        if (spot <= s0) { price = Vs[0]; lo = 0; }
+        else if (spot >= sn) { price = Vs[n]; lo = n; }
+        else {
+            lo = min(max(last_node_le(x_min, dx, n, spot), 0), n - 1);
+            const double s_lo = node_s(x_min, dx, lo), s_hi = node_s(x_min, dx, lo + 1);
+            const double wgt = __dsub_rn(spot, s_lo) / __dsub_rn(s_hi, s_lo);
+            price = __dadd_rn(__dmul_rn(__dsub_rn(1.0, wgt), Vs[lo]), __dmul_rn(wgt, Vs[lo + 1]));
+        }
+        const int gi = nearest_node(x_min, dx, n, spot, true);
+        for (int q = 0; q < 3; ++q) { sv[q] = Vs[gi - 1 + q]; ss[q] = node_s(x_min, dx, gi - 1 + q); }
+        sv[3] = 0.0; ss[3] = 0.0;
+        const double h1 = __dsub_rn(ss[1], ss[0]);
+        const double h2 = __dsub_rn(ss[2], ss[1]);
+        const double h12 = __dadd_rn(h1, h2);
+        delta = __dadd_rn(__dadd_rn(__dmul_rn(-h2 / __dmul_rn(h1, h12), sv[0]),
+                                    __dmul_rn(__dsub_rn(h2, h1) / __dmul_rn(h1, h2), sv[1])),
+                          __dmul_rn(h1 / __dmul_rn(h2, h12), sv[2]));
+        gamma = __dmul_rn(2.0, __dadd_rn(__dsub_rn(sv[0] / __dmul_rn(h1, h12), sv[1] / __dmul_rn(h1, h2)),
+                                         sv[2] / __dmul_rn(h2, h12)));
+        idx_a = lo;
+        idx_b = gi;
+    }
+    O.price[sid] = price;
+    if (O.delta) O.delta[sid] = delta;
+    if (O.gamma) O.gamma[sid] = gamma;
+    if (O.stencil_v) for (int q = 0; q < 4; ++q) O.stencil_v[4 * sid + q] = sv[q];
+    if (O.stencil_s) for (int q = 0; q < 4; ++q) O.stencil_s[4 * sid + q] = ss[q];
+    if (O.idx) {
+        O.idx[4 * sid + 0] = idx_a;
+        O.idx[4 * sid + 1] = idx_b;
+        O.idx[4 * sid + 2] = ex_lo;
+        O.idx[4 * sid + 3] = ex_hi;
+    }
+    if (O.status) O.status[sid] = flagged ? flagged : (isfinite(price) ? 0 : 1);
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------
 
 template <int C, int WARPS>
@@ -1015,65 +1079,9 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
     }
     __syncthreads();
     if (t != 0) return;
-    int *ishare = sm.ish;
-
-    const int ex_lo = (AMER && ishare[7] >= 0) ? ishare[6] : -1;
-    const int ex_hi = (AMER && ishare[7] >= 0) ? ishare[7] : -1;
-    double price, delta, gamma, sv[4], ss[4];
-    int idx_a, idx_b;
-    if (snap) {
-        const int i_near = min(max(spot_idx, 1), n - 2);
-        const double Sx = node_s(x_min, dx, spot_idx);
-        for (int q = 0; q < 4; ++q) { sv[q] = Vs[i_near - 1 + q]; ss[q] = node_s(x_min, dx, i_near - 1 + q); }
-        price = Vs[spot_idx];
-        const double z0 = ss[0] - Sx, z1 = ss[1] - Sx, z2 = ss[2] - Sx, z3 = ss[3] - Sx;
-        const double f01 = (sv[1] - sv[0]) / (z1 - z0);
-        const double f12 = (sv[2] - sv[1]) / (z2 - z1);
-        const double f23 = (sv[3] - sv[2]) / (z3 - z2);
-        const double f012 = (f12 - f01) / (z2 - z0);
-        const double f123 = (f23 - f12) / (z3 - z1);
-        const double f0123 = (f123 - f012) / (z3 - z0);
-        delta = f01 + f012 * (-(z0 + z1)) + f0123 * (z0 * z1 + z0 * z2 + z1 * z2);
-        gamma = 2.0 * f012 - 2.0 * f0123 * (z0 + z1 + z2);
-        idx_a = spot_idx;
-        idx_b = strike_idx;
-    } else {
-        const double s0 = node_s(x_min, dx, 0);
-        int lo = 0;
-        if (spot <= s0) { price = Vs[0]; lo = 0; }
-        else if (spot >= sn) { price = Vs[n]; lo = n; }
-        else {
-            lo = min(max(last_node_le(x_min, dx, n, spot), 0), n - 1);
-            const double s_lo = node_s(x_min, dx, lo), s_hi = node_s(x_min, dx, lo + 1);
-            const double wgt = __dsub_rn(spot, s_lo) / __dsub_rn(s_hi, s_lo);
-            price = __dadd_rn(__dmul_rn(__dsub_rn(1.0, wgt), Vs[lo]), __dmul_rn(wgt, Vs[lo + 1]));
-        }
-        const int gi = nearest_node(x_min, dx, n, spot, true);
-        for (int q = 0; q < 3; ++q) { sv[q] = Vs[gi - 1 + q]; ss[q] = node_s(x_min, dx, gi - 1 + q); }
-        sv[3] = 0.0; ss[3] = 0.0;
-        const double h1 = __dsub_rn(ss[1], ss[0]);
-        const double h2 = __dsub_rn(ss[2], ss[1]);
-        const double h12 = __dadd_rn(h1, h2);
-        delta = __dadd_rn(__dadd_rn(__dmul_rn(-h2 / __dmul_rn(h1, h12), sv[0]),
-                                    __dmul_rn(__dsub_rn(h2, h1) / __dmul_rn(h1, h2), sv[1])),
-                          __dmul_rn(h1 / __dmul_rn(h2, h12), sv[2]));
-        gamma = __dmul_rn(2.0, __dadd_rn(__dsub_rn(sv[0] / __dmul_rn(h1, h12), sv[1] / __dmul_rn(h1, h2)),
-                                         sv[2] / __dmul_rn(h2, h12)));
-        idx_a = lo;
-        idx_b = gi;
-    }
-    O.price[sid] = price;
-    if (O.delta) O.delta[sid] = delta;
-    if (O.gamma) O.gamma[sid] = gamma;
-    if (O.stencil_v) for (int q = 0; q < 4; ++q) O.stencil_v[4 * sid + q] = sv[q];
-    if (O.stencil_s) for (int q = 0; q < 4; ++q) O.stencil_s[4 * sid + q] = ss[q];
-    if (O.idx) {
-        O.idx[4 * sid + 0] = idx_a;
-        O.idx[4 * sid + 1] = idx_b;
-        O.idx[4 * sid + 2] = ex_lo;
-        O.idx[4 * sid + 3] = ex_hi;
-    }
-    if (O.status) O.status[sid] = ishare[5] ? ishare[5] : (isfinite(price) ? 0 : 1);
+    const int ex_lo = (AMER && sm.ish[7] >= 0) ? sm.ish[6] : -1;
+    const int ex_hi = (AMER && sm.ish[7] >= 0) ? sm.ish[7] : -1;
+    read_out(O, sid, Vs, n, snap, x_min, dx, spot, spot_idx, strike_idx, ex_lo, ex_hi, sm.ish[5]);
 }
 
 }  // namespace cta

@@ -1,5 +1,8 @@
 // fdm_cta_inst.cu -- one size class of fdm_cta_kernel (compiled with -DFDM_INST_W=4|5|8|16 warps) and its launcher.
 #include "fdm_cta.cuh"
+#if FDM_INST_W == 16
+#include "fdm_exact.cuh"
+#endif
 
 #ifndef FDM_INST_W
 #error "compile with -DFDM_INST_W=<warps per CTA>"
@@ -39,3 +42,24 @@ int FDM_CAT(fdm_launch_cta_, FDM_INST_W)(const FdmBatch &b, const FdmOut &o, cud
     if (n_launches) *n_launches += launches;
     return FDM_OK;
 }
+
+#if FDM_INST_W == 16
+// fdm_exact_kernel over the solves the CTA kernels flagged FDM_STATUS_STIFF (fdm_exact.cuh); needs out.status
+int fdm_launch_cta_exact(const FdmBatch &b, const FdmOut &o, cudaStream_t st, int32_t *n_launches)
+{
+    if (!o.status) return FDM_OK;
+    const size_t smem = cta::exact_smem_bytes(b.n_space_max);
+    FDM_CUDA(cudaFuncSetAttribute(cta::fdm_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t per = cta::EXACT_THREADS, max_grid = 0x7fffffff;
+    int launches = 0;
+    for (int64_t first = 0; first < b.n_solves; first += max_grid * per) {
+        const int64_t left = b.n_solves - first;
+        const int64_t count = (left < max_grid * per) ? (left + per - 1) / per : max_grid;
+        cta::fdm_exact_kernel<<<dim3((unsigned)count), dim3(cta::EXACT_THREADS), smem, st>>>(b, o, first);
+        ++launches;
+        FDM_CUDA(cudaGetLastError());
+    }
+    if (n_launches) *n_launches += launches;
+    return FDM_OK;
+}
+#endif

@@ -28,6 +28,8 @@ FDM_DECL_LEAN(4) FDM_DECL_LEAN(7) FDM_DECL_LEAN(8) FDM_DECL_LEAN(10) FDM_DECL_LE
     int fdm_launch_cta_##W(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american, bool any_linear, \
                            bool any_div, int n_lo, int32_t *n_launches);
 FDM_DECL_CTA(4) FDM_DECL_CTA(5) FDM_DECL_CTA(8) FDM_DECL_CTA(16)
+// fdm_exact_kernel: the reference's step literally, for solves the CTA kernels flagged FDM_STATUS_STIFF
+int fdm_launch_cta_exact(const FdmBatch &b, const FdmOut &o, cudaStream_t st, int32_t *n_launches);
 
 // fdm_rowvar_kernel<C>: C rows per lane, up to 32 C nodes; n_lo = largest node count of the class below
 #define FDM_DECL_ROWVAR(C)                                                                                       \

@@ -67,7 +67,9 @@ extern "C" {
 /* per-solve status (FdmOut.status, FdmBookOut.status) */
 #define FDM_STATUS_OK           0
 #define FDM_STATUS_NONFINITE    1   /* price is not finite */
-#define FDM_STATUS_STIFF        2   /* CTA kernel: pivots not converged inside its table (best effort result) */
+#define FDM_STATUS_STIFF        2   /* CTA kernel: pivots not converged inside its table.  With FdmOut.status given, such solves
+                                       are solved again by the exact (serial Thomas) kernel and end with status 0; without a
+                                       status array the best-effort result stands */
 #define FDM_STATUS_SINGULAR     3   /* row-varying solves: a pivot of the Thomas factorisation vanished (the reference raises
                                        ZeroDivisionError, discrete_barrier_fdm_pricer_2.py:271-279); price is NaN */
 #define FDM_STATUS_NOT_SOLVED  -1   /* no kernel took the solve: n_space outside [3, n_space_max], launch hints that miss
