@@ -448,6 +448,9 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
     const double *lc = ph.slot + 3 * C * 32;
     if (AMER) {
         american_rhs<C, RELU_FP64>(V, L, ph.q, ph.pd);
+    } else if (ph.q == 1.0) {                              // theta = 1/2 (CTA-uniform): the old V itself, a register rename
+#pragma unroll
+        for (int k = 0; k < C; ++k) L[k] = V[k];
     } else {
 #pragma unroll
         for (int k = 0; k < C; ++k) L[k] = ph.q * V[k];
