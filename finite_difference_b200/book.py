@@ -685,7 +685,7 @@ class DeviceBookRun:
         self._host, self._dev = {}, {}
 
         def dev_ptr(name, arr):
-            h = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+            h = torch.from_numpy(np.array(arr, order="C", copy=True)).pin_memory()
             d = h.to(self.device, non_blocking=False)
             self._host[name], self._dev[name] = h, d
             return d.data_ptr()

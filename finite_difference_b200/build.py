@@ -22,17 +22,19 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC"]
 
 LEAN_CLASSES = (10, 13, 16)
-LEAN_ALL_CLASSES = (4, 7, 8, 10, 13, 16)      # with -DFDM_LEAN_ALL_CLASSES (layout parity tests at the other sizes)
+LEAN_ALL_CLASSES = (4, 7, 8, 10, 13, 16)
+CTA_CLASSES = ((4, 12), (4, 16), (5, 14), (5, 16), (8, 12), (8, 16), (16, 12), (16, 16))   # = FDM_CTA_CLASSES, fdm_internal.h      # with -DFDM_LEAN_ALL_CLASSES (layout parity tests at the other sizes)
 
 # (object name, source, defines)
 def units(lean_classes=LEAN_CLASSES):
     u = [("api", "fdm_api.cu", [])]
     u += [(f"warp_{c}", "fdm_warp_inst.cu", [f"-DFDM_INST_C={c}"]) for c in (4, 8, 13, 16)]
     u += [(f"lean_{c}", "fdm_lean_inst.cu", [f"-DFDM_INST_C={c}"]) for c in lean_classes]
-    u += [(f"cta_{w}", "fdm_cta_inst.cu", [f"-DFDM_INST_W={w}"]) for w in (4, 5, 8, 16)]
+    u += [(f"cta_{w}" if c == 16 else f"cta_{w}x{c}", "fdm_cta_inst.cu", [f"-DFDM_INST_W={w}", f"-DFDM_INST_C={c}"])
+          for w, c in CTA_CLASSES]
     u += [(f"rowvar_{c}", "fdm_rowvar_inst.cu", [f"-DFDM_INST_C={c}"]) for c in (7, 10, 13, 19, 26, 32)]
     # the large instances first: the longest compile bounds the build
-    order = {"cta_16": 0, "cta_8": 1, "cta_5": 2, "cta_4": 3}
+    order = {"cta_16": 0, "cta_16x12": 0, "cta_8": 1, "cta_8x12": 1, "cta_5": 2, "cta_5x14": 2, "cta_4": 3, "cta_4x12": 3}
     return sorted(u, key=lambda x: order.get(x[0], 10))
 
 

@@ -212,14 +212,16 @@ int launch(const FdmBatch &b, const FdmOut &o, cudaStream_t st, int family_mask,
         if (rc != FDM_OK) return rc;
     }
     if (large) {
-        // one launch per CTA size class that can be populated: 4 / 5 / 8 / 16 warps of 16 slots per thread serve
-        // up to 2048 / 2560 / 4096 / 8192 interior rows; a solve runs in the smallest class that holds it
+        // one launch per CTA size class that can be populated;
+        // size classes in ascending capacity (32 W C interior rows); a solve runs in the smallest class that holds it
         // (n_lo = largest n_space of the class below), other classes' CTAs exit at once
         const int rows_max = b.n_space_max - 1;
-        rc = fdm_launch_cta_4(b, o, st, am, lin, dv, FDM_WARP_MAX_N_SPACE, n_launches);
-        if (rc == FDM_OK && rows_max > 2048) rc = fdm_launch_cta_5(b, o, st, am, lin, dv, 2049, n_launches);
-        if (rc == FDM_OK && rows_max > 2560) rc = fdm_launch_cta_8(b, o, st, am, lin, dv, 2561, n_launches);
-        if (rc == FDM_OK && rows_max > 4096) rc = fdm_launch_cta_16(b, o, st, am, lin, dv, 4097, n_launches);
+        int n_lo = FDM_WARP_MAX_N_SPACE;
+#define FDM_RUN_CTA(W, C)                                                                                          \
+        if (rc == FDM_OK && rows_max + 1 > n_lo) rc = fdm_launch_cta_##W##x##C(b, o, st, am, lin, dv, n_lo, n_launches); \
+        n_lo = 32 * W * C + 1;
+        FDM_CTA_CLASSES(FDM_RUN_CTA)
+#undef FDM_RUN_CTA
         // what the CTA kernels flagged FDM_STATUS_STIFF is solved again by fdm_exact_kernel (one CTA screens 256 solves)
         if (rc == FDM_OK) rc = fdm_launch_cta_exact(b, o, st, n_launches);
     }

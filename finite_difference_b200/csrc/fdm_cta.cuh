@@ -124,7 +124,6 @@ struct Sm {
     double *nmp;    // [C] powers NM^k of the steady-state forward multiplier (row-0 correction)
     double *scw;    // [2][5][32] masked level weights of the scalar warps' scans (forward, backward): a^(2^lv) or 0
     double *smv;    // [0] GF NCC^-k0, factor of the row-0 correction  [1] xs at slot 0 of the owner of row 0, current step
-                    // [2] Kc: what the Dirichlet carry leaves in [1] through the k0 dead slots below row 0
 };
 
 enum { CST_NM = 0, CST_NCC, CST_INV, CST_AF, CST_AB, CST_HF1, CST_HF2, CST_HB1, CST_HB2, CST_TOP, CST_PD };
@@ -138,7 +137,6 @@ struct Ph {
     double gz;              // row-0 correction weight of this thread: GF * NM^(row of slot 0), 0 where it does not reach
     int smc;                // this warp applies the row-0 correction in step_c
     int bar3;               // the correction reaches beyond the warp of row 0: a third block barrier per step
-    double cF;              // owner of row 0: NM^-(k0+1), turns the Dirichlet term of row 0 into a forward carry; else 0
     const double *invw;     // warp of row 0: pivot scaling by slot and lane, 0 on the dead slots below row 0
     double cA, cB;          // boundary coefficients of this thread (row-0 owner: A_L, B_L; last thread: A_U, B_U)
     int Kf, Kb;             // terms of the warp-to-warp Horner sums
@@ -249,11 +247,6 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
             double unw = 1.0;
             for (int k = 0; k < pad % C; ++k) unw /= pv_ncc[P];
             sm.smv[0] = GF * unw;
-            // dead slot j of the owner of row 0 carries u_j = NM^(j+1) carry: sum_j NCC^j u_j reaches its slot 0
-            const double nmc = pv_nm[P], rho = pv_nm[P] * pv_ncc[P];
-            double kc = 0.0, rj = 1.0;
-            for (int k = 0; k < pad % C; ++k) { kc += rj; rj *= rho; }
-            sm.smv[2] = nmc * kc;
         }
         sm.ish[12] = wz;
         // growth-factor matching (fdm_b200.cu, growth_matched_pd); the linear march folds p + delta into inv
@@ -283,23 +276,21 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
 #ifdef FDM_CTA_EXP_NOTBL          // timing experiment only (wrong results): no table warps
     if (ph.cls == 2) ph.cls = 1;
 #endif
-    ph.gz = 0.0; ph.cF = 0.0; ph.smc = 0; ph.bar3 = 0; ph.invw = sm.r2;
+    ph.gz = 0.0; ph.smc = 0; ph.bar3 = 0; ph.invw = sm.r2;
     if (row0_mode<C, WARPS, AMER>()) {
         const int wz = sm.ish[12];
         ph.smc = (wz >= 0 && w >= wf && w <= wz) ? 1 : 0;
         ph.bar3 = (wz > wf) ? 1 : 0;
         ph.gz = 0.0;
-        ph.cF = 0.0;
         ph.invw = sm.r2;
         if (wz >= 0) {
             // dead lanes below row 0 stay at exactly zero with a zero pivot scaling (V = 0 * xs - 0); the owner of
             // row 0 has dead AND live slots: its warp reads the scaling by slot from shared memory
-            const int t0 = pad / C, k0 = pad % C;
+            const int t0 = pad / C;
             if (w == wf) {
 #pragma unroll
                 for (int k = 0; k < C; ++k) sm.r2[k * 32 + lane] = (t * C + k >= pad) ? ph.INV : 0.0;
             }
-            if (t == t0) ph.cF = 1.0 / pow(ph.NM, (double)(k0 + 1));
             if (t < t0) ph.INV = 0.0;
         }
         const int e0 = t * C - pad;                                  // row of slot 0 (negative inside the padding)
@@ -436,11 +427,13 @@ __device__ __forceinline__ double warp_scan_tab(double e, const double *__restri
 
 // ---- the three phases of one time step (barriers sit between them, outside any branch) -----------
 
-// RHS, forward local pass, intra-warp scan.  k0 >= 0 on the thread that owns row 0: its Dirichlet term
-// is added to R there.
-template <int C, int WARPS, bool AMER, bool TBL, bool R0>
+// RHS, forward local pass, intra-warp scan.  INJ: this warp holds row 0; k0 >= 0 on the thread that owns it, and the
+// Dirichlet term of row 0 is added to R at that slot.  (It used to enter the scalar owner as a carry below the thread's
+// slot 0, scaled by NM^-(k0+1): with a small NM and row 0 high up in its thread the dead slots then carried values
+// 1e7 times the signal and their cancellation cost seven digits -- 2e-9 on a 555-node barrier grid with k0 = 10.)
+template <int C, int WARPS, bool AMER, bool TBL, bool INJ>
 __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph &ph, const Sm &sm, const int k0,
-                                       const double cin_f, const double carryF, double &e1_keep, double &Eprev)
+                                       const double cin_f, double &e1_keep, double &Eprev)
 {
     constexpr int H = C / 2;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -455,7 +448,7 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
 #pragma unroll
         for (int k = 0; k < C; ++k) L[k] = ph.q * V[k];
     }
-    if (TBL && k0 >= 0) {
+    if (INJ && k0 >= 0) {
 #pragma unroll
         for (int k = 0; k < C; ++k) if (k == k0) V[k] += cin_f;
     }
@@ -465,7 +458,6 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
 #pragma unroll
     for (int k = H; k < C; ++k) e2 = fma(TBL ? nm[k * 32 + lane] : ph.NM, e2, V[k]);
     double e_end = fma(TBL ? lc[LC_HF2 * 32 + lane] : sm.cst[CST_HF2], e1, e2);
-    if (!TBL && R0) e_end = fma(sm.cst[CST_AF], carryF, e_end);  // Dirichlet term of row 0 as a carry into its owner
     const double E = (!TBL && SCAN_TABLE) ? warp_scan_tab<true>(e_end, sm.scw, lane)
                                           : warp_scan<TBL, true>(e_end, TBL ? lc[LC_AF * 32 + lane] : sm.cst[CST_AF], lane);
     if (lane == 31) sm.part[0 * WARPS + w] = E;           // pE_f
@@ -474,9 +466,9 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
     e1_keep = e1;
 }
 
-template <int C, int WARPS, bool AMER, bool TBL, bool R0, bool K1>
+template <int C, int WARPS, bool AMER, bool TBL, bool K1>
 __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &sm, const int wf, const double cin_b,
-                                       const double e1_fwd, const double Eprev, const double carryF, double &e1_keep,
+                                       const double e1_fwd, const double Eprev, double &e1_keep,
                                        double &Enext, double &eend_keep)
 {
     constexpr int H = C / 2;
@@ -490,7 +482,7 @@ __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &s
 #pragma unroll 1
         for (int v = max(wf, w - ph.Kf); v < w; ++v) S = fma(sm.part[1 * WARPS + v], S, sm.part[0 * WARPS + v]);
     }
-    const double cs = fma(TBL ? lc[LC_PAF * 32 + lane] : sm.PAc[lane], S, Eprev) + ((TBL || !R0) ? 0.0 : carryF);
+    const double cs = fma(TBL ? lc[LC_PAF * 32 + lane] : sm.PAc[lane], S, Eprev);
     {
         double c1 = cs;
         double c2 = fma(TBL ? lc[LC_HF1 * 32 + lane] : sm.cst[CST_HF1], cs, e1_fwd);
@@ -938,15 +930,15 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                 double cin_n = ph.cB * w_now - ph.cA * w_next;
                 const double cin_b = cin * top_mult;            // enters the top row through its ncc
                 double e1f = 0.0, Eprev = 0.0, e1b = 0.0, Enext = 0.0, eend_b = 0.0;
-                const double carryF = R0 ? cin * ph.cF : 0.0;   // non-zero on the owner of row 0 in row-0-correction mode
                 constexpr bool ANY = ROLE == ROLE_ANY;
                 const bool tbl = ANY ? ph.cls == 2 : ROLE == ROLE_TBL;
                 const bool scl = ANY ? ph.cls == 1 : (ROLE != ROLE_TBL && ROLE != ROLE_PAD);
-                if (tbl) step_a<C, WARPS, AMER, true, R0>(V, L, ph, sm, k0, cin, 0.0, e1f, Eprev);
-                else if (scl) step_a<C, WARPS, AMER, false, R0>(V, L, ph, sm, -1, 0.0, carryF, e1f, Eprev);
+                constexpr bool OWN = ANY || ROLE == ROLE_OWNER;   // the scalar warp that holds row 0 (row-0 correction mode)
+                if (tbl) step_a<C, WARPS, AMER, true, true>(V, L, ph, sm, k0, cin, e1f, Eprev);
+                else if (scl) step_a<C, WARPS, AMER, false, OWN>(V, L, ph, sm, k0, cin, e1f, Eprev);
                 FDM_CTA_STEP_SYNC();
-                if (tbl) step_b<C, WARPS, AMER, true, R0, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, 0.0, e1b, Enext, eend_b);
-                else if (scl) step_b<C, WARPS, AMER, false, R0, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, carryF, e1b, Enext, eend_b);
+                if (tbl) step_b<C, WARPS, AMER, true, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, e1b, Enext, eend_b);
+                else if (scl) step_b<C, WARPS, AMER, false, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, e1b, Enext, eend_b);
                 FDM_CTA_STEP_SYNC();
                 const bool r0c = ANY || ROLE == ROLE_PAD ? row0_corr : (ROLE == ROLE_SCALAR_R0 || ROLE == ROLE_OWNER || ROLE == ROLE_SMC);
                 if (tbl) step_c<C, WARPS, AMER, true, K1>(V, L, ph, sm, cin_b, e1b, Enext);
@@ -959,7 +951,7 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                     if (scl) {
                         cs_b = bwd_carry<WARPS, K1>(ph, sm, Enext);
                         if ((ANY || ROLE == ROLE_OWNER) && k0 >= 0)
-                            sm.smv[1] = fma(-sm.smv[2], carryF, fma(sm.cst[CST_AB], cs_b, eend_b));
+                            sm.smv[1] = fma(sm.cst[CST_AB], cs_b, eend_b);
                     }
                     if (ph.bar3) __syncthreads(); else __syncwarp();
                     if (scl) {

@@ -1,19 +1,25 @@
-// fdm_cta_inst.cu -- one size class of fdm_cta_kernel (compiled with -DFDM_INST_W=4|5|8|16 warps) and its launcher.
+// fdm_cta_inst.cu -- one size class of fdm_cta_kernel (compiled with -DFDM_INST_W=<warps per CTA> and
+// -DFDM_INST_C=<slots per thread>, default 16) and its launcher fdm_launch_cta_<W>x<C>.
 #include "fdm_cta.cuh"
-#if FDM_INST_W == 16
-#include "fdm_exact.cuh"
-#endif
 
 #ifndef FDM_INST_W
 #error "compile with -DFDM_INST_W=<warps per CTA>"
 #endif
+#ifndef FDM_INST_C
+#define FDM_INST_C 16
+#endif
+#define FDM_HOSTS_EXACT (FDM_INST_W == 16 && FDM_INST_C == 16)
+#if FDM_HOSTS_EXACT
+#include "fdm_exact.cuh"
+#endif
 #define FDM_CAT2(a, b) a##b
 #define FDM_CAT(a, b) FDM_CAT2(a, b)
 
-int FDM_CAT(fdm_launch_cta_, FDM_INST_W)(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american,
-                                         bool any_linear, bool any_div, int n_lo, int32_t *n_launches)
+int FDM_CAT(FDM_CAT(FDM_CAT(fdm_launch_cta_, FDM_INST_W), x), FDM_INST_C)(
+    const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american, bool any_linear, bool any_div, int n_lo,
+    int32_t *n_launches)
 {
-    constexpr int C = 16, WARPS = FDM_INST_W;
+    constexpr int C = FDM_INST_C, WARPS = FDM_INST_W;
     (void)any_div;
     const bool trace = o.ex_trace != nullptr;
     const size_t smem = (size_t)cta::smem_doubles<C, WARPS>() * sizeof(double);
@@ -43,7 +49,7 @@ int FDM_CAT(fdm_launch_cta_, FDM_INST_W)(const FdmBatch &b, const FdmOut &o, cud
     return FDM_OK;
 }
 
-#if FDM_INST_W == 16
+#if FDM_HOSTS_EXACT
 // fdm_exact_kernel over the solves the CTA kernels flagged FDM_STATUS_STIFF (fdm_exact.cuh); needs out.status
 int fdm_launch_cta_exact(const FdmBatch &b, const FdmOut &o, cudaStream_t st, int32_t *n_launches)
 {

@@ -23,11 +23,13 @@ FDM_DECL_WARP(4) FDM_DECL_WARP(8) FDM_DECL_WARP(13) FDM_DECL_WARP(16)
                             bool any_div, int32_t *n_launches);
 FDM_DECL_LEAN(4) FDM_DECL_LEAN(7) FDM_DECL_LEAN(8) FDM_DECL_LEAN(10) FDM_DECL_LEAN(13) FDM_DECL_LEAN(16)
 
-// fdm_cta_kernel<16, W>: W warps of 16 slots per thread; n_lo = largest n_space of the class below
-#define FDM_DECL_CTA(W)                                                                                          \
-    int fdm_launch_cta_##W(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american, bool any_linear, \
-                           bool any_div, int n_lo, int32_t *n_launches);
-FDM_DECL_CTA(4) FDM_DECL_CTA(5) FDM_DECL_CTA(8) FDM_DECL_CTA(16)
+// fdm_cta_kernel<C, W>: W warps of C slots per thread serve up to 32 W C interior rows; n_lo = largest n_space of the
+// class below.  The classes, in ascending capacity (FDM_CTA_CLASSES(X) expands X(W, C) for each):
+#define FDM_CTA_CLASSES(X) X(4, 12) X(4, 16) X(5, 14) X(5, 16) X(8, 12) X(8, 16) X(16, 12) X(16, 16)
+#define FDM_DECL_CTA(W, C)                                                                                       \
+    int fdm_launch_cta_##W##x##C(const FdmBatch &b, const FdmOut &o, cudaStream_t st, bool any_american,        \
+                                 bool any_linear, bool any_div, int n_lo, int32_t *n_launches);
+FDM_CTA_CLASSES(FDM_DECL_CTA)
 // fdm_exact_kernel: the reference's step literally, for solves the CTA kernels flagged FDM_STATUS_STIFF
 int fdm_launch_cta_exact(const FdmBatch &b, const FdmOut &o, cudaStream_t st, int32_t *n_launches);
 

@@ -119,8 +119,10 @@ def test_cfg4_full_size_one_solve():
 
 
 # Row-0 correction mode of the CTA kernel (fdm_cta.cuh, setup_phase): small time steps so that the correction's NM^i
-# tail dies inside the grid, every size class, row 0 at different slots of its owner thread (pad % 16).
-ROW0_SIZES = [600, 777, 1234, 2047, 2133, 2500, 3333, 4097, 6000, 8000, 8193]
+# tail dies inside the grid, every size class (4x12, 4x16, 5x14, 5x16, 8x12, 8x16, 16x12, 16x16 warps x slots: up to
+# 1536 / 2048 / 2240 / 2560 / 3072 / 4096 / 6144 / 8192 interior rows), a full class (no padding) and the first size of
+# the next one, row 0 at different slots of its owner thread (pad % C).
+ROW0_SIZES = [600, 777, 1234, 1537, 1538, 2047, 2133, 2241, 2242, 2500, 2900, 3073, 3333, 4097, 6000, 6145, 6146, 8000, 8193]
 
 
 @pytest.mark.parametrize("n", ROW0_SIZES)
@@ -154,7 +156,8 @@ def test_barrier_row0_mode_vs_oracle(n):
 # a solve runs depends on the stiffness theta*dt*alpha of its time step.  Volatility bands at the time steps of the
 # benchmark shapes (8192 nodes, dt = 1e-4; 2048 nodes, dt = 2.5e-3) walk through one-term sums without and with the
 # third barrier, and multi-term sums; calls and puts put the moving boundary in the last / the first warp.
-STIFF_CASES = [(n, m, T, sig, call) for (n, m, T) in ((8192, 200, 0.02), (2048, 100, 0.25), (4096, 120, 0.03))
+STIFF_CASES = [(n, m, T, sig, call) for (n, m, T) in ((8192, 200, 0.02), (2048, 100, 0.25), (4096, 120, 0.03), (2200, 100, 0.25),
+                                                      (5000, 120, 0.03))
                for sig in (0.16, 0.28, 0.35, 0.45) for call in (False, True)]
 
 
@@ -175,7 +178,7 @@ def test_american_stiffness_bands_vs_oracle(n, m, T, sig, call):
 @pytest.mark.parametrize("sig", (0.12, 0.3, 0.5))
 def test_barrier_stiffness_bands_vs_oracle(sig):
     # 16-warp linear class (table warps + scalar warps) and the 5-warp class of the barrier scenario runner
-    for n, m, T in ((8192, 200, 0.02), (2133, 125, 0.25)):
+    for n, m, T in ((8192, 200, 0.02), (2133, 125, 0.25), (2400, 125, 0.25), (1400, 125, 0.25)):
         S0, K, r, b = 100.0, 97.0, 0.04, 0.02
         mon = [T * 0.25, T * 0.5, T * 0.75]
         batch = hostlogic.build_barrier_batch([S0], [K], [T], [sig], [r], [b], [True], ["down-and-out"], [88.0], [None],
