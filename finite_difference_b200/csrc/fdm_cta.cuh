@@ -119,24 +119,30 @@ struct Sm {
     double *cst;    // phase constants of the scalar-coefficient warps: NM NCC INV aF aB hF1 hF2 hB1 hB2 top_mult pd
     double *PAc;    // [64] exclusive lane products of those warps, forward / backward
     double *wb;     // [32] moving Dirichlet values of the next 32 steps
-    int *ish;       // [0] P [1] spot node [2] strike node [3,4] KO range [5] status [6,7] ex lo/hi [8] Kf [9] Kb
+    int *ish;       // [13] row-0 Dirichlet term by slot  [14,15] scan levels  [0] P [1] spot node [2] strike node [3,4] KO range [5] status [6,7] ex lo/hi [8] Kf [9] Kb
                     // [10] first table warp [11] last table warp [12] last warp the row-0 correction reaches (-1: table mode)
     double *nmp;    // [C] powers NM^k of the steady-state forward multiplier (row-0 correction)
     double *scw;    // [2][5][32] masked level weights of the scalar warps' scans (forward, backward): a^(2^lv) or 0
     double *smv;    // [0] GF NCC^-k0, factor of the row-0 correction  [1] xs at slot 0 of the owner of row 0, current step
+                    // [2] Kc: what the Dirichlet carry leaves in [1] through the dead slots below row 0
+                    // [3] [4] the carry enters below slot 0 / below slot C/2 (1 or 0)  [5] its weight at the thread's end
 };
 
 enum { CST_NM = 0, CST_NCC, CST_INV, CST_AF, CST_AB, CST_HF1, CST_HF2, CST_HB1, CST_HB2, CST_TOP, CST_PD };
 enum { LC_AF = 0, LC_AB, LC_HF1, LC_HF2, LC_HB1, LC_HB2, LC_PAF, LC_PAB };
 
 // warp roles of the specialised time loops (kernel): fixed per warp for a phase
-enum { ROLE_ANY = -1, ROLE_PAD = 0, ROLE_TBL, ROLE_SCALAR, ROLE_SCALAR_R0, ROLE_OWNER, ROLE_SMC };
+enum { ROLE_ANY = -1, ROLE_PAD = 0, ROLE_TBL, ROLE_SCALAR, ROLE_SCALAR_R0, ROLE_OWNER, ROLE_SMC, ROLE_OWNER_H, ROLE_OWNER_SLOT };
+// how the scalar owner warp of row 0 receives the Dirichlet term of row 0 (setup_phase)
+enum { INJ_NONE = 0, INJ_CARRY0, INJ_CARRYH, INJ_SLOT, INJ_RUNTIME };   // carry below slot 0 / below slot C/2 / by slot
 
 struct Ph {
     double q, pd, NM, NCC, INV;
     double gz;              // row-0 correction weight of this thread: GF * NM^(row of slot 0), 0 where it does not reach
     int smc;                // this warp applies the row-0 correction in step_c
     int bar3;               // the correction reaches beyond the warp of row 0: a third block barrier per step
+    double cF;              // owner of row 0, carry form: NM^-(k0+1), turns the Dirichlet term of row 0 into a forward carry; else 0
+    int inj;                // owner warp: the Dirichlet term of row 0 is added at its slot instead (setup_phase)
     const double *invw;     // warp of row 0: pivot scaling by slot and lane, 0 on the dead slots below row 0
     double cA, cB;          // boundary coefficients of this thread (row-0 owner: A_L, B_L; last thread: A_U, B_U)
     int Kf, Kb;             // terms of the warp-to-warp Horner sums
@@ -247,6 +253,25 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
             double unw = 1.0;
             for (int k = 0; k < pad % C; ++k) unw /= pv_ncc[P];
             sm.smv[0] = GF * unw;
+            // How the Dirichlet term of row 0 reaches its slot k0 = pad % C of the scalar owner warp (row-0 correction
+            // mode).  As a carry scaled by NM^-(k0'+1) that enters the thread's forward chains k0' dead slots below row 0
+            // -- below slot 0, or below slot C/2 (the second half-chain) when row 0 sits in the upper half: free, but the
+            // k0' dead slots then hold u_j = NM^(j+1) carry, which the backward pass sums into [1]; the predicted sum
+            // [2] * carry is taken out again, a cancellation that costs a factor rho^-k0' in precision (2e-9 on a
+            // 555-node barrier grid when the carry always entered below slot 0: k0 = 10, rho = 0.2).  So only while
+            // rho^-k0' <= 1e3; otherwise the term is added at its slot (ish[13]).
+            const int k0s = pad % C, kinj = (k0s >= C / 2) ? C / 2 : 0;
+            const double nmc = pv_nm[P], rho = pv_nm[P] * pv_ncc[P];
+            double kc = 0.0, rj = 1.0, lead = nmc, afx = 1.0;
+            for (int k = 0; k < k0s - kinj; ++k) { kc += rj; rj *= rho; }
+            for (int k = 0; k < kinj; ++k) lead *= pv_ncc[P];
+            for (int k = kinj; k < C; ++k) afx *= nmc;
+            const bool by_slot = !(fabs(rj) >= 1e-3);            // rj = rho^k0'
+            sm.smv[2] = by_slot ? 0.0 : lead * kc;
+            sm.smv[3] = kinj == 0 ? 1.0 : 0.0;                   // the carry enters below slot 0 ...
+            sm.smv[4] = kinj == 0 ? 0.0 : 1.0;                   // ... or below slot C/2
+            sm.smv[5] = afx;                                     // what it leaves at the end of the thread: NM^(C - kinj)
+            sm.ish[13] = by_slot ? 1 : 0;
         }
         sm.ish[12] = wz;
         // growth-factor matching (fdm_b200.cu, growth_matched_pd); the linear march folds p + delta into inv
@@ -276,7 +301,7 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
 #ifdef FDM_CTA_EXP_NOTBL          // timing experiment only (wrong results): no table warps
     if (ph.cls == 2) ph.cls = 1;
 #endif
-    ph.gz = 0.0; ph.smc = 0; ph.bar3 = 0; ph.invw = sm.r2;
+    ph.gz = 0.0; ph.cF = 0.0; ph.inj = 0; ph.smc = 0; ph.bar3 = 0; ph.invw = sm.r2;
     if (row0_mode<C, WARPS, AMER>()) {
         const int wz = sm.ish[12];
         ph.smc = (wz >= 0 && w >= wf && w <= wz) ? 1 : 0;
@@ -286,11 +311,13 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
         if (wz >= 0) {
             // dead lanes below row 0 stay at exactly zero with a zero pivot scaling (V = 0 * xs - 0); the owner of
             // row 0 has dead AND live slots: its warp reads the scaling by slot from shared memory
-            const int t0 = pad / C;
+            const int t0 = pad / C, k0 = pad % C;
+            ph.inj = sm.ish[13];
             if (w == wf) {
 #pragma unroll
                 for (int k = 0; k < C; ++k) sm.r2[k * 32 + lane] = (t * C + k >= pad) ? ph.INV : 0.0;
             }
+            if (t == t0 && !ph.inj) ph.cF = 1.0 / pow(ph.NM, (double)((k0 >= C / 2 ? k0 - C / 2 : k0) + 1));
             if (t < t0) ph.INV = 0.0;
         }
         const int e0 = t * C - pad;                                  // row of slot 0 (negative inside the padding)
@@ -380,6 +407,13 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
             if (!got_b && worst_b < TRUNC_EPS) { Kb = K; got_b = true; }
         }
         sm.ish[8] = Kf; sm.ish[9] = Kb;
+        // levels of the scalar warps' lane scans: level lv adds the terms 2^lv .. 2^(lv+1) - 1 lanes away
+        auto scan_levels = [](double a) {
+            a = fabs(a);
+            const double a8 = (a * a) * (a * a) * ((a * a) * (a * a));
+            return !(a8 >= TRUNC_EPS) ? 3 : (!(a8 * a8 >= TRUNC_EPS) ? 4 : 5);
+        };
+        sm.ish[14] = scan_levels(sm.cst[CST_AF]); sm.ish[15] = scan_levels(sm.cst[CST_AB]);
     }
     __syncthreads();
     ph.Kf = sm.ish[8]; ph.Kb = sm.ish[9];
@@ -413,12 +447,28 @@ constexpr bool SCAN_TABLE = false;
 #else
 constexpr bool SCAN_TABLE = true;
 #endif
-template <bool UP>
-__device__ __forceinline__ double warp_scan_tab(double e, const double *__restrict__ wt, int lane)
+// `levels` (3..5, uniform over the CTA): the lane-to-lane multiplier a = NM^C is small, and after L levels the scan
+// holds the 2^L nearest lanes' terms; what is left out weighs |a|^(2^L), below TRUNC_EPS for the levels skipped
+// (setup_phase).  A level is a dependent SHFL + DFMA, ~36 cycles in which the warp has nothing else to do: 1000-node
+// American grids +8 %, 3000 / 6000 nodes +3 / +2 %, 8192-node barrier grids +2 %.  Not (SKIP = false) in the 16 x 16
+// American class, whose loops sit at the 128-register cap: the two uniform branches cost it 3..5 % (cfg4: 8.25e11
+// without, 7.84e11 with) whether levels are skipped or not.
+template <int C, int WARPS, bool AMER>
+__host__ __device__ constexpr bool scan_level_skip()
+{
+#ifdef FDM_CTA_NO_LEVEL_SKIP
+    return false;
+#else
+    return !(AMER && WARPS == 16 && C == 16);
+#endif
+}
+template <bool UP, bool SKIP>
+__device__ __forceinline__ double warp_scan_tab(double e, const double *__restrict__ wt, int lane, const int levels)
 {
     double E = e;
 #pragma unroll
     for (int lv = 0; lv < 5; ++lv) {
+        if (SKIP && lv >= 3 && lv >= levels) break;
         const double tE = UP ? __shfl_up_sync(FULL, E, 1 << lv) : __shfl_down_sync(FULL, E, 1 << lv);
         E = fma(wt[lv * 32 + lane], tE, E);
     }
@@ -427,13 +477,13 @@ __device__ __forceinline__ double warp_scan_tab(double e, const double *__restri
 
 // ---- the three phases of one time step (barriers sit between them, outside any branch) -----------
 
-// RHS, forward local pass, intra-warp scan.  INJ: this warp holds row 0; k0 >= 0 on the thread that owns it, and the
-// Dirichlet term of row 0 is added to R at that slot.  (It used to enter the scalar owner as a carry below the thread's
-// slot 0, scaled by NM^-(k0+1): with a small NM and row 0 high up in its thread the dead slots then carried values
-// 1e7 times the signal and their cancellation cost seven digits -- 2e-9 on a 555-node barrier grid with k0 = 10.)
-template <int C, int WARPS, bool AMER, bool TBL, bool INJ>
+// RHS, forward local pass, intra-warp scan.  k0 >= 0 on the thread that owns row 0.  TBL: its Dirichlet term is added
+// to R at that slot.  INJ (the scalar warp that holds row 0, row-0 correction mode): at its slot too (INJ_SLOT), or as
+// the carry carryF into one of the thread's two half-chains (INJ_CARRY0 / INJ_CARRYH); setup_phase says which, and
+// each form has its own time loop (the owner is the warp the others wait for: every instruction on it shows).
+template <int C, int WARPS, bool AMER, bool TBL, int INJ>
 __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph &ph, const Sm &sm, const int k0,
-                                       const double cin_f, double &e1_keep, double &Eprev)
+                                       const double cin_f, const double carryF, double &e1_keep, double &Eprev)
 {
     constexpr int H = C / 2;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -448,9 +498,17 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
 #pragma unroll
         for (int k = 0; k < C; ++k) L[k] = ph.q * V[k];
     }
-    if (INJ && k0 >= 0) {
+    if (TBL && k0 >= 0) {
 #pragma unroll
         for (int k = 0; k < C; ++k) if (k == k0) V[k] += cin_f;
+    }
+    if (INJ == INJ_SLOT || (INJ == INJ_RUNTIME && ph.inj)) {
+        // predicated adds (k0 = -1 off the owner thread), in PTX: from `if (k == k0) V[k] += cin` the compiler builds a
+        // tree of indirect branches through constant-memory jump tables on the one warp every other warp waits for
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+            asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p add.rn.f64 %0, %0, %3;\n\t}"
+                : "+d"(V[k]) : "r"(k0), "r"(k), "d"(cin_f));
     }
     double e1 = 0.0, e2 = 0.0;
 #pragma unroll
@@ -458,7 +516,10 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
 #pragma unroll
     for (int k = H; k < C; ++k) e2 = fma(TBL ? nm[k * 32 + lane] : ph.NM, e2, V[k]);
     double e_end = fma(TBL ? lc[LC_HF2 * 32 + lane] : sm.cst[CST_HF2], e1, e2);
-    const double E = (!TBL && SCAN_TABLE) ? warp_scan_tab<true>(e_end, sm.scw, lane)
+    if (INJ == INJ_CARRY0) e_end = fma(sm.cst[CST_AF], carryF, e_end);
+    if (INJ == INJ_CARRYH) e_end = fma(sm.cst[CST_HF2], carryF, e_end);
+    if (INJ == INJ_RUNTIME) e_end = fma(sm.smv[5], carryF, e_end);               // Dirichlet term of row 0 as a carry into its owner
+    const double E = (!TBL && SCAN_TABLE) ? warp_scan_tab<true, scan_level_skip<C, WARPS, AMER>()>(e_end, sm.scw, lane, sm.ish[14])
                                           : warp_scan<TBL, true>(e_end, TBL ? lc[LC_AF * 32 + lane] : sm.cst[CST_AF], lane);
     if (lane == 31) sm.part[0 * WARPS + w] = E;           // pE_f
     const double up = __shfl_up_sync(FULL, E, 1);
@@ -466,9 +527,9 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
     e1_keep = e1;
 }
 
-template <int C, int WARPS, bool AMER, bool TBL, bool K1>
+template <int C, int WARPS, bool AMER, bool TBL, int INJ, bool K1>
 __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &sm, const int wf, const double cin_b,
-                                       const double e1_fwd, const double Eprev, double &e1_keep,
+                                       const double e1_fwd, const double Eprev, const double carryF, double &e1_keep,
                                        double &Enext, double &eend_keep)
 {
     constexpr int H = C / 2;
@@ -482,10 +543,16 @@ __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &s
 #pragma unroll 1
         for (int v = max(wf, w - ph.Kf); v < w; ++v) S = fma(sm.part[1 * WARPS + v], S, sm.part[0 * WARPS + v]);
     }
-    const double cs = fma(TBL ? lc[LC_PAF * 32 + lane] : sm.PAc[lane], S, Eprev);
+    // the owner's Dirichlet carry enters below slot 0 or below slot C/2; it is known before the barrier, so its sums
+    // with Eprev and e1_fwd are off the path that waits for S
+    double ep = Eprev, e1x = e1_fwd;
+    if (INJ == INJ_CARRYH) e1x = e1_fwd + carryF;
+    if (INJ == INJ_RUNTIME) { ep = fma(sm.smv[3], carryF, Eprev); e1x = fma(sm.smv[4], carryF, e1_fwd); }
+    double cs = fma(TBL ? lc[LC_PAF * 32 + lane] : sm.PAc[lane], S, ep);
+    if (INJ == INJ_CARRY0) cs += carryF;
     {
         double c1 = cs;
-        double c2 = fma(TBL ? lc[LC_HF1 * 32 + lane] : sm.cst[CST_HF1], cs, e1_fwd);
+        double c2 = fma(TBL ? lc[LC_HF1 * 32 + lane] : sm.cst[CST_HF1], cs, e1x);
 #pragma unroll
         for (int k = 0; k < H; ++k) { c1 = fma(TBL ? nm[k * 32 + lane] : ph.NM, c1, V[k]); V[k] = c1; }
 #pragma unroll
@@ -498,7 +565,7 @@ __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &s
 #pragma unroll
     for (int k = H - 1; k >= 0; --k) e2 = fma(TBL ? ncc[k * 32 + lane] : ph.NCC, e2, V[k]);
     const double e_end = fma(TBL ? lc[LC_HB2 * 32 + lane] : sm.cst[CST_HB2], e1, e2);
-    const double E = (!TBL && SCAN_TABLE) ? warp_scan_tab<false>(e_end, sm.scw + 160, lane)
+    const double E = (!TBL && SCAN_TABLE) ? warp_scan_tab<false, scan_level_skip<C, WARPS, AMER>()>(e_end, sm.scw + 160, lane, sm.ish[15])
                                           : warp_scan<TBL, false>(e_end, TBL ? lc[LC_AB * 32 + lane] : sm.cst[CST_AB], lane);
     if (lane == 0) sm.part[2 * WARPS + w] = E;            // pE_b
     const double dn = __shfl_down_sync(FULL, E, 1);
@@ -933,14 +1000,18 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                 constexpr bool ANY = ROLE == ROLE_ANY;
                 const bool tbl = ANY ? ph.cls == 2 : ROLE == ROLE_TBL;
                 const bool scl = ANY ? ph.cls == 1 : (ROLE != ROLE_TBL && ROLE != ROLE_PAD);
-                constexpr bool OWN = ANY || ROLE == ROLE_OWNER;   // the scalar warp that holds row 0 (row-0 correction mode)
-                if (tbl) step_a<C, WARPS, AMER, true, true>(V, L, ph, sm, k0, cin, e1f, Eprev);
-                else if (scl) step_a<C, WARPS, AMER, false, OWN>(V, L, ph, sm, k0, cin, e1f, Eprev);
+                // the scalar warp that holds row 0 (row-0 correction mode) and how the Dirichlet term of row 0 enters it
+                constexpr int INJ = !R0 ? INJ_NONE : (ANY ? INJ_RUNTIME : (ROLE == ROLE_OWNER ? INJ_CARRY0
+                                    : (ROLE == ROLE_OWNER_H ? INJ_CARRYH : (ROLE == ROLE_OWNER_SLOT ? INJ_SLOT : INJ_NONE))));
+                constexpr bool OWN = INJ != INJ_NONE;
+                const double carryF = (OWN && INJ != INJ_SLOT) ? cin * ph.cF : 0.0;   // non-zero on the owner thread
+                if (tbl) step_a<C, WARPS, AMER, true, INJ_NONE>(V, L, ph, sm, k0, cin, 0.0, e1f, Eprev);
+                else if (scl) step_a<C, WARPS, AMER, false, INJ>(V, L, ph, sm, k0, cin, carryF, e1f, Eprev);
                 FDM_CTA_STEP_SYNC();
-                if (tbl) step_b<C, WARPS, AMER, true, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, e1b, Enext, eend_b);
-                else if (scl) step_b<C, WARPS, AMER, false, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, e1b, Enext, eend_b);
+                if (tbl) step_b<C, WARPS, AMER, true, INJ_NONE, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, 0.0, e1b, Enext, eend_b);
+                else if (scl) step_b<C, WARPS, AMER, false, INJ, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, carryF, e1b, Enext, eend_b);
                 FDM_CTA_STEP_SYNC();
-                const bool r0c = ANY || ROLE == ROLE_PAD ? row0_corr : (ROLE == ROLE_SCALAR_R0 || ROLE == ROLE_OWNER || ROLE == ROLE_SMC);
+                const bool r0c = ANY || ROLE == ROLE_PAD ? row0_corr : (ROLE == ROLE_SCALAR_R0 || OWN || ROLE == ROLE_SMC);
                 if (tbl) step_c<C, WARPS, AMER, true, K1>(V, L, ph, sm, cin_b, e1b, Enext);
                 else if (!r0c) {
                     if (scl) step_c<C, WARPS, AMER, false, K1>(V, L, ph, sm, cin_b, e1b, Enext);
@@ -950,12 +1021,12 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                     double cs_b = 0.0;
                     if (scl) {
                         cs_b = bwd_carry<WARPS, K1>(ph, sm, Enext);
-                        if ((ANY || ROLE == ROLE_OWNER) && k0 >= 0)
-                            sm.smv[1] = fma(sm.cst[CST_AB], cs_b, eend_b);
+                        if (OWN && k0 >= 0)
+                            sm.smv[1] = fma(-sm.smv[2], carryF, fma(sm.cst[CST_AB], cs_b, eend_b));
                     }
                     if (ph.bar3) __syncthreads(); else __syncwarp();
                     if (scl) {
-                        const bool own = ANY ? w == wf : ROLE == ROLE_OWNER;
+                        const bool own = ANY ? w == wf : OWN;
                         const bool smc = ANY ? ph.smc != 0 : ROLE == ROLE_SMC;
                         if (own) step_cs<C, WARPS, AMER, true, true>(V, L, ph, sm, cs_b, cin_b, e1b);
                         else if (smc) step_cs<C, WARPS, AMER, true, false>(V, L, ph, sm, cs_b, cin_b, e1b);
@@ -1001,13 +1072,15 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
             time_loop(IntC<ROLE_ANY>{}, IntC<0>{});
 #else
             const int role = ph.cls == 0 ? ROLE_PAD : (ph.cls == 2 ? ROLE_TBL : (!row0_corr ? ROLE_SCALAR
-                             : (w == wf ? ROLE_OWNER : (ph.smc ? ROLE_SMC : ROLE_SCALAR_R0))));
+                             : (w == wf ? (ph.inj ? ROLE_OWNER_SLOT : (sm.smv[4] != 0.0 ? ROLE_OWNER_H : ROLE_OWNER)) : (ph.smc ? ROLE_SMC : ROLE_SCALAR_R0))));
             auto by_role = [&](auto k1_tag) {
                 switch (role) {
                 case ROLE_PAD: time_loop(IntC<ROLE_PAD>{}, k1_tag); break;
                 case ROLE_TBL: time_loop(IntC<ROLE_TBL>{}, k1_tag); break;
                 case ROLE_SCALAR: time_loop(IntC<ROLE_SCALAR>{}, k1_tag); break;
                 case ROLE_OWNER: if constexpr (R0) time_loop(IntC<ROLE_OWNER>{}, k1_tag); break;
+                case ROLE_OWNER_H: if constexpr (R0) time_loop(IntC<ROLE_OWNER_H>{}, k1_tag); break;
+                case ROLE_OWNER_SLOT: if constexpr (R0) time_loop(IntC<ROLE_OWNER_SLOT>{}, k1_tag); break;
                 case ROLE_SMC: if constexpr (R0) time_loop(IntC<ROLE_SMC>{}, k1_tag); break;
                 default: if constexpr (R0) time_loop(IntC<ROLE_SCALAR_R0>{}, k1_tag); break;
                 }
