@@ -95,7 +95,7 @@ __device__ __forceinline__ int nearest_node(double x_min, double dx, int n, doub
 template <int C, int WARPS>
 struct Layout {
     static constexpr int NT = 32 * WARPS;
-    static constexpr int NP = NT * C + 2;
+    static constexpr int NP = NT * C + 16;                           // n + 1 nodes, rounded up to a block of jsw()
     // warps that may carry per-slot coefficients: 6 x 512 slots hold the padding plus a head of up to ~3000
     // rows (alpha*dt up to ~4e4 at 8193 nodes); stiffer solves are flagged with status 2
     // Per-slot coefficient tables serve the rare table mode only (pivots not converged / far-reaching row-0 tail); two
@@ -128,7 +128,7 @@ struct Sm {
                     // [3] [4] the carry enters below slot 0 / below slot C/2 (1 or 0)  [5] its weight at the thread's end
 };
 
-enum { CST_NM = 0, CST_NCC, CST_INV, CST_AF, CST_AB, CST_HF1, CST_HF2, CST_HB1, CST_HB2, CST_TOP, CST_PD };
+enum { CST_NM = 0, CST_NCC, CST_INV, CST_AF, CST_AB, CST_HF1, CST_HF2, CST_HB1, CST_HB2, CST_TOP, CST_PD, CST_BS };
 enum { LC_AF = 0, LC_AB, LC_HF1, LC_HF2, LC_HB1, LC_HB2, LC_PAF, LC_PAB };
 
 // warp roles of the specialised time loops (kernel): fixed per warp for a phase
@@ -137,7 +137,7 @@ enum { ROLE_ANY = -1, ROLE_PAD = 0, ROLE_TBL, ROLE_SCALAR, ROLE_SCALAR_R0, ROLE_
 enum { INJ_NONE = 0, INJ_CARRY0, INJ_CARRYH, INJ_SLOT, INJ_RUNTIME };   // carry below slot 0 / below slot C/2 / by slot
 
 struct Ph {
-    double q, pd, NM, NCC, INV;
+    double q, pd, NM, NCC, INV;   // pd: growth-matched p - q + delta (linear); American: kappa (setup_phase)
     double gz;              // row-0 correction weight of this thread: GF * NM^(row of slot 0), 0 where it does not reach
     int smc;                // this warp applies the row-0 correction in step_c
     int bar3;               // the correction reaches beyond the warp of row 0: a third block barrier per step
@@ -277,9 +277,19 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
         // growth-factor matching (fdm_b200.cu, growth_matched_pd); the linear march folds p + delta into inv
         const double pd = fast ? growth_pd_from_ref(A_L, den_ref, cp_ref, A_U, B_L, B_C, B_U, ph.q, pv_inv[P])
                           : ((P < cap && P < n_int) ? growth_matched_pd(A_L, A_C, A_U, B_L, B_C, B_U, ph.q, pv_inv[P], n_int) : 1.0);
+        double bs = 1.0;
         if (!AMER) {
             const double scale = p + (pd - 1.0);
             for (int i = 0; i <= P; ++i) pv_inv[i] *= scale;
+            bs = 1.0 / scale;
+        } else {
+            // American state between steps: (vc, L = 2 dt lambda) with V = vc + L / 2, not (V, L): the right-hand side
+            // R = (pd + q) V + dt lambda = (pd + q) vc + s L, s = (pd + q + 1) / 2, is ONE fma once the system is
+            // solved for R / s = kappa vc + L (pivot scaling times s, Dirichlet terms over s), and the projection
+            // no longer forms V: 9 FP64 instructions per node-step instead of 10.
+            const double s = 0.5 * (pd + ph.q + 1.0);
+            for (int i = 0; i <= P; ++i) pv_inv[i] *= s;
+            bs = 1.0 / s;
         }
         const int wf = pad / (32 * C);                              // warp that holds row 0
         int wl = min((pad + P - 1) / (32 * C), WARPS - 1);          // last warp with a head row
@@ -288,12 +298,13 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
         sm.ish[0] = P; sm.ish[10] = wf; sm.ish[11] = min(wl, wf + LY::SLOTS - 1);
         sm.cst[CST_NM] = pv_nm[P]; sm.cst[CST_NCC] = pv_ncc[P]; sm.cst[CST_INV] = pv_inv[P];
         sm.cst[CST_TOP] = (sm.ish[11] == WARPS - 1) ? 1.0 : 1.0 / pv_ncc[P];
-        sm.cst[CST_PD] = pd;
+        sm.cst[CST_PD] = AMER ? (pd + ph.q) * bs : pd;            // American: kappa
+        sm.cst[CST_BS] = bs;
     }
     __syncthreads();
     const int P = sm.ish[0], wf = sm.ish[10], wl = sm.ish[11];
     ph.NM = sm.cst[CST_NM]; ph.NCC = sm.cst[CST_NCC]; ph.INV = sm.cst[CST_INV]; ph.pd = sm.cst[CST_PD];
-    const double bscale = AMER ? 1.0 : 1.0 / (p + (ph.pd - 1.0));   // the linear march solves for R / (p + delta)
+    const double bscale = sm.cst[CST_BS];               // the march solves for R / (p + delta) (linear), R / s (American)
     const bool owner0 = (t == pad / C);
     ph.cA = owner0 ? A_L * bscale : ((t == LY::NT - 1) ? A_U * bscale : 0.0);
     ph.cB = owner0 ? B_L * bscale : ((t == LY::NT - 1) ? B_U * bscale : 0.0);
@@ -490,7 +501,15 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
     const double *nm = ph.slot;
     const double *lc = ph.slot + 3 * C * 32;
     if (AMER) {
-        american_rhs<C, RELU_FP64>(V, L, ph.q, ph.pd);
+        // state (vc, L = 2 dt lambda): subtrahend G = q V + dt lambda = q vc + (q + 1) / 2 L, scaled rhs kappa vc + L
+        if (ph.q == 1.0) {
+#pragma unroll
+            for (int k = 0; k < C; ++k) { const double g = V[k] + L[k]; V[k] = fma(ph.pd, V[k], L[k]); L[k] = g; }
+        } else {
+            const double hq = 0.5 * (ph.q + 1.0);
+#pragma unroll
+            for (int k = 0; k < C; ++k) { const double g = fma(ph.q, V[k], hq * L[k]); V[k] = fma(ph.pd, V[k], L[k]); L[k] = g; }
+        }
     } else if (ph.q == 1.0) {                              // theta = 1/2 (CTA-uniform): the old V itself, a register rename
 #pragma unroll
         for (int k = 0; k < C; ++k) L[k] = V[k];
@@ -602,7 +621,9 @@ __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph 
             else           { c2 = fma(TBL ? ncc[k * 32 + lane] : ph.NCC, c2, V[k]); xs = c2; }
             const double vc = fma(TBL ? inv[k * 32 + lane] : ph.INV, xs, -L[k]);
             if (AMER) {
-                american_project<RELU_FP64>(sm.r0[k * NT + t], vc, V[k], L[k]);
+                const double d = sm.r0[k * NT + t] - vc;         // exercise iff phi > vc (fd_american_option_pricer.py:496)
+                L[k] = d + fabs(d);                              // 2 dt lambda_new, ONE FP64 instruction
+                V[k] = vc;
             } else {
                 V[k] = vc;
             }
@@ -648,7 +669,9 @@ __device__ __forceinline__ void step_cs(double (&V)[C], double (&L)[C], const Ph
             if (CORR) xs = fma(gzx, sm.nmp[k], xs);
             const double vc = fma(INVT ? ph.invw[k * 32 + lane] : ph.INV, xs, -L[k]);
             if (AMER) {
-                american_project<RELU_FP64>(sm.r0[k * NT + t], vc, V[k], L[k]);
+                const double d = sm.r0[k * NT + t] - vc;         // exercise iff phi > vc (fd_american_option_pricer.py:496)
+                L[k] = d + fabs(d);                              // 2 dt lambda_new, ONE FP64 instruction
+                V[k] = vc;
             } else {
                 V[k] = vc;
             }
@@ -657,7 +680,13 @@ __device__ __forceinline__ void step_cs(double (&V)[C], double (&L)[C], const Ph
 }
 
 // ---- dividend jump (fd_american_option_pricer.py:321-386, :517-548) ------------------------------
-// ys, mu, cz: shared arrays of n+1 doubles.
+// Where node j lives in the jump's shared arrays.  Thread t works on C consecutive nodes, so in the plain [j] layout
+// the lanes of a warp are C doubles apart: at C = 16 all 32 lanes hit one pair of banks and every access took 32
+// wavefronts -- the jump was bound by exactly that (8192 nodes: 237k cycles per jump, ~60 % of it bank conflicts).
+// XOR-ing the low four bits with the next four spreads a warp's access over all banks within the same 16-node block.
+__device__ __forceinline__ int jsw(const int j) { return j ^ ((j >> 4) & 15); }
+
+// ys, mu, cz: shared arrays of n+1 doubles in jsw() order.
 // Works on shared memory only (value vector in ys[], result returned in mu[]) and is not inlined, so its
 // registers do not weigh on the time loop.  Returns the new boundary node value of this thread.
 template <int C, int WARPS>
@@ -669,74 +698,109 @@ __device__ __noinline__ double dividend_jump(double Vb, double cash, bool is_cal
     const int t = threadIdx.x;
     const int nn = n + 1;
     const bool owner0 = (t == pad / C);
-    if (owner0) ys[0] = Vb;
-    if (t == NT - 1) ys[n] = Vb;
+#ifdef FDM_CTA_PROFILE
+    long long jt[6]; int ji = 0;
+#define JTICK() jt[ji++] = clock64()
+#else
+#define JTICK()
+#endif
+    JTICK();
+    if (owner0) ys[jsw(0)] = Vb;
+    if (t == NT - 1) ys[jsw(n)] = Vb;
     __syncthreads();
     // The spline's tridiagonal system (:338-359) is diagonally dominant: the forward recurrences forget
     // their start like 0.27^k and so does the back substitution.  Every thread therefore warm-starts
     // G rows outside its own rows (exactly at the true ends) and keeps only its own rows: all rows are
     // eliminated in parallel, in the reference's operation order, to within 0.27^G of the serial sweep.
-    constexpr int G = 40;
+    // Per row: the knots follow s_{i+1} = s_i e^{dx} from an exact start (an exponential per row before), one
+    // reciprocal serves the two quotients by l and 3 / h_{i-1} is the previous row's 3 / h_i (four IEEE divisions per
+    // row before); G = 30 warm-up rows leave 0.27^30 = 1e-17 of a wrong start.  237k -> see DESIGN.md cycles per jump
+    // at 8192 nodes; the quotients differ from the reference's in the last bit, the jumped values by ~1e-14 relative.
+    constexpr int G = 30;
     const int j_first = max(t * C - pad + 1, 1);           // this thread's interior knots [j_first, j_last]
     const int j_last = t * C + C - pad;
     const bool has_rows = j_last >= 1;
     if (has_rows) {
         const int i0 = max(1, j_first - G);
+        const double edx = exp(dx);
         double x_im1 = node_s(x_min, dx, i0 - 1), x_i = node_s(x_min, dx, i0);
         double mu_prev = 0.0, z_prev = 0.0;
+        double y_im1 = ys[jsw(i0 - 1)], y_i = ys[jsw(i0)];
+        double r3_prev = 3.0 * __drcp_rn(__dsub_rn(x_i, x_im1));
+#pragma unroll 2
         for (int i = i0; i <= j_last; ++i) {
-            const double x_ip1 = node_s(x_min, dx, i + 1);
+            const double x_ip1 = x_i * edx;
+            const double y_ip1 = ys[jsw(i + 1)];
             const double h_i = __dsub_rn(x_ip1, x_i);
             const double h_im1 = __dsub_rn(x_i, x_im1);
-            const double alpha = __dsub_rn(__dmul_rn(3.0 / h_i, __dsub_rn(ys[i + 1], ys[i])),
-                                           __dmul_rn(3.0 / h_im1, __dsub_rn(ys[i], ys[i - 1])));
+            const double r3 = 3.0 * __drcp_rn(h_i);
+            const double alpha = __dsub_rn(__dmul_rn(r3, __dsub_rn(y_ip1, y_i)), __dmul_rn(r3_prev, __dsub_rn(y_i, y_im1)));
             const double l = __dsub_rn(__dmul_rn(2.0, __dsub_rn(x_ip1, x_im1)), __dmul_rn(h_im1, mu_prev));
-            mu_prev = h_i / l;
-            z_prev = __dsub_rn(alpha, __dmul_rn(h_im1, z_prev)) / l;
-            if (i >= j_first) { mu[i] = mu_prev; cz[i] = z_prev; }
-            x_im1 = x_i;
-            x_i = x_ip1;
+            const double rl = __drcp_rn(l);
+            mu_prev = h_i * rl;
+            z_prev = __dsub_rn(alpha, __dmul_rn(h_im1, z_prev)) * rl;
+            if (i >= j_first) { mu[jsw(i)] = mu_prev; cz[jsw(i)] = z_prev; }
+            x_im1 = x_i; x_i = x_ip1;
+            y_im1 = y_i; y_i = y_ip1;
+            r3_prev = r3;
         }
     }
-    if (owner0) { mu[0] = 0.0; cz[0] = 0.0; }
-    if (t == NT - 1) cz[nn - 1] = 0.0;
+    if (owner0) { mu[jsw(0)] = 0.0; cz[jsw(0)] = 0.0; }
+    if (t == NT - 1) cz[jsw(nn - 1)] = 0.0;
+    JTICK();
     __syncthreads();
+    JTICK();
     // back substitution c[j] = z[j] - mu[j] c[j+1] (:358-359); results parked in V until every thread has read z
     if (has_rows) {
         const int i1 = min(n - 1, j_last + G);
         double c_next = 0.0;
-        for (int j = i1; j > j_last; --j) c_next = __dsub_rn(cz[j], __dmul_rn(mu[j], c_next));
+        for (int j = i1; j > j_last; --j) c_next = __dsub_rn(cz[jsw(j)], __dmul_rn(mu[jsw(j)], c_next));
 #pragma unroll
         for (int k = C - 1; k >= 0; --k) {
             const int j = t * C + k - pad + 1;
-            if (j >= 1) { c_next = __dsub_rn(cz[j], __dmul_rn(mu[j], c_next)); V[k] = c_next; }
+            if (j >= 1) { c_next = __dsub_rn(cz[jsw(j)], __dmul_rn(mu[jsw(j)], c_next)); V[k] = c_next; }
         }
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < C; ++k) {
         const int j = t * C + k - pad + 1;
-        if (j >= 1) cz[j] = V[k];
+        if (j >= 1) cz[jsw(j)] = V[k];
     }
     __syncthreads();
+    JTICK();
     const double s_lo = node_s(x_min, dx, 0), s_hi = node_s(x_min, dx, n);
-    auto eval = [&](int jnode) -> double {
-        const double Sj = node_s(x_min, dx, jnode);
+    const double edx_eval = exp(dx);
+    // A thread's nodes are consecutive, so S_j - cash rises from slot to slot and so does its bracket: the first node
+    // of a thread takes the node value and the bracket from the exponential / the logarithm, the following ones walk
+    // (S_j and the bracket's knots by multiplication with e^dx: a few ulp of drift over a thread's C nodes, against
+    // four exponentials, a logarithm and three divisions per node before; the spline is C2 across a knot).
+    int br_j = -1;
+    double br_x = 0.0, br_x1 = 0.0;
+    auto eval = [&](const double Sj, const bool walk) -> double {
         const double Sq = __dsub_rn(Sj, cash);
         double cont;
-        if (Sq <= s_lo) cont = ys[0];
-        else if (Sq >= s_hi) cont = ys[n];
+        if (Sq <= s_lo) cont = ys[jsw(0)];
+        else if (Sq >= s_hi) cont = ys[jsw(n)];
         else {
-            int j = last_node_le(x_min, dx, n, Sq);           // == the reference's binary search (:375-382)
-            j = min(max(j, 0), nn - 2);
-            const double xj = node_s(x_min, dx, j), xj1 = node_s(x_min, dx, j + 1);
-            const double h = __dsub_rn(xj1, xj);
-            const double cj = cz[j], cj1 = cz[j + 1];
-            const double bj = __dsub_rn(__dsub_rn(ys[j + 1], ys[j]) / h,
-                                        __dmul_rn(h, __dadd_rn(cj1, __dmul_rn(2.0, cj))) / 3.0);
-            const double dj = __dsub_rn(cj1, cj) / __dmul_rn(3.0, h);
+            if (!walk || br_j < 0) {
+                int j = last_node_le(x_min, dx, n, Sq);       // == the reference's binary search (:375-382)
+                br_j = min(max(j, 0), nn - 2);
+                br_x = node_s(x_min, dx, br_j);
+                br_x1 = br_x * edx_eval;
+            } else {
+                while (br_j < nn - 2 && br_x1 <= Sq) { ++br_j; br_x = br_x1; br_x1 *= edx_eval; }
+            }
+            const int j = br_j;
+            // (one reciprocal: the quotients differ from the reference's in the last bit)
+            const double xj = br_x, xj1 = br_x1;
+            const double h = __dsub_rn(xj1, xj), rh = __drcp_rn(h);
+            const double cj = cz[jsw(j)], cj1 = cz[jsw(j + 1)];
+            const double bj = __dsub_rn(__dmul_rn(__dsub_rn(ys[jsw(j + 1)], ys[jsw(j)]), rh),
+                                        __dmul_rn(__dmul_rn(h, __dadd_rn(cj1, __dmul_rn(2.0, cj))), 1.0 / 3.0));
+            const double dj = __dmul_rn(__dmul_rn(__dsub_rn(cj1, cj), rh), 1.0 / 3.0);
             const double dq = __dsub_rn(Sq, xj);
-            double acc = __dadd_rn(ys[j], __dmul_rn(bj, dq));
+            double acc = __dadd_rn(ys[jsw(j)], __dmul_rn(bj, dq));
             acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(cj, dq), dq));
             acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(__dmul_rn(dj, dq), dq), dq));
             cont = acc;
@@ -748,15 +812,29 @@ __device__ __noinline__ double dividend_jump(double Vb, double cash, bool is_cal
         return cont;
     };
     // mu[] is free once cz[] holds the spline's c coefficients: the jumped values go there
-#pragma unroll
-    for (int k = 0; k < C; ++k) {
-        const int j = t * C + k - pad + 1;
-        if (j >= 1) mu[j] = eval(j);
+    {
+        double Sj = 0.0;
+        bool first = true;
+#pragma unroll 1
+        for (int k = 0; k < C; ++k) {
+            const int j = t * C + k - pad + 1;
+            if (j < 1) continue;
+            Sj = first ? node_s(x_min, dx, j) : Sj * edx_eval;
+            mu[jsw(j)] = eval(Sj, !first);
+            first = false;
+        }
     }
     double nb = Vb;
-    if (owner0) nb = eval(0);
-    if (t == NT - 1) nb = eval(n);
+    if (owner0) nb = eval(s_lo, false);
+    if (t == NT - 1) nb = eval(s_hi, false);
+    JTICK();
     __syncthreads();
+    JTICK();
+#ifdef FDM_CTA_PROFILE
+    if (blockIdx.x == 40 && (threadIdx.x == 32 * (WARPS - 1) || threadIdx.x == 32 * (WARPS / 2) + 5))
+        printf("jump t=%d: elimination %lld | wait %lld | back-subst+store %lld | eval %lld | wait %lld\n", t, jt[1] - jt[0], jt[2] - jt[1],
+               jt[3] - jt[2], jt[4] - jt[3], jt[5] - jt[4]);
+#endif
     return nb;
 }
 
@@ -1094,19 +1172,23 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
 #endif
 #endif
         }
+        if (AMER) {                                             // V = vc + dt lambda (L keeps lambda for the read-out)
+#pragma unroll
+            for (int k = 0; k < C; ++k) V[k] = fma(0.5, L[k], V[k]);
+        }
         if (cash != 0.0) {
             CTA_TICK(0);
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < C; ++k) {
                 const int j = t * C + k - pad + 1;
-                if (j >= 1) sm.r1[j] = V[k];
+                if (j >= 1) sm.r1[jsw(j)] = V[k];
             }
             Vb = dividend_jump<C, WARPS>(Vb, cash, is_call, k_eff, n, pad, x_min, dx, sm.r1, sm.r2, sm.r0);
 #pragma unroll
             for (int k = 0; k < C; ++k) {
                 const int j = t * C + k - pad + 1;
-                V[k] = (j >= 1) ? sm.r2[j] : 0.0;
+                V[k] = (j >= 1) ? sm.r2[jsw(j)] : 0.0;
             }
             __syncthreads();
             fill_payoff(false);                                 // r0 held cz during the jump
