@@ -108,7 +108,8 @@ struct Layout {
     static constexpr int SLOT_DOUBLES = 3 * C * 32 + 8 * 32;         // nm, ncc, inv [k][lane] + 8 per-lane constants
     static constexpr int R2 = NP > SLOTS * SLOT_DOUBLES ? NP : SLOTS * SLOT_DOUBLES;
     static constexpr int SMALL = 4 * WARPS + 16 + 64 + 32 + 8 + C + 8 + 320;   // part, cst, PAc, wb, ishare, nmp, smv, scw
-    static constexpr int TOTAL = 2 * NP + R2 + SMALL;
+    static constexpr int TOTAL = 2 * NP + R2 + SMALL;           // American
+    static constexpr int TOTAL_LINEAR = NP + R2 + SMALL;        // no payoff table r0 (and no dividend jumps: see the kernel)
 };
 
 struct Sm {
@@ -488,6 +489,18 @@ __device__ __forceinline__ double warp_scan_tab(double e, const double *__restri
 
 // ---- the three phases of one time step (barriers sit between them, outside any branch) -----------
 
+// Register-light linear march (see lin_vc): no copy of V_old.
+// (Not in the 16-warp class: one CTA per SM either way, and the extra instruction costs 8192-node barrier grids 8 %.)
+template <int C, int WARPS, bool AMER>
+__host__ __device__ constexpr bool lin_light()
+{
+#ifdef FDM_CTA_NO_LIN_LIGHT
+    return false;
+#else
+    return !AMER && WARPS != 16;
+#endif
+}
+
 // RHS, forward local pass, intra-warp scan.  k0 >= 0 on the thread that owns row 0.  TBL: its Dirichlet term is added
 // to R at that slot.  INJ (the scalar warp that holds row 0, row-0 correction mode): at its slot too (INJ_SLOT), or as
 // the carry carryF into one of the thread's two half-chains (INJ_CARRY0 / INJ_CARRYH); setup_phase says which, and
@@ -510,13 +523,16 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
 #pragma unroll
             for (int k = 0; k < C; ++k) { const double g = fma(ph.q, V[k], hq * L[k]); V[k] = fma(ph.pd, V[k], L[k]); L[k] = g; }
         }
-    } else if (ph.q == 1.0) {                              // theta = 1/2 (CTA-uniform): the old V itself, a register rename
+    } else if (!lin_light<C, WARPS, AMER>()) {
+        if (ph.q == 1.0) {                                 // theta = 1/2 (CTA-uniform): the old V itself, a register rename
 #pragma unroll
-        for (int k = 0; k < C; ++k) L[k] = V[k];
-    } else {
+            for (int k = 0; k < C; ++k) L[k] = V[k];
+        } else {
 #pragma unroll
-        for (int k = 0; k < C; ++k) L[k] = ph.q * V[k];
+            for (int k = 0; k < C; ++k) L[k] = ph.q * V[k];
+        }
     }
+    // (lin_light: the linear march keeps no subtrahend q V_old, the last pass rebuilds V_old from u, see lin_vc)
     if (TBL && k0 >= 0) {
 #pragma unroll
         for (int k = 0; k < C; ++k) if (k == k0) V[k] += cin_f;
@@ -549,7 +565,7 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
 template <int C, int WARPS, bool AMER, bool TBL, int INJ, bool K1>
 __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &sm, const int wf, const double cin_b,
                                        const double e1_fwd, const double Eprev, const double carryF, double &e1_keep,
-                                       double &Enext, double &eend_keep)
+                                       double &Enext, double &eend_keep, double &csf_keep)
 {
     constexpr int H = C / 2;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -569,6 +585,7 @@ __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &s
     if (INJ == INJ_RUNTIME) { ep = fma(sm.smv[3], carryF, Eprev); e1x = fma(sm.smv[4], carryF, e1_fwd); }
     double cs = fma(TBL ? lc[LC_PAF * 32 + lane] : sm.PAc[lane], S, ep);
     if (INJ == INJ_CARRY0) cs += carryF;
+    csf_keep = cs;
     {
         double c1 = cs;
         double c2 = fma(TBL ? lc[LC_HF1 * 32 + lane] : sm.cst[CST_HF1], cs, e1x);
@@ -593,9 +610,23 @@ __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &s
     eend_keep = e_end;
 }
 
+// Linear march, last pass.  The new value is vc = INV xs - q V_old, and V_old is not kept: the system is solved for
+// R = V_old (setup_phase scales it), so V_old = u_k - nm_k u_{k-1} with u still in the registers (u_{-1} is the forward
+// carry into the thread).  One FP64 instruction more per node than with a copy of V_old, but half the register file:
+// 4 / 4 / 3 resident CTAs of 4 / 5 / 8 warps instead of 4 / 3 / 2, and no 2 C register moves per step.
+//   u_k, um: u of this slot and of the slot below;  returns vc.
+template <bool Q1>
+__device__ __forceinline__ double lin_vc(const double inv, const double xs, const double nm, const double um, const double u_k,
+                                         const double q)
+{
+    const double t = fma(nm, um, -u_k);                      // -V_old
+    return Q1 ? fma(inv, xs, t) : fma(inv, xs, q * t);
+}
+
 template <int C, int WARPS, bool AMER, bool TBL, bool K1>
 __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph &ph, const Sm &sm, const double cin_b,
-                                       const double e1_bwd, const double Enext)
+                                       const double e1_bwd, const double Enext, const double cs_f, const int k0,
+                                       const double cin_f)
 {
     constexpr int H = C / 2;
     constexpr int NT = 32 * WARPS;
@@ -611,6 +642,11 @@ __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph 
     const double cs = fma(TBL ? lc[LC_PAB * 32 + lane] : sm.PAc[32 + lane], S, Enext);
     double c1 = cs + cin_b;
     double c2 = fma(TBL ? lc[LC_HB1 * 32 + lane] : sm.cst[CST_HB1], cs, e1_bwd);
+    const double *nm = ph.slot;
+    const double uH = V[H - 1];                                  // overwritten before slot H is reached
+    constexpr bool LIGHT = lin_light<C, WARPS, AMER>();
+    auto slots = [&](auto q1_tag) {
+    constexpr bool Q1 = decltype(q1_tag)::value != 0;
 #pragma unroll
     for (int i = 0; i < H; ++i) {
 #pragma unroll
@@ -619,7 +655,15 @@ __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph 
             double xs;
             if (half == 0) { c1 = fma(TBL ? ncc[k * 32 + lane] : ph.NCC, c1, V[k]); xs = c1; }
             else           { c2 = fma(TBL ? ncc[k * 32 + lane] : ph.NCC, c2, V[k]); xs = c2; }
-            const double vc = fma(TBL ? inv[k * 32 + lane] : ph.INV, xs, -L[k]);
+            double vc;
+            if (!LIGHT) vc = fma(TBL ? inv[k * 32 + lane] : ph.INV, xs, -L[k]);
+            else {
+                vc = lin_vc<Q1>(TBL ? inv[k * 32 + lane] : ph.INV, xs, TBL ? nm[k * 32 + lane] : ph.NM,
+                                k == 0 ? cs_f : (k == H ? uH : V[k - 1]), V[k], ph.q);
+                // a table warp adds the Dirichlet term of row 0 to R at its slot: R = V_old + cin there
+                if (TBL) asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p fma.rn.f64 %0, %3, %4, %0;\n\t}"
+                             : "+d"(vc) : "r"(k0), "r"(k), "d"(ph.q), "d"(cin_f));
+            }
             if (AMER) {
                 const double d = sm.r0[k * NT + t] - vc;         // exercise iff phi > vc (fd_american_option_pricer.py:496)
                 L[k] = d + fabs(d);                              // 2 dt lambda_new, ONE FP64 instruction
@@ -629,6 +673,8 @@ __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph 
             }
         }
     }
+    };
+    if (!LIGHT || ph.q == 1.0) slots(IntC<1>{}); else slots(IntC<0>{});   // theta = 1/2 but for the Rannacher steps
 }
 
 // step_c of a scalar-coefficient warp with the backward carry `cs` already summed (bwd_carry).  CORR: the row-0
@@ -647,9 +693,11 @@ __device__ __forceinline__ double bwd_carry(const Ph &ph, const Sm &sm, const do
     return fma(sm.PAc[32 + lane], S, Enext);
 }
 
-template <int C, int WARPS, bool AMER, bool CORR, bool INVT>
+// SLOTINJ: this warp added the Dirichlet term of row 0 to R at its slot (R = V_old + cin there).
+template <int C, int WARPS, bool AMER, bool CORR, bool INVT, bool SLOTINJ>
 __device__ __forceinline__ void step_cs(double (&V)[C], double (&L)[C], const Ph &ph, const Sm &sm, const double cs,
-                                        const double cin_b, const double e1_bwd)
+                                        const double cin_b, const double e1_bwd, const double cs_f, const int k0,
+                                        const double cin_f)
 {
     constexpr int H = C / 2;
     constexpr int NT = 32 * WARPS;
@@ -658,6 +706,10 @@ __device__ __forceinline__ void step_cs(double (&V)[C], double (&L)[C], const Ph
     double c2 = fma(sm.cst[CST_HB1], cs, e1_bwd);
     const int lane = t & 31;
     const double gzx = CORR ? -(ph.gz * sm.smv[1]) : 0.0;
+    const double uH = V[H - 1];                                  // overwritten before slot H is reached
+    constexpr bool LIGHT = lin_light<C, WARPS, AMER>();
+    auto slots = [&](auto q1_tag) {
+    constexpr bool Q1 = decltype(q1_tag)::value != 0;
 #pragma unroll
     for (int i = 0; i < H; ++i) {
 #pragma unroll
@@ -667,7 +719,17 @@ __device__ __forceinline__ void step_cs(double (&V)[C], double (&L)[C], const Ph
             if (half == 0) { c1 = fma(ph.NCC, c1, V[k]); xs = c1; }
             else           { c2 = fma(ph.NCC, c2, V[k]); xs = c2; }
             if (CORR) xs = fma(gzx, sm.nmp[k], xs);
-            const double vc = fma(INVT ? ph.invw[k * 32 + lane] : ph.INV, xs, -L[k]);
+            double vc;
+            if (!LIGHT) vc = fma(INVT ? ph.invw[k * 32 + lane] : ph.INV, xs, -L[k]);
+            else {
+                const double iv = INVT ? ph.invw[k * 32 + lane] : ph.INV;
+                vc = lin_vc<Q1>(iv, xs, ph.NM, k == 0 ? cs_f : (k == H ? uH : V[k - 1]), V[k], ph.q);
+                if (SLOTINJ) asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p fma.rn.f64 %0, %3, %4, %0;\n\t}"
+                                 : "+d"(vc) : "r"(k0), "r"(k), "d"(ph.q), "d"(cin_f));
+                // dead slots (below row 0 in its warp) stay at exactly zero: their u is not (carry form), and the
+                // rebuilt V_old there is rounding noise of it
+                if (INVT) vc = (iv != 0.0) ? vc : 0.0;
+            }
             if (AMER) {
                 const double d = sm.r0[k * NT + t] - vc;         // exercise iff phi > vc (fd_american_option_pricer.py:496)
                 L[k] = d + fabs(d);                              // 2 dt lambda_new, ONE FP64 instruction
@@ -677,6 +739,8 @@ __device__ __forceinline__ void step_cs(double (&V)[C], double (&L)[C], const Ph
             }
         }
     }
+    };
+    if (!LIGHT || ph.q == 1.0) slots(IntC<1>{}); else slots(IntC<0>{});   // theta = 1/2 but for the Rannacher steps
 }
 
 // ---- dividend jump (fd_american_option_pricer.py:321-386, :517-548) ------------------------------
@@ -905,7 +969,7 @@ static __device__ __noinline__ void read_out(const FdmOut &O, const int64_t sid,
 // ---- the kernel ------------------------------------------------------------------------------------
 
 template <int C, int WARPS>
-constexpr int smem_doubles() { return Layout<C, WARPS>::TOTAL; }
+constexpr int smem_doubles(const bool american) { return american ? Layout<C, WARPS>::TOTAL : Layout<C, WARPS>::TOTAL_LINEAR; }
 
 // resident CTAs per SM the registers are sized for.  More, smaller-budget CTAs beat fewer fat ones: every CTA is
 // latency-bound between its two block barriers, and independent CTAs fill each other's gaps (2133-node barrier
@@ -919,11 +983,23 @@ constexpr int smem_doubles() { return Layout<C, WARPS>::TOTAL; }
 #ifndef FDM_CTA8_BLOCKS
 #define FDM_CTA8_BLOCKS 2
 #endif
-template <int C, int WARPS>
-constexpr int cta_min_blocks() { return WARPS == 4 ? FDM_CTA4_BLOCKS : (WARPS == 5 ? FDM_CTA5_BLOCKS : (WARPS == 8 ? FDM_CTA8_BLOCKS : 1)); }
+// The linear march keeps one register array (V), not two: a resident CTA more in the 5- and 8-warp classes.
+#ifndef FDM_CTA5_BLOCKS_LINEAR
+#define FDM_CTA5_BLOCKS_LINEAR 4
+#endif
+#ifndef FDM_CTA8_BLOCKS_LINEAR
+#define FDM_CTA8_BLOCKS_LINEAR 3
+#endif
+template <int C, int WARPS, bool AMER>
+constexpr int cta_min_blocks()
+{
+    constexpr bool light = lin_light<C, WARPS, AMER>();
+    return WARPS == 4 ? FDM_CTA4_BLOCKS : (WARPS == 5 ? (light ? FDM_CTA5_BLOCKS_LINEAR : FDM_CTA5_BLOCKS)
+                      : (WARPS == 8 ? (light ? FDM_CTA8_BLOCKS_LINEAR : FDM_CTA8_BLOCKS) : 1));
+}
 
 template <int C, int WARPS, bool AMER, bool TRACE>
-__global__ void __launch_bounds__(32 * WARPS, cta_min_blocks<C, WARPS>())
+__global__ void __launch_bounds__(32 * WARPS, cta_min_blocks<C, WARPS, AMER>())
 fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int want_american, const int n_lo)
 {
     using LY = Layout<C, WARPS>;
@@ -931,8 +1007,8 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
     constexpr int NP = LY::NP;
     extern __shared__ double smem[];
     Sm sm;
-    sm.r0 = smem;
-    sm.r1 = sm.r0 + NP;
+    sm.r0 = smem;                                       // American only
+    sm.r1 = sm.r0 + (AMER ? NP : 0);
     sm.r2 = sm.r1 + NP;
     sm.part = sm.r2 + LY::R2;
     sm.cst = sm.part + 4 * WARPS;
@@ -989,7 +1065,7 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
         for (int k = 0; k < C; ++k) {
             const int j = t * C + k - pad + 1;
             const double pv = (j >= 1) ? payoff(node_s(x_min, dx, j), k_eff, is_call) : 0.0;
-            sm.r0[k * NT + t] = pv;
+            if (AMER) sm.r0[k * NT + t] = pv;
             if (set_v) { V[k] = pv; L[k] = 0.0; }
         }
     };
@@ -1017,6 +1093,20 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
 #define CTA_TICK(slot)
 #endif
     const int seg_b = B.seg_begin[sid], seg_e = B.seg_begin[sid + 1];
+    if (!AMER) {
+        // The linear kernel has no shared memory for the spline of a dividend jump (what it saves buys a resident CTA
+        // more per SM).  No pricer of the reference marches a European / barrier solve through cash dividends -- they
+        // are escrowed -- so such a solve, if a caller of the C ABI builds one, is left to fdm_exact_kernel.
+        bool has_div = false;
+        for (int seg = seg_b; seg < seg_e; ++seg) has_div |= B.seg_div[seg] != 0.0;
+        if (has_div) {                                          // CTA-uniform
+            if (t == 0) {
+                if (O.status) O.status[sid] = FDM_STATUS_STIFF;
+                else if (O.price) O.price[sid] = __longlong_as_double(0x7ff8000000000000ll);   // nobody to hand it to
+            }
+            return;
+        }
+    }
     int mon_i = 0, mon_e = 0;
     if (ko && B.mon_begin) { mon_i = B.mon_begin[sid]; mon_e = B.mon_end ? B.mon_end[sid] : B.mon_begin[sid + 1]; }
     int next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
@@ -1074,7 +1164,7 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                 w_next = fetch_boundary(m + 1);
                 double cin_n = ph.cB * w_now - ph.cA * w_next;
                 const double cin_b = cin * top_mult;            // enters the top row through its ncc
-                double e1f = 0.0, Eprev = 0.0, e1b = 0.0, Enext = 0.0, eend_b = 0.0;
+                double e1f = 0.0, Eprev = 0.0, e1b = 0.0, Enext = 0.0, eend_b = 0.0, csf = 0.0;
                 constexpr bool ANY = ROLE == ROLE_ANY;
                 const bool tbl = ANY ? ph.cls == 2 : ROLE == ROLE_TBL;
                 const bool scl = ANY ? ph.cls == 1 : (ROLE != ROLE_TBL && ROLE != ROLE_PAD);
@@ -1086,13 +1176,13 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                 if (tbl) step_a<C, WARPS, AMER, true, INJ_NONE>(V, L, ph, sm, k0, cin, 0.0, e1f, Eprev);
                 else if (scl) step_a<C, WARPS, AMER, false, INJ>(V, L, ph, sm, k0, cin, carryF, e1f, Eprev);
                 FDM_CTA_STEP_SYNC();
-                if (tbl) step_b<C, WARPS, AMER, true, INJ_NONE, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, 0.0, e1b, Enext, eend_b);
-                else if (scl) step_b<C, WARPS, AMER, false, INJ, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, carryF, e1b, Enext, eend_b);
+                if (tbl) step_b<C, WARPS, AMER, true, INJ_NONE, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, 0.0, e1b, Enext, eend_b, csf);
+                else if (scl) step_b<C, WARPS, AMER, false, INJ, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, carryF, e1b, Enext, eend_b, csf);
                 FDM_CTA_STEP_SYNC();
                 const bool r0c = ANY || ROLE == ROLE_PAD ? row0_corr : (ROLE == ROLE_SCALAR_R0 || OWN || ROLE == ROLE_SMC);
-                if (tbl) step_c<C, WARPS, AMER, true, K1>(V, L, ph, sm, cin_b, e1b, Enext);
+                if (tbl) step_c<C, WARPS, AMER, true, K1>(V, L, ph, sm, cin_b, e1b, Enext, csf, k0, cin);
                 else if (!r0c) {
-                    if (scl) step_c<C, WARPS, AMER, false, K1>(V, L, ph, sm, cin_b, e1b, Enext);
+                    if (scl) step_c<C, WARPS, AMER, false, K1>(V, L, ph, sm, cin_b, e1b, Enext, csf, -1, 0.0);
                 } else {
                     // row-0 correction: the owner of row 0 knows xs at its slot 0 (= NCC^k0 xs_0: its padding slots pass
                     // the value through) from the local pass and its carry, before the last pass starts
@@ -1106,9 +1196,11 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                     if (scl) {
                         const bool own = ANY ? w == wf : OWN;
                         const bool smc = ANY ? ph.smc != 0 : ROLE == ROLE_SMC;
-                        if (own) step_cs<C, WARPS, AMER, true, true>(V, L, ph, sm, cs_b, cin_b, e1b);
-                        else if (smc) step_cs<C, WARPS, AMER, true, false>(V, L, ph, sm, cs_b, cin_b, e1b);
-                        else step_cs<C, WARPS, AMER, false, false>(V, L, ph, sm, cs_b, cin_b, e1b);
+                        constexpr bool SLOTINJ = INJ == INJ_SLOT || INJ == INJ_RUNTIME;
+                        const int k0s = (INJ == INJ_SLOT || (INJ == INJ_RUNTIME && ph.inj)) ? k0 : -1;
+                        if (own) step_cs<C, WARPS, AMER, true, true, SLOTINJ>(V, L, ph, sm, cs_b, cin_b, e1b, csf, k0s, cin);
+                        else if (smc) step_cs<C, WARPS, AMER, true, false, false>(V, L, ph, sm, cs_b, cin_b, e1b, csf, -1, 0.0);
+                        else step_cs<C, WARPS, AMER, false, false, false>(V, L, ph, sm, cs_b, cin_b, e1b, csf, -1, 0.0);
                     }
                 }
                 Vb = w_now;                                     // V[0] = V_min, V[-1] = V_max (:505-506)
@@ -1176,7 +1268,7 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
 #pragma unroll
             for (int k = 0; k < C; ++k) V[k] = fma(0.5, L[k], V[k]);
         }
-        if (cash != 0.0) {
+        if (AMER && cash != 0.0) {
             CTA_TICK(0);
             __syncthreads();
 #pragma unroll

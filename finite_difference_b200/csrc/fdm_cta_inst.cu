@@ -22,13 +22,14 @@ int FDM_CAT(FDM_CAT(FDM_CAT(fdm_launch_cta_, FDM_INST_W), x), FDM_INST_C)(
     constexpr int C = FDM_INST_C, WARPS = FDM_INST_W;
     (void)any_div;
     const bool trace = o.ex_trace != nullptr;
-    const size_t smem = (size_t)cta::smem_doubles<C, WARPS>() * sizeof(double);
+    const size_t smem = (size_t)cta::smem_doubles<C, WARPS>(true) * sizeof(double);
+    const size_t smem_lin = (size_t)cta::smem_doubles<C, WARPS>(false) * sizeof(double);
     auto k_am = cta::fdm_cta_kernel<C, WARPS, true, false>;
     auto k_amt = cta::fdm_cta_kernel<C, WARPS, true, true>;
     auto k_lin = cta::fdm_cta_kernel<C, WARPS, false, false>;
     FDM_CUDA(cudaFuncSetAttribute(k_am, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FDM_CUDA(cudaFuncSetAttribute(k_amt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FDM_CUDA(cudaFuncSetAttribute(k_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FDM_CUDA(cudaFuncSetAttribute(k_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin));
     const int64_t max_grid = 0x7fffffff;
     int launches = 0;
     for (int64_t first = 0; first < b.n_solves; first += max_grid) {
@@ -40,7 +41,7 @@ int FDM_CAT(FDM_CAT(FDM_CAT(fdm_launch_cta_, FDM_INST_W), x), FDM_INST_C)(
             ++launches;
         }
         if (any_linear) {
-            k_lin<<<grid, block, smem, st>>>(b, o, first, 0, n_lo);
+            k_lin<<<grid, block, smem_lin, st>>>(b, o, first, 0, n_lo);
             ++launches;
         }
         FDM_CUDA(cudaGetLastError());
