@@ -8,7 +8,7 @@ sweep run literally."""
 import numpy as np
 import pytest
 
-from finite_difference_b200 import hostlogic, solve_host
+from finite_difference_b200 import _lib, hostlogic, solve_host
 from finite_difference_b200.batch import SolveBatch
 from oracle import oracle
 
@@ -73,3 +73,22 @@ def test_flagged_solves_with_dividends_are_rescued(n_space, n_time):
         assert abs(res.price[i] - o.price) <= 1e-10 * max(abs(o.price), 1e-2)
         steps = o.ex_trace.shape[0]
         assert np.array_equal(res.ex_trace[i, :steps], o.ex_trace), i
+
+
+def test_linear_solve_with_cash_dividends_on_a_large_grid():
+    """A European march through cash dividends on a CTA-kernel grid: no pricer of the reference builds one (its
+    European / barrier pricers escrow dividends), so there is no oracle for it; the linear CTA kernel keeps no spline
+    arrays and hands such a solve to fdm_exact_kernel.  It must come back solved (status 0), not skipped, and agree
+    with the same contract on a warp-kernel grid to discretisation accuracy."""
+    divs = [[(0.3, 2.0), (0.8, 1.5)]]
+    res = {}
+    for n in (500, 1000, 2133):
+        b = hostlogic.build_american_batch([100.0], [100.0], [1.0], [0.3], [0.05], [0.05], [False], [n], [400], [2], [False],
+                                           div_taus=divs)
+        b.flags = (b.flags & ~_lib.FLAG_AMERICAN).astype(np.int32)
+        r = solve_host(b)
+        assert r.status[0] == 0, (n, r.status[0])
+        assert np.isfinite(r.price[0]) and r.price[0] > 0.0
+        res[n] = float(r.price[0])
+    assert abs(res[1000] - res[500]) <= 2e-3 * res[500], res
+    assert abs(res[2133] - res[1000]) <= 1e-3 * res[1000], res
