@@ -31,11 +31,27 @@ namespace rowvar {
 
 enum { T_AE = 0, T_BE, T_CE, T_RB, T_MM, T_NCS, T_N };        // explicit sub/diag/sup, 1/beta, -sub/beta, -c*
 
-template <int C>
-__host__ __device__ constexpr int smem_doubles() { return T_N * 32 * C + 2 * SCAN_LEVELS * 32; }
+// IMPL: the kernel instance for marches whose every step is fully implicit (rannacher_steps >= n_steps -- the regime
+// in which the reference class prices at all).  With theta = 1 the explicit operator is the
+// identity (a_expl = c_expl = 0, b_expl = 1, :373-375 and :404-406), so the right-hand side is V itself: three tables
+// and three of the eight shared-memory loads per node-step go, and so does half of the shared memory per warp (the
+// march is bound by shared-memory bandwidth and by the number of resident warps).  Marches with a theta = 1/2 phase run
+// in the general instance; every launch issues both and each warp decides by its solve.
+// per-lane constants of a phase: products of the lane's multipliers over its lower / upper half of rows, forward and
+// backward (the local passes run as two half-chains), and over all its rows backward
+enum { LC_PF1 = 0, LC_PF2, LC_PB1, LC_PB2, LC_PBALL, LC_N };
 
-template <int C>
-constexpr int min_blocks() { return C <= 10 ? 8 : (C <= 19 ? 4 : 2); }
+template <bool IMPL> __host__ __device__ constexpr int n_tables() { return IMPL ? 3 : (int)T_N; }
+template <bool IMPL> __host__ __device__ constexpr int tab_of(const int t) { return IMPL ? t - T_RB : t; }
+
+template <int C, bool IMPL>
+__host__ __device__ constexpr int smem_doubles() { return n_tables<IMPL>() * 32 * C + (2 * SCAN_LEVELS + LC_N) * 32; }
+
+#ifndef FDM_ROWVAR_IMPL_BLOCKS
+#define FDM_ROWVAR_IMPL_BLOCKS 12
+#endif
+template <int C, bool IMPL>
+constexpr int min_blocks() { return (IMPL && C > 10 && C <= 19) ? FDM_ROWVAR_IMPL_BLOCKS : (C <= 10 ? 8 : (C <= 19 ? 4 : 2)); }
 
 struct RowCoef { double sub, diag, sup, ae, be, ce; };
 
@@ -87,7 +103,7 @@ __device__ __forceinline__ RowCoef row_coef(const int i, const int N, const doub
 
 // Coefficient tables and scan multipliers of one theta phase.  Returns false on a vanishing pivot (the reference raises
 // ZeroDivisionError, :271-279).
-template <int C>
+template <int C, bool IMPL>
 __device__ __noinline__ bool setup_phase(double *tab, double *Af, double *Ab, const int lane, const int N,
                                          const double *__restrict__ s, const double sig, const double r, const double dt,
                                          const double theta, const double dS, const int bar_j, const double hm, const double hp)
@@ -113,6 +129,7 @@ __device__ __noinline__ bool setup_phase(double *tab, double *Af, double *Ab, co
         cstar = (i < N) ? c.sup / beta : 0.0;
     }
     double pm = 1.0, pc = 1.0;                                   // products of the lane's forward / backward multipliers
+    double pf1 = 1.0, pf2 = 1.0, pb1 = 1.0, pb2 = 1.0;           // ... over its lower (k < C/2) and upper rows
     __syncwarp();
 #pragma unroll 1
     for (int k = 0; k < C; ++k) {
@@ -120,18 +137,28 @@ __device__ __noinline__ bool setup_phase(double *tab, double *Af, double *Ab, co
         const RowCoef c = row_coef(i, N, s, sig, r, dt, theta, dS, bar_j, hm, hp);
         const double beta = __dsub_rn(c.diag, __dmul_rn(c.sub, cstar));
         ok &= fabs(beta) >= 1e-14;
-        const double rb = 1.0 / beta;
-        cstar = (i < N) ? c.sup / beta : 0.0;                    // c*_N = 0 (:280); padding rows: 0
-        const double mm = -__dmul_rn(c.sub, rb);
-        tab[(T_AE * C + k) * 32 + lane] = c.ae;
-        tab[(T_BE * C + k) * 32 + lane] = c.be;
-        tab[(T_CE * C + k) * 32 + lane] = c.ce;
-        tab[(T_RB * C + k) * 32 + lane] = rb;
-        tab[(T_MM * C + k) * 32 + lane] = mm;
-        tab[(T_NCS * C + k) * 32 + lane] = -cstar;
+        // Rows N (the upper Dirichlet row, x_N = w_hi, :361-365) and beyond (padding) take no right-hand side (1 / beta
+        // stored as 0) and pass the backward carry through (-c* stored as 1): w_hi enters as the carry into the top of the
+        // warp and arrives at row N unchanged, wherever row N sits in its lane -- no per-row select in the time loop.
+        const double rb = (i < N) ? 1.0 / beta : 0.0;
+        cstar = (i < N) ? c.sup / beta : -1.0;                   // c*_N = 0 (:280)
+        const double mm = (i < N) ? -__dmul_rn(c.sub, 1.0 / beta) : 0.0;
+        if (!IMPL) {
+            tab[(T_AE * C + k) * 32 + lane] = c.ae;
+            tab[(T_BE * C + k) * 32 + lane] = c.be;
+            tab[(T_CE * C + k) * 32 + lane] = c.ce;
+        }
+        tab[(tab_of<IMPL>(T_RB) * C + k) * 32 + lane] = rb;
+        tab[(tab_of<IMPL>(T_MM) * C + k) * 32 + lane] = mm;
+        tab[(tab_of<IMPL>(T_NCS) * C + k) * 32 + lane] = -cstar;
         pm *= mm;
         pc *= -cstar;
+        if (k < C / 2) { pf1 *= mm; pb2 *= -cstar; } else { pf2 *= mm; pb1 *= -cstar; }
+        if (i >= N) cstar = 0.0;                                 // (what the pivot recurrence of a later row would see)
     }
+    double *lc = Ab + SCAN_LEVELS * 32;
+    lc[LC_PF1 * 32 + lane] = pf1; lc[LC_PF2 * 32 + lane] = pf2;
+    lc[LC_PB1 * 32 + lane] = pb1; lc[LC_PB2 * 32 + lane] = pb2; lc[LC_PBALL * 32 + lane] = pc;
     // Kogge-Stone level multipliers (as fdm_warp_kernel's setup_phase)
     double af = pm, ab = pc;
 #pragma unroll
@@ -148,12 +175,13 @@ __device__ __noinline__ bool setup_phase(double *tab, double *Af, double *Ab, co
     return !__any_sync(FULL, !ok);
 }
 
-template <int C>
-__global__ void __launch_bounds__(32, min_blocks<C>())
+template <int C, bool IMPL>
+__global__ void __launch_bounds__(32, min_blocks<C, IMPL>())
 fdm_rowvar_kernel(const FdmRowVarBatch B, const FdmRowVarOut O, const int64_t first, const int n_lo)
 {
     extern __shared__ double smem[];
-    double *tab = smem, *Af = tab + T_N * 32 * C, *Ab = Af + SCAN_LEVELS * 32;
+    double *tab = smem, *Af = tab + n_tables<IMPL>() * 32 * C, *Ab = Af + SCAN_LEVELS * 32;
+    constexpr int tRB = tab_of<IMPL>(T_RB), tMM = tab_of<IMPL>(T_MM), tNCS = tab_of<IMPL>(T_NCS);
 
     const int64_t sid = first + blockIdx.x;
     if (sid >= B.n_solves) return;
@@ -167,6 +195,7 @@ fdm_rowvar_kernel(const FdmRowVarBatch B, const FdmRowVarOut O, const int64_t fi
     const bool is_call = flags & FDM_FLAG_CALL;
     const double sig = B.sigma[sid], r = B.r[sid], strike = B.strike[sid], tenor = B.tenor[sid], dt = B.dt[sid];
     const int M = B.n_steps[sid], rann = B.rannacher[sid];
+    if ((rann >= M) != IMPL) return;                             // the other instance's solve
     const int bar_j = B.bar_j[sid];
     const double hm = B.h_minus[sid], hp = B.h_plus[sid];
     const double dS = __dsub_rn(s[1], s[0]);                     // :345
@@ -182,13 +211,18 @@ fdm_rowvar_kernel(const FdmRowVarBatch B, const FdmRowVarOut O, const int64_t fi
             if (i <= N && (s[i] <= lo || s[i] >= up)) ko_mask |= 1u << k;
         }
     }
-    double V[C], R[C];
+    // IMPL: the right-hand side g = V / beta is formed in place (no R[]), and up to 19 rows per lane the two sweeps'
+    // multipliers live in the registers that frees -- one shared-memory load per node-step (1 / beta) instead of five.
+    constexpr bool REGTAB = IMPL && C <= 19;
+    double V[C], R[IMPL ? 1 : C], MMr[REGTAB ? C : 1], NCr[REGTAB ? C : 1];
+    double (&D)[C] = *reinterpret_cast<double (*)[C]>(IMPL ? &V[0] : &R[0]);
 #pragma unroll
     for (int k = 0; k < C; ++k) {
         const int i = lane * C + k;
         V[k] = (i <= N) ? B.v_terminal[nb + i] : 0.0;
     }
-    const int top_lane = N / C, top_k = N - top_lane * C;
+    auto mm_of = [&](const int k) -> double { return REGTAB ? MMr[k] : tab[(tMM * C + k) * 32 + lane]; };
+    auto ncs_of = [&](const int k) -> double { return REGTAB ? NCr[k] : tab[(tNCS * C + k) * 32 + lane]; };
     int mon_i = B.mon_begin ? B.mon_begin[sid] : 0;
     const int mon_e = B.mon_begin ? B.mon_begin[sid + 1] : 0;
     int next_mon = (mon_i < mon_e) ? B.mon_step[mon_i] : -1;
@@ -200,9 +234,13 @@ fdm_rowvar_kernel(const FdmRowVarBatch B, const FdmRowVarOut O, const int64_t fi
     while (step < M && !bad) {
         const bool implicit_phase = step < rann;                 // theta = 1 while (M - m) < rannacher_steps, :351
         const int step_end = implicit_phase ? min(rann, M) : M;
-        if (!setup_phase<C>(tab, Af, Ab, lane, N, s, sig, r, dt, implicit_phase ? 1.0 : 0.5, dS, bar_j, hm, hp)) {
+        if (!setup_phase<C, IMPL>(tab, Af, Ab, lane, N, s, sig, r, dt, implicit_phase ? 1.0 : 0.5, dS, bar_j, hm, hp)) {
             bad = true;
             break;
+        }
+        if (REGTAB) {
+#pragma unroll
+            for (int k = 0; k < C; ++k) { MMr[k] = tab[(tMM * C + k) * 32 + lane]; NCr[k] = tab[(tNCS * C + k) * 32 + lane]; }
         }
 #pragma unroll 1
         for (; step < step_end; ++step) {
@@ -215,37 +253,59 @@ fdm_rowvar_kernel(const FdmRowVarBatch B, const FdmRowVarOut O, const int64_t fi
             const double kd = __shfl_sync(FULL, my_w, step - fill_base);
             const double w_lo = is_call ? 0.0 : kd, w_hi = is_call ? __dsub_rn(s_top, kd) : 0.0;
             // right-hand side
-            const double below = __shfl_up_sync(FULL, V[C - 1], 1), above = __shfl_down_sync(FULL, V[0], 1);
+            double below = 0.0, above = 0.0;
+            if (!IMPL) { below = __shfl_up_sync(FULL, V[C - 1], 1); above = __shfl_down_sync(FULL, V[0], 1); }
 #pragma unroll
             for (int k = 0; k < C; ++k) {
-                const double vm = (k == 0) ? below : V[k - 1], vp = (k == C - 1) ? above : V[k + 1];
-                double rhs = __dmul_rn(tab[(T_AE * C + k) * 32 + lane], vm);
-                rhs = fma(tab[(T_BE * C + k) * 32 + lane], V[k], rhs);
-                rhs = fma(tab[(T_CE * C + k) * 32 + lane], vp, rhs);
+                double rhs = V[k];                               // theta = 1: 0 V_{i-1} + 1 V_i + 0 V_{i+1}
+                if (!IMPL) {
+                    const double vm = (k == 0) ? below : V[k - 1], vp = (k == C - 1) ? above : V[k + 1];
+                    rhs = __dmul_rn(tab[(T_AE * C + k) * 32 + lane], vm);
+                    rhs = fma(tab[(T_BE * C + k) * 32 + lane], V[k], rhs);
+                    rhs = fma(tab[(T_CE * C + k) * 32 + lane], vp, rhs);
+                }
                 if (k == 0 && lane == 0) rhs = w_lo;
-                if (k == top_k && lane == top_lane) rhs = w_hi;
-                R[k] = __dmul_rn(rhs, tab[(T_RB * C + k) * 32 + lane]);          // g_i = rhs_i / beta_i
+                D[k] = __dmul_rn(rhs, tab[(tRB * C + k) * 32 + lane]);           // g_i = rhs_i / beta_i (0 from row N on)
             }
-            // forward: d_i = g_i + mm_i d_{i-1}
-            double e = 0.0;
+            constexpr int H = C / 2;
+            const double *lc = Ab + SCAN_LEVELS * 32;
+            // forward: d_i = g_i + mm_i d_{i-1}; two half-chains per lane
+            double e1 = 0.0, e2 = 0.0;
 #pragma unroll
-            for (int k = 0; k < C; ++k) e = fma(tab[(T_MM * C + k) * 32 + lane], e, R[k]);
+            for (int k = 0; k < H; ++k) e1 = fma(mm_of(k), e1, D[k]);
+#pragma unroll
+            for (int k = H; k < C; ++k) e2 = fma(mm_of(k), e2, D[k]);
+            double e = fma(lc[LC_PF2 * 32 + lane], e1, e2);
 #pragma unroll
             for (int lv = 0; lv < SCAN_LEVELS; ++lv) e = fma(Af[lv * 32 + lane], __shfl_up_sync(FULL, e, 1 << lv), e);
             double c = __shfl_up_sync(FULL, e, 1);
             c = (lane == 0) ? 0.0 : c;
+            {
+                double c1 = c, c2 = fma(lc[LC_PF1 * 32 + lane], c, e1);
 #pragma unroll
-            for (int k = 0; k < C; ++k) { c = fma(tab[(T_MM * C + k) * 32 + lane], c, R[k]); R[k] = c; }
-            // backward: x_i = d_i - c*_i x_{i+1}
-            e = 0.0;
+                for (int k = 0; k < H; ++k) { c1 = fma(mm_of(k), c1, D[k]); D[k] = c1; }
 #pragma unroll
-            for (int k = C - 1; k >= 0; --k) e = fma(tab[(T_NCS * C + k) * 32 + lane], e, R[k]);
+                for (int k = H; k < C; ++k) { c2 = fma(mm_of(k), c2, D[k]); D[k] = c2; }
+            }
+            // backward: x_i = d_i - c*_i x_{i+1}; w_hi is the carry into the top of the warp
+            e1 = 0.0; e2 = 0.0;
+#pragma unroll
+            for (int k = C - 1; k >= H; --k) e1 = fma(ncs_of(k), e1, D[k]);
+#pragma unroll
+            for (int k = H - 1; k >= 0; --k) e2 = fma(ncs_of(k), e2, D[k]);
+            e = fma(lc[LC_PB2 * 32 + lane], e1, e2);
+            if (lane == 31) e = fma(lc[LC_PBALL * 32 + lane], w_hi, e);
 #pragma unroll
             for (int lv = 0; lv < SCAN_LEVELS; ++lv) e = fma(Ab[lv * 32 + lane], __shfl_down_sync(FULL, e, 1 << lv), e);
             c = __shfl_down_sync(FULL, e, 1);
-            c = (lane == 31) ? 0.0 : c;
+            c = (lane == 31) ? w_hi : c;
+            {
+                double c1 = c, c2 = fma(lc[LC_PB1 * 32 + lane], c, e1);
 #pragma unroll
-            for (int k = C - 1; k >= 0; --k) { c = fma(tab[(T_NCS * C + k) * 32 + lane], c, R[k]); V[k] = c; }
+                for (int k = C - 1; k >= H; --k) { c1 = fma(ncs_of(k), c1, D[k]); V[k] = c1; }
+#pragma unroll
+                for (int k = H - 1; k >= 0; --k) { c2 = fma(ncs_of(k), c2, D[k]); V[k] = c2; }
+            }
             if (step + 1 == next_mon) {                          // knock-out projection, :423-425
 #pragma unroll
                 for (int k = 0; k < C; ++k) if (ko_mask & (1u << k)) V[k] = 0.0;
