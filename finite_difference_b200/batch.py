@@ -314,7 +314,7 @@ class DeviceBatch:
         self._t = {}
 
         def dev_ptr(name, arr):
-            t = torch.from_numpy(arr).to(self.device, non_blocking=False)
+            t = torch.from_numpy(arr if arr.flags.writeable else arr.copy()).to(self.device, non_blocking=False)
             self._t[name] = t
             return t.data_ptr()
 

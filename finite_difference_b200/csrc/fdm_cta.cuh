@@ -144,7 +144,7 @@ struct Ph {
     int bar3;               // the correction reaches beyond the warp of row 0: a third block barrier per step
     double cF;              // owner of row 0, carry form: NM^-(k0+1), turns the Dirichlet term of row 0 into a forward carry; else 0
     int inj;                // owner warp: the Dirichlet term of row 0 is added at its slot instead (setup_phase)
-    const double *invw;     // warp of row 0: pivot scaling by slot and lane, 0 on the dead slots below row 0
+    int e0;                 // row of this thread's slot 0 (negative inside the padding below row 0)
     double cA, cB;          // boundary coefficients of this thread (row-0 owner: A_L, B_L; last thread: A_U, B_U)
     int Kf, Kb;             // terms of the warp-to-warp Horner sums
     int cls;                // 0 padding only, 1 scalar coefficients, 2 per-slot coefficients
@@ -313,22 +313,17 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
 #ifdef FDM_CTA_EXP_NOTBL          // timing experiment only (wrong results): no table warps
     if (ph.cls == 2) ph.cls = 1;
 #endif
-    ph.gz = 0.0; ph.cF = 0.0; ph.inj = 0; ph.smc = 0; ph.bar3 = 0; ph.invw = sm.r2;
+    ph.gz = 0.0; ph.cF = 0.0; ph.inj = 0; ph.smc = 0; ph.bar3 = 0; ph.e0 = t * C - pad;
     if (row0_mode<C, WARPS, AMER>()) {
         const int wz = sm.ish[12];
         ph.smc = (wz >= 0 && w >= wf && w <= wz) ? 1 : 0;
         ph.bar3 = (wz > wf) ? 1 : 0;
         ph.gz = 0.0;
-        ph.invw = sm.r2;
         if (wz >= 0) {
             // dead lanes below row 0 stay at exactly zero with a zero pivot scaling (V = 0 * xs - 0); the owner of
-            // row 0 has dead AND live slots: its warp reads the scaling by slot from shared memory
+            // row 0 has dead AND live slots: step_cs tells them apart by ph.e0
             const int t0 = pad / C, k0 = pad % C;
             ph.inj = sm.ish[13];
-            if (w == wf) {
-#pragma unroll
-                for (int k = 0; k < C; ++k) sm.r2[k * 32 + lane] = (t * C + k >= pad) ? ph.INV : 0.0;
-            }
             if (t == t0 && !ph.inj) ph.cF = 1.0 / pow(ph.NM, (double)((k0 >= C / 2 ? k0 - C / 2 : k0) + 1));
             if (t < t0) ph.INV = 0.0;
         }
@@ -697,46 +692,60 @@ __device__ __forceinline__ double bwd_carry(const Ph &ph, const Sm &sm, const do
 template <int C, int WARPS, bool AMER, bool CORR, bool INVT, bool SLOTINJ>
 __device__ __forceinline__ void step_cs(double (&V)[C], double (&L)[C], const Ph &ph, const Sm &sm, const double cs,
                                         const double cin_b, const double e1_bwd, const double cs_f, const int k0,
-                                        const double cin_f)
+                                        const double cin_f, const double xs_row0)
 {
     constexpr int H = C / 2;
     constexpr int NT = 32 * WARPS;
     const int t = threadIdx.x;
     double c1 = cs + cin_b;
     double c2 = fma(sm.cst[CST_HB1], cs, e1_bwd);
-    const int lane = t & 31;
-    const double gzx = CORR ? -(ph.gz * sm.smv[1]) : 0.0;
+    const double gzx = CORR ? -(ph.gz * xs_row0) : 0.0;
     const double uH = V[H - 1];                                  // overwritten before slot H is reached
     constexpr bool LIGHT = lin_light<C, WARPS, AMER>();
+    // Slots in the order the two half-chains visit them; the payoff and the correction's NM^k are fetched PF slots
+    // ahead.  (Left to the compiler, each load sat right in front of its use at the 128-register cap: the owner warp of
+    // row 0, the one with the correction, spent 890 cycles in this pass on 2133-node barrier grids against 270 for the
+    // other warps -- and every other warp of the CTA waits for it at the next barrier.)
+    auto kseq = [](const int j) -> int { return (j & 1) == 0 ? C - 1 - (j >> 1) : H - 1 - (j >> 1); };
+    constexpr int PF = 4;
     auto slots = [&](auto q1_tag) {
     constexpr bool Q1 = decltype(q1_tag)::value != 0;
+    double pphi[AMER ? C + PF : 1], pnm[CORR ? C + PF : 1];
 #pragma unroll
-    for (int i = 0; i < H; ++i) {
+    for (int j = 0; j < PF; ++j) {
+        if (AMER) pphi[j] = sm.r0[kseq(j) * NT + t];
+        if (CORR) pnm[j] = sm.nmp[kseq(j)];
+    }
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int k = half == 0 ? C - 1 - i : H - 1 - i;
-            double xs;
-            if (half == 0) { c1 = fma(ph.NCC, c1, V[k]); xs = c1; }
-            else           { c2 = fma(ph.NCC, c2, V[k]); xs = c2; }
-            if (CORR) xs = fma(gzx, sm.nmp[k], xs);
-            double vc;
-            if (!LIGHT) vc = fma(INVT ? ph.invw[k * 32 + lane] : ph.INV, xs, -L[k]);
-            else {
-                const double iv = INVT ? ph.invw[k * 32 + lane] : ph.INV;
-                vc = lin_vc<Q1>(iv, xs, ph.NM, k == 0 ? cs_f : (k == H ? uH : V[k - 1]), V[k], ph.q);
-                if (SLOTINJ) asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p fma.rn.f64 %0, %3, %4, %0;\n\t}"
-                                 : "+d"(vc) : "r"(k0), "r"(k), "d"(ph.q), "d"(cin_f));
-                // dead slots (below row 0 in its warp) stay at exactly zero: their u is not (carry form), and the
-                // rebuilt V_old there is rounding noise of it
-                if (INVT) vc = (iv != 0.0) ? vc : 0.0;
-            }
-            if (AMER) {
-                const double d = sm.r0[k * NT + t] - vc;         // exercise iff phi > vc (fd_american_option_pricer.py:496)
-                L[k] = d + fabs(d);                              // 2 dt lambda_new, ONE FP64 instruction
-                V[k] = vc;
-            } else {
-                V[k] = vc;
-            }
+    for (int j = 0; j < C; ++j) {
+        const int k = kseq(j);
+        if (j + PF < C) {
+            if (AMER) pphi[j + PF] = sm.r0[kseq(j + PF) * NT + t];
+            if (CORR) pnm[j + PF] = sm.nmp[kseq(j + PF)];
+        }
+        double xs;
+        if ((j & 1) == 0) { c1 = fma(ph.NCC, c1, V[k]); xs = c1; }
+        else              { c2 = fma(ph.NCC, c2, V[k]); xs = c2; }
+        if (CORR) xs = fma(gzx, pnm[j], xs);
+        // the warp of row 0: zero pivot scaling on the dead slots below row 0 (ph.INV is 0 on its dead lanes already)
+        const bool live = !INVT || ph.e0 + k >= 0;
+        const double iv = live ? ph.INV : 0.0;
+        double vc;
+        if (!LIGHT) vc = fma(iv, xs, -L[k]);
+        else {
+            vc = lin_vc<Q1>(iv, xs, ph.NM, k == 0 ? cs_f : (k == H ? uH : V[k - 1]), V[k], ph.q);
+            if (SLOTINJ) asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p fma.rn.f64 %0, %3, %4, %0;\n\t}"
+                             : "+d"(vc) : "r"(k0), "r"(k), "d"(ph.q), "d"(cin_f));
+            // dead slots stay at exactly zero: their u is not (carry form), and the rebuilt V_old there is rounding
+            // noise of it
+            if (INVT) vc = live ? vc : 0.0;
+        }
+        if (AMER) {
+            const double d = pphi[j] - vc;                       // exercise iff phi > vc (fd_american_option_pricer.py:496)
+            L[k] = d + fabs(d);                                  // 2 dt lambda_new, ONE FP64 instruction
+            V[k] = vc;
+        } else {
+            V[k] = vc;
         }
     }
     };
@@ -1088,9 +1097,14 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
 #ifdef FDM_CTA_PROFILE
     long long prof_acc[3] = {0, 0, 0};
     long long prof_t = clock64();
+    long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ph_t = 0;            // step_a | barrier | step_b | barrier | step_c
+#define PH_TICK(slot) do { const long long t_ = clock64(); ph_acc[slot] += t_ - ph_t; ph_t = t_; } while (0)
+#define PH_START() ph_t = clock64()
 #define CTA_TICK(slot) do { const long long t_ = clock64(); prof_acc[slot] += t_ - prof_t; prof_t = t_; } while (0)
 #else
 #define CTA_TICK(slot)
+#define PH_TICK(slot)
+#define PH_START()
 #endif
     const int seg_b = B.seg_begin[sid], seg_e = B.seg_begin[sid + 1];
     if (!AMER) {
@@ -1173,12 +1187,17 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                                     : (ROLE == ROLE_OWNER_H ? INJ_CARRYH : (ROLE == ROLE_OWNER_SLOT ? INJ_SLOT : INJ_NONE))));
                 constexpr bool OWN = INJ != INJ_NONE;
                 const double carryF = (OWN && INJ != INJ_SLOT) ? cin * ph.cF : 0.0;   // non-zero on the owner thread
+                PH_START();
                 if (tbl) step_a<C, WARPS, AMER, true, INJ_NONE>(V, L, ph, sm, k0, cin, 0.0, e1f, Eprev);
                 else if (scl) step_a<C, WARPS, AMER, false, INJ>(V, L, ph, sm, k0, cin, carryF, e1f, Eprev);
+                PH_TICK(0);
                 FDM_CTA_STEP_SYNC();
+                PH_TICK(1);
                 if (tbl) step_b<C, WARPS, AMER, true, INJ_NONE, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, 0.0, e1b, Enext, eend_b, csf);
                 else if (scl) step_b<C, WARPS, AMER, false, INJ, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, carryF, e1b, Enext, eend_b, csf);
+                PH_TICK(2);
                 FDM_CTA_STEP_SYNC();
+                PH_TICK(3);
                 const bool r0c = ANY || ROLE == ROLE_PAD ? row0_corr : (ROLE == ROLE_SCALAR_R0 || OWN || ROLE == ROLE_SMC);
                 if (tbl) step_c<C, WARPS, AMER, true, K1>(V, L, ph, sm, cin_b, e1b, Enext, csf, k0, cin);
                 else if (!r0c) {
@@ -1186,23 +1205,34 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                 } else {
                     // row-0 correction: the owner of row 0 knows xs at its slot 0 (= NCC^k0 xs_0: its padding slots pass
                     // the value through) from the local pass and its carry, before the last pass starts
-                    double cs_b = 0.0;
+                    // (xs_row0: within the owner warp by shuffle; through shared memory and a third block barrier only when
+                    // the correction reaches beyond it)
+                    // (not in the 16 x 16 American class, see scan_level_skip: there the shuffle form measured 2.5 % slower)
+                    constexpr bool BY_SHFL = scan_level_skip<C, WARPS, AMER>();
+                    double cs_b = 0.0, xs_row0 = 0.0;
                     if (scl) {
                         cs_b = bwd_carry<WARPS, K1>(ph, sm, Enext);
-                        if (OWN && k0 >= 0)
-                            sm.smv[1] = fma(-sm.smv[2], carryF, fma(sm.cst[CST_AB], cs_b, eend_b));
+                        if (OWN && (BY_SHFL || k0 >= 0)) {
+                            xs_row0 = fma(-sm.smv[2], carryF, fma(sm.cst[CST_AB], cs_b, eend_b));
+                            if ((!BY_SHFL || ph.bar3) && k0 >= 0) sm.smv[1] = xs_row0;
+                        }
                     }
-                    if (ph.bar3) __syncthreads(); else __syncwarp();
+                    PH_TICK(5);
+                    if (ph.bar3) { __syncthreads(); xs_row0 = sm.smv[1]; }
+                    else if (!BY_SHFL) { __syncwarp(); if (OWN) xs_row0 = sm.smv[1]; }
+                    else if (OWN) xs_row0 = __shfl_sync(FULL, xs_row0, (pad / C) & 31);
+                    PH_TICK(6);
                     if (scl) {
                         const bool own = ANY ? w == wf : OWN;
                         const bool smc = ANY ? ph.smc != 0 : ROLE == ROLE_SMC;
                         constexpr bool SLOTINJ = INJ == INJ_SLOT || INJ == INJ_RUNTIME;
                         const int k0s = (INJ == INJ_SLOT || (INJ == INJ_RUNTIME && ph.inj)) ? k0 : -1;
-                        if (own) step_cs<C, WARPS, AMER, true, true, SLOTINJ>(V, L, ph, sm, cs_b, cin_b, e1b, csf, k0s, cin);
-                        else if (smc) step_cs<C, WARPS, AMER, true, false, false>(V, L, ph, sm, cs_b, cin_b, e1b, csf, -1, 0.0);
-                        else step_cs<C, WARPS, AMER, false, false, false>(V, L, ph, sm, cs_b, cin_b, e1b, csf, -1, 0.0);
+                        if (own) step_cs<C, WARPS, AMER, true, true, SLOTINJ>(V, L, ph, sm, cs_b, cin_b, e1b, csf, k0s, cin, xs_row0);
+                        else if (smc) step_cs<C, WARPS, AMER, true, false, false>(V, L, ph, sm, cs_b, cin_b, e1b, csf, -1, 0.0, xs_row0);
+                        else step_cs<C, WARPS, AMER, false, false, false>(V, L, ph, sm, cs_b, cin_b, e1b, csf, -1, 0.0, 0.0);
                     }
                 }
+                PH_TICK(4);
                 Vb = w_now;                                     // V[0] = V_min, V[-1] = V_max (:505-506)
                 ++gstep;
                 if (TRACE && trace) {
@@ -1291,6 +1321,9 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
     // ---- read-out: stage the value vector by node in shared memory, thread 0 finishes -------------
     CTA_TICK(0);
 #ifdef FDM_CTA_PROFILE
+    if (blockIdx.x == 40 && (threadIdx.x & 31) == 0)
+        printf("  warp %2d per step: step_a %lld | wait %lld | step_b %lld | wait %lld | step_c %lld (carry+publish %lld, sync %lld)\n", threadIdx.x >> 5, ph_acc[0] / max(gstep, 1),
+               ph_acc[1] / max(gstep, 1), ph_acc[2] / max(gstep, 1), ph_acc[3] / max(gstep, 1), ph_acc[4] / max(gstep, 1), ph_acc[5] / max(gstep, 1), ph_acc[6] / max(gstep, 1));
     if (blockIdx.x == 40 && threadIdx.x == 32 * (WARPS - 1))
         printf("cta<%d warps> n=%d steps=%d cycles: prologue+loops %lld | setup_phase %lld | dividend jumps %lld\n", WARPS, n, gstep,
                prof_acc[0], prof_acc[1], prof_acc[2]);
