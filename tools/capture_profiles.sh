@@ -9,7 +9,7 @@ python bench.py --impl reference > gpurun_out/${R}_bench_reference_n1.json 2>/de
 python bench.py --steps 2 --warmup 3 --no-cpu --no-others > gpurun_out/${R}_plain_launches.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_cfg3_ncu_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-others > gpurun_out/${R}_ncu_launches.log 2>&1
-for spec in "am500 fdm_lean_kernel 20000" "am500div fdm_lean_kernel 5000" "am400 fdm_lean_kernel 20000" "bar400 fdm_lean_kernel 20000" "cfg4 fdm_cta_kernel<\(int\)16,.\(int\)16 148" "dbfp fdm_cta_kernel<\(int\)16,.\(int\)5 1184" "p2 fdm_rowvar_kernel 2048"; do
+for spec in "am500 fdm_lean_kernel 20000" "am500div fdm_lean_kernel 5000" "am400 fdm_lean_kernel 20000" "bar400 fdm_lean_kernel 20000" "cfg4 fdm_cta_kernel<\(int\)16,.\(int\)16 148" "dbfp fdm_cta_kernel<\(int\)14,.\(int\)5 1184" "p2 fdm_rowvar_kernel<\(int\)19,.\(bool\)1 3552"; do
   set -- $spec
   python tools/ncu_shapes.py $1 $3 > gpurun_out/${R}_plain_$1.log 2>&1 && \
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s 1 -c 1 \

@@ -10,7 +10,7 @@ shape = sys.argv[1]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 batch = {"am500": lambda: american(n or 20000, 500, 500, True), "am500div": lambda: american_div(n or 5000, 500, 500), "am400": lambda: american(n or 20000, 400, 400, False),
          "bar400": lambda: barrier(n or 20000, 400, 400), "cfg4": lambda: cfg4(n or 148, 8192, 1000, divs=False),
-         "dbfp": lambda: barrier(n or 1184, 2132, 500),
+         "dbfp": lambda: barrier(n or 1184, 2132, 500),      # 2133-node grids: the 5-warp x 14-slot class
          "bar8192": lambda: barrier_T(n or 148, 8192, 2000, 0.2), "am8192": lambda: american_T(n or 148, 8192, 2000, 0.2),
          "p2": None}[shape]
 import numpy as np
