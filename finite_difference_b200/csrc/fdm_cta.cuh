@@ -1,7 +1,7 @@
 // fdm_cta.cuh -- one CTA per PDE solve, for grids too large for one warp's registers
 // (514 .. 8193 space nodes; BASELINE config 4 is 8192 nodes x 10 000 steps).
 //
-// Same step algebra as fdm_warp_kernel (see the header of fdm_b200.cu), different residency:
+// Same step algebra as fdm_warp_kernel (see the header of fdm_warp.cuh), different residency:
 //   * thread t of the CTA owns C contiguous slots; slot s holds interior row s - pad, so the padding
 //     sits BELOW row 0 and the last slot of the last thread is the top row.  V and dt*lambda stay in
 //     registers, the payoff lives in shared memory ([k][t] layout, conflict-free);
@@ -20,12 +20,13 @@
 //   Two block-wide barriers per time step.  (Tried and dropped: passing the warp totals through a shared-memory
 //   ring with per-warp progress counters instead of the barriers -- the warps need their nearest neighbours only --
 //   measured 8..10 % slower on 2048..8192-node grids: the warps stay in lock-step anyway and the polls cost issue slots.)
-//   * size classes: 4 / 5 / 8 / 16 warps of 16 slots per thread serve up to 2048 / 2560 / 4096 / 8192 rows; a solve
-//     runs in the smallest class that holds it (2133-node barrier grids: 5 warps, two CTAs per SM).
-//   Measured and dropped (round 1, tools/time_cta3.py): 8 slots per thread with twice the warps (8-12 % slower on
-//   2048..4096 rows: the per-warp scan and control overhead doubles); the scans' masked level weights precomputed in
-//   shared memory (30 instructions fewer per warp-step, no change in time); no block barriers at all (+5 % at most:
-//   the barriers are not what the step waits for).
+//   * size classes (warps x slots per thread): 4x12, 4x16, 5x14, 5x16, 8x12, 8x16, 16x12, 16x16 serve up to 1536 / 2048 /
+//     2240 / 2560 / 3072 / 4096 / 6144 / 8192 rows; a solve runs in the smallest class that holds it (2133-node barrier
+//     grids: 5x14, four CTAs per SM).
+//   * American state between steps: (vc, 2 dt lambda), not (V, 2 dt lambda) -- 9 FP64 instructions per node-step; the
+//     linear march keeps V only and rebuilds V_old from u in its last pass (lin_vc; not in the 16-warp class).
+//   What was measured and dropped (more slots per thread with fewer warps, shared-memory progress counters instead of the
+//   barriers, named barriers per warp pair, the lean kernel's step order, ...) is listed in DESIGN.md section 3.
 //
 // Included by fdm_cta_inst.cu (one translation unit per size class).
 
