@@ -1,0 +1,72 @@
+"""Seeded random sweep of the CTA kernel's geometry against the oracle: grid sizes across all eight size classes
+(row 0 at any slot of its owner thread, any amount of padding), step counts and volatilities that walk through the
+one-term / multi-term warp sums, the row-0 correction reaching or not reaching the next warp, the three forms of the
+owner warp's Dirichlet term and 3 / 4 / 5 lane-scan levels.  (The fixed-size tests had missed a seven-digit loss of
+precision that only showed with row 0 high up in its thread and a small forward multiplier.)
+Bar: every node 1e-10 relative (+1e-12 of the vector's scale), price 1e-10, exercise interval identical at every step."""
+import numpy as np
+import pytest
+
+from finite_difference_b200 import hostlogic, solve_host
+from finite_difference_b200.batch import SolveBatch
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+REL = 1e-10
+
+
+def _v_close(V, ref):
+    tol = REL * np.abs(ref) + 1e-12 * np.max(np.abs(ref))
+    bad = np.abs(V - ref) > tol
+    assert not bad.any(), (int(bad.sum()), float(np.max(np.abs(V - ref) / (np.abs(ref) + 1e-300))))
+
+
+def _cases(seed, count):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(count):
+        n = int(rng.integers(514, 8194))
+        if rng.uniform() < 0.35:                                  # cluster around the class boundaries
+            n = int(rng.choice([1537, 2049, 2241, 2561, 3073, 4097, 6145, 8193]) + rng.integers(-20, 3))
+            n = min(max(n, 514), 8193)
+        out.append(dict(n=n, m=int(rng.integers(12, 260)), T=float(rng.choice([0.04, 0.1, 0.25, 0.5, 1.0, 2.0])),
+                        sig=float(rng.uniform(0.08, 0.7)), r=float(rng.uniform(0.0, 0.1)), q=float(rng.uniform(0.0, 0.05)),
+                        K=float(rng.uniform(80, 125)), call=bool(rng.uniform() < 0.5), rann=int(rng.choice([0, 2, 4]))))
+    return out
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_american_random_geometry(seed):
+    cases = _cases(seed, 14)
+    parts = [hostlogic.build_american_batch([100.0], [c["K"]], [c["T"]], [c["sig"]], [c["r"]], [c["r"] - c["q"]], [c["call"]],
+                                            [c["n"]], [c["m"]], [c["rann"]], [False]) for c in cases]
+    res = solve_host(SolveBatch.concat(parts), dump=True, trace=True)
+    for i, c in enumerate(cases):
+        o = oracle.american_solve(100.0, c["K"], c["T"], c["sig"], c["r"], c["r"] - c["q"], c["call"], 0, c["n"], c["m"], c["rann"],
+                                  trace=True)
+        assert res.status[i] == 0, (c, res.status[i])
+        _v_close(res.V[i, : c["n"] + 1], o.V)
+        assert abs(res.price[i] - o.price) <= REL * max(abs(o.price), 1e-2), c
+        assert np.array_equal(res.ex_trace[i, : o.ex_trace.shape[0]], o.ex_trace), c
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23])
+def test_barrier_random_geometry(seed):
+    cases = _cases(seed, 14)
+    rng = np.random.default_rng(seed + 100)
+    parts, specs = [], []
+    for c in cases:
+        kind = str(rng.choice(["down-and-out", "up-and-out"]))
+        lo, up = (float(rng.uniform(60, 95)), None) if kind == "down-and-out" else (None, float(rng.uniform(110, 160)))
+        mon = sorted(float(x) for x in rng.uniform(0.05, 0.95, int(rng.integers(1, 7))) * c["T"])
+        reb = float(rng.choice([0.0, 1.5]))
+        specs.append((kind, lo, up, mon, reb))
+        parts.append(hostlogic.build_barrier_batch([100.0], [c["K"]], [c["T"]], [c["sig"]], [c["r"]], [c["r"] - c["q"]], [c["call"]],
+                                                   [kind], [lo], [up], [reb], [mon], [c["n"]], [c["m"]]))
+    res = solve_host(SolveBatch.concat(parts), dump=True)
+    for i, (c, (kind, lo, up, mon, reb)) in enumerate(zip(cases, specs)):
+        o = oracle.barrier_solve(100.0, c["K"], c["T"], c["sig"], c["r"], c["r"] - c["q"], c["call"], kind, lo, up, reb, mon,
+                                 c["n"], c["m"], True)
+        assert res.status[i] == 0, (c, res.status[i])
+        _v_close(res.V[i, : c["n"] + 1], o.V)
+        assert abs(res.price[i] - o.price) <= REL * max(abs(o.price), 1e-2), c
