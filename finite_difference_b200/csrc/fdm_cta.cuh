@@ -561,7 +561,7 @@ __device__ __forceinline__ void step_a(double (&V)[C], double (&L)[C], const Ph 
 template <int C, int WARPS, bool AMER, bool TBL, int INJ, bool K1>
 __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &sm, const int wf, const double cin_b,
                                        const double e1_fwd, const double Eprev, const double carryF, double &e1_keep,
-                                       double &Enext, double &eend_keep, double &csf_keep)
+                                       double &Enext, double &eend_keep, double &csf_keep, double &cmid_keep)
 {
     constexpr int H = C / 2;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -585,6 +585,7 @@ __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &s
     {
         double c1 = cs;
         double c2 = fma(TBL ? lc[LC_HF1 * 32 + lane] : sm.cst[CST_HF1], cs, e1x);
+        cmid_keep = c2;                                     // what slot C/2 sees below it (the owner's carry included)
 #pragma unroll
         for (int k = 0; k < H; ++k) { c1 = fma(TBL ? nm[k * 32 + lane] : ph.NM, c1, V[k]); V[k] = c1; }
 #pragma unroll
@@ -607,8 +608,9 @@ __device__ __forceinline__ void step_b(double (&V)[C], const Ph &ph, const Sm &s
 }
 
 // Linear march, last pass.  The new value is vc = INV xs - q V_old, and V_old is not kept: the system is solved for
-// R = V_old (setup_phase scales it), so V_old = u_k - nm_k u_{k-1} with u still in the registers (u_{-1} is the forward
-// carry into the thread).  One FP64 instruction more per node than with a copy of V_old, but half the register file:
+// R = V_old (setup_phase scales it), so V_old = u_k - nm_k u_{k-1} with u still in the registers; below slot 0 and below
+// slot C/2, u_{k-1} is the value the half-chain was started with (cs_f, c_mid: the forward carry into the thread, the
+// owner's Dirichlet carry included -- not V[C/2 - 1], which lacks that carry when row 0 sits at slot C/2).  One FP64 instruction more per node than with a copy of V_old, but half the register file:
 // 4 / 4 / 3 resident CTAs of 4 / 5 / 8 warps instead of 4 / 3 / 2, and no 2 C register moves per step.
 //   u_k, um: u of this slot and of the slot below;  returns vc.
 template <bool Q1>
@@ -621,8 +623,8 @@ __device__ __forceinline__ double lin_vc(const double inv, const double xs, cons
 
 template <int C, int WARPS, bool AMER, bool TBL, bool K1>
 __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph &ph, const Sm &sm, const double cin_b,
-                                       const double e1_bwd, const double Enext, const double cs_f, const int k0,
-                                       const double cin_f)
+                                       const double e1_bwd, const double Enext, const double cs_f, const double c_mid,
+                                       const int k0, const double cin_f)
 {
     constexpr int H = C / 2;
     constexpr int NT = 32 * WARPS;
@@ -639,7 +641,6 @@ __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph 
     double c1 = cs + cin_b;
     double c2 = fma(TBL ? lc[LC_HB1 * 32 + lane] : sm.cst[CST_HB1], cs, e1_bwd);
     const double *nm = ph.slot;
-    const double uH = V[H - 1];                                  // overwritten before slot H is reached
     constexpr bool LIGHT = lin_light<C, WARPS, AMER>();
     auto slots = [&](auto q1_tag) {
     constexpr bool Q1 = decltype(q1_tag)::value != 0;
@@ -655,7 +656,7 @@ __device__ __forceinline__ void step_c(double (&V)[C], double (&L)[C], const Ph 
             if (!LIGHT) vc = fma(TBL ? inv[k * 32 + lane] : ph.INV, xs, -L[k]);
             else {
                 vc = lin_vc<Q1>(TBL ? inv[k * 32 + lane] : ph.INV, xs, TBL ? nm[k * 32 + lane] : ph.NM,
-                                k == 0 ? cs_f : (k == H ? uH : V[k - 1]), V[k], ph.q);
+                                k == 0 ? cs_f : (k == H ? c_mid : V[k - 1]), V[k], ph.q);
                 // a table warp adds the Dirichlet term of row 0 to R at its slot: R = V_old + cin there
                 if (TBL) asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p fma.rn.f64 %0, %3, %4, %0;\n\t}"
                              : "+d"(vc) : "r"(k0), "r"(k), "d"(ph.q), "d"(cin_f));
@@ -692,8 +693,8 @@ __device__ __forceinline__ double bwd_carry(const Ph &ph, const Sm &sm, const do
 // SLOTINJ: this warp added the Dirichlet term of row 0 to R at its slot (R = V_old + cin there).
 template <int C, int WARPS, bool AMER, bool CORR, bool INVT, bool SLOTINJ>
 __device__ __forceinline__ void step_cs(double (&V)[C], double (&L)[C], const Ph &ph, const Sm &sm, const double cs,
-                                        const double cin_b, const double e1_bwd, const double cs_f, const int k0,
-                                        const double cin_f, const double xs_row0)
+                                        const double cin_b, const double e1_bwd, const double cs_f, const double c_mid,
+                                        const int k0, const double cin_f, const double xs_row0)
 {
     constexpr int H = C / 2;
     constexpr int NT = 32 * WARPS;
@@ -701,7 +702,6 @@ __device__ __forceinline__ void step_cs(double (&V)[C], double (&L)[C], const Ph
     double c1 = cs + cin_b;
     double c2 = fma(sm.cst[CST_HB1], cs, e1_bwd);
     const double gzx = CORR ? -(ph.gz * xs_row0) : 0.0;
-    const double uH = V[H - 1];                                  // overwritten before slot H is reached
     constexpr bool LIGHT = lin_light<C, WARPS, AMER>();
     // Slots in the order the two half-chains visit them; the payoff and the correction's NM^k are fetched PF slots
     // ahead.  (Left to the compiler, each load sat right in front of its use at the 128-register cap: the owner warp of
@@ -734,7 +734,7 @@ __device__ __forceinline__ void step_cs(double (&V)[C], double (&L)[C], const Ph
         double vc;
         if (!LIGHT) vc = fma(iv, xs, -L[k]);
         else {
-            vc = lin_vc<Q1>(iv, xs, ph.NM, k == 0 ? cs_f : (k == H ? uH : V[k - 1]), V[k], ph.q);
+            vc = lin_vc<Q1>(iv, xs, ph.NM, k == 0 ? cs_f : (k == H ? c_mid : V[k - 1]), V[k], ph.q);
             if (SLOTINJ) asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p fma.rn.f64 %0, %3, %4, %0;\n\t}"
                              : "+d"(vc) : "r"(k0), "r"(k), "d"(ph.q), "d"(cin_f));
             // dead slots stay at exactly zero: their u is not (carry form), and the rebuilt V_old there is rounding
@@ -1179,7 +1179,7 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                 w_next = fetch_boundary(m + 1);
                 double cin_n = ph.cB * w_now - ph.cA * w_next;
                 const double cin_b = cin * top_mult;            // enters the top row through its ncc
-                double e1f = 0.0, Eprev = 0.0, e1b = 0.0, Enext = 0.0, eend_b = 0.0, csf = 0.0;
+                double e1f = 0.0, Eprev = 0.0, e1b = 0.0, Enext = 0.0, eend_b = 0.0, csf = 0.0, cmid = 0.0;
                 constexpr bool ANY = ROLE == ROLE_ANY;
                 const bool tbl = ANY ? ph.cls == 2 : ROLE == ROLE_TBL;
                 const bool scl = ANY ? ph.cls == 1 : (ROLE != ROLE_TBL && ROLE != ROLE_PAD);
@@ -1194,15 +1194,15 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                 PH_TICK(0);
                 FDM_CTA_STEP_SYNC();
                 PH_TICK(1);
-                if (tbl) step_b<C, WARPS, AMER, true, INJ_NONE, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, 0.0, e1b, Enext, eend_b, csf);
-                else if (scl) step_b<C, WARPS, AMER, false, INJ, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, carryF, e1b, Enext, eend_b, csf);
+                if (tbl) step_b<C, WARPS, AMER, true, INJ_NONE, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, 0.0, e1b, Enext, eend_b, csf, cmid);
+                else if (scl) step_b<C, WARPS, AMER, false, INJ, K1>(V, ph, sm, wf, cin_b, e1f, Eprev, carryF, e1b, Enext, eend_b, csf, cmid);
                 PH_TICK(2);
                 FDM_CTA_STEP_SYNC();
                 PH_TICK(3);
                 const bool r0c = ANY || ROLE == ROLE_PAD ? row0_corr : (ROLE == ROLE_SCALAR_R0 || OWN || ROLE == ROLE_SMC);
-                if (tbl) step_c<C, WARPS, AMER, true, K1>(V, L, ph, sm, cin_b, e1b, Enext, csf, k0, cin);
+                if (tbl) step_c<C, WARPS, AMER, true, K1>(V, L, ph, sm, cin_b, e1b, Enext, csf, cmid, k0, cin);
                 else if (!r0c) {
-                    if (scl) step_c<C, WARPS, AMER, false, K1>(V, L, ph, sm, cin_b, e1b, Enext, csf, -1, 0.0);
+                    if (scl) step_c<C, WARPS, AMER, false, K1>(V, L, ph, sm, cin_b, e1b, Enext, csf, cmid, -1, 0.0);
                 } else {
                     // row-0 correction: the owner of row 0 knows xs at its slot 0 (= NCC^k0 xs_0: its padding slots pass
                     // the value through) from the local pass and its carry, before the last pass starts
@@ -1228,9 +1228,9 @@ fdm_cta_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int 
                         const bool smc = ANY ? ph.smc != 0 : ROLE == ROLE_SMC;
                         constexpr bool SLOTINJ = INJ == INJ_SLOT || INJ == INJ_RUNTIME;
                         const int k0s = (INJ == INJ_SLOT || (INJ == INJ_RUNTIME && ph.inj)) ? k0 : -1;
-                        if (own) step_cs<C, WARPS, AMER, true, true, SLOTINJ>(V, L, ph, sm, cs_b, cin_b, e1b, csf, k0s, cin, xs_row0);
-                        else if (smc) step_cs<C, WARPS, AMER, true, false, false>(V, L, ph, sm, cs_b, cin_b, e1b, csf, -1, 0.0, xs_row0);
-                        else step_cs<C, WARPS, AMER, false, false, false>(V, L, ph, sm, cs_b, cin_b, e1b, csf, -1, 0.0, 0.0);
+                        if (own) step_cs<C, WARPS, AMER, true, true, SLOTINJ>(V, L, ph, sm, cs_b, cin_b, e1b, csf, cmid, k0s, cin, xs_row0);
+                        else if (smc) step_cs<C, WARPS, AMER, true, false, false>(V, L, ph, sm, cs_b, cin_b, e1b, csf, cmid, -1, 0.0, xs_row0);
+                        else step_cs<C, WARPS, AMER, false, false, false>(V, L, ph, sm, cs_b, cin_b, e1b, csf, cmid, -1, 0.0, 0.0);
                     }
                 }
                 PH_TICK(4);

@@ -3,6 +3,8 @@
 one-term / multi-term warp sums, the row-0 correction reaching or not reaching the next warp, the three forms of the
 owner warp's Dirichlet term and 3 / 4 / 5 lane-scan levels.  (The fixed-size tests had missed a seven-digit loss of
 precision that only showed with row 0 high up in its thread and a small forward multiplier.)
+Time steps up to alpha dt ~ 6000; beyond that (a dozen steps on 7000 nodes) the growth-factor matching is good for
+alpha dt * steps * 2^-53, which passes 1e-10 (tests/test_gpu_stiff.py holds those cases to their own bound).
 Bar: every node 1e-10 relative (+1e-12 of the vector's scale), price 1e-10, exercise interval identical at every step."""
 import numpy as np
 import pytest
@@ -50,7 +52,9 @@ def test_american_random_geometry(seed):
         assert np.array_equal(res.ex_trace[i, : o.ex_trace.shape[0]], o.ex_trace), c
 
 
-@pytest.mark.parametrize("seed", [21, 22, 23])
+# (110, 125: rebate paid in a knocked-out region next to row 0, with row 0 at slot C/2 of its thread -- the case the
+# linear march's rebuilt V_old got wrong by the Dirichlet term until the sweep found it)
+@pytest.mark.parametrize("seed", [21, 22, 23, 110, 125])
 def test_barrier_random_geometry(seed):
     cases = _cases(seed, 14)
     rng = np.random.default_rng(seed + 100)
