@@ -439,6 +439,13 @@ __device__ __noinline__ double dividend_jump(const double Vb, const double cash,
     constexpr int GM = 14;
     const int j_first = row0 + 1;                              // this lane's interior knots j_first .. j_first + cnt - 1
     double mur[C], zr[C];
+#ifdef FDM_LEAN_PROFILE
+    long long jt[8]; int ji = 0;
+#define LJ_TICK() jt[ji++] = clock64()
+#else
+#define LJ_TICK()
+#endif
+    LJ_TICK();
     if (lane == 0) { Bv[0] = Vb; A[0] = node_s(x_min, dx, 0); }
     if (lane == 31) { Bv[n] = Vb; A[n] = node_s(x_min, dx, n); }
     // Knots of the own rows: one exponential for the first, then s_{j+1} = s_j e^dx (16 multiplications instead of 16
@@ -458,6 +465,7 @@ __device__ __noinline__ double dividend_jump(const double Vb, const double cash,
         }
     }
     __syncwarp();
+    LJ_TICK();
     // ---- forward: warm-up of the pivot recurrence, then the lane's own rows ----------------------------------
     double mu_prev = 0.0, z_prev = 0.0, prod = 1.0;
     {
@@ -490,6 +498,7 @@ __device__ __noinline__ double dividend_jump(const double Vb, const double cash,
             x_im1 = x_i; x_i = x_ip1; y_im1 = y_i; y_i = y_ip1; t_im1 = t_i;
         }
     }
+    LJ_TICK();
     {
         // carry into this lane = true z at the last row of the lane below
         const double e1 = __shfl_up_sync(FULL, z_prev, 1), e2 = __shfl_up_sync(FULL, z_prev, 2), e3 = __shfl_up_sync(FULL, z_prev, 3);
@@ -519,6 +528,7 @@ __device__ __noinline__ double dividend_jump(const double Vb, const double cash,
     if (lane == 0) Z[0] = 0.0;
     if (lane == 31) Z[n] = 0.0;
     __syncwarp();
+    LJ_TICK();
     // ---- evaluation at S_j - D, :517-548: nodes q = -1 (node 0, lane 0), 0 .. cnt-1 (own), cnt (node n, lane 31) -------
     const double s_lo = A[0], s_hi = A[n];
     int jj = -1;                                               // bracket of the previous node (monotone in j)
@@ -559,6 +569,12 @@ __device__ __noinline__ double dividend_jump(const double Vb, const double cash,
 #pragma unroll 1
     for (int k = 0; k < cnt; ++k) Bv[j_first + k] = zr[k];
     __syncwarp();
+    LJ_TICK();
+#ifdef FDM_LEAN_PROFILE
+    if (blockIdx.x == 1000 && lane == 5)
+        printf("lean jump: knots %lld | elimination %lld | back-substitution %lld | evaluation %lld\n", jt[1] - jt[0], jt[2] - jt[1],
+               jt[3] - jt[2], jt[4] - jt[3]);
+#endif
     return nb;
 }
 
