@@ -292,7 +292,10 @@ struct CarryShf {
 // one times a power of two, so the results are bit-identical to the (vc, 3 dt lambda) form.
 // The optional last slot is handled without branches: on lanes that do not hold it its multipliers are 1 / 0 and
 // its V, L stay 0, which makes it the identity in both sweeps.
-template <int C, bool AMER, int TERMS>
+// HALF: 1 / 0 = theta is / is not 1/2, known at compile time (the linear time loops are compiled for both: left to a
+// runtime test, ptxas if-converts the C multiplications q V of the other case into predicated DMULs that issue in every
+// step -- 13 of 234 instructions of a 400-node Crank-Nicolson step); -1 = ph.half decides (American: a real branch).
+template <int C, bool AMER, int TERMS, int HALF>
 __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const Ph<C> &ph, const double cin_f,
                                            const double cin_b, const bool last, const Tables<C> &T, const int lane)
 {
@@ -317,7 +320,7 @@ __device__ __forceinline__ void march_step(double (&V)[C], double (&L)[C], const
                 L[k] = g;
             }
         }
-    } else if (ph.half) {
+    } else if (HALF == 1 || (HALF < 0 && ph.half)) {
         // theta = 1/2: q = 1, the subtrahend is the old V itself -- a register rename, not an FP64 instruction
         // (13 of the 111 FP64 instructions of a 400-node Crank-Nicolson step)
 #pragma unroll
@@ -727,13 +730,13 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
             // The time loop is compiled once per carry form (TT = 2 / 4 / 6 direct terms, 0 = scan), so the step has no
             // branches on ph.terms: ~35 fewer instructions per warp-step (BRA / UISETP / PLOP3 and the shuffle
             // temporaries' moves) and a tighter schedule.  Measured on B200: +5..14 % on every lean shape.
-            auto time_loop = [&](auto tt) {
-            constexpr int TT = decltype(tt)::value;
+            auto time_loop = [&](auto tt, auto hh) {
+            constexpr int TT = decltype(tt)::value, HH = decltype(hh)::value;
             for (; m < m_end; ++m) {
                 const double w_now = w_next;
                 w_next = fetch_boundary(m + 1);
                 double cin_n = LCV(ph, T, lane, cB, LC_CB) * w_now - LCV(ph, T, lane, cA, LC_CA) * w_next;
-                march_step<C, AMER, TT>(V, L, ph, (lane == 0) ? cin : 0.0, (lane == 31) ? cin : 0.0, last, T, lane);
+                march_step<C, AMER, TT, HH>(V, L, ph, (lane == 0) ? cin : 0.0, (lane == 31) ? cin : 0.0, last, T, lane);
                 Vb = w_now;                                     // V[0] = V_min, V[-1] = V_max, :505-506
                 ++gstep;
                 if (TRACE && trace) {
@@ -769,12 +772,17 @@ fdm_lean_kernel(const FdmBatch B, const FdmOut O, const int64_t first, const int
                 cin = cin_n;
             }
             };
-            switch (ph.terms) {
-            case 2: time_loop(IntC<2>{}); break;
-            case 4: time_loop(IntC<4>{}); break;
-            case 6: time_loop(IntC<6>{}); break;
-            default: time_loop(IntC<0>{}); break;
-            }
+            auto by_terms = [&](auto hh) {
+                switch (ph.terms) {
+                case 2: time_loop(IntC<2>{}, hh); break;
+                case 4: time_loop(IntC<4>{}, hh); break;
+                case 6: time_loop(IntC<6>{}, hh); break;
+                default: time_loop(IntC<0>{}, hh); break;
+                }
+            };
+            if (AMER) by_terms(IntC<-1>{});
+            else if (ph.half) by_terms(IntC<1>{});
+            else by_terms(IntC<0>{});
         }
         if (retry) break;
         const double cash = B.seg_div[seg];
