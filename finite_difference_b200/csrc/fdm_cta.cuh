@@ -297,6 +297,10 @@ __device__ __forceinline__ void setup_phase(double theta, double dt, double a, d
         int wl = min((pad + P - 1) / (32 * C), WARPS - 1);          // last warp with a head row
         if (wz >= 0) wl = wf - 1;                                   // row-0 correction: no table warps
         else if (wl - wf + 1 > LY::SLOTS) sm.ish[5] = 2;            // more table warps than staged slots
+        // theta alpha dt beyond ~1.5e4 (a dozen time steps on thousands of nodes): the hoisted factorisation's growth
+        // matching is good for ~1e-10 there and no better (1.2e-10 seen at alpha dt = 6e4 on 7346 nodes x 21 steps in the
+        // random sweep); such a solve is left to the literal sweep of fdm_exact_kernel as well
+        if (fabs(A_L) > 1.5e4 || fabs(A_U) > 1.5e4) sm.ish[5] = 2;
         sm.ish[0] = P; sm.ish[10] = wf; sm.ish[11] = min(wl, wf + LY::SLOTS - 1);
         sm.cst[CST_NM] = pv_nm[P]; sm.cst[CST_NCC] = pv_ncc[P]; sm.cst[CST_INV] = pv_inv[P];
         sm.cst[CST_TOP] = (sm.ish[11] == WARPS - 1) ? 1.0 : 1.0 / pv_ncc[P];

@@ -3,8 +3,8 @@
 one-term / multi-term warp sums, the row-0 correction reaching or not reaching the next warp, the three forms of the
 owner warp's Dirichlet term and 3 / 4 / 5 lane-scan levels.  (The fixed-size tests had missed a seven-digit loss of
 precision that only showed with row 0 high up in its thread and a small forward multiplier.)
-Time steps up to alpha dt ~ 6000; beyond that (a dozen steps on 7000 nodes) the growth-factor matching is good for
-alpha dt * steps * 2^-53, which passes 1e-10 (tests/test_gpu_stiff.py holds those cases to their own bound).
+Time steps of any stiffness: beyond theta alpha dt = 1.5e4 (a dozen steps on thousands of nodes, where the hoisted march's
+growth matching is good for ~1e-10 and no better) the CTA kernel hands the solve to fdm_exact_kernel.
 Bar: every node 1e-10 relative (+1e-12 of the vector's scale), price 1e-10, exercise interval identical at every step."""
 import numpy as np
 import pytest

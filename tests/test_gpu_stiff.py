@@ -92,3 +92,17 @@ def test_linear_solve_with_cash_dividends_on_a_large_grid():
         res[n] = float(r.price[0])
     assert abs(res[1000] - res[500]) <= 2e-3 * res[500], res
     assert abs(res[2133] - res[1000]) <= 1e-3 * res[1000], res
+
+
+def test_extreme_alpha_dt_goes_to_the_literal_sweep():
+    """alpha dt = 6e4 (7346 nodes, 21 steps, sigma 0.5): found by the random sweep at 1.2e-10 in the hoisted CTA march;
+    beyond theta alpha dt = 1.5e4 the solve is handed to fdm_exact_kernel and meets the bar with room."""
+    kw = dict(K=104.0, T=1.0, sig=0.515, r=0.03, q=0.01)
+    for call in (False, True):
+        b = hostlogic.build_american_batch([100.0], [kw["K"]], [kw["T"]], [kw["sig"]], [kw["r"]], [kw["r"] - kw["q"]], [call], [7346], [21], [2], [False])
+        res = solve_host(b, dump=True)
+        o = oracle.american_solve(100.0, kw["K"], kw["T"], kw["sig"], kw["r"], kw["r"] - kw["q"], call, 0, 7346, 21, 2)
+        assert res.status[0] == 0
+        scale = np.max(np.abs(o.V))
+        assert np.all(np.abs(res.V[0, :7347] - o.V) <= 2e-11 * np.abs(o.V) + 1e-12 * scale)
+        assert abs(res.price[0] - o.price) <= 2e-11 * abs(o.price)
