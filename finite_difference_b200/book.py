@@ -595,12 +595,14 @@ class BarrierBook:
 
     def _parity_legs(self, out):
         """``none`` -> closed-form BS, knock-in -> BS minus knock-out (discrete_barrier_fdm_pricer_cn.py:489-500, :522-535)."""
-        kinds = np.array(self.barrier_type)
-        needs_bs = np.isin(kinds, ("none", "down-and-in", "up-and-in"))
-        if needs_bs.any():
-            bs = self._vanilla_bs()
+        masks = getattr(self, "_parity_masks", None)
+        if masks is None:                                       # once per book (0.8 ms on 10 k rows: as much as the H2D + D2H)
+            kinds = np.array(self.barrier_type)
             none = kinds == "none"
-            ki = needs_bs & ~none
+            masks = self._parity_masks = (none, np.isin(kinds, ("down-and-in", "up-and-in")))
+        none, ki = masks
+        if none.any() or ki.any():
+            bs = self._vanilla_bs()
             for k in ("price", "delta", "gamma", "vega", "theta"):
                 if k in out:
                     out[k] = np.where(none, bs[k], np.where(ki, bs[k] - out[k], out[k]))
