@@ -35,6 +35,12 @@ struct Arena {
     std::mutex mu;
     char *p = nullptr;
     size_t bytes = 0;
+    // the book host entries: a pinned mirror of the arena's input / output prefix (one H2D and one D2H per call instead of
+    // one staged copy from pageable memory per array) and a stream + event pair kept across calls
+    char *hp = nullptr;
+    size_t hbytes = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
 };
 Arena g_arenas[MAX_DEVICES];
 
@@ -56,6 +62,38 @@ cudaError_t arena_get(Arena &a, size_t bytes, char **out)
 }
 
 inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// caller holds a.mu and has the arena's device current
+cudaError_t arena_host(Arena &a, size_t bytes, char **out)
+{
+    if (a.hp && bytes > a.hbytes) {
+        cudaFreeHost(a.hp);
+        a.hp = nullptr;
+        a.hbytes = 0;
+    }
+    if (!a.hp) {
+        const cudaError_t e = cudaHostAlloc((void **)&a.hp, bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) { a.hp = nullptr; return e; }
+        a.hbytes = bytes;
+    }
+    *out = a.hp;
+    return cudaSuccess;
+}
+
+cudaError_t arena_stream(Arena &a)
+{
+    cudaError_t e = cudaSuccess;
+    if (!a.st) e = cudaStreamCreateWithFlags(&a.st, cudaStreamNonBlocking);
+    if (e == cudaSuccess && !a.e0) e = cudaEventCreate(&a.e0);
+    if (e == cudaSuccess && !a.e1) e = cudaEventCreate(&a.e1);
+    return e;
+}
+
+// drains the arena's stream before the arena lock is released, on every exit path
+struct StreamDrain {
+    cudaStream_t st;
+    ~StreamDrain() { if (st) cudaStreamSynchronize(st); }
+};
 
 // stream + two events of one host-entry call; on every exit path the stream is drained before it is destroyed, so
 // nothing queued on it can still touch the arena when the arena's lock is released
@@ -647,7 +685,9 @@ int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int6
     // per-option outputs
     const size_t o_d[6] = {take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8)};
     const size_t o_lo = take(n * 4), o_hi = take(n * 4), o_st = take(n * 4);
+    const size_t o_end = off;
     const size_t i_oi = take(ho->out_index ? n * 4 : 0);
+    const size_t stage_end = off;                       // [0, stage_end) is mirrored in pinned host memory
     // expanded descriptors and per-solve results
     const size_t o_ws = take(fdm_american_book_workspace(n, ndiv, hb->what, hb->use_richardson));
 
@@ -658,23 +698,18 @@ int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int6
     std::lock_guard<std::mutex> arena_lock(ar.mu);
     char *arena = nullptr;
     FDM_CUDA(arena_get(ar, off, &arena));
-    CallCtx cx;
-    FDM_TRY(cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking));
-    FDM_TRY(cudaEventCreate(&cx.e0));
-    FDM_TRY(cudaEventCreate(&cx.e1));
-    if (rc != FDM_OK) return rc;
-    cudaStream_t st = cx.st;
+    char *hp = nullptr;
+    FDM_CUDA(arena_host(ar, stage_end, &hp));
+    FDM_CUDA(arena_stream(ar));
+    cudaStream_t st = ar.st;
+    StreamDrain drain{st};
+    struct { cudaEvent_t e0, e1; } cx = {ar.e0, ar.e1};
+    auto put = [&](size_t o, const void *src, size_t bytes) { if (src && bytes) memcpy(hp + o, src, bytes); };
     const double *hd[6] = {hb->spot, hb->strike, hb->T, hb->sigma, hb->r, hb->b};
-    for (int i = 0; i < 6; ++i) FDM_TRY(cudaMemcpyAsync(arena + i_d[i], hd[i], n * 8, cudaMemcpyHostToDevice, st));
-    FDM_TRY(cudaMemcpyAsync(arena + i_fl, hb->flags, n * 4, cudaMemcpyHostToDevice, st));
-    FDM_TRY(cudaMemcpyAsync(arena + i_ns, hb->n_space, n * 4, cudaMemcpyHostToDevice, st));
-    FDM_TRY(cudaMemcpyAsync(arena + i_nt, hb->n_time, n * 4, cudaMemcpyHostToDevice, st));
-    FDM_TRY(cudaMemcpyAsync(arena + i_rn, hb->rannacher, n * 4, cudaMemcpyHostToDevice, st));
-    if (ndiv) {
-        FDM_TRY(cudaMemcpyAsync(arena + i_db, hb->div_begin, (n + 1) * 4, cudaMemcpyHostToDevice, st));
-        FDM_TRY(cudaMemcpyAsync(arena + i_dt, hb->div_tau, ndiv * 8, cudaMemcpyHostToDevice, st));
-        FDM_TRY(cudaMemcpyAsync(arena + i_dc, hb->div_cash, ndiv * 8, cudaMemcpyHostToDevice, st));
-    }
+    for (int i = 0; i < 6; ++i) put(i_d[i], hd[i], n * 8);
+    put(i_fl, hb->flags, n * 4); put(i_ns, hb->n_space, n * 4); put(i_nt, hb->n_time, n * 4); put(i_rn, hb->rannacher, n * 4);
+    if (ndiv) { put(i_db, hb->div_begin, (n + 1) * 4); put(i_dt, hb->div_tau, ndiv * 8); put(i_dc, hb->div_cash, ndiv * 8); }
+    FDM_TRY(cudaMemcpyAsync(arena, hp, o_d[0], cudaMemcpyHostToDevice, st));       // every input array in one copy
 
     FdmAmericanBook db = *hb;
     db.spot = (const double *)(arena + i_d[0]); db.strike = (const double *)(arena + i_d[1]);
@@ -694,7 +729,8 @@ int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int6
     dbo.ex_lo = (int32_t *)(arena + o_lo); dbo.ex_hi = (int32_t *)(arena + o_hi); dbo.status = (int32_t *)(arena + o_st);
     dbo.out_index = nullptr;
     if (ho->out_index) {
-        FDM_TRY(cudaMemcpyAsync(arena + i_oi, ho->out_index, n * 4, cudaMemcpyHostToDevice, st));
+        put(i_oi, ho->out_index, n * 4);
+        FDM_TRY(cudaMemcpyAsync(arena + i_oi, hp + i_oi, n * 4, cudaMemcpyHostToDevice, st));
         dbo.out_index = (const int32_t *)(arena + i_oi);
     }
 
@@ -705,14 +741,15 @@ int fdm_american_book_host(const FdmAmericanBook *hb, const FdmBookOut *ho, int6
         if (lrc != FDM_OK) rc = lrc;
         FDM_TRY(cudaEventRecord(cx.e1, st));
     }
-    auto d2h = [&](void *dst, size_t o, size_t bytes) {
-        if (dst && bytes) FDM_TRY(cudaMemcpyAsync(dst, arena + o, bytes, cudaMemcpyDeviceToHost, st));
-    };
+    auto get = [&](void *dst, size_t o, size_t bytes) { if (dst && bytes) memcpy(dst, hp + o, bytes); };
     if (rc == FDM_OK) {
-        d2h(ho->price_log2, o_d[0], n * 8); d2h(ho->price, o_d[1], n * 8); d2h(ho->delta, o_d[2], n * 8);
-        d2h(ho->gamma, o_d[3], n * 8); d2h(ho->vega, o_d[4], n * 8); d2h(ho->theta, o_d[5], n * 8);
-        d2h(ho->ex_lo, o_lo, n * 4); d2h(ho->ex_hi, o_hi, n * 4); d2h(ho->status, o_st, n * 4);
+        FDM_TRY(cudaMemcpyAsync(hp + o_d[0], arena + o_d[0], o_end - o_d[0], cudaMemcpyDeviceToHost, st));   // every result column
         FDM_TRY(cudaStreamSynchronize(st));
+        if (rc == FDM_OK) {
+            get(ho->price_log2, o_d[0], n * 8); get(ho->price, o_d[1], n * 8); get(ho->delta, o_d[2], n * 8);
+            get(ho->gamma, o_d[3], n * 8); get(ho->vega, o_d[4], n * 8); get(ho->theta, o_d[5], n * 8);
+            get(ho->ex_lo, o_lo, n * 4); get(ho->ex_hi, o_hi, n * 4); get(ho->status, o_st, n * 4);
+        }
         if (kernel_ms && rc == FDM_OK) FDM_TRY(cudaEventElapsedTime(kernel_ms, cx.e0, cx.e1));
     }
     return rc;
@@ -809,7 +846,9 @@ int fdm_barrier_book_host(const FdmBarrierBook *hb, const FdmBookOut *ho, int64_
     const size_t i_mb = take(nmon ? (n + 1) * 4 : 0), i_ms = take(nmon * 4);
     const size_t o_d[5] = {take(n * 8), take(n * 8), take(n * 8), take(n * 8), take(n * 8)};
     const size_t o_st = take(n * 4);
+    const size_t o_end = off;
     const size_t i_oi = take(ho->out_index ? n * 4 : 0);
+    const size_t stage_end = off;                       // [0, stage_end) is mirrored in pinned host memory
     const size_t o_ws = take(fdm_barrier_book_workspace(n, hb->what));
 
     int dev = 0;
@@ -819,21 +858,17 @@ int fdm_barrier_book_host(const FdmBarrierBook *hb, const FdmBookOut *ho, int64_
     std::lock_guard<std::mutex> arena_lock(ar.mu);
     char *arena = nullptr;
     FDM_CUDA(arena_get(ar, off, &arena));
-    CallCtx cx;
-    FDM_TRY(cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking));
-    FDM_TRY(cudaEventCreate(&cx.e0));
-    FDM_TRY(cudaEventCreate(&cx.e1));
-    if (rc != FDM_OK) return rc;
-    cudaStream_t st = cx.st;
-    for (int i = 0; i < ND; ++i)
-        if (hd[i]) FDM_TRY(cudaMemcpyAsync(arena + i_d[i], hd[i], n * 8, cudaMemcpyHostToDevice, st));
-    FDM_TRY(cudaMemcpyAsync(arena + i_fl, hb->flags, n * 4, cudaMemcpyHostToDevice, st));
-    FDM_TRY(cudaMemcpyAsync(arena + i_ns, hb->n_space, n * 4, cudaMemcpyHostToDevice, st));
-    FDM_TRY(cudaMemcpyAsync(arena + i_nt, hb->n_time, n * 4, cudaMemcpyHostToDevice, st));
-    if (nmon) {
-        FDM_TRY(cudaMemcpyAsync(arena + i_mb, hb->mon_begin, (n + 1) * 4, cudaMemcpyHostToDevice, st));
-        FDM_TRY(cudaMemcpyAsync(arena + i_ms, hb->mon_step, nmon * 4, cudaMemcpyHostToDevice, st));
-    }
+    char *hp = nullptr;
+    FDM_CUDA(arena_host(ar, stage_end, &hp));
+    FDM_CUDA(arena_stream(ar));
+    cudaStream_t st = ar.st;
+    StreamDrain drain{st};
+    struct { cudaEvent_t e0, e1; } cx = {ar.e0, ar.e1};
+    auto put = [&](size_t o, const void *src, size_t bytes) { if (src && bytes) memcpy(hp + o, src, bytes); };
+    for (int i = 0; i < ND; ++i) put(i_d[i], hd[i], n * 8);
+    put(i_fl, hb->flags, n * 4); put(i_ns, hb->n_space, n * 4); put(i_nt, hb->n_time, n * 4);
+    if (nmon) { put(i_mb, hb->mon_begin, (n + 1) * 4); put(i_ms, hb->mon_step, nmon * 4); }
+    FDM_TRY(cudaMemcpyAsync(arena, hp, o_d[0], cudaMemcpyHostToDevice, st));       // every input array in one copy
     FdmBarrierBook db = *hb;
     const double **dp[ND] = {&db.S0, &db.K, &db.T, &db.sigma, &db.r_disc, &db.b_carry, &db.x_min, &db.dx, &db.barrier,
                              &db.rebate, &db.barrier_up};
@@ -849,7 +884,8 @@ int fdm_barrier_book_host(const FdmBarrierBook *hb, const FdmBookOut *ho, int64_
     dbo.price = (double *)(arena + o_d[0]); dbo.delta = (double *)(arena + o_d[1]); dbo.gamma = (double *)(arena + o_d[2]);
     dbo.vega = (double *)(arena + o_d[3]); dbo.theta = (double *)(arena + o_d[4]); dbo.status = (int32_t *)(arena + o_st);
     if (ho->out_index) {
-        FDM_TRY(cudaMemcpyAsync(arena + i_oi, ho->out_index, n * 4, cudaMemcpyHostToDevice, st));
+        put(i_oi, ho->out_index, n * 4);
+        FDM_TRY(cudaMemcpyAsync(arena + i_oi, hp + i_oi, n * 4, cudaMemcpyHostToDevice, st));
         dbo.out_index = (const int32_t *)(arena + i_oi);
     }
 
@@ -859,13 +895,14 @@ int fdm_barrier_book_host(const FdmBarrierBook *hb, const FdmBookOut *ho, int64_
         if (lrc != FDM_OK) rc = lrc;
         FDM_TRY(cudaEventRecord(cx.e1, st));
     }
-    auto d2h = [&](void *dst, size_t o, size_t bytes) {
-        if (dst && bytes) FDM_TRY(cudaMemcpyAsync(dst, arena + o, bytes, cudaMemcpyDeviceToHost, st));
-    };
+    auto get = [&](void *dst, size_t o, size_t bytes) { if (dst && bytes) memcpy(dst, hp + o, bytes); };
     if (rc == FDM_OK) {
-        d2h(ho->price, o_d[0], n * 8); d2h(ho->delta, o_d[1], n * 8); d2h(ho->gamma, o_d[2], n * 8);
-        d2h(ho->vega, o_d[3], n * 8); d2h(ho->theta, o_d[4], n * 8); d2h(ho->status, o_st, n * 4);
+        FDM_TRY(cudaMemcpyAsync(hp + o_d[0], arena + o_d[0], o_end - o_d[0], cudaMemcpyDeviceToHost, st));   // every result column
         FDM_TRY(cudaStreamSynchronize(st));
+        if (rc == FDM_OK) {
+            get(ho->price, o_d[0], n * 8); get(ho->delta, o_d[1], n * 8); get(ho->gamma, o_d[2], n * 8);
+            get(ho->vega, o_d[3], n * 8); get(ho->theta, o_d[4], n * 8); get(ho->status, o_st, n * 4);
+        }
         if (kernel_ms && rc == FDM_OK) FDM_TRY(cudaEventElapsedTime(kernel_ms, cx.e0, cx.e1));
     }
     return rc;
@@ -1031,12 +1068,16 @@ int fdm_release_workspace(void)
     for (int d = 0; d < MAX_DEVICES; ++d) {
         Arena &a = g_arenas[d];
         std::lock_guard<std::mutex> arena_lock(a.mu);
-        if (a.p) {
+        if (a.p || a.hp || a.st) {
             cudaSetDevice(d);
-            cudaFree(a.p);
+            if (a.st) cudaStreamSynchronize(a.st);
+            if (a.p) cudaFree(a.p);
+            if (a.hp) cudaFreeHost(a.hp);
+            if (a.e0) cudaEventDestroy(a.e0);
+            if (a.e1) cudaEventDestroy(a.e1);
+            if (a.st) cudaStreamDestroy(a.st);
         }
-        a.p = nullptr;
-        a.bytes = 0;
+        a.p = nullptr; a.bytes = 0; a.hp = nullptr; a.hbytes = 0; a.st = nullptr; a.e0 = a.e1 = nullptr;
     }
     if (have_cur) cudaSetDevice(cur);
     return FDM_OK;
